@@ -1,0 +1,376 @@
+"""CPU oracle for the PL-NeRF ray-rendering hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A numpy (float32) restatement of the reference's algorithm for the path named by BASELINE.json
+(render -> render_rays -> PE + coarse/fine MLP -> piecewise-linear quadrature -> inverse-CDF
+sampler).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module; the product package never does.
+
+Pinning: the reference has no tests or golden vectors of its own, so this oracle is
+pinned against outputs of the reference itself, imported unmodified from /root/reference in the
+build container by ``tests/golden/make_golden.py`` (fixtures committed under ``tests/golden``).
+``tests/test_oracle_golden.py`` checks every function below against those fixtures.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+Arithmetic notes that matter for bit-parity of the integer outputs:
+torch CPU ``cumsum``/``cumprod`` on float32 accumulate left-to-right in float64 and round each
+prefix to float32 -- ``_cumsum32``/``_cumprod32`` do exactly that.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+def _f(x):
+    return np.asarray(x, dtype=F32)
+
+
+def _cumsum32(x):
+    return np.cumsum(x.astype(np.float64), axis=-1).astype(F32)
+
+
+def _cumprod32(x):
+    return np.cumprod(x.astype(np.float64), axis=-1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
+# Positional encoding -- run_nerf_helpers.py:24-72 (Embedder.embed / get_embedder)
+# --------------------------------------------------------------------------------------------
+def embed(x, multires):
+    """[x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)], 3-wide blocks
+    (run_nerf_helpers.py:36-54).  multires < 0 -> identity (i_embed == -1, :58-59)."""
+    x = _f(x)
+    if multires < 0:
+        return x
+    outs = [x]
+    for k in range(multires):
+        freq = F32(2.0 ** k)
+        xf = x * freq
+        outs.append(np.sin(xf))
+        outs.append(np.cos(xf))
+    return np.concatenate(outs, -1).astype(F32)
+
+
+def embed_dim(multires):
+    return 3 if multires < 0 else 3 + 6 * multires
+
+
+# --------------------------------------------------------------------------------------------
+# MLP -- run_nerf_helpers.py:105-128 (NeRF.forward)
+# --------------------------------------------------------------------------------------------
+def _linear(h, params, name):
+    return h @ params[name + ".weight"].T + params[name + ".bias"]
+
+
+def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use_viewdirs=True):
+    """x [M, input_ch+input_ch_views] -> [M,4] (viewdirs) or [M,output_ch]
+    (run_nerf_helpers.py:105-128)."""
+    x = _f(x)
+    input_pts, input_views = x[:, :input_ch], x[:, input_ch:input_ch + input_ch_views]
+    h = input_pts
+    for i in range(D):
+        h = np.maximum(_linear(h, params, f"pts_linears.{i}"), F32(0))
+        if i in skips:
+            h = np.concatenate([input_pts, h], -1)
+    if use_viewdirs:
+        alpha = _linear(h, params, "alpha_linear")
+        feature = _linear(h, params, "feature_linear")
+        h = np.concatenate([feature, input_views], -1)
+        h = np.maximum(_linear(h, params, "views_linears.0"), F32(0))
+        rgb = _linear(h, params, "rgb_linear")
+        return np.concatenate([rgb, alpha], -1).astype(F32)
+    return _linear(h, params, "output_linear").astype(F32)
+
+
+def run_network(pts, viewdirs, params, multires=10, multires_views=4, netchunk=1024 * 64, **net_kw):
+    """run_plnerf.py:68-92 (batchify + run_network): flatten, PE, broadcast+PE dirs, chunked MLP."""
+    pts = _f(pts)
+    flat = pts.reshape(-1, pts.shape[-1])
+    embedded = embed(flat, multires)
+    if viewdirs is not None:
+        dirs = np.broadcast_to(_f(viewdirs)[:, None, :], pts.shape).reshape(-1, 3)
+        embedded = np.concatenate([embedded, embed(dirs, multires_views)], -1)
+    outs = [nerf_forward(params, embedded[i:i + netchunk], **net_kw)
+            for i in range(0, embedded.shape[0], netchunk)]
+    out = np.concatenate(outs, 0)
+    return out.reshape(list(pts.shape[:-1]) + [out.shape[-1]])
+
+
+# --------------------------------------------------------------------------------------------
+# Quadrature -- run_plnerf.py:504-624
+# --------------------------------------------------------------------------------------------
+def _norm3(rays_d):
+    return np.sqrt(np.sum(_f(rays_d) ** 2, -1, keepdims=True)).astype(F32)
+
+
+def compute_weights(raw, z_vals, rays_d, noise=0.0):
+    """Piecewise-constant weights, run_plnerf.py:504-513."""
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = np.concatenate([dists, np.full_like(dists[..., :1], 1e10)], -1)
+    dists = dists * _norm3(rays_d)
+    sigma = np.maximum(raw[..., 3] + _f(noise), F32(0))
+    alpha = F32(1.0) - np.exp(-sigma * dists)
+    trans = _cumprod32(np.concatenate([np.ones((alpha.shape[0], 1), F32),
+                                       F32(1.0) - alpha + F32(1e-10)], -1))[:, :-1]
+    return (alpha * trans).astype(F32)
+
+
+def compute_weights_piecewise_linear(raw, z_vals, near, far, rays_d, noise=0.0):
+    """PL weights, tau, T -- run_plnerf.py:516-550."""
+    z = np.concatenate([near, z_vals, far], -1)
+    dists = (z[..., 1:] - z[..., :-1]) * _norm3(rays_d)
+    n = raw.shape[0]
+    tau = np.concatenate([np.full((n, 1), 1e-10, F32), raw[..., 3] + _f(noise),
+                          np.full((n, 1), 1e10, F32)], -1).astype(F32)
+    tau = np.maximum(tau, F32(0))
+    interval_ave_tau = F32(0.5) * (tau[..., 1:] + tau[..., :-1])
+    expr = np.exp(-interval_ave_tau * dists).astype(F32)
+    T = _cumprod32(np.concatenate([np.ones((n, 1), F32), expr], -1))
+    weights = ((F32(1) - expr) * T[:, :-1]).astype(F32)
+    return weights, tau, T
+
+
+def _sigmoid(x):
+    return (F32(1) / (F32(1) + np.exp(-x))).astype(F32)
+
+
+def raw2outputs(raw, z_vals, near, far, rays_d, mode, color_mode, noise=0.0, white_bkgd=False,
+                farcolorfix=False):
+    """run_plnerf.py:553-624.  ``noise`` is the already-scaled additive density noise
+    (randn*raw_noise_std in the reference, :569-576) or 0."""
+    raw = _f(raw)
+    z_vals = _f(z_vals)
+    rgb = _sigmoid(raw[..., :3])
+    if mode == "linear":
+        weights, tau, T = compute_weights_piecewise_linear(raw, z_vals, near, far, rays_d, noise)
+        if color_mode == "midpoint":
+            last = np.zeros_like(rgb[:, -1:, :]) if farcolorfix else rgb[:, -1:, :]
+            cc = np.concatenate([rgb[:, :1, :], rgb, last], 1)
+            rgb_mid = F32(0.5) * (cc[:, 1:, :] + cc[:, :-1, :])
+            rgb_map = np.sum(weights[..., None] * rgb_mid, -2, dtype=F32)
+        elif color_mode == "left":
+            cc = np.concatenate([rgb[:, :1, :], rgb], 1)
+            rgb_map = np.sum(weights[..., None] * cc, -2, dtype=F32)
+        else:
+            raise ValueError(color_mode)
+        zz = np.concatenate([near, z_vals, far], -1)
+        z_mid = F32(0.5) * (zz[..., 1:] + zz[..., :-1])
+        depth_map = np.sum(weights * z_mid, -1, dtype=F32)
+    elif mode == "constant":
+        weights = compute_weights(raw, z_vals, rays_d, noise)
+        rgb_map = np.sum(weights[..., None] * rgb, -2, dtype=F32)
+        depth_map = np.sum(weights * z_vals, -1, dtype=F32)
+        tau = None
+        T = None
+    else:
+        raise ValueError(mode)
+    acc_map = np.sum(weights, -1, dtype=F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        disp_map = (F32(1.0) / np.maximum(F32(1e-10), depth_map / acc_map)).astype(F32)
+    if white_bkgd:
+        rgb_map = rgb_map + (F32(1.0) - acc_map[..., None])
+    return rgb_map.astype(F32), disp_map, acc_map, weights, depth_map, tau, T
+
+
+# --------------------------------------------------------------------------------------------
+# Samplers -- run_nerf_helpers.py:241-284 (constant) and :340-445 (PL)
+# --------------------------------------------------------------------------------------------
+def _searchsorted_right(cdf, u):
+    """torch.searchsorted(cdf, u, right=True) per row: first index i with cdf[i] > u."""
+    return np.sum(cdf[:, None, :] <= u[:, :, None], -1).astype(np.int64)
+
+
+def sample_pdf(bins, weights, u):
+    """Piecewise-constant inverse CDF, run_nerf_helpers.py:241-284, with the uniforms ``u``
+    [N,Ni] supplied by the caller.  Returns (samples, inds)."""
+    bins = _f(bins)
+    u = _f(u)
+    weights = _f(weights) + F32(1e-5)
+    pdf = weights / np.sum(weights, -1, keepdims=True, dtype=F32)
+    cdf = _cumsum32(pdf)
+    cdf = np.concatenate([np.zeros_like(cdf[..., :1]), cdf], -1)
+    inds = _searchsorted_right(cdf, u)
+    below = np.maximum(0, inds - 1)
+    above = np.minimum(cdf.shape[-1] - 1, inds)
+    cdf_b = np.take_along_axis(cdf, below, -1)
+    cdf_a = np.take_along_axis(cdf, above, -1)
+    bins_b = np.take_along_axis(bins, below, -1)
+    bins_a = np.take_along_axis(bins, above, -1)
+    denom = cdf_a - cdf_b
+    denom = np.where(denom < F32(1e-5), F32(1), denom)
+    t = (u - cdf_b) / denom
+    return (bins_b + t * (bins_a - bins_b)).astype(F32), inds
+
+
+def _ln_term(T_left, u, eps):
+    # run_nerf_helpers.py:341 / :353
+    return -np.log(np.maximum(eps, (F32(1) - u) / np.maximum(eps, T_left)))
+
+
+def pw_linear_sample_increasing(s_left, s_right, T_left, tau_left, tau_right, u, epsilon=1e-3):
+    """run_nerf_helpers.py:340-349."""
+    eps = F32(epsilon)
+    ln_term = _ln_term(T_left, u, eps)
+    disc = tau_left ** 2 + (F32(2) * (tau_right - tau_left) * ln_term) / np.maximum(eps, s_right - s_left)
+    t = ((s_right - s_left) * (-tau_left + np.sqrt(np.maximum(eps, disc)))) / np.maximum(eps, tau_right - tau_left)
+    t = np.minimum(np.maximum(t, eps), s_right - s_left)   # torch.clamp(min, max): max wins
+    return (s_left + t).astype(F32)
+
+
+def pw_linear_sample_decreasing(s_left, s_right, T_left, tau_left, tau_right, u, epsilon=1e-3):
+    """run_nerf_helpers.py:352-361."""
+    eps = F32(epsilon)
+    ln_term = _ln_term(T_left, u, eps)
+    disc = tau_left ** 2 - (F32(2) * (tau_left - tau_right) * ln_term) / np.maximum(eps, s_right - s_left)
+    t = ((s_right - s_left) * (tau_left - np.sqrt(np.maximum(eps, disc)))) / np.maximum(eps, tau_left - tau_right)
+    t = np.minimum(np.maximum(t, eps), s_right - s_left)
+    return (s_left + t).astype(F32)
+
+
+def sample_pdf_reformulation(bins, weights, tau, T, near, far, u, zero_threshold=1e-4, epsilon_=1e-3):
+    """PL inverse-CDF sampler, run_nerf_helpers.py:364-445, uniforms supplied.
+    Returns (samples, inds) with inds the int64 searchsorted result (:397)."""
+    bins = np.concatenate([_f(near), _f(bins), _f(far)], -1)
+    u = _f(u)
+    cdf = _cumsum32(_f(weights))
+    cdf = np.concatenate([np.zeros_like(cdf[..., :1]), cdf], -1)
+    cdf[:, -1] = 1.0
+    inds = _searchsorted_right(cdf, u)
+    below = np.maximum(0, inds - 1)
+    above = np.minimum(cdf.shape[-1] - 1, inds)
+    g = lambda a, i: np.take_along_axis(a, i, -1)
+    s_left, s_right = g(bins, below), g(bins, above)
+    T_left = g(T, below)
+    tau_left, tau_right = g(tau, below), g(tau, above)
+    tau_diff = tau[..., 1:] - tau[..., :-1]
+    if below.max(initial=0) >= tau_diff.shape[-1]:
+        # the reference raises here too (SURVEY.md 8c caveat 3: u == 1.0 with det=True)
+        raise IndexError("index out of range in tau_diff gather (u must be < 1)")
+    tau_diff_g = g(tau_diff, below)
+    zt = F32(zero_threshold)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        inc = pw_linear_sample_increasing(s_left, s_right, T_left, tau_left, tau_right, u, epsilon_)
+        dec = pw_linear_sample_decreasing(s_left, s_right, T_left, tau_left, tau_right, u, epsilon_)
+    samples = np.where((tau_diff_g < zt) & (tau_diff_g > -zt), s_left, F32(-1.0))
+    samples = np.where(tau_diff_g >= zt, inc, samples)
+    samples = np.where(tau_diff_g <= -zt, dec, samples)
+    samples = np.where(np.isnan(samples), s_left, samples)
+    return samples.astype(F32), inds
+
+
+# --------------------------------------------------------------------------------------------
+# render_rays / render -- run_plnerf.py:95-175, 627-758
+# --------------------------------------------------------------------------------------------
+def stratified_z(near, far, N_samples, t_rand=None, lindisp=False):
+    """run_plnerf.py:683-705.  t_rand None -> perturb == 0."""
+    # torch.linspace(0,1,steps) in fp32 (ATen RangeFactories): step = fl32(1/(n-1)); first half
+    # start + step*i, second half end - step*(n-1-i), each evaluated with ONE rounding (fused
+    # multiply-add: verified bit-exact against torch 2.11 CPU; the CUDA kernel contracts the same
+    # way).  The product step32*k is exact in float64, so float64 arithmetic + one cast is an fma.
+    step = np.float64(F32(1.0) / F32(N_samples - 1)) if N_samples > 1 else np.float64(0)
+    idx = np.arange(N_samples)
+    half = N_samples // 2
+    t_vals = np.where(idx < half, step * idx, 1.0 - step * (N_samples - 1 - idx)).astype(F32)
+    if not lindisp:
+        z = near * (F32(1) - t_vals) + far * t_vals
+    else:
+        z = F32(1) / (F32(1) / near * (F32(1) - t_vals) + F32(1) / far * t_vals)
+    z = np.broadcast_to(z, (near.shape[0], N_samples)).astype(F32)
+    if t_rand is not None:
+        mids = F32(0.5) * (z[..., 1:] + z[..., :-1])
+        upper = np.concatenate([mids, z[..., -1:]], -1)
+        lower = np.concatenate([z[..., :1], mids], -1)
+        z = lower + (upper - lower) * _f(t_rand)
+    return z.astype(F32)
+
+
+def render_rays(ray_batch, params_coarse, params_fine, N_samples, mode, color_mode, N_importance=0,
+                t_rand=None, u=None, noise0=0.0, noise1=0.0, lindisp=False, white_bkgd=False,
+                zero_tol=1e-4, epsilon=1e-3, farcolorfix=False, constant_init=False, retraw=False,
+                multires=10, multires_views=4, net_kw=None):
+    """run_plnerf.py:627-758 with the random draws (t_rand, u, noise) made explicit."""
+    net_kw = net_kw or {}
+    ray_batch = _f(ray_batch)
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
+    near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
+    z_vals = stratified_z(near, far, N_samples, t_rand, lindisp)
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[:, :, None]
+    if constant_init:
+        mode = "constant"
+    q = lambda p, prm: run_network(p, viewdirs, prm, multires, multires_views, **net_kw)
+    raw = q(pts, params_coarse)
+    rgb_map, disp_map, acc_map, weights, depth_map, tau, T = raw2outputs(
+        raw, z_vals, near, far, rays_d, mode, color_mode, noise0, white_bkgd, farcolorfix)
+    ret = {}
+    if N_importance > 0:
+        ret.update(rgb0=rgb_map, disp0=disp_map, depth0=depth_map, acc0=acc_map)
+        ret.update(z_vals0=z_vals, weights0=weights, raw0=raw)
+        if mode == "linear":
+            ret.update(tau0=tau, T0=T)
+            z_samples, inds = sample_pdf_reformulation(z_vals, weights, tau, T, near, far, u,
+                                                       zero_tol, epsilon)
+        else:
+            z_mid = F32(0.5) * (z_vals[..., 1:] + z_vals[..., :-1])
+            z_samples, inds = sample_pdf(z_mid, weights[..., 1:-1], u)
+        ret.update(inds=inds, z_samples_raw=z_samples)
+        z_samples = np.minimum(np.maximum(z_samples, near), far)
+        z_vals = np.sort(np.concatenate([z_vals, z_samples], -1), -1)
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[:, :, None]
+        raw = q(pts, params_fine if params_fine is not None else params_coarse)
+        rgb_map, disp_map, acc_map, weights, depth_map, tau, T = raw2outputs(
+            raw, z_vals, near, far, rays_d, mode, color_mode, noise1, white_bkgd, farcolorfix)
+        ret["z_std"] = np.std(z_samples.astype(F32), -1).astype(F32)
+        ret["z_vals"] = z_vals
+    ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map)
+    if retraw:
+        ret["raw"] = raw
+    return ret
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """run_nerf_helpers.py:184-201."""
+    rays_o, rays_d = _f(rays_o), _f(rays_d)
+    t = -(F32(near) + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    sx = F32(-1.0 / (W / (2.0 * focal)))
+    sy = F32(-1.0 / (H / (2.0 * focal)))
+    o0 = sx * rays_o[..., 0] / rays_o[..., 2]
+    o1 = sy * rays_o[..., 1] / rays_o[..., 2]
+    o2 = F32(1.0) + F32(2.0 * near) / rays_o[..., 2]
+    d0 = sx * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
+    d1 = sy * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
+    d2 = F32(-2.0 * near) / rays_o[..., 2]
+    return np.stack([o0, o1, o2], -1).astype(F32), np.stack([d0, d1, d2], -1).astype(F32)
+
+
+def pack_rays(H, W, K, rays_o, rays_d, near, far, use_viewdirs, ndc):
+    """The ray-batch packing done by render(), run_plnerf.py:140-164 -> [N, 8|11]."""
+    rays_o, rays_d = _f(rays_o).reshape(-1, 3), _f(rays_d).reshape(-1, 3)
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d / np.sqrt(np.sum(rays_d ** 2, -1, keepdims=True))
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1.0, rays_o, rays_d)
+    nearv = F32(near) * np.ones_like(rays_d[..., :1])
+    farv = F32(far) * np.ones_like(rays_d[..., :1])
+    cols = [rays_o, rays_d, nearv, farv] + ([viewdirs] if use_viewdirs else [])
+    return np.concatenate(cols, -1).astype(F32)
+
+
+def render(H, W, K, rays_o, rays_d, chunk=1024 * 32, ndc=True, near=0.0, far=1.0, use_viewdirs=False,
+           t_rand=None, u=None, noise0=None, noise1=None, **kwargs):
+    """run_plnerf.py:110-175 + batchify_rays :95-107 (chunked over rays, dict of concatenated
+    outputs).  Per-ray random tensors are sliced per chunk."""
+    rays = pack_rays(H, W, K, rays_o, rays_d, near, far, use_viewdirs, ndc)
+    outs = {}
+    sl = lambda a, i: None if a is None else a[i:i + chunk]
+    for i in range(0, rays.shape[0], chunk):
+        kw = dict(kwargs)
+        if noise0 is not None:
+            kw["noise0"] = noise0[i:i + chunk]
+        if noise1 is not None:
+            kw["noise1"] = noise1[i:i + chunk]
+        r = render_rays(rays[i:i + chunk], t_rand=sl(t_rand, i), u=sl(u, i), **kw)
+        for k, v in r.items():
+            outs.setdefault(k, []).append(v)
+    return {k: np.concatenate(v, 0) for k, v in outs.items()}
