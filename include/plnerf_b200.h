@@ -1,0 +1,199 @@
+/*
+ * plnerf_b200 -- C ABI of the B200-native (sm_100a) PL-NeRF ray-rendering hot path.
+ *
+ * The reference (mikacuy/PL-NeRF) is pure Python/PyTorch and has no FFI layer; its pluggable seams
+ * are Python callables.  Each entry point below replaces one of those
+ * callables; the citation is the reference interface it stands in for (paths relative to the
+ * reference repo root).  The Python host side (pl-nerf_b200/run_plnerf.py, run_nerf_helpers.py)
+ * binds these through ctypes with torch tensors as device buffers; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated; buffers are caller-owned,
+ *     row-major, contiguous unless a stride is given;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - every function returns 0 on success, <0 on error (PLNERF_E_*), never throws or aborts;
+ *     plnerf_last_error() returns a thread-local message for the last failure;
+ *   - optional pointers may be NULL where documented;
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns PLNERF_E_CUDA.
+ */
+#ifndef PLNERF_B200_H
+#define PLNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLNERF_ABI_VERSION 1
+
+enum {
+  PLNERF_OK = 0,
+  PLNERF_E_BADARG = -1,      /* null pointer, negative size, misaligned buffer */
+  PLNERF_E_UNSUPPORTED = -2, /* shape outside what the sm_100a kernels implement */
+  PLNERF_E_CUDA = -3,        /* CUDA runtime error (message in plnerf_last_error) */
+  PLNERF_E_WORKSPACE = -4    /* workspace too small */
+};
+
+enum { PLNERF_MODE_CONSTANT = 0, PLNERF_MODE_LINEAR = 1 };      /* --mode, run_plnerf.py:906 */
+enum { PLNERF_COLOR_MIDPOINT = 0, PLNERF_COLOR_LEFT = 1 };      /* --color_mode, run_plnerf.py:908 */
+enum { PLNERF_PREC_BF16 = 0,    /* one bf16 tcgen05 MMA per product, fp32 accumulate (fast)      */
+       PLNERF_PREC_BF16X3 = 1   /* hi/lo bf16 split, 3 MMAs per product (~fp32 products, parity) */ };
+
+#define PLNERF_MAX_DEPTH 16
+
+/* Architecture of one NeRF MLP: mirrors NeRF.__init__ (run_nerf_helpers.py:77-103). */
+typedef struct plnerf_net_desc {
+  int32_t D;               /* trunk depth (8) */
+  int32_t W;               /* trunk width (256; the only width the tcgen05 kernel implements) */
+  int32_t input_ch;        /* 3 + 6*multires (63) or 3 */
+  int32_t input_ch_views;  /* 3 + 6*multires_views (27), 3, or 0 */
+  int32_t output_ch;       /* only read when use_viewdirs == 0 (4 or 5) */
+  int32_t use_viewdirs;
+  int32_t n_skips;
+  int32_t skips[PLNERF_MAX_DEPTH]; /* layer indices i after which [input_pts, h] is concatenated */
+} plnerf_net_desc;
+
+/* fp32 parameters in the reference's state_dict layout ([out,in] row-major weights), i.e. the
+ * tensors of NeRF.state_dict() (run_nerf_helpers.py:85-103), passed by device pointer. */
+typedef struct plnerf_net_params {
+  const float* pts_w[PLNERF_MAX_DEPTH]; /* pts_linears.i.weight */
+  const float* pts_b[PLNERF_MAX_DEPTH]; /* pts_linears.i.bias   */
+  const float* views_w;   /* views_linears.0.weight [W/2, W + input_ch_views] */
+  const float* views_b;
+  const float* feature_w; /* feature_linear [W,W]   (use_viewdirs) */
+  const float* feature_b;
+  const float* alpha_w;   /* alpha_linear [1,W]     (use_viewdirs) */
+  const float* alpha_b;
+  const float* rgb_w;     /* rgb_linear [3,W/2]     (use_viewdirs) */
+  const float* rgb_b;
+  const float* output_w;  /* output_linear [output_ch,W] (!use_viewdirs) */
+  const float* output_b;
+} plnerf_net_params;
+
+/* Everything render_rays() receives besides tensors (run_plnerf.py:627-646). */
+typedef struct plnerf_render_cfg {
+  int32_t N_samples;
+  int32_t N_importance;
+  int32_t mode;           /* PLNERF_MODE_*; constant_init is applied by the caller (mode=constant) */
+  int32_t color_mode;     /* PLNERF_COLOR_* */
+  int32_t white_bkgd;
+  int32_t lindisp;
+  int32_t farcolorfix;
+  int32_t perturb;        /* != 0: stratified jitter + random u (run_plnerf.py:691-705) */
+  float raw_noise_std;
+  float zero_tol;         /* 1e-4 */
+  float epsilon;          /* 1e-3 */
+  int32_t multires;       /* xyz PE frequencies (10); -1 = identity */
+  int32_t multires_views; /* dir PE frequencies (4);  -1 = identity */
+  int32_t precision;      /* PLNERF_PREC_* */
+  uint64_t seed;          /* Philox key for draws not supplied explicitly */
+  uint64_t ray_id_offset; /* global index of ray 0 (keeps RNG invariant to chunking / sharding) */
+} plnerf_render_cfg;
+
+/* Output / intermediate buffers of one render_rays call.  NULL = not wanted.  */
+typedef struct plnerf_render_out {
+  float* rgb_map;   /* [n,3]  */
+  float* disp_map;  /* [n]    */
+  float* acc_map;   /* [n]    */
+  float* depth_map; /* [n]    */
+  float* raw;       /* [n, S_last, 4] raw of the last pass (retraw), may be NULL */
+  float* rgb0;      /* [n,3]  coarse outputs, only written when N_importance > 0 */
+  float* disp0;
+  float* acc0;
+  float* depth0;
+  float* z_std;     /* [n]    */
+  float* z_vals;    /* [n, N_samples+N_importance] merged depths (or [n,N_samples]), may be NULL */
+  int64_t* inds;    /* [n, N_importance] searchsorted indices, may be NULL */
+} plnerf_render_out;
+
+const char* plnerf_last_error(void);
+int plnerf_abi_version(void);
+/* Number of CUDA kernels this library has launched since load (claim for bench.py gpu_launches). */
+uint64_t plnerf_launch_count(void);
+
+/* ---- a5: Embedder.embed / get_embedder (run_nerf_helpers.py:24-72) ---------------------------
+ * x [n,3] -> out [n, 3+6*multires]  (multires < 0: copy). */
+int plnerf_encode(const float* x, int64_t n, int multires, float* out, void* stream);
+
+/* ---- a3 (first part): stratified depths, render_rays (run_plnerf.py:683-705) -----------------
+ * rays [n, stride] (cols 6,7 = near, far).  t_rand [n,Ns] explicit jitter in [0,1) or NULL;
+ * with t_rand == NULL, perturb != 0 draws Philox(seed, ray id, sample) jitter. */
+int plnerf_stratified_z(const float* rays, int64_t n, int stride, int N_samples, int lindisp,
+                        int perturb, const float* t_rand, uint64_t seed, uint64_t ray_id_offset,
+                        float* z_vals, void* stream);
+
+/* ---- weights: repack NeRF.state_dict() tensors into the kernel's streaming layout -------------
+ * (bf16 hi[/lo] K-major UMMA core-matrix panels in layer order + fp32 bias/head block).  Must be
+ * re-run whenever the parameters change (after optimizer.step()). */
+size_t plnerf_packed_bytes(const plnerf_net_desc* desc, int precision);
+int plnerf_pack_weights(const plnerf_net_desc* desc, const plnerf_net_params* params, int precision,
+                        void* packed, void* stream);
+
+/* ---- a4+a5+a7: network_query_fn == run_network (run_plnerf.py:78-92) --------------------------
+ * pts = rays_o + rays_d * z (never materialised), PE, MLP.  rays [n, stride] with cols 0-2 origin,
+ * 3-5 direction, last 3 = unit viewdir when desc->use_viewdirs.  z [n,S] -> raw [n,S,4].
+ * ws: workspace of plnerf_query_workspace_bytes(desc, n) bytes. */
+size_t plnerf_query_workspace_bytes(const plnerf_net_desc* desc, int64_t n_rays);
+int plnerf_network_query(const plnerf_net_desc* desc, const void* packed, int precision,
+                         int multires, int multires_views, const float* rays, int64_t n, int stride,
+                         const float* z, int S, float* raw, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a7: NeRF.forward (run_nerf_helpers.py:105-128) on already-embedded rows ------------------
+ * x [m, input_ch + input_ch_views] -> out [m,4] (use_viewdirs) or [m,output_ch].
+ * ws: plnerf_query_workspace_bytes(desc, m). */
+int plnerf_mlp_forward(const plnerf_net_desc* desc, const void* packed, int precision,
+                       const float* x, int64_t m, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a8/a9/a10: raw2outputs + compute_weights{,_piecewise_linear} (run_plnerf.py:504-624) -----
+ * raw [n,S,raw_stride>=4], z [n,S], rays [n,stride] (dir cols 3-5, near/far cols 6,7).
+ * noise [n,S] additive density noise already scaled by raw_noise_std, or NULL.
+ * Optional outputs: weights [n,S+1] (linear) / [n,S] (constant); tau,T [n,S+2] (linear only). */
+int plnerf_raw2outputs(const float* raw, int raw_stride, const float* z, const float* rays,
+                       int64_t n, int stride, int S, int mode, int color_mode, int white_bkgd,
+                       int farcolorfix, const float* noise, float* rgb_map, float* disp_map,
+                       float* acc_map, float* depth_map, float* weights, float* tau, float* T,
+                       void* stream);
+
+/* ---- a11: sample_pdf_reformulation (+pw_linear_sample_*) (run_nerf_helpers.py:340-445) --------
+ * z [n,S], weights [n,S+1], tau,T [n,S+2], rays (near/far cols 6,7), u [n,Ni] in [0,1) or NULL
+ * (Philox).  -> samples [n,Ni] (unclamped, unsorted), inds [n,Ni] int64 or NULL. */
+int plnerf_sample_pdf_pl(const float* z, const float* weights, const float* tau, const float* T,
+                         const float* rays, int64_t n, int stride, int S, int Ni, const float* u,
+                         uint64_t seed, uint64_t ray_id_offset, float zero_tol, float epsilon,
+                         float* samples, int64_t* inds, void* stream);
+
+/* ---- a12: sample_pdf (run_nerf_helpers.py:241-284) ---------------------------------------------
+ * bins [n,nb], weights [n,nb-1] (raw, the +1e-5 and normalisation happen inside). */
+int plnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb, int Ni,
+                      const float* u, uint64_t seed, uint64_t ray_id_offset, float* samples,
+                      int64_t* inds, void* stream);
+
+/* ---- a13: clamp + sort-merge + z_std (run_plnerf.py:728-734, :752) ----------------------------
+ * z [n,S] ascending, samples [n,Ni] -> z_out [n,S+Ni] ascending; z_std [n] or NULL. */
+int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n,
+                         int stride, int S, int Ni, float* z_out, float* z_std, void* stream);
+
+/* ---- a3: render_rays (run_plnerf.py:627-758), forward ------------------------------------------
+ * rays [n, stride] = [o(3), d(3), near, far, (viewdir(3))].  Explicit draws (any may be NULL):
+ * t_rand [n,Ns], u [n,Ni], noise0 [n,Ns], noise1 [n,Ns+Ni] (already scaled).
+ * fine_desc/fine_packed NULL -> the coarse network is used for the fine pass (network_fine=None).
+ */
+size_t plnerf_render_workspace_bytes(const plnerf_render_cfg* cfg, const plnerf_net_desc* desc,
+                                     int64_t n_rays);
+int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc,
+                           const void* coarse_packed, const plnerf_net_desc* fine_desc,
+                           const void* fine_packed, const float* rays, int64_t n, int stride,
+                           const float* t_rand, const float* u, const float* noise0,
+                           const float* noise1, const plnerf_render_out* out, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ---- debug: single-tile tcgen05 GEMM used by the test-suite to pin descriptor encodings --------
+ * D[128,N] = A[128,K] * B[N,K]^T, bf16-rounded operands, fp32 accumulate (K%16==0, N%16==0<=256).*/
+int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLNERF_B200_H */

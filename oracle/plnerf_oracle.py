@@ -61,24 +61,44 @@ def _linear(h, params, name):
     return h @ params[name + ".weight"].T + params[name + ".bias"]
 
 
-def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use_viewdirs=True):
+def bf16_round(x):
+    """Round float32 to the nearest bfloat16 (ties to even), returned as float32."""
+    x = np.ascontiguousarray(x, dtype=F32)
+    b = x.view(np.uint32)
+    r = ((b + np.uint32(0x7FFF) + ((b >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).astype(np.uint32)
+    return r.view(F32).reshape(x.shape)
+
+
+def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use_viewdirs=True,
+                 emulate_bf16=False):
     """x [M, input_ch+input_ch_views] -> [M,4] (viewdirs) or [M,output_ch]
-    (run_nerf_helpers.py:105-128)."""
+    (run_nerf_helpers.py:105-128).
+
+    emulate_bf16=True restates the arithmetic of the fast tcgen05 kernel (NOT of the reference):
+    GEMM operands (activations, PE inputs, trunk/feature/views weights) rounded to bf16 with fp32
+    accumulation; biases, the alpha / rgb / output_linear heads and the viewdir columns of
+    views_linears stay fp32 and read the un-rounded fp32 activations."""
     x = _f(x)
+    rnd = bf16_round if emulate_bf16 else (lambda a: a)
     input_pts, input_views = x[:, :input_ch], x[:, input_ch:input_ch + input_ch_views]
-    h = input_pts
+    pts_q = rnd(input_pts)
+    h = pts_q
+    h32 = None
     for i in range(D):
-        h = np.maximum(_linear(h, params, f"pts_linears.{i}"), F32(0))
+        w, b = params[f"pts_linears.{i}.weight"], params[f"pts_linears.{i}.bias"]
+        h32 = np.maximum(h @ rnd(w).T + b, F32(0))
+        h = rnd(h32)
         if i in skips:
-            h = np.concatenate([input_pts, h], -1)
+            h = np.concatenate([pts_q, h], -1)
     if use_viewdirs:
-        alpha = _linear(h, params, "alpha_linear")
-        feature = _linear(h, params, "feature_linear")
-        h = np.concatenate([feature, input_views], -1)
-        h = np.maximum(_linear(h, params, "views_linears.0"), F32(0))
-        rgb = _linear(h, params, "rgb_linear")
+        alpha = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
+        feature = rnd(h @ rnd(params["feature_linear.weight"]).T + params["feature_linear.bias"])
+        wv, bv = params["views_linears.0.weight"], params["views_linears.0.bias"]
+        W = feature.shape[1]
+        hv = np.maximum(feature @ rnd(wv[:, :W]).T + (input_views @ wv[:, W:].T + bv), F32(0))
+        rgb = hv @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
         return np.concatenate([rgb, alpha], -1).astype(F32)
-    return _linear(h, params, "output_linear").astype(F32)
+    return (h32 @ params["output_linear.weight"].T + params["output_linear.bias"]).astype(F32)
 
 
 def run_network(pts, viewdirs, params, multires=10, multires_views=4, netchunk=1024 * 64, **net_kw):
@@ -175,8 +195,23 @@ def raw2outputs(raw, z_vals, near, far, rays_d, mode, color_mode, noise=0.0, whi
 # Samplers -- run_nerf_helpers.py:241-284 (constant) and :340-445 (PL)
 # --------------------------------------------------------------------------------------------
 def _searchsorted_right(cdf, u):
-    """torch.searchsorted(cdf, u, right=True) per row: first index i with cdf[i] > u."""
-    return np.sum(cdf[:, None, :] <= u[:, :, None], -1).astype(np.int64)
+    """torch.searchsorted(cdf, u, right=True) per row, as ATen computes it: the upper-bound binary
+    search  `mid = start + (end-start)//2; if !(cdf[mid] > u) start = mid+1 else end = mid`
+    (identical to "first i with cdf[i] > u" on sorted rows, and well defined when the forced
+    cdf[-1] = 1.0 makes the row non-monotone by an ulp)."""
+    n, m = cdf.shape[0], cdf.shape[1]
+    start = np.zeros(u.shape, np.int64)
+    end = np.full(u.shape, m, np.int64)
+    for _ in range(int(np.ceil(np.log2(m + 1))) + 1):
+        active = start < end
+        mid = start + ((end - start) >> 1)
+        midc = np.minimum(mid, m - 1)
+        val = np.take_along_axis(cdf, midc, -1)
+        go_right = active & ~(val > u)
+        go_left = active & (val > u)
+        start = np.where(go_right, mid + 1, start)
+        end = np.where(go_left, mid, end)
+    return start
 
 
 def sample_pdf(bins, weights, u):

@@ -1,0 +1,218 @@
+// C ABI of libplnerf_b200 (declared in include/plnerf_b200.h): argument validation, error plumbing
+// and the render_rays orchestration (reference run_plnerf.py:627-758) on one CUDA stream.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace plnerf {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return PLNERF_E_CUDA;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
+
+// workspace carving for render_rays
+struct RenderWs {
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1;
+  void* mlp_ws; size_t mlp_ws_bytes;
+  size_t total;
+};
+static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+static RenderWs carve(const plnerf_render_cfg* c, const plnerf_net_desc* d, int64_t n, uint8_t* base) {
+  RenderWs w;
+  size_t off = 0;
+  const int Ns = c->N_samples, Ni = c->N_importance, S1 = Ns + Ni;
+  auto take = [&](size_t floats) { float* p = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float)); return p; };
+  const int ch0 = 4 > (d->use_viewdirs ? 4 : d->output_ch) ? 4 : (d->use_viewdirs ? 4 : d->output_ch);
+  w.z0 = take((size_t)n * Ns);
+  w.raw0 = take((size_t)n * Ns * ch0);
+  w.w0 = take((size_t)n * (Ns + 1));
+  w.tau0 = take((size_t)n * (Ns + 2));
+  w.T0 = take((size_t)n * (Ns + 2));
+  w.zs = take((size_t)n * (Ni > 0 ? Ni : 1));
+  w.z1 = take((size_t)n * S1);
+  w.raw1 = take((size_t)n * S1 * ch0);
+  w.mlp_ws = base + off;
+  w.mlp_ws_bytes = mlp_workspace_bytes(d, n);
+  off += align_up(w.mlp_ws_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace plnerf
+
+using namespace plnerf;
+
+extern "C" {
+
+const char* plnerf_last_error(void) { return g_err; }
+int plnerf_abi_version(void) { return PLNERF_ABI_VERSION; }
+uint64_t plnerf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int plnerf_encode(const float* x, int64_t n, int multires, float* out, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (x && out)), "encode: null argument");
+  PLNERF_CHECK_ARG(multires <= 16, "encode: multires too large");
+  return launch_encode(x, n, multires, out, (cudaStream_t)stream);
+}
+
+int plnerf_stratified_z(const float* rays, int64_t n, int stride, int N_samples, int lindisp, int perturb,
+                        const float* t_rand, uint64_t seed, uint64_t ray_id_offset, float* z_vals, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (rays && z_vals)), "stratified_z: null argument");
+  PLNERF_CHECK_ARG(stride >= 8 && N_samples >= 1, "stratified_z: need stride >= 8 and N_samples >= 1");
+  return launch_stratified_z(rays, n, stride, N_samples, lindisp, perturb, t_rand, seed, ray_id_offset, z_vals,
+                             (cudaStream_t)stream);
+}
+
+size_t plnerf_packed_bytes(const plnerf_net_desc* desc, int precision) { return mlp_packed_bytes(desc, precision); }
+
+int plnerf_pack_weights(const plnerf_net_desc* desc, const plnerf_net_params* params, int precision, void* packed,
+                        void* stream) {
+  return mlp_pack(desc, params, precision, packed, (cudaStream_t)stream);
+}
+
+size_t plnerf_query_workspace_bytes(const plnerf_net_desc* desc, int64_t n_rays) { return mlp_workspace_bytes(desc, n_rays); }
+
+int plnerf_network_query(const plnerf_net_desc* desc, const void* packed, int precision, int multires,
+                         int multires_views, const float* rays, int64_t n, int stride, const float* z, int S,
+                         float* raw, void* ws, size_t ws_bytes, void* stream) {
+  PLNERF_CHECK_ARG(desc, "network_query: null desc");
+  return mlp_query(desc, packed, precision, multires, multires_views, rays, n, stride, z, S, raw,
+                   desc->use_viewdirs ? 4 : desc->output_ch, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int plnerf_mlp_forward(const plnerf_net_desc* desc, const void* packed, int precision, const float* x, int64_t m,
+                       float* out, void* ws, size_t ws_bytes, void* stream) {
+  return mlp_forward_embedded(desc, packed, precision, x, m, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int plnerf_raw2outputs(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n, int stride,
+                       int S, int mode, int color_mode, int white_bkgd, int farcolorfix, const float* noise,
+                       float* rgb_map, float* disp_map, float* acc_map, float* depth_map, float* weights, float* tau,
+                       float* T, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (raw && z && rays)), "raw2outputs: null argument");
+  PLNERF_CHECK_ARG(raw_stride >= 4 && stride >= 8 && S >= 1, "raw2outputs: need raw_stride >= 4, stride >= 8, S >= 1");
+  PLNERF_CHECK_ARG(mode == PLNERF_MODE_LINEAR || mode == PLNERF_MODE_CONSTANT, "raw2outputs: bad mode %d", mode);
+  PLNERF_CHECK_ARG(color_mode == PLNERF_COLOR_MIDPOINT || color_mode == PLNERF_COLOR_LEFT, "raw2outputs: bad color_mode %d", color_mode);
+  return launch_composite(raw, raw_stride, z, rays, n, stride, S, mode, color_mode, white_bkgd, farcolorfix, noise,
+                          0.f, 0, 0, 0, rgb_map, disp_map, acc_map, depth_map, weights, tau, T, (cudaStream_t)stream);
+}
+
+int plnerf_sample_pdf_pl(const float* z, const float* weights, const float* tau, const float* T, const float* rays,
+                         int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray_id_offset,
+                         float zero_tol, float epsilon, float* samples, int64_t* inds, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && weights && tau && T && rays && samples)), "sample_pdf_pl: null argument");
+  PLNERF_CHECK_ARG(stride >= 8 && S >= 1 && Ni >= 0, "sample_pdf_pl: bad sizes");
+  return launch_sample_pl(z, weights, tau, T, rays, n, stride, S, Ni, u, seed, ray_id_offset, zero_tol, epsilon,
+                          samples, inds, (cudaStream_t)stream);
+}
+
+int plnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb, int Ni, const float* u,
+                      uint64_t seed, uint64_t ray_id_offset, float* samples, int64_t* inds, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (bins && weights && samples)), "sample_pdf: null argument");
+  return launch_sample_const(bins, nb, 0, weights, nb - 1, n, nb, Ni, u, seed, ray_id_offset, samples, inds,
+                             (cudaStream_t)stream);
+}
+
+int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
+                         int Ni, float* z_out, float* z_std, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && samples && rays && z_out)), "merge_samples: null argument");
+  PLNERF_CHECK_ARG(stride >= 8 && S >= 1 && Ni >= 1, "merge_samples: bad sizes");
+  return launch_merge(z, samples, rays, n, stride, S, Ni, z_out, z_std, (cudaStream_t)stream);
+}
+
+size_t plnerf_render_workspace_bytes(const plnerf_render_cfg* cfg, const plnerf_net_desc* desc, int64_t n_rays) {
+  if (!cfg || !desc || n_rays < 0) return 0;
+  return carve(cfg, desc, n_rays, nullptr).total;
+}
+
+int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked,
+                           const plnerf_net_desc* fdesc, const void* fpacked, const float* rays, int64_t n, int stride,
+                           const float* t_rand, const float* u, const float* noise0, const float* noise1,
+                           const plnerf_render_out* out, void* ws, size_t ws_bytes, void* stream) {
+  PLNERF_CHECK_ARG(cfg && cdesc && cpacked && out, "render_rays: null argument");
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || rays), "render_rays: null rays");
+  PLNERF_CHECK_ARG(stride >= 8, "render_rays: ray stride must be >= 8");
+  PLNERF_CHECK_ARG(cfg->N_samples >= 2 && cfg->N_importance >= 0, "render_rays: need N_samples >= 2, N_importance >= 0");
+  PLNERF_CHECK_ARG(cfg->mode == PLNERF_MODE_LINEAR || cfg->mode == PLNERF_MODE_CONSTANT, "render_rays: bad mode");
+  PLNERF_CHECK_ARG(out->rgb_map && out->disp_map && out->acc_map && out->depth_map, "render_rays: rgb/disp/acc/depth outputs are required");
+  if (n == 0) return PLNERF_OK;
+  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; }
+  PLNERF_CHECK_ARG(fdesc->use_viewdirs == cdesc->use_viewdirs, "render_rays: coarse/fine use_viewdirs differ");
+  const size_t need = carve(cfg, cdesc, n, nullptr).total;
+  if (!ws || ws_bytes < need) { set_error("render_rays: workspace too small: need %zu bytes, got %zu", need, ws_bytes); return PLNERF_E_WORKSPACE; }
+  PLNERF_CHECK_ARG(((uintptr_t)ws & 255) == 0, "render_rays: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  RenderWs w = carve(cfg, cdesc, n, static_cast<uint8_t*>(ws));
+  const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
+  const bool fine = Ni > 0;
+  int rc;
+  // (1) stratified depths (run_plnerf.py:683-705)
+  float* z0 = (!fine && out->z_vals) ? out->z_vals : w.z0;
+  rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, z0, st);
+  if (rc) return rc;
+  // (2) coarse network query (:714)
+  float* raw0 = (!fine && out->raw) ? out->raw : w.raw0;
+  rc = mlp_query(cdesc, cpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z0, Ns, raw0, chc,
+                 w.mlp_ws, w.mlp_ws_bytes, st);
+  if (rc) return rc;
+  // (3) coarse quadrature (:715)
+  const float std0 = (!noise0) ? cfg->raw_noise_std : 0.f;
+  rc = launch_composite(raw0, chc, z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                        noise0, std0, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0,
+                        fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
+                        fine ? out->acc0 : out->acc_map, fine ? out->depth0 : out->depth_map,
+                        fine ? w.w0 : nullptr, fine ? w.tau0 : nullptr, fine ? w.T0 : nullptr, st);
+  if (rc) return rc;
+  if (!fine) return PLNERF_OK;
+  // (4) importance sampling (:721-726)
+  if (cfg->mode == PLNERF_MODE_LINEAR) {
+    rc = launch_sample_pl(z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed, cfg->ray_id_offset,
+                          cfg->zero_tol, cfg->epsilon, w.zs, out->inds, st);
+  } else {
+    // bins = z_mid [Ns-1], weights[..., 1:-1] [Ns-2]
+    rc = launch_sample_const(z0, Ns, 1, w.w0 + 1, Ns, n, Ns - 1, Ni, u, cfg->seed, cfg->ray_id_offset, w.zs, out->inds, st);
+  }
+  if (rc) return rc;
+  // (5) detach / clamp / sort-merge / z_std (:728-734, :752)
+  float* z1 = out->z_vals ? out->z_vals : w.z1;
+  rc = launch_merge(z0, w.zs, rays, n, stride, Ns, Ni, z1, out->z_std, st);
+  if (rc) return rc;
+  // (6) fine network query (:737-739) and quadrature (:741)
+  float* raw1 = out->raw ? out->raw : w.raw1;
+  rc = mlp_query(fdesc, fpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z1, S1, raw1, chf,
+                 w.mlp_ws, w.mlp_ws_bytes, st);
+  if (rc) return rc;
+  const float std1 = (!noise1) ? cfg->raw_noise_std : 0.f;
+  rc = launch_composite(raw1, chf, z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                        noise1, std1, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1, out->rgb_map, out->disp_map,
+                        out->acc_map, out->depth_map, nullptr, nullptr, nullptr, st);
+  return rc;
+}
+
+int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
+  return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
+}
+
+// test-only variant with explicit operand mode and descriptor strides (not part of the product ABI)
+int plnerf_debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo,
+                              float* D, void* stream) {
+  return debug_umma_gemm_ex(A, B, N, K, a_mode, lbo, sbo, D, (cudaStream_t)stream);
+}
+
+}  // extern "C"

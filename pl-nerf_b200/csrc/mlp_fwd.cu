@@ -1,0 +1,819 @@
+// Fused NeRF MLP forward for sm_100a (B200): positional encoding + 8x256 trunk + heads in ONE
+// persistent, warp-specialised kernel.   Replaces run_network / NeRF.forward
+// (reference run_plnerf.py:78-92, run_nerf_helpers.py:105-128).
+//
+// Design (DESIGN.md section "K1"):
+//   * one CTA per SM, each CTA walks 128-sample tiles (rows of the flattened [rays*S] samples);
+//   * activations never leave the SM: the 128x256 hidden state lives in TENSOR MEMORY as bf16
+//     (tcgen05.mma "TS" form, A operand from TMEM); only the 63-wide positional encoding tile is a
+//     shared-memory ("SS") operand;
+//   * weights are pre-packed (plnerf_pack_weights) into the exact shared-memory image the MMA wants
+//     (K-major 8x16B core-matrix panels, no swizzle) in streaming order and pulled through a ring
+//     of 16 KB stages with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx);
+//   * each 256-wide layer is issued as two N=128 halves with separate fp32 accumulators
+//     (TMEM cols [0,128) and [128,256)); the epilogue of half a (bias, ReLU, bf16 pack, tcgen05.st
+//     into the *other* activation buffer) runs while the tensor pipe works on half b, and the next
+//     layer's first K-steps only depend on half a -- the tensor pipe does not wait for epilogues;
+//   * heads with tiny N run on CUDA cores inside the epilogue from the fp32 accumulators:
+//     alpha (256->1), rgb (128->3), output_linear (256->output_ch); the viewdir part of
+//     views_linears is constant per ray and enters as a per-ray fp32 bias (k_viewbias);
+//   * precision: PLNERF_PREC_BF16 = one MMA per product; PLNERF_PREC_BF16X3 = activations and
+//     weights split hi+lo in bf16 and three MMAs (hi*hi + lo*hi + hi*lo), ~2^-16 relative product
+//     error, used for the 1e-4 parity gate against the fp32 reference.
+//
+// TMEM map (512 columns): D_a [0,128) D_b [128,256); bf16 mode: A0 [256,384) A1 [384,512)
+// (double buffered 128x256 bf16 = 128 columns each); bf16x3 mode: A_hi [256,384) A_lo [384,512).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ops.cuh"
+#include "umma.cuh"
+
+namespace plnerf {
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KS_BYTES = 4096;      // one K=16 step of one 128-neuron half (2 panels x 128 rows x 16 B)
+constexpr int KS_PER_STAGE = 4;
+constexpr int STAGE_BYTES = KS_PER_STAGE * KS_BYTES;  // 16 KB
+constexpr int MAX_LAYERS = PLNERF_MAX_DEPTH + 2;
+constexpr int MAX_PE_KS = 4;        // input_ch <= 64
+constexpr int PE_TILE_BYTES = MAX_PE_KS * KS_BYTES;   // 16 KB
+constexpr int MAX_CONST_FLOATS = 4096;                // biases + small heads staged in smem
+constexpr int MAX_STAGES = 12;
+constexpr int NUM_THREADS = 256;    // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int MAX_OUT_CH = 8;
+
+enum { EPI_RELU_A = 0, EPI_LINEAR_A = 1, EPI_VIEWS = 2, EPI_RELU_HEAD = 3 };
+enum { FLAG_ALPHA = 1, FLAG_OUTHEAD = 2 };
+
+struct LayerPlan {
+  int16_t n_pe_ks;   // K=16 steps taken from the PE tile (shared memory operand)
+  int16_t n_h_ks;    // K=16 steps taken from the hidden state (TMEM operand)
+  int8_t n_halves;   // 2 for N=256, 1 for N=128
+  int8_t epi;
+  int8_t flags;
+  int8_t pad;
+  int32_t bias_off;  // float offset into the tail/const block
+  // packing sources (host/pack kernel only)
+  const float* W;
+  int32_t ldw;
+  int32_t pe_col0;   // source column of the PE part (or -1)
+  int32_t h_col0;    // source column of the hidden part (or -1)
+};
+
+struct NetPlan {
+  int32_t n_layers;
+  LayerPlan L[MAX_LAYERS];
+  int32_t input_ch, input_ch_views, out_ch, use_viewdirs, pe_ks, precision;
+  // tail (fp32) offsets, in floats
+  int32_t alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off, out_w_off, out_b_off, dirw_off, views_b_off;
+  int32_t const_floats;  // prefix of the tail staged in shared memory (everything but dirw)
+  int32_t tail_floats;
+  int64_t weight_bytes;  // bf16 stream
+};
+
+// Walks desc -> plan.  Returns 0 or an error code.
+int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params* p, NetPlan* out) {
+  if (!d) { set_error("net desc is null"); return PLNERF_E_BADARG; }
+  if (d->W != 256) { set_error("only W=256 is implemented by the tcgen05 kernel (got %d)", d->W); return PLNERF_E_UNSUPPORTED; }
+  if (d->D < 1 || d->D > PLNERF_MAX_DEPTH) { set_error("D=%d out of range", d->D); return PLNERF_E_UNSUPPORTED; }
+  if (d->input_ch < 1 || d->input_ch > 64) { set_error("input_ch=%d not in [1,64]", d->input_ch); return PLNERF_E_UNSUPPORTED; }
+  if (d->use_viewdirs && (d->input_ch_views < 1 || d->input_ch_views > 64)) { set_error("input_ch_views=%d not in [1,64]", d->input_ch_views); return PLNERF_E_UNSUPPORTED; }
+  if (!d->use_viewdirs && (d->output_ch < 1 || d->output_ch > MAX_OUT_CH)) { set_error("output_ch=%d not in [1,%d]", d->output_ch, MAX_OUT_CH); return PLNERF_E_UNSUPPORTED; }
+  if (precision != PLNERF_PREC_BF16 && precision != PLNERF_PREC_BF16X3) { set_error("bad precision %d", precision); return PLNERF_E_BADARG; }
+  if (d->n_skips < 0 || d->n_skips > PLNERF_MAX_DEPTH) { set_error("bad n_skips"); return PLNERF_E_BADARG; }
+  NetPlan& P = *out;
+  memset(&P, 0, sizeof(P));
+  P.input_ch = d->input_ch; P.input_ch_views = d->use_viewdirs ? d->input_ch_views : 0;
+  P.out_ch = d->use_viewdirs ? 4 : d->output_ch; P.use_viewdirs = d->use_viewdirs;
+  P.pe_ks = (d->input_ch + 15) / 16; P.precision = precision;
+  auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
+  int nl = 0, foff = 0;
+  for (int i = 0; i < d->D; ++i) {
+    LayerPlan& L = P.L[nl++];
+    const bool first = (i == 0), skip_in = (i > 0) && is_skip(i - 1);
+    L.n_pe_ks = (first || skip_in) ? P.pe_ks : 0;
+    L.n_h_ks = first ? 0 : 16;
+    L.n_halves = 2;
+    L.epi = EPI_RELU_A; L.flags = 0;
+    L.bias_off = foff; foff += 256;
+    L.W = p ? p->pts_w[i] : nullptr;
+    L.ldw = first ? d->input_ch : (skip_in ? 256 + d->input_ch : 256);
+    L.pe_col0 = (first || skip_in) ? 0 : -1;
+    L.h_col0 = first ? -1 : (skip_in ? d->input_ch : 0);
+    if (i == d->D - 1) {
+      // the reference concatenates [input_pts, h] after a skip layer even when it is the last one
+      if (is_skip(i)) { set_error("a skip at the last trunk layer is not supported"); return PLNERF_E_UNSUPPORTED; }
+      if (d->use_viewdirs) L.flags = FLAG_ALPHA;
+      else { L.epi = EPI_RELU_HEAD; L.flags = FLAG_OUTHEAD; }
+    }
+  }
+  if (d->use_viewdirs) {
+    LayerPlan& F = P.L[nl++];
+    F.n_pe_ks = 0; F.n_h_ks = 16; F.n_halves = 2; F.epi = EPI_LINEAR_A; F.flags = 0;
+    F.bias_off = foff; foff += 256;
+    F.W = p ? p->feature_w : nullptr; F.ldw = 256; F.pe_col0 = -1; F.h_col0 = 0;
+    LayerPlan& V = P.L[nl++];
+    V.n_pe_ks = 0; V.n_h_ks = 16; V.n_halves = 1; V.epi = EPI_VIEWS; V.flags = 0;
+    V.bias_off = foff; P.views_b_off = foff; foff += 128;
+    V.W = p ? p->views_w : nullptr; V.ldw = 256 + d->input_ch_views; V.pe_col0 = -1; V.h_col0 = 0;
+    P.alpha_w_off = foff; foff += 256;
+    P.alpha_b_off = foff; foff += 1;
+    P.rgb_w_off = foff; foff += 3 * 128;
+    P.rgb_b_off = foff; foff += 3;
+    foff = (foff + 3) & ~3;
+    P.const_floats = foff;
+    P.dirw_off = foff; foff += 128 * d->input_ch_views;
+  } else {
+    P.out_w_off = foff; foff += d->output_ch * 256;
+    P.out_b_off = foff; foff += d->output_ch;
+    foff = (foff + 3) & ~3;
+    P.const_floats = foff;
+  }
+  P.tail_floats = (foff + 3) & ~3;
+  P.n_layers = nl;
+  if (P.const_floats > MAX_CONST_FLOATS) { set_error("const block too large"); return PLNERF_E_UNSUPPORTED; }
+  int64_t wb = 0;
+  const int nsplit = (precision == PLNERF_PREC_BF16X3) ? 2 : 1;
+  for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * (P.L[l].n_pe_ks + P.L[l].n_h_ks) * KS_BYTES * nsplit;
+  P.weight_bytes = wb;
+  return PLNERF_OK;
+}
+
+// =============================================================================================
+// weight packing
+// =============================================================================================
+struct PackArgs {
+  NetPlan plan;
+  uint8_t* dst;   // bf16 stream
+  float* tail;    // fp32 tail
+  plnerf_net_params prm;
+};
+
+// one block (256 threads) per 4 KB K-step block; thread u -> 16-byte unit (panel = u/128, row = u%128)
+__global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ PackArgs a) {
+  const NetPlan& P = a.plan;
+  const int nsplit = (P.precision == PLNERF_PREC_BF16X3) ? 2 : 1;
+  int blk = blockIdx.x;
+  // locate (layer, half, stage, rep, j)
+  int l = 0, h = 0;
+  for (; l < P.n_layers; ++l) {
+    const int per_half = (P.L[l].n_pe_ks + P.L[l].n_h_ks) * nsplit;
+    const int per_layer = per_half * P.L[l].n_halves;
+    if (blk < per_layer) { h = blk / per_half; blk -= h * per_half; break; }
+    blk -= per_layer;
+  }
+  if (l >= P.n_layers) return;
+  const LayerPlan& L = P.L[l];
+  const int total_ks = L.n_pe_ks + L.n_h_ks;
+  // within a half: stages of <=4 K-steps, each stage = [hi blocks][lo blocks]
+  int ks0 = 0, rep = 0, j = 0;
+  for (;; ks0 += KS_PER_STAGE) {
+    const int nks = min(KS_PER_STAGE, total_ks - ks0);
+    if (blk < nks * nsplit) { rep = blk / nks; j = blk - rep * nks; break; }
+    blk -= nks * nsplit;
+  }
+  const int ks = ks0 + j;
+  const int u = threadIdx.x;
+  const int panel = u >> 7, row = u & 127;
+  const int n = h * 128 + row;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int col = -1;
+    if (ks < L.n_pe_ks) {
+      const int c = ks * 16 + panel * 8 + e;
+      if (c < P.input_ch) col = L.pe_col0 + c;
+    } else {
+      col = L.h_col0 + (ks - L.n_pe_ks) * 16 + panel * 8 + e;
+    }
+    v[e] = (col >= 0) ? L.W[(int64_t)n * L.ldw + col] : 0.0f;
+    if (rep == 1) v[e] = v[e] - ptx::bf16_round(v[e]);   // lo part
+  }
+  uint4 q;
+  q.x = ptx::pack_bf16(v[0], v[1]); q.y = ptx::pack_bf16(v[2], v[3]);
+  q.z = ptx::pack_bf16(v[4], v[5]); q.w = ptx::pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(a.dst + (int64_t)blockIdx.x * KS_BYTES + (size_t)u * 16) = q;
+}
+
+__global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
+  const NetPlan& P = a.plan;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.tail_floats) return;
+  float v = 0.f;
+  // biases
+  int trunk_layers = P.use_viewdirs ? P.n_layers - 2 : P.n_layers;
+  bool done = false;
+  for (int l = 0; l < P.n_layers && !done; ++l) {
+    const int nb = P.L[l].n_halves * 128;
+    const int o = P.L[l].bias_off;
+    if (i >= o && i < o + nb) {
+      const float* b = (l < trunk_layers) ? a.prm.pts_b[l] : (l == trunk_layers ? a.prm.feature_b : a.prm.views_b);
+      v = b[i - o]; done = true;
+    }
+  }
+  if (!done) {
+    if (P.use_viewdirs) {
+      if (i >= P.alpha_w_off && i < P.alpha_w_off + 256) v = a.prm.alpha_w[i - P.alpha_w_off];
+      else if (i == P.alpha_b_off) v = a.prm.alpha_b[0];
+      else if (i >= P.rgb_w_off && i < P.rgb_w_off + 384) v = a.prm.rgb_w[i - P.rgb_w_off];
+      else if (i >= P.rgb_b_off && i < P.rgb_b_off + 3) v = a.prm.rgb_b[i - P.rgb_b_off];
+      else if (i >= P.dirw_off && i < P.dirw_off + 128 * P.input_ch_views) {
+        const int k = i - P.dirw_off;
+        const int n = k / P.input_ch_views, jv = k - n * P.input_ch_views;
+        v = a.prm.views_w[(int64_t)n * (256 + P.input_ch_views) + 256 + jv];
+      }
+    } else {
+      if (i >= P.out_w_off && i < P.out_w_off + P.out_ch * 256) v = a.prm.output_w[i - P.out_w_off];
+      else if (i >= P.out_b_off && i < P.out_b_off + P.out_ch) v = a.prm.output_b[i - P.out_b_off];
+    }
+  }
+  a.tail[i] = v;
+}
+
+// =============================================================================================
+// per-ray view bias:  vb[r][n] = views_b[n] + sum_j Wv[n][256+j] * gamma_dir(viewdir_r)_j   (fp32)
+// (the viewdir columns of views_linears[0], run_nerf_helpers.py:117-121, are constant per ray)
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_viewbias(const float* __restrict__ tail, int views_b_off, int dirw_off,
+                                                  int icv, int multires_views, const float* __restrict__ rays,
+                                                  int stride, const float* __restrict__ x_emb, int x_ld, int x_col0,
+                                                  int64_t n, float* __restrict__ vb) {
+  __shared__ float emb[64];
+  const int64_t r = blockIdx.x;
+  if (r >= n) return;
+  const int t = threadIdx.x;
+  if (t < icv) {
+    float v;
+    if (x_emb) {
+      v = x_emb[r * (int64_t)x_ld + x_col0 + t];
+    } else {
+      const float* vd = rays + r * (int64_t)stride + (stride - 3);
+      if (multires_views < 0 || t < 3) v = vd[t % 3];
+      else {
+        const int k = (t - 3) / 6, rem = (t - 3) % 6;
+        const float a = vd[rem % 3] * exp2f((float)k);
+        v = (rem < 3) ? sinf(a) : cosf(a);
+      }
+    }
+    emb[t] = v;
+  }
+  __syncthreads();
+  float acc = tail[views_b_off + t];
+  const float* w = tail + dirw_off + t * icv;
+  for (int j = 0; j < icv; ++j) acc = fmaf(w[j], emb[j], acc);
+  vb[r * 128 + t] = acc;
+}
+
+// =============================================================================================
+// the fused MLP kernel
+// =============================================================================================
+struct MlpArgs {
+  NetPlan plan;
+  const uint8_t* w;       // packed bf16 stream
+  const float* tail;      // fp32 consts
+  // fused-query inputs
+  const float* rays; int stride; const float* z; int S; int multires;
+  // embedded-input mode
+  const float* x_emb; int x_ld;
+  const float* viewbias;  // [rows/vb_div, 128]
+  int vb_div;
+  int64_t M;              // total rows
+  int64_t n_tiles;
+  float* out; int out_stride;
+  int n_stages;
+};
+
+struct SmemLayout {
+  uint32_t pe_hi, pe_lo, ring, consts, bars;  // byte offsets
+  uint32_t total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int n_stages) {
+  SmemLayout s;
+  s.pe_hi = 0;
+  s.pe_lo = PE_TILE_BYTES;
+  s.ring = 2 * PE_TILE_BYTES;
+  s.consts = s.ring + (uint32_t)n_stages * STAGE_BYTES;
+  s.bars = s.consts + MAX_CONST_FLOATS * 4;
+  s.total = s.bars + 512;
+  return s;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constant__ MlpArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const NetPlan& P = A.plan;
+  const SmemLayout SL = smem_layout(A.n_stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool x3 = (P.precision == PLNERF_PREC_BF16X3);
+  const int nsplit = x3 ? 2 : 1;
+
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const uint32_t s_pe_hi = sbase + SL.pe_hi, s_pe_lo = sbase + SL.pe_lo, s_ring = sbase + SL.ring;
+  float* consts = reinterpret_cast<float*>(smem + SL.consts);
+  const uint32_t s_bars = sbase + SL.bars;
+  // barrier map (8 bytes each)
+  auto w_full = [&](int s) { return s_bars + 8u * s; };
+  auto w_empty = [&](int s) { return s_bars + 8u * (MAX_STAGES + s); };
+  const uint32_t d_full0 = s_bars + 8u * (2 * MAX_STAGES);      // [2]
+  const uint32_t a_ready0 = s_bars + 8u * (2 * MAX_STAGES + 2);  // [2]
+  const uint32_t pe_ready = s_bars + 8u * (2 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SL.bars + 8u * (2 * MAX_STAGES + 6));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < A.n_stages; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
+    ptx::mbar_init(d_full0, 1); ptx::mbar_init(d_full0 + 8, 1);
+    ptx::mbar_init(a_ready0, 128); ptx::mbar_init(a_ready0 + 8, 128);
+    ptx::mbar_init(pe_ready, 128);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  constexpr uint32_t COL_DA = 0, COL_A0 = 256, COL_A1 = 384;
+  // activation buffer written by the epilogue of layer l (and read by layer l+1)
+  auto a_out_col = [&](int l) -> uint32_t { return x3 ? COL_A0 : ((l & 1) ? COL_A1 : COL_A0); };
+
+  if (warp == 0) {
+    // ===================== TMA producer: stream the packed weights through the ring ==============
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const uint8_t* src = A.w;
+        for (int l = 0; l < P.n_layers; ++l) {
+          const int total_ks = P.L[l].n_pe_ks + P.L[l].n_h_ks;
+          for (int h = 0; h < P.L[l].n_halves; ++h) {
+            for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
+              const uint32_t bytes = (uint32_t)min(KS_PER_STAGE, total_ks - ks0) * KS_BYTES;
+              for (int rep = 0; rep < nsplit; ++rep) {
+                ptx::mbar_wait(w_empty(slot), phase ^ 1);
+                ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
+                ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot));
+                src += bytes;
+                if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
+      uint32_t slot = 0, phase = 0;
+      uint32_t uses[2] = {0, 0}, waited[2] = {0, 0};
+      auto wait_epi = [&](int h) {
+        while (waited[h] < uses[h]) { ptx::mbar_wait(a_ready0 + 8u * h, waited[h] & 1); ++waited[h]; }
+      };
+      uint32_t tile_iter = 0;
+      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+        ptx::mbar_wait(pe_ready, tile_iter & 1);
+        ptx::tc_fence_after();
+        for (int l = 0; l < P.n_layers; ++l) {
+          const LayerPlan& L = P.L[l];
+          const int total_ks = L.n_pe_ks + L.n_h_ks;
+          const uint32_t a_in = tmem + (l > 0 ? a_out_col(l - 1) : COL_A0);
+          const uint32_t a_in_lo = tmem + COL_A1;  // bf16x3 only
+          for (int h = 0; h < L.n_halves; ++h) {
+            wait_epi(h);
+            ptx::tc_fence_after();
+            const uint32_t d = tmem + COL_DA + 128u * h;
+            uint32_t acc = 0;
+            for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
+              const int nks = min(KS_PER_STAGE, total_ks - ks0);
+              for (int rep = 0; rep < nsplit; ++rep) {
+                ptx::mbar_wait(w_full(slot), phase);
+                ptx::tc_fence_after();
+                for (int j = 0; j < nks; ++j) {
+                  const int ks = ks0 + j;
+                  const uint64_t bd = ptx::smem_desc(s_ring + slot * STAGE_BYTES + j * KS_BYTES, 2048, 128);
+                  if (ks < L.n_pe_ks) {
+                    const uint64_t ad_hi = ptx::smem_desc(s_pe_hi + ks * KS_BYTES, 2048, 128);
+                    if (rep == 0) {
+                      ptx::mma_ss(d, ad_hi, bd, idesc, acc); acc = 1;
+                      if (x3) ptx::mma_ss(d, ptx::smem_desc(s_pe_lo + ks * KS_BYTES, 2048, 128), bd, idesc, 1);
+                    } else {
+                      ptx::mma_ss(d, ad_hi, bd, idesc, 1);
+                    }
+                  } else {
+                    const int jh = ks - L.n_pe_ks;
+                    if (jh >= 8) { wait_epi(1); ptx::tc_fence_after(); }
+                    if (rep == 0) {
+                      ptx::mma_ts(d, a_in + 8u * jh, bd, idesc, acc); acc = 1;
+                      if (x3) ptx::mma_ts(d, a_in_lo + 8u * jh, bd, idesc, 1);
+                    } else {
+                      ptx::mma_ts(d, a_in + 8u * jh, bd, idesc, 1);
+                    }
+                  }
+                }
+                ptx::mma_commit(w_empty(slot));
+                if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
+              }
+            }
+            ptx::mma_commit(d_full0 + 8u * h);
+            ++uses[h];
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps: PE prologue, bias/ReLU/pack, heads, output ==========
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    uint32_t seen[2] = {0, 0};
+    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+      const int64_t g = tile * TILE_M + row;
+      const bool valid = g < A.M;
+      const int64_t gc = valid ? g : (A.M - 1);
+      // ---------------- prologue: positional encoding of this row -> PE tile (smem, bf16 [hi,lo])
+      {
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = 0.f;
+        if (A.x_emb) {
+          const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i < P.input_ch) v[i] = xr[i];
+        } else {
+          const int64_t ray = gc / A.S;
+          const float* rp = A.rays + ray * (int64_t)A.stride;
+          const float zz = A.z[gc];
+          float p[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));  // o + d*z, two roundings
+          v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+          if (A.multires > 0) {
+            float f = 1.0f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+              if (k < A.multires) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  float s, co;
+                  sincosf(p[c] * f, &s, &co);
+                  v[3 + 6 * k + c] = s;
+                  v[3 + 6 * k + 3 + c] = co;
+                }
+              }
+              f *= 2.0f;
+            }
+          }
+        }
+#pragma unroll
+        for (int pnl = 0; pnl < 2 * MAX_PE_KS; ++pnl) {
+          if (pnl < 2 * P.pe_ks) {
+            uint4 hi;
+            hi.x = ptx::pack_bf16(v[8 * pnl + 0], v[8 * pnl + 1]); hi.y = ptx::pack_bf16(v[8 * pnl + 2], v[8 * pnl + 3]);
+            hi.z = ptx::pack_bf16(v[8 * pnl + 4], v[8 * pnl + 5]); hi.w = ptx::pack_bf16(v[8 * pnl + 6], v[8 * pnl + 7]);
+            *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
+            if (x3) {
+              float lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) lo[e] = v[8 * pnl + e] - ptx::bf16_round(v[8 * pnl + e]);
+              uint4 l4;
+              l4.x = ptx::pack_bf16(lo[0], lo[1]); l4.y = ptx::pack_bf16(lo[2], lo[3]);
+              l4.z = ptx::pack_bf16(lo[4], lo[5]); l4.w = ptx::pack_bf16(lo[6], lo[7]);
+              *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(pe_ready);
+      }
+      float alpha_acc = 0.f;
+      float head[MAX_OUT_CH];
+#pragma unroll
+      for (int c = 0; c < MAX_OUT_CH; ++c) head[c] = 0.f;
+      const float* vbrow = A.viewbias ? (A.viewbias + (gc / A.vb_div) * 128) : nullptr;
+
+      for (int l = 0; l < P.n_layers; ++l) {
+        const LayerPlan& L = P.L[l];
+        const uint32_t a_out = tmem + lane_addr + a_out_col(l);
+        const uint32_t a_out_lo = tmem + lane_addr + COL_A1;
+        bool b_prewaited = false;
+        for (int h = 0; h < L.n_halves; ++h) {
+          if (!(h == 1 && b_prewaited)) { ptx::mbar_wait(d_full0 + 8u * h, seen[h] & 1); ++seen[h]; }
+          if (x3 && h == 0 && L.n_halves == 2) {
+            // bf16x3 keeps ONE activation buffer: half b's MMAs still read it, wait for them too
+            ptx::mbar_wait(d_full0 + 8u, seen[1] & 1); ++seen[1]; b_prewaited = true;
+          }
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * c, r);
+            ptx::tmem_ld_wait();
+            const int n0 = h * 128 + c * 32;
+            float val[32];
+            if (L.epi == EPI_VIEWS) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(vbrow + n0 + i);
+                val[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
+                val[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
+                val[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
+                val[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+              }
+              const float* rw = consts + P.rgb_w_off + n0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                head[0] = fmaf(val[i], rw[i], head[0]);
+                head[1] = fmaf(val[i], rw[128 + i], head[1]);
+                head[2] = fmaf(val[i], rw[256 + i], head[2]);
+              }
+            } else {
+              const float* bias = consts + L.bias_off + n0;
+              const bool relu = (L.epi != EPI_LINEAR_A);
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
+                val[i] = __uint_as_float(r[i]) + b4.x;
+                val[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+                val[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
+                val[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+              }
+              if (relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) val[i] = fmaxf(val[i], 0.f);
+              }
+              if (L.flags & FLAG_ALPHA) {
+                const float* aw = consts + P.alpha_w_off + n0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) alpha_acc = fmaf(val[i], aw[i], alpha_acc);
+              }
+              if (L.flags & FLAG_OUTHEAD) {
+#pragma unroll
+                for (int ch = 0; ch < MAX_OUT_CH; ++ch) {
+                  if (ch < P.out_ch) {
+                    const float* ow = consts + P.out_w_off + ch * 256 + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
+                  }
+                }
+              }
+              if (L.epi != EPI_RELU_HEAD) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+                ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+                if (x3) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    pk[i] = ptx::pack_bf16(val[2 * i] - ptx::bf16_round(val[2 * i]),
+                                           val[2 * i + 1] - ptx::bf16_round(val[2 * i + 1]));
+                  ptx::tmem_st16(a_out_lo + (uint32_t)(n0 >> 1), pk);
+                }
+              }
+            }
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(a_ready0 + 8u * h);
+        }
+      }
+      if (valid) {
+        float* o = A.out + g * (int64_t)A.out_stride;
+        if (P.use_viewdirs) {
+          o[0] = head[0] + consts[P.rgb_b_off + 0];
+          o[1] = head[1] + consts[P.rgb_b_off + 1];
+          o[2] = head[2] + consts[P.rgb_b_off + 2];
+          o[3] = alpha_acc + consts[P.alpha_b_off];
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < MAX_OUT_CH; ++ch)
+            if (ch < P.out_ch) o[ch] = head[ch] + consts[P.out_b_off + ch];
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// debug: single tile GEMM  D[128,N] = A[128,K] * B[N,K]^T  through the same primitives
+// (N in {128,256}, K % 16 == 0, K <= 256).  a_mode 0 = A from shared memory panels (SS),
+// 1 = A from tensor memory (TS).  lbo/sbo are passed explicitly so tests can pin the encoding.
+// =============================================================================================
+__global__ void __launch_bounds__(128, 1) k_debug_gemm(const float* __restrict__ Ag, const float* __restrict__ Bg, int N, int K,
+                                                       int a_mode, uint32_t lbo, uint32_t sbo, float* __restrict__ Dg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: A panels [K/8][128 rows][16B] | B panels per 128-row half: [half][K/8][128][16B] | barrier | tmem slot
+  const int kp = K / 8;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)kp * 2048;
+  const int nh = N / 128;
+  uint8_t* sBar = sB + (size_t)nh * kp * 2048;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 16);
+  const uint32_t bar = ptx::smem_u32(sBar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x;
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  // B -> smem panels (generic-proxy stores + proxy fence)
+  for (int idx = threadIdx.x; idx < N * kp; idx += 128) {
+    const int n = idx % N, p = idx / N;
+    uint32_t w[4];
+    for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16(Bg[(size_t)n * K + p * 8 + 2 * e], Bg[(size_t)n * K + p * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(sB + ((size_t)(n / 128) * kp + p) * 2048 + (n % 128) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+  // A -> smem panels or TMEM columns [256, 256+K/2)
+  if (a_mode == 0) {
+    for (int p = 0; p < kp; ++p) {
+      uint32_t w[4];
+      for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16(Ag[(size_t)row * K + p * 8 + 2 * e], Ag[(size_t)row * K + p * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(sA + (size_t)p * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = 2 * (c0 + i);
+        pk[i] = (k < K) ? ptx::pack_bf16(Ag[(size_t)row * K + k], Ag[(size_t)row * K + k + 1]) : 0u;
+      }
+      ptx::tmem_st16(tmem + lane_addr + 256u + (uint32_t)c0, pk);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
+    for (int h = 0; h < nh; ++h) {
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t bd = ptx::smem_desc(ptx::smem_u32(sB + ((size_t)h * kp + 2 * ks) * 2048), lbo, sbo);
+        if (a_mode == 0) ptx::mma_ss(tmem + 128u * h, ptx::smem_desc(ptx::smem_u32(sA + (size_t)(2 * ks) * 2048), lbo, sbo), bd, idesc, ks > 0);
+        else ptx::mma_ts(tmem + 128u * h, tmem + 256u + 8u * ks, bd, idesc, ks > 0);
+      }
+    }
+    ptx::mma_commit(bar);
+  }
+  ptx::mbar_wait(bar, 0);
+  ptx::tc_fence_after();
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tmem + lane_addr + 32u * c, r);
+    ptx::tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) Dg[(size_t)row * N + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+int g_num_sms = 0;
+int g_max_smem = 0;
+int query_device() {
+  if (g_num_sms) return PLNERF_OK;
+  int dev = 0;
+  PLNERF_CUDA(cudaGetDevice(&dev));
+  int sms = 0, smem = 0, major = 0;
+  PLNERF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PLNERF_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  PLNERF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) { set_error("plnerf_b200 needs an sm_100a (B200) device, found compute capability %d.x", major); return PLNERF_E_UNSUPPORTED; }
+  g_num_sms = sms; g_max_smem = smem;
+  return PLNERF_OK;
+}
+
+int launch_mlp(MlpArgs& a, cudaStream_t st) {
+  int rc = query_device();
+  if (rc) return rc;
+  int n_stages = MAX_STAGES;
+  while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
+  a.n_stages = n_stages;
+  const SmemLayout SL = smem_layout(n_stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    attr_set = true;
+  }
+  a.n_tiles = ceil_div(a.M, TILE_M);
+  const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
+  k_mlp_fwd<<<grid, NUM_THREADS, SL.total, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_mlp_fwd");
+  return PLNERF_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision) {
+  NetPlan P;
+  if (build_plan(d, precision, nullptr, &P)) return 0;
+  return (size_t)P.weight_bytes + (size_t)P.tail_floats * 4;
+}
+
+int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision, void* packed, cudaStream_t st) {
+  PLNERF_CHECK_ARG(p && packed, "pack_weights: null argument");
+  PLNERF_CHECK_ARG(((uintptr_t)packed & 15) == 0, "pack_weights: packed buffer must be 16-byte aligned");
+  PackArgs a;
+  int rc = build_plan(d, precision, p, &a.plan);
+  if (rc) return rc;
+  for (int i = 0; i < d->D; ++i) PLNERF_CHECK_ARG(p->pts_w[i] && p->pts_b[i], "pack_weights: pts_linears.%d missing", i);
+  if (d->use_viewdirs) PLNERF_CHECK_ARG(p->views_w && p->views_b && p->feature_w && p->feature_b && p->alpha_w && p->alpha_b && p->rgb_w && p->rgb_b, "pack_weights: viewdirs head parameters missing");
+  else PLNERF_CHECK_ARG(p->output_w && p->output_b, "pack_weights: output_linear missing");
+  a.dst = static_cast<uint8_t*>(packed);
+  a.tail = reinterpret_cast<float*>(a.dst + a.plan.weight_bytes);
+  a.prm = *p;
+  const unsigned nblk = (unsigned)(a.plan.weight_bytes / KS_BYTES);
+  k_pack_weights<<<nblk, 256, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_pack_weights");
+  k_pack_tail<<<(unsigned)ceil_div(a.plan.tail_floats, 256), 256, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_pack_tail");
+  return PLNERF_OK;
+}
+
+size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays) {
+  if (!d || n_rays < 0) return 0;
+  return d->use_viewdirs ? (size_t)n_rays * 128 * sizeof(float) + 256 : 256;
+}
+
+static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int precision, MlpArgs& a, int64_t vb_rows,
+                          int multires_views, const float* rays, int stride, const float* x_emb, int x_ld, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
+  int rc = build_plan(d, precision, nullptr, &a.plan);
+  if (rc) return rc;
+  PLNERF_CHECK_ARG(packed && ((uintptr_t)packed & 15) == 0, "packed weights null or misaligned");
+  a.w = static_cast<const uint8_t*>(packed);
+  a.tail = reinterpret_cast<const float*>(a.w + a.plan.weight_bytes);
+  a.viewbias = nullptr;
+  if (d->use_viewdirs) {
+    const size_t need = (size_t)vb_rows * 128 * sizeof(float);
+    if (!ws || ws_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes); return PLNERF_E_WORKSPACE; }
+    float* vb = static_cast<float*>(ws);
+    k_viewbias<<<(unsigned)vb_rows, 128, 0, st>>>(a.tail, a.plan.views_b_off, a.plan.dirw_off, d->input_ch_views, multires_views,
+                                                  rays, stride, x_emb, x_ld, d->input_ch, vb_rows, vb);
+    PLNERF_LAUNCH_CHECK("k_viewbias");
+    a.viewbias = vb;
+  }
+  return launch_mlp(a, st);
+}
+
+int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
+              const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
+              void* ws, size_t ws_bytes, cudaStream_t st) {
+  PLNERF_CHECK_ARG(d && rays && z && raw, "network_query: null argument");
+  PLNERF_CHECK_ARG(n >= 0 && S > 0, "network_query: bad sizes");
+  if (n == 0) return PLNERF_OK;
+  const int want_ic = multires < 0 ? 3 : 3 + 6 * multires;
+  PLNERF_CHECK_ARG(want_ic == d->input_ch && multires <= 10, "network_query: multires=%d does not match input_ch=%d", multires, d->input_ch);
+  if (d->use_viewdirs) {
+    const int want_icv = multires_views < 0 ? 3 : 3 + 6 * multires_views;
+    PLNERF_CHECK_ARG(want_icv == d->input_ch_views, "network_query: multires_views=%d does not match input_ch_views=%d", multires_views, d->input_ch_views);
+    PLNERF_CHECK_ARG(stride >= 11, "network_query: use_viewdirs needs rays with a viewdir (stride >= 11)");
+  }
+  PLNERF_CHECK_ARG(stride >= 8, "network_query: ray stride must be >= 8");
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rays = rays; a.stride = stride; a.z = z; a.S = S; a.multires = multires;
+  a.x_emb = nullptr; a.x_ld = 0; a.vb_div = S; a.M = n * S; a.out = raw; a.out_stride = raw_stride;
+  return run_mlp_common(d, packed, precision, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st);
+}
+
+int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
+                         float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PLNERF_CHECK_ARG(d && x && out, "mlp_forward: null argument");
+  PLNERF_CHECK_ARG(m >= 0, "mlp_forward: bad size");
+  if (m == 0) return PLNERF_OK;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.S = 1; a.multires = 0;
+  a.x_emb = x; a.x_ld = d->input_ch + (d->use_viewdirs ? d->input_ch_views : 0);
+  a.vb_div = 1; a.M = m; a.out = out; a.out_stride = d->use_viewdirs ? 4 : d->output_ch;
+  return run_mlp_common(d, packed, precision, a, m, 0, nullptr, 0, x, a.x_ld, ws, ws_bytes, st);
+}
+
+int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st) {
+  PLNERF_CHECK_ARG(A && B && D, "debug_umma_gemm: null argument");
+  PLNERF_CHECK_ARG((N == 128 || N == 256) && K % 16 == 0 && K >= 16 && K <= 256, "debug_umma_gemm: N in {128,256}, K%%16==0, K<=256");
+  int rc = query_device();
+  if (rc) return rc;
+  const size_t smem = (size_t)(K / 8) * 2048 * (1 + N / 128) + 64;
+  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+  k_debug_gemm<<<1, 128, smem, st>>>(A, B, N, K, a_mode, lbo, sbo, D);
+  PLNERF_LAUNCH_CHECK("k_debug_gemm");
+  return PLNERF_OK;
+}
+
+int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st) {
+  return debug_umma_gemm_ex(A, B, N, K, 0, 2048, 128, D, st);
+}
+
+}  // namespace plnerf

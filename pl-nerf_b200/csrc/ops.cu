@@ -1,0 +1,495 @@
+// Non-GEMM operators of the PL-NeRF hot path (sm_100a): positional encoding, stratified depths,
+// piecewise-linear / piecewise-constant quadrature (raw2outputs), the inverse-CDF samplers and the
+// clamp + sort-merge.  One warp per ray, lanes striped along the sample axis (coalesced), prefix
+// products / sums as warp-shuffle scans in fp64 rounded per element to fp32 (what torch's CPU
+// cumprod/cumsum produce).  All of these are HBM-bound streaming kernels.
+//
+// Reference call sites are cited per kernel (paths relative to the reference repo).
+#include <math.h>
+
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace plnerf {
+
+// =============================================================================================
+// a5  Embedder.embed  (run_nerf_helpers.py:36-54)
+// =============================================================================================
+__global__ void k_encode(const float* __restrict__ x, int64_t n, int L, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, xyz)
+  if (idx >= n * 3) return;
+  const int64_t row = idx / 3;
+  const int c = (int)(idx - row * 3);
+  const int od = (L < 0) ? 3 : 3 + 6 * L;
+  const float v = x[idx];
+  float* o = out + row * od;
+  o[c] = v;
+  float f = 1.0f;
+  for (int k = 0; k < L; ++k) {
+    const float a = v * f;  // exact: power-of-two scale
+    o[3 + 6 * k + c] = sinf(a);
+    o[3 + 6 * k + 3 + c] = cosf(a);
+    f *= 2.0f;
+  }
+}
+
+// =============================================================================================
+// a3  stratified depths  (run_plnerf.py:683-705)
+// =============================================================================================
+__device__ __forceinline__ float linspace01(int i, int n, float step) {
+  // torch.linspace(0,1,n): first half start + step*i, second half end - step*(n-1-i), one rounding
+  return (i < n / 2) ? step * (float)i : fmaf(-step, (float)(n - 1 - i), 1.0f);
+}
+
+__device__ __forceinline__ float base_z(float near, float far, float t, int lindisp) {
+  const float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  const float a = __fmul_rn(__fdiv_rn(1.0f, near), omt);
+  const float b = __fmul_rn(__fdiv_rn(1.0f, far), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void k_stratified_z(const float* __restrict__ rays, int64_t n, int stride, int Ns, int lindisp,
+                               int perturb, const float* __restrict__ t_rand, uint64_t seed,
+                               uint64_t ray0, float* __restrict__ z_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * Ns) return;
+  const int64_t r = idx / Ns;
+  const int i = (int)(idx - r * Ns);
+  const float near = rays[r * stride + 6], far = rays[r * stride + 7];
+  const float step = (Ns > 1) ? __fdiv_rn(1.0f, (float)(Ns - 1)) : 0.0f;
+  const float zi = base_z(near, far, linspace01(i, Ns, step), lindisp);
+  float z = zi;
+  if (perturb) {
+    float lower = zi, upper = zi;
+    if (i > 0) {
+      const float zp = base_z(near, far, linspace01(i - 1, Ns, step), lindisp);
+      lower = __fmul_rn(0.5f, __fadd_rn(zi, zp));
+    }
+    if (i < Ns - 1) {
+      const float zn = base_z(near, far, linspace01(i + 1, Ns, step), lindisp);
+      upper = __fmul_rn(0.5f, __fadd_rn(zn, zi));
+    }
+    const float t = t_rand ? t_rand[idx] : philox_uniform(seed, ray0 + (uint64_t)r, RNG_STREAM_TRAND, (uint32_t)i);
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
+  }
+  z_out[idx] = z;
+}
+
+// =============================================================================================
+// a8/a9/a10  raw2outputs  (run_plnerf.py:504-624)
+// =============================================================================================
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, 1.0f + expf(-x)); }
+
+struct CompositeArgs {
+  const float* raw; int raw_stride;
+  const float* z; const float* rays; int64_t n; int stride; int S;
+  int color_mode, white_bkgd, farcolorfix;
+  const float* noise;       // explicit additive noise [n,S] or null
+  float noise_std;          // >0 with noise == null: Philox normal * std
+  uint64_t seed, ray0; uint32_t noise_stream;
+  float *rgb_map, *disp_map, *acc_map, *depth_map, *weights, *tau, *T;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_composite(CompositeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= a.n) return;
+  const int S = a.S;
+  const float* ray = a.rays + r * a.stride;
+  const float dx = ray[3], dy = ray[4], dz = ray[5];
+  const float near = ray[6], far = ray[7];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float* raw = a.raw + r * (int64_t)S * a.raw_stride;
+  const float* z = a.z + r * (int64_t)S;
+
+  auto sigma_at = [&](int k) -> float {  // density of sample k incl. noise, before relu
+    float s = raw[(int64_t)k * a.raw_stride + 3];
+    if (a.noise) s = __fadd_rn(s, a.noise[r * (int64_t)S + k]);
+    else if (a.noise_std > 0.f)
+      s = __fadd_rn(s, __fmul_rn(philox_normal(a.seed, a.ray0 + (uint64_t)r, a.noise_stream, (uint32_t)k), a.noise_std));
+    return s;
+  };
+  auto color_at = [&](int k, int c) -> float { return sigmoidf_(raw[(int64_t)k * a.raw_stride + c]); };
+
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_w = 0.f;
+  double carry = 1.0;
+
+  if (MODE == PLNERF_MODE_LINEAR) {
+    // knots s = [near, z_0..z_{S-1}, far] (S+2), tau = relu([1e-10, sigma.., 1e10]); S+1 intervals
+    auto knot = [&](int k) -> float { return k == 0 ? near : (k == S + 1 ? far : z[k - 1]); };
+    auto tau_at = [&](int k) -> float {
+      return k == 0 ? 1e-10f : (k == S + 1 ? 1e10f : fmaxf(sigma_at(k - 1), 0.0f));
+    };
+    const int nI = S + 1;
+    if (lane == 0 && a.T) a.T[r * (int64_t)(S + 2)] = 1.0f;
+    for (int base = 0; base < nI; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < nI;
+      float e = 1.0f, s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+      if (valid) {
+        s0 = knot(i); s1 = knot(i + 1);
+        t0 = tau_at(i); t1 = tau_at(i + 1);
+        const float dist = __fmul_rn(__fsub_rn(s1, s0), dnorm);
+        const float ave = __fmul_rn(0.5f, __fadd_rn(t1, t0));
+        e = expf(__fmul_rn(-ave, dist));
+      }
+      const double incl = warp_incl_scan_mul((double)e, lane) * carry;
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = carry;
+      carry = __shfl_sync(0xffffffffu, incl, 31);
+      if (valid) {
+        const float Ti = (float)excl;
+        const float w = __fmul_rn(__fsub_rn(1.0f, e), Ti);
+        if (a.weights) a.weights[r * (int64_t)(S + 1) + i] = w;
+        if (a.T) a.T[r * (int64_t)(S + 2) + i + 1] = (float)incl;
+        if (a.tau) {
+          a.tau[r * (int64_t)(S + 2) + i] = t0;
+          if (i == S) a.tau[r * (int64_t)(S + 2) + S + 1] = t1;
+        }
+        // colours: cc = [c_0, c_0..c_{S-1}, c_{S-1}|0] (midpoint) or [c_0, c_0..c_{S-1}] (left)
+        const int kl = max(i - 1, 0);
+        const int kr = min(i, S - 1);
+        float cr, cg, cb;
+        if (a.color_mode == PLNERF_COLOR_MIDPOINT) {
+          const bool zero_right = a.farcolorfix && (i == S);
+          const float lr = color_at(kl, 0), lg = color_at(kl, 1), lb = color_at(kl, 2);
+          float rr = 0.f, rg = 0.f, rb = 0.f;
+          if (!zero_right) {
+            if (kr == kl) { rr = lr; rg = lg; rb = lb; }
+            else { rr = color_at(kr, 0); rg = color_at(kr, 1); rb = color_at(kr, 2); }
+          }
+          cr = __fmul_rn(0.5f, __fadd_rn(rr, lr));
+          cg = __fmul_rn(0.5f, __fadd_rn(rg, lg));
+          cb = __fmul_rn(0.5f, __fadd_rn(rb, lb));
+        } else {
+          cr = color_at(kl, 0); cg = color_at(kl, 1); cb = color_at(kl, 2);
+        }
+        acc_r += w * cr; acc_g += w * cg; acc_b += w * cb;
+        acc_d += w * __fmul_rn(0.5f, __fadd_rn(s1, s0));
+        acc_w += w;
+      }
+    }
+  } else {
+    // constant: dists = [z_{i+1}-z_i, 1e10]*|d|, alpha = 1-exp(-relu(sigma)*dist),
+    // w = alpha * cumprod([1, 1-alpha+1e-10])[:-1]
+    for (int base = 0; base < S; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < S;
+      float alpha = 0.f, om = 1.0f, zi = 0.f;
+      if (valid) {
+        zi = z[i];
+        const float d0 = (i < S - 1) ? __fsub_rn(z[i + 1], zi) : 1e10f;
+        const float dist = __fmul_rn(d0, dnorm);
+        const float sg = fmaxf(sigma_at(i), 0.0f);
+        alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sg, dist)));
+        om = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      }
+      const double incl = warp_incl_scan_mul((double)om, lane) * carry;
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = carry;
+      carry = __shfl_sync(0xffffffffu, incl, 31);
+      if (valid) {
+        const float w = __fmul_rn(alpha, (float)excl);
+        if (a.weights) a.weights[r * (int64_t)S + i] = w;
+        acc_r += w * color_at(i, 0); acc_g += w * color_at(i, 1); acc_b += w * color_at(i, 2);
+        acc_d += w * zi;
+        acc_w += w;
+      }
+    }
+  }
+  acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
+  acc_d = warp_sum(acc_d); acc_w = warp_sum(acc_w);
+  if (lane == 0) {
+    const float q = __fdiv_rn(acc_d, acc_w);
+    const float disp = (q != q) ? q : __fdiv_rn(1.0f, fmaxf(1e-10f, q));
+    if (a.white_bkgd) {
+      const float bg = __fsub_rn(1.0f, acc_w);
+      acc_r += bg; acc_g += bg; acc_b += bg;
+    }
+    if (a.rgb_map) { a.rgb_map[r * 3 + 0] = acc_r; a.rgb_map[r * 3 + 1] = acc_g; a.rgb_map[r * 3 + 2] = acc_b; }
+    if (a.disp_map) a.disp_map[r] = disp;
+    if (a.acc_map) a.acc_map[r] = acc_w;
+    if (a.depth_map) a.depth_map[r] = acc_d;
+  }
+}
+
+int launch_composite(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n,
+                     int stride, int S, int mode, int color_mode, int white_bkgd, int farcolorfix,
+                     const float* noise, float noise_std, uint64_t seed, uint64_t ray0, uint32_t noise_stream,
+                     float* rgb_map, float* disp_map, float* acc_map, float* depth_map, float* weights,
+                     float* tau, float* T, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  CompositeArgs a;
+  a.raw = raw; a.raw_stride = raw_stride; a.z = z; a.rays = rays; a.n = n; a.stride = stride; a.S = S;
+  a.color_mode = color_mode; a.white_bkgd = white_bkgd; a.farcolorfix = farcolorfix;
+  a.noise = noise; a.noise_std = noise_std; a.seed = seed; a.ray0 = ray0; a.noise_stream = noise_stream;
+  a.rgb_map = rgb_map; a.disp_map = disp_map; a.acc_map = acc_map; a.depth_map = depth_map;
+  a.weights = weights; a.tau = tau; a.T = T;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div(n * 32, threads);
+  if (mode == PLNERF_MODE_LINEAR) k_composite<PLNERF_MODE_LINEAR><<<blocks, threads, 0, st>>>(a);
+  else k_composite<PLNERF_MODE_CONSTANT><<<blocks, threads, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_composite");
+  return PLNERF_OK;
+}
+
+// =============================================================================================
+// samplers
+// =============================================================================================
+// torch.searchsorted(cdf, u, right=True): ATen's upper-bound loop, reproduced step for step so the
+// result is identical even where rounding makes cdf non-monotone at its forced last element.
+__device__ __forceinline__ int upper_bound_torch(const float* cdf, int n, float u) {
+  int start = 0, end = n;
+  while (start < end) {
+    const int mid = start + ((end - start) >> 1);
+    if (!(cdf[mid] > u)) start = mid + 1; else end = mid;
+  }
+  return start;
+}
+
+// a11  sample_pdf_reformulation + pw_linear_sample_{in,de}creasing  (run_nerf_helpers.py:340-445)
+struct SamplePLArgs {
+  const float *z, *w, *tau, *T, *rays;
+  int64_t n; int stride, S, Ni;
+  const float* u; uint64_t seed, ray0;
+  float zero_tol, eps;
+  float* samples; int64_t* inds;
+};
+
+__global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int S = a.S, nk = S + 2;
+  float* cdf = smem + (size_t)wib * 4 * nk;
+  float* s = cdf + nk;
+  float* T = s + nk;
+  float* tau = T + nk;
+  const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
+  // knots, T, tau -> smem; cdf = [0, cumsum(w)] with fp64 accumulation, last forced to 1
+  for (int k = lane; k < nk; k += 32) {
+    s[k] = (k == 0) ? near : (k == S + 1 ? far : a.z[r * (int64_t)S + k - 1]);
+    T[k] = a.T[r * (int64_t)nk + k];
+    tau[k] = a.tau[r * (int64_t)nk + k];
+  }
+  double carry = 0.0;
+  if (lane == 0) cdf[0] = 0.0f;
+  for (int base = 0; base < S + 1; base += 32) {
+    const int i = base + lane;
+    const double wv = (i < S + 1) ? (double)a.w[r * (int64_t)(S + 1) + i] : 0.0;
+    const double incl = warp_incl_scan_add(wv, lane) + carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    if (i < S + 1) cdf[i + 1] = (i == S) ? 1.0f : (float)incl;
+  }
+  __syncwarp();
+  const float eps = a.eps, tol = a.zero_tol;
+  for (int k = lane; k < a.Ni; k += 32) {
+    const float u = a.u ? a.u[r * (int64_t)a.Ni + k]
+                        : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+    const int ind = upper_bound_torch(cdf, nk, u);
+    const int below = max(0, ind - 1);
+    const int above = min(nk - 1, ind);
+    const float s_l = s[below], s_r = s[above];
+    const float T_l = T[below];
+    const float tau_l = tau[below], tau_r = tau[above];
+    // tau_diff gathered at `below` from tau[1:]-tau[:-1] (size S+1); the reference raises for
+    // below == S+1 (only reachable with u >= 1): we clamp instead of faulting.
+    const int bd = min(below, S);
+    const float dtau = __fsub_rn(tau[bd + 1], tau[bd]);
+    float x;
+    if (dtau < tol && dtau > -tol) {
+      x = s_l;
+    } else {
+      const float ln_term = -logf(fmaxf(eps, __fdiv_rn(__fsub_rn(1.0f, u), fmaxf(eps, T_l))));
+      const float ds = __fsub_rn(s_r, s_l);
+      float t;
+      if (dtau >= tol) {
+        const float disc = __fadd_rn(__fmul_rn(tau_l, tau_l),
+                                     __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_r, tau_l)), ln_term), fmaxf(eps, ds)));
+        t = __fdiv_rn(__fmul_rn(ds, __fadd_rn(-tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_r, tau_l)));
+      } else {
+        const float disc = __fsub_rn(__fmul_rn(tau_l, tau_l),
+                                     __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_l, tau_r)), ln_term), fmaxf(eps, ds)));
+        t = __fdiv_rn(__fmul_rn(ds, __fsub_rn(tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_l, tau_r)));
+      }
+      // torch.clamp(t, min=eps, max=ds): min(max(t, eps), ds) -- max wins, NaN propagates
+      if (t == t) t = fminf(fmaxf(t, eps), ds);
+      x = __fadd_rn(s_l, t);
+      if (x != x) x = s_l;
+    }
+    a.samples[r * (int64_t)a.Ni + k] = x;
+    if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+  }
+}
+
+int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
+                     int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0,
+                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st) {
+  if (n == 0 || Ni == 0) return PLNERF_OK;
+  SamplePLArgs a{z, w, tau, T, rays, n, stride, S, Ni, u, seed, ray0, zero_tol, eps, samples, inds};
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * 4 * (S + 2) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("sample_pdf_pl: N_samples=%d too large", S); return PLNERF_E_UNSUPPORTED; }
+  k_sample_pl<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_sample_pl");
+  return PLNERF_OK;
+}
+
+// a12  sample_pdf  (run_nerf_helpers.py:241-284)
+struct SampleConstArgs {
+  const float* bins; int bins_stride; int bins_mid;   // bins_mid: bins_k = .5*(z[k+1]+z[k]) from z rows
+  const float* w; int w_stride;                      // weights row stride (slice [1:-1] of a wider row)
+  int64_t n; int nb, Ni;
+  const float* u; uint64_t seed, ray0;
+  float* samples; int64_t* inds;
+};
+
+__global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int nb = a.nb, nw = nb - 1;
+  float* cdf = smem + (size_t)wib * 2 * nb;
+  float* bins = cdf + nb;
+  const float* brow = a.bins + r * (int64_t)a.bins_stride;
+  for (int k = lane; k < nb; k += 32)
+    bins[k] = a.bins_mid ? __fmul_rn(0.5f, __fadd_rn(brow[k + 1], brow[k])) : brow[k];
+  const float* wrow = a.w + r * (int64_t)a.w_stride;
+  float tot = 0.f;
+  for (int k = lane; k < nw; k += 32) tot += __fadd_rn(wrow[k], 1e-5f);
+  tot = warp_sum(tot);
+  double carry = 0.0;
+  if (lane == 0) cdf[0] = 0.0f;
+  for (int base = 0; base < nw; base += 32) {
+    const int i = base + lane;
+    const double pv = (i < nw) ? (double)__fdiv_rn(__fadd_rn(wrow[i], 1e-5f), tot) : 0.0;
+    const double incl = warp_incl_scan_add(pv, lane) + carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    if (i < nw) cdf[i + 1] = (float)incl;
+  }
+  __syncwarp();
+  for (int k = lane; k < a.Ni; k += 32) {
+    const float u = a.u ? a.u[r * (int64_t)a.Ni + k]
+                        : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+    const int ind = upper_bound_torch(cdf, nb, u);
+    const int below = max(0, ind - 1);
+    const int above = min(nb - 1, ind);
+    float denom = __fsub_rn(cdf[above], cdf[below]);
+    if (denom < 1e-5f) denom = 1.0f;
+    const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
+    a.samples[r * (int64_t)a.Ni + k] = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+    if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+  }
+}
+
+int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
+                        int64_t n, int nb, int Ni, const float* u, uint64_t seed, uint64_t ray0,
+                        float* samples, int64_t* inds, cudaStream_t st) {
+  if (n == 0 || Ni == 0) return PLNERF_OK;
+  if (nb < 2) { set_error("sample_pdf: need at least 2 bins"); return PLNERF_E_BADARG; }
+  SampleConstArgs a{bins, bins_stride, bins_mid, w, w_stride, n, nb, Ni, u, seed, ray0, samples, inds};
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * 2 * nb * sizeof(float);
+  if (smem > 48 * 1024) { set_error("sample_pdf: %d bins too many", nb); return PLNERF_E_UNSUPPORTED; }
+  k_sample_const<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_sample_const");
+  return PLNERF_OK;
+}
+
+// a13  clamp + sort(cat(z_vals, z_samples)) + std   (run_plnerf.py:728-734, :752)
+// Rank-sort the Ni clamped samples inside the warp, then merge the two ascending lists by binary
+// searches (coarse depths first on ties) -- the output is the sorted multiset, like torch.sort.
+struct MergeArgs {
+  const float *z, *samples, *rays; int64_t n; int stride, S, Ni; float *z_out, *z_std;
+};
+
+__global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int S = a.S, Ni = a.Ni;
+  float* zc = smem + (size_t)wib * (S + 2 * Ni);
+  float* xs = zc + S;
+  float* xsorted = xs + Ni;
+  const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
+  for (int k = lane; k < S; k += 32) zc[k] = a.z[r * (int64_t)S + k];
+  float sum = 0.f;
+  for (int k = lane; k < Ni; k += 32) {
+    float x = a.samples[r * (int64_t)Ni + k];
+    if (x == x) x = fminf(fmaxf(x, near), far);  // torch.clamp(x, near, far); NaN propagates
+    xs[k] = x;
+    sum += x;
+  }
+  __syncwarp();
+  if (a.z_std) {  // torch.std(z_samples, unbiased=False)
+    const float mean = __fdiv_rn(warp_sum(sum), (float)Ni);
+    float v = 0.f;
+    for (int k = lane; k < Ni; k += 32) { const float d = xs[k] - mean; v += d * d; }
+    v = warp_sum(v);
+    if (lane == 0) a.z_std[r] = sqrtf(__fdiv_rn(v, (float)Ni));
+  }
+  // rank sort (stable): rank_k = #{m: x_m < x_k or (x_m == x_k and m < k)}; NaNs sort last
+  for (int k = lane; k < Ni; k += 32) {
+    const float x = xs[k];
+    int rank = 0;
+    if (x == x) {
+      for (int m = 0; m < Ni; ++m) {
+        const float y = xs[m];
+        rank += (y < x) || (y == x && m < k);
+      }
+    } else {
+      for (int m = 0; m < Ni; ++m) { const float y = xs[m]; rank += (y == y) || (m < k); }
+    }
+    xsorted[rank] = x;
+  }
+  __syncwarp();
+  float* out = a.z_out + r * (int64_t)(S + Ni);
+  for (int i = lane; i < S; i += 32) {  // coarse i lands after every sample strictly smaller
+    const float v = zc[i];
+    int lo = 0, hi = Ni;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (xsorted[mid] < v) lo = mid + 1; else hi = mid; }
+    out[i + lo] = v;
+  }
+  for (int k = lane; k < Ni; k += 32) {  // sample k lands after every coarse depth <= it
+    const float v = xsorted[k];
+    int lo = 0, hi = S;
+    if (v == v) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= v) lo = mid + 1; else hi = mid; } }
+    else lo = S;
+    out[k + lo] = v;
+  }
+}
+
+int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
+                 int Ni, float* z_out, float* z_std, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  MergeArgs a{z, samples, rays, n, stride, S, Ni, z_out, z_std};
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (S + 2 * Ni) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
+  k_merge<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_merge");
+  return PLNERF_OK;
+}
+
+int launch_encode(const float* x, int64_t n, int L, float* out, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  k_encode<<<(unsigned)ceil_div(n * 3, 256), 256, 0, st>>>(x, n, L, out);
+  PLNERF_LAUNCH_CHECK("k_encode");
+  return PLNERF_OK;
+}
+
+int launch_stratified_z(const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
+                        const float* t_rand, uint64_t seed, uint64_t ray0, float* z, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  k_stratified_z<<<(unsigned)ceil_div(n * Ns, 256), 256, 0, st>>>(rays, n, stride, Ns, lindisp, perturb, t_rand,
+                                                                   seed, ray0, z);
+  PLNERF_LAUNCH_CHECK("k_stratified_z");
+  return PLNERF_OK;
+}
+
+}  // namespace plnerf

@@ -1,0 +1,40 @@
+// Internal launch wrappers shared by api.cu / render.cu (device pointers, explicit stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/plnerf_b200.h"
+
+namespace plnerf {
+
+int launch_encode(const float* x, int64_t n, int L, float* out, cudaStream_t st);
+int launch_stratified_z(const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
+                        const float* t_rand, uint64_t seed, uint64_t ray0, float* z, cudaStream_t st);
+int launch_composite(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n,
+                     int stride, int S, int mode, int color_mode, int white_bkgd, int farcolorfix,
+                     const float* noise, float noise_std, uint64_t seed, uint64_t ray0, uint32_t noise_stream,
+                     float* rgb_map, float* disp_map, float* acc_map, float* depth_map, float* weights,
+                     float* tau, float* T, cudaStream_t st);
+int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
+                     int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0,
+                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st);
+int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
+                        int64_t n, int nb, int Ni, const float* u, uint64_t seed, uint64_t ray0,
+                        float* samples, int64_t* inds, cudaStream_t st);
+int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
+                 int Ni, float* z_out, float* z_std, cudaStream_t st);
+
+// ---- fused MLP (mlp_fwd.cu) ----------------------------------------------------------------
+size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision);
+int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision, void* packed, cudaStream_t st);
+size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays);
+// Fused query: rows = n*S samples of rays (PE computed in-kernel).
+int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
+              const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
+              void* ws, size_t ws_bytes, cudaStream_t st);
+// NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
+int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
+                         float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);
+
+}  // namespace plnerf

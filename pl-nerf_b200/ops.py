@@ -1,0 +1,331 @@
+"""torch-tensor front end of the C ABI: every function takes/returns CUDA float32 tensors and
+enqueues the sm_100a kernels on ``torch.cuda.current_stream()``.  torch is only the allocator and
+stream provider here.  CPU tensors are rejected: there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+
+_PREC = {"bf16": L.PREC_BF16, "bf16x3": L.PREC_BF16X3}
+_default_precision = os.environ.get("PLNERF_PRECISION", "bf16")
+
+
+def set_precision(name):
+    """'bf16' (one tcgen05 MMA per product, default) or 'bf16x3' (hi/lo split, ~fp32 products)."""
+    global _default_precision
+    if name not in _PREC:
+        raise ValueError(f"precision must be one of {list(_PREC)}")
+    _default_precision = name
+
+
+def get_precision():
+    return _default_precision
+
+
+def _prec(p):
+    return _PREC[p if p is not None else _default_precision]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: plnerf_b200 only runs on CUDA tensors (no CPU fallback); got device {t.device}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def launch_count():
+    return int(L.lib().plnerf_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+def encode(x, multires):
+    """Embedder.embed (run_nerf_helpers.py:53-54): [..., 3] -> [..., 3+6*multires]."""
+    x = _f32(x, "x")
+    shp = x.shape
+    x2 = x.reshape(-1, 3)
+    od = 3 if multires < 0 else 3 + 6 * multires
+    out = torch.empty((x2.shape[0], od), device=x.device, dtype=torch.float32)
+    L.check(L.lib().plnerf_encode(_p(x2), x2.shape[0], multires, _p(out), _stream()))
+    return out.reshape(*shp[:-1], od)
+
+
+def stratified_z(rays, N_samples, lindisp=False, perturb=True, t_rand=None, seed=0, ray_id_offset=0):
+    """render_rays' depth sampling (run_plnerf.py:683-705).  rays [n, >=8]."""
+    rays = _f32(rays, "rays")
+    n = rays.shape[0]
+    z = torch.empty((n, N_samples), device=rays.device, dtype=torch.float32)
+    if t_rand is not None:
+        t_rand = _f32(t_rand, "t_rand")
+        assert t_rand.shape == (n, N_samples)
+    L.check(L.lib().plnerf_stratified_z(_p(rays), n, rays.shape[1], N_samples, int(bool(lindisp)),
+                                         int(bool(perturb)), _p(t_rand), seed, ray_id_offset, _p(z), _stream()))
+    return z
+
+
+def raw2outputs(raw, z_vals, rays, mode, color_mode, noise=None, white_bkgd=False, farcolorfix=False,
+                want_weights=True):
+    """raw2outputs (run_plnerf.py:553-624).  rays [n, >=8] carries rays_d (cols 3-5), near, far (6,7).
+    Returns (rgb_map, disp_map, acc_map, weights, depth_map, tau, T)."""
+    raw = _f32(raw, "raw")
+    z_vals = _f32(z_vals, "z_vals")
+    rays = _f32(rays, "rays")
+    n, S = z_vals.shape
+    dev = raw.device
+    lin = mode == "linear"
+    if mode not in ("linear", "constant"):
+        raise ValueError(f"mode must be 'linear' or 'constant', got {mode!r}")
+    if color_mode not in ("midpoint", "left"):
+        raise ValueError(f"color_mode must be 'midpoint' or 'left', got {color_mode!r}")
+    rgb = torch.empty((n, 3), device=dev)
+    disp = torch.empty((n,), device=dev)
+    acc = torch.empty((n,), device=dev)
+    depth = torch.empty((n,), device=dev)
+    w = torch.empty((n, S + 1 if lin else S), device=dev) if want_weights else None
+    tau = torch.empty((n, S + 2), device=dev) if (lin and want_weights) else None
+    T = torch.empty((n, S + 2), device=dev) if (lin and want_weights) else None
+    if noise is not None:
+        noise = _f32(noise, "noise")
+    L.check(L.lib().plnerf_raw2outputs(_p(raw), raw.shape[-1], _p(z_vals), _p(rays), n, rays.shape[1], S,
+                                        L.MODE_LINEAR if lin else L.MODE_CONSTANT,
+                                        L.COLOR_MIDPOINT if color_mode == "midpoint" else L.COLOR_LEFT,
+                                        int(bool(white_bkgd)), int(bool(farcolorfix)), _p(noise), _p(rgb), _p(disp),
+                                        _p(acc), _p(depth), _p(w), _p(tau), _p(T), _stream()))
+    return rgb, disp, acc, w, depth, tau, T
+
+
+def sample_pdf_pl(z_vals, weights, tau, T, rays, N_importance, u=None, seed=0, ray_id_offset=0, zero_tol=1e-4,
+                  epsilon=1e-3, return_inds=False):
+    """sample_pdf_reformulation (run_nerf_helpers.py:364-445) with near/far taken from rays cols 6,7."""
+    z_vals, weights, tau, T, rays = (_f32(t, k) for t, k in ((z_vals, "z_vals"), (weights, "weights"),
+                                                              (tau, "tau"), (T, "T"), (rays, "rays")))
+    n, S = z_vals.shape
+    out = torch.empty((n, N_importance), device=z_vals.device)
+    inds = torch.empty((n, N_importance), device=z_vals.device, dtype=torch.int64) if return_inds else None
+    if u is not None:
+        u = _f32(u, "u")
+    L.check(L.lib().plnerf_sample_pdf_pl(_p(z_vals), _p(weights), _p(tau), _p(T), _p(rays), n, rays.shape[1], S,
+                                          N_importance, _p(u), seed, ray_id_offset, zero_tol, epsilon, _p(out),
+                                          _p(inds), _stream()))
+    return (out, inds) if return_inds else out
+
+
+def sample_pdf(bins, weights, N_importance, u=None, seed=0, ray_id_offset=0, return_inds=False):
+    """sample_pdf (run_nerf_helpers.py:241-284): bins [n,nb], weights [n,nb-1]."""
+    bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
+    n, nb = bins.shape
+    assert weights.shape == (n, nb - 1)
+    out = torch.empty((n, N_importance), device=bins.device)
+    inds = torch.empty((n, N_importance), device=bins.device, dtype=torch.int64) if return_inds else None
+    if u is not None:
+        u = _f32(u, "u")
+    L.check(L.lib().plnerf_sample_pdf(_p(bins), _p(weights), n, nb, N_importance, _p(u), seed, ray_id_offset,
+                                       _p(out), _p(inds), _stream()))
+    return (out, inds) if return_inds else out
+
+
+def merge_samples(z_vals, z_samples, rays):
+    """clamp + sort(cat) + std (run_plnerf.py:728-734, :752) -> (z_merged, z_std)."""
+    z_vals, z_samples, rays = _f32(z_vals, "z_vals"), _f32(z_samples, "z_samples"), _f32(rays, "rays")
+    n, S = z_vals.shape
+    Ni = z_samples.shape[1]
+    out = torch.empty((n, S + Ni), device=z_vals.device)
+    std = torch.empty((n,), device=z_vals.device)
+    L.check(L.lib().plnerf_merge_samples(_p(z_vals), _p(z_samples), _p(rays), n, rays.shape[1], S, Ni, _p(out),
+                                          _p(std), _stream()))
+    return out, std
+
+
+# ------------------------------------------------------------------------------------------------
+# packed networks
+# ------------------------------------------------------------------------------------------------
+def net_desc_of(net):
+    """plnerf_net_desc from a NeRF-like module (attrs of run_nerf_helpers.py:81-86)."""
+    d = L.NetDesc()
+    d.D, d.W = int(net.D), int(net.W)
+    d.input_ch, d.input_ch_views = int(net.input_ch), int(net.input_ch_views)
+    d.use_viewdirs = int(bool(net.use_viewdirs))
+    d.output_ch = int(net.output_linear.out_features) if not net.use_viewdirs else 4
+    skips = list(net.skips)
+    d.n_skips = len(skips)
+    for i, s in enumerate(skips):
+        d.skips[i] = int(s)
+    return d
+
+
+class PackedNet:
+    """Device-side packed copy of one NeRF's parameters (bf16 K-major panels + fp32 tail),
+    refreshed lazily whenever a parameter's version counter changes (e.g. after optimizer.step())."""
+
+    def __init__(self, net):
+        self.desc = net_desc_of(net)
+        self.buf = {}
+        self.version = {}
+
+    def _versions(self, net):
+        return tuple((p.data_ptr(), p._version) for p in net.parameters())
+
+    def get(self, net, precision):
+        prec = _prec(precision)
+        ver = self._versions(net)
+        if self.version.get(prec) == ver and prec in self.buf:
+            return self.buf[prec]
+        first = next(net.parameters())
+        if not first.is_cuda:
+            raise RuntimeError("plnerf_b200: the NeRF module must live on a CUDA device (no CPU fallback)")
+        nbytes = L.lib().plnerf_packed_bytes(C.byref(self.desc), prec)
+        if nbytes == 0:
+            L.check(-2)
+        if prec not in self.buf or self.buf[prec].numel() != nbytes:
+            self.buf[prec] = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
+        prm = L.NetParams()
+        sd = {k: v.detach() for k, v in net.named_parameters()}
+        keep = []
+
+        def ptr(name):
+            t = sd[name]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        for i in range(self.desc.D):
+            prm.pts_w[i] = ptr(f"pts_linears.{i}.weight")
+            prm.pts_b[i] = ptr(f"pts_linears.{i}.bias")
+        if self.desc.use_viewdirs:
+            for f, nme in (("views_w", "views_linears.0.weight"), ("views_b", "views_linears.0.bias"),
+                           ("feature_w", "feature_linear.weight"), ("feature_b", "feature_linear.bias"),
+                           ("alpha_w", "alpha_linear.weight"), ("alpha_b", "alpha_linear.bias"),
+                           ("rgb_w", "rgb_linear.weight"), ("rgb_b", "rgb_linear.bias")):
+                setattr(prm, f, ptr(nme))
+        else:
+            prm.output_w = ptr("output_linear.weight")
+            prm.output_b = ptr("output_linear.bias")
+        L.check(L.lib().plnerf_pack_weights(C.byref(self.desc), C.byref(prm), prec, _p(self.buf[prec]), _stream()))
+        self.version[prec] = ver
+        return self.buf[prec]
+
+
+def packed_of(net):
+    """Per-module PackedNet cache stored on the module itself."""
+    pk = net.__dict__.get("_plnerf_packed")
+    if pk is None:
+        pk = PackedNet(net)
+        net.__dict__["_plnerf_packed"] = pk
+    return pk
+
+
+def _multires_of(ch):
+    if ch == 3:
+        return -1
+    if ch < 3 or (ch - 3) % 6:
+        raise RuntimeError(f"plnerf_b200: {ch} input channels is not a NeRF positional encoding (3 + 6*L)")
+    return (ch - 3) // 6
+
+
+def network_query(net, rays, z_vals, precision=None):
+    """run_network (run_plnerf.py:78-92) fused: rays [n, 8|11], z_vals [n,S] -> raw [n,S,C]."""
+    rays, z_vals = _f32(rays, "rays"), _f32(z_vals, "z_vals")
+    pk = packed_of(net)
+    buf = pk.get(net, precision)
+    n, S = z_vals.shape
+    ch = 4 if pk.desc.use_viewdirs else pk.desc.output_ch
+    raw = torch.empty((n, S, ch), device=rays.device)
+    wsb = L.lib().plnerf_query_workspace_bytes(C.byref(pk.desc), n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=rays.device)
+    mr = _multires_of(pk.desc.input_ch)
+    mrv = _multires_of(pk.desc.input_ch_views) if pk.desc.use_viewdirs else -1
+    L.check(L.lib().plnerf_network_query(C.byref(pk.desc), _p(buf), _prec(precision), mr, mrv, _p(rays), n,
+                                          rays.shape[1], _p(z_vals), S, _p(raw), _p(ws), wsb, _stream()))
+    return raw
+
+
+def mlp_forward(net, x, precision=None):
+    """NeRF.forward (run_nerf_helpers.py:105-128) on embedded rows x [m, input_ch+input_ch_views]."""
+    x = _f32(x, "x")
+    pk = packed_of(net)
+    buf = pk.get(net, precision)
+    width = pk.desc.input_ch + (pk.desc.input_ch_views if pk.desc.use_viewdirs else 0)
+    if x.shape[-1] < width:
+        raise RuntimeError(f"NeRF.forward: expected at least {width} input channels, got {x.shape[-1]}")
+    x2 = x.reshape(-1, x.shape[-1])[:, :width].contiguous()
+    m = x2.shape[0]
+    ch = 4 if pk.desc.use_viewdirs else pk.desc.output_ch
+    out = torch.empty((m, ch), device=x.device)
+    wsb = L.lib().plnerf_query_workspace_bytes(C.byref(pk.desc), m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().plnerf_mlp_forward(C.byref(pk.desc), _p(buf), _prec(precision), _p(x2), m, _p(out), _p(ws), wsb,
+                                        _stream()))
+    return out.reshape(*x.shape[:-1], ch)
+
+
+def render_rays_fwd(rays, net_coarse, net_fine, N_samples, N_importance, mode, color_mode, perturb=True,
+                    white_bkgd=False, lindisp=False, raw_noise_std=0.0, zero_tol=1e-4, epsilon=1e-3, farcolorfix=False,
+                    t_rand=None, u=None, noise0=None, noise1=None, seed=0, ray_id_offset=0, retraw=False,
+                    want_z=False, want_inds=False, precision=None):
+    """Whole render_rays forward (run_plnerf.py:627-758) in one C call.  Returns the reference's dict."""
+    rays = _f32(rays, "rays")
+    n = rays.shape[0]
+    dev = rays.device
+    pkc = packed_of(net_coarse)
+    bufc = pkc.get(net_coarse, precision)
+    pkf, buff = None, None
+    if N_importance > 0 and net_fine is not None:
+        pkf = packed_of(net_fine)
+        buff = pkf.get(net_fine, precision)
+    cfg = L.RenderCfg()
+    cfg.N_samples, cfg.N_importance = N_samples, N_importance
+    cfg.mode = L.MODE_LINEAR if mode == "linear" else L.MODE_CONSTANT
+    if mode not in ("linear", "constant"):
+        raise ValueError(f"mode must be 'linear' or 'constant', got {mode!r}")
+    if color_mode not in ("midpoint", "left"):
+        raise ValueError(f"color_mode must be 'midpoint' or 'left', got {color_mode!r}")
+    cfg.color_mode = L.COLOR_MIDPOINT if color_mode == "midpoint" else L.COLOR_LEFT
+    cfg.white_bkgd, cfg.lindisp, cfg.farcolorfix = int(bool(white_bkgd)), int(bool(lindisp)), int(bool(farcolorfix))
+    cfg.perturb = int(bool(perturb))
+    cfg.raw_noise_std, cfg.zero_tol, cfg.epsilon = float(raw_noise_std), float(zero_tol), float(epsilon)
+    cfg.multires = _multires_of(pkc.desc.input_ch)
+    cfg.multires_views = _multires_of(pkc.desc.input_ch_views) if pkc.desc.use_viewdirs else -1
+    cfg.precision = _prec(precision)
+    cfg.seed, cfg.ray_id_offset = int(seed), int(ray_id_offset)
+    S_last = N_samples + N_importance
+    ch = 4 if pkc.desc.use_viewdirs else pkc.desc.output_ch
+    o = L.RenderOut()
+    ret = {}
+
+    def new(key, shape, field=None, dtype=torch.float32):
+        t = torch.empty(shape, device=dev, dtype=dtype)
+        setattr(o, field or key, t.data_ptr())
+        ret[key] = t
+        return t
+    new("rgb_map", (n, 3)); new("disp_map", (n,)); new("acc_map", (n,)); new("depth_map", (n,))
+    if retraw:
+        new("raw", (n, S_last, ch))
+    if N_importance > 0:
+        new("rgb0", (n, 3)); new("disp0", (n,)); new("depth0", (n,)); new("acc0", (n,)); new("z_std", (n,))
+        if want_inds:
+            new("inds", (n, N_importance), dtype=torch.int64)
+    if want_z:
+        new("z_vals", (n, S_last))
+    opt = lambda t, nm: None if t is None else _f32(t, nm)
+    t_rand, u, noise0, noise1 = opt(t_rand, "t_rand"), opt(u, "u"), opt(noise0, "noise0"), opt(noise1, "noise1")
+    wsb = L.lib().plnerf_render_workspace_bytes(C.byref(cfg), C.byref(pkc.desc), n)
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    L.check(L.lib().plnerf_render_rays_fwd(C.byref(cfg), C.byref(pkc.desc), _p(bufc),
+                                            C.byref(pkf.desc) if pkf else None, _p(buff), _p(rays), n, rays.shape[1],
+                                            _p(t_rand), _p(u), _p(noise0), _p(noise1), C.byref(o),
+                                            C.c_void_p(ws.data_ptr() + off), wsb, _stream()))
+    return ret

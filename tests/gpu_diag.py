@@ -1,0 +1,63 @@
+"""Bring-up diagnostics for the tcgen05 path (not collected by pytest).  Run on the GPU box:
+    timeout 120 python tests/gpu_diag.py gemm      # descriptor encodings: which (lbo,sbo) is right
+    timeout 120 python tests/gpu_diag.py mlp       # fused MLP vs oracle on a few hundred rows
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
+import plnerf_b200  # noqa: E402
+from plnerf_b200 import _lib as L, ops  # noqa: E402
+import plnerf_oracle as O  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gemm():
+    rs = np.random.RandomState(0)
+    for a_mode in (0, 1):
+        for (lbo, sbo) in ((2048, 128), (128, 2048)):
+            for N, K in ((128, 16), (128, 64), (256, 256)):
+                A = rs.randn(128, K).astype(np.float32)
+                B = rs.randn(N, K).astype(np.float32)
+                ref = O.bf16_round(A).astype(np.float64) @ O.bf16_round(B).astype(np.float64).T
+                D = torch.zeros((128, N), device="cuda")
+                dA, dB = dev(A), dev(B)
+                rc = L.lib().plnerf_debug_umma_gemm_ex(dA.data_ptr(), dB.data_ptr(), N, K, a_mode, lbo, sbo,
+                                                       D.data_ptr(), None)
+                torch.cuda.synchronize()
+                out = D.cpu().numpy()
+                err = np.abs(out - ref).max() / np.abs(ref).max()
+                print(f"a_mode={a_mode} lbo={lbo} sbo={sbo} N={N} K={K} rc={rc} relerr={err:.3e} "
+                      f"out[0,:4]={out[0,:4]} ref[0,:4]={ref[0,:4]}", flush=True)
+
+
+def mlp():
+    from util import case_params, load_golden, oracle_net_kw
+    from plnerf_b200.run_nerf_helpers import NeRF
+    for name in ("lego_linear_mid", "lego_left_noise_lindisp"):
+        g = load_golden(name)
+        cfg, kw, pc, pf = case_params(name)
+        net = NeRF(D=kw["D"], W=kw["W"], input_ch=kw["input_ch"], input_ch_views=kw["input_ch_views"],
+                   output_ch=kw["output_ch"], skips=list(kw["skips"]), use_viewdirs=kw["use_viewdirs"])
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in pc.items()})
+        net = net.cuda()
+        for prec in ("bf16", "bf16x3"):
+            with torch.no_grad():
+                raw = ops.network_query(net, dev(g["ray_batch"]), dev(g["z_vals0"]), precision=prec)
+            torch.cuda.synchronize()
+            raw = raw.cpu().numpy()
+            ref = g["raw0"][..., :raw.shape[-1]]
+            scale = np.abs(ref).reshape(-1, ref.shape[-1]).max(0)
+            err = (np.abs(raw - ref) / scale).reshape(-1, ref.shape[-1]).max(0)
+            print(f"{name} {prec}: per-channel max err / scale = {err}  raw[0,0]={raw[0,0]} ref[0,0]={ref[0,0]}", flush=True)
+
+
+if __name__ == "__main__":
+    {"gemm": gemm, "mlp": mlp}[sys.argv[1]]()

@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/plnerf_b200.h declares; host-only entry points behave (no GPU compute here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import plnerf_b200
+from plnerf_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    plnerf_b200.build()
+    return L.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "plnerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(plnerf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/plnerf_b200.h but not exported"
+    assert set(syms) == set(L.PUBLIC_SYMBOLS)
+
+
+def test_abi_version_and_packed_size(lib):
+    assert lib.plnerf_abi_version() == 1
+    d = L.NetDesc()
+    d.D, d.W, d.input_ch, d.input_ch_views, d.output_ch, d.use_viewdirs, d.n_skips = 8, 256, 63, 27, 5, 1, 1
+    d.skips[0] = 4
+    # bf16 stream: (4 + 7*16 + 4 + 16) K-steps * 2 halves * 4 KiB + views 16 * 4 KiB, + fp32 tail
+    n_fast = lib.plnerf_packed_bytes(C.byref(d), L.PREC_BF16)
+    n_x3 = lib.plnerf_packed_bytes(C.byref(d), L.PREC_BF16X3)
+    ks = (4 + 7 * 16 + 4) * 2 + 16 * 2 + 16
+    tail = n_fast - ks * 4096
+    assert 0 < tail < 64 * 1024
+    assert n_x3 == 2 * ks * 4096 + tail
+
+
+def test_unsupported_shapes_fail_loudly(lib):
+    d = L.NetDesc()
+    d.D, d.W, d.input_ch, d.input_ch_views, d.output_ch, d.use_viewdirs, d.n_skips = 8, 128, 63, 27, 5, 1, 0
+    assert lib.plnerf_packed_bytes(C.byref(d), L.PREC_BF16) == 0
+    assert b"W=256" in lib.plnerf_last_error()
+
+
+def test_bad_arguments_return_codes(lib):
+    rc = lib.plnerf_encode(None, 4, 10, None, None)
+    assert rc == -1 and b"null" in lib.plnerf_last_error()
+    rc = lib.plnerf_stratified_z(None, 0, 4, 64, 0, 1, None, 0, 0, None, None)
+    assert rc == -1  # stride < 8
+
+
+def test_reference_module_surface():
+    """Names the reference's run_plnerf.py star-imports / looks up must exist with the same signatures."""
+    import inspect
+    import plnerf_b200.run_nerf_helpers as H
+    import plnerf_b200.run_plnerf as R
+    for n in ("img2mse", "mse2psnr", "to8b", "to16b", "Embedder", "get_embedder", "NeRF", "get_rays", "get_rays_np",
+              "ndc_rays", "sample_pdf", "sample_pdf_reformulation", "pw_linear_sample_increasing",
+              "pw_linear_sample_decreasing"):
+        assert hasattr(H, n), n
+    ref_args = ["ray_batch", "network_fn", "network_query_fn", "N_samples", "mode", "color_mode", "retraw", "lindisp",
+                "perturb", "N_importance", "network_fine", "white_bkgd", "raw_noise_std", "verbose", "pytest",
+                "quad_solution_v2", "zero_tol", "epsilon", "farcolorfix", "constant_init"]
+    assert list(inspect.signature(R.render_rays).parameters)[:len(ref_args)] == ref_args
+    assert list(inspect.signature(R.render).parameters)[:10] == ["H", "W", "K", "chunk", "rays", "c2w", "ndc", "near",
+                                                                 "far", "use_viewdirs"]
+    net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    want = dict(plnerf_b200.synth.nerf_param_shapes(output_ch=5))
+    assert shapes == want
+    assert sum(v.numel() for v in net.parameters()) == 595844
+
+
+def test_no_cpu_fallback():
+    import torch
+    import plnerf_b200.run_nerf_helpers as H
+    net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(4, 90))
