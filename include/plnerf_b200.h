@@ -189,6 +189,12 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
                            const float* noise1, const plnerf_render_out* out, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---- measurement hooks (bench.py): time every fused-MLP launch with CUDA events on its own stream --
+ * plnerf_profile_enable(1) starts recording (and clears old records); plnerf_profile_read
+ * synchronises the recorded events and returns the summed device time, launch count and rows. */
+int plnerf_profile_enable(int on);
+int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_rows);
+
 /* ---- debug: single-tile tcgen05 GEMM used by the test-suite to pin descriptor encodings --------
  * D[128,N] = A[128,K] * B[N,K]^T, bf16-rounded operands, fp32 accumulate (K%16==0, N%16==0<=256).*/
 int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream);

@@ -57,8 +57,35 @@ def embed_dim(multires):
 # --------------------------------------------------------------------------------------------
 # MLP -- run_nerf_helpers.py:105-128 (NeRF.forward)
 # --------------------------------------------------------------------------------------------
+try:  # the reference runs its Linear layers through torch's CPU BLAS (MKL sgemm); use the same
+    import torch as _torch  # library for the big GEMMs so that the timed CPU baseline is not handicapped
+except Exception:  # pragma: no cover
+    _torch = None
+USE_TORCH_BLAS = _torch is not None
+
+
+def _affine(h, w, b, relu=False):
+    """(h @ w.T + b), optionally ReLU'd, in float32.  Large batches go through torch's CPU kernels
+    (F.linear = MKL sgemm with fused bias, like the reference's nn.Linear); tiny ones stay numpy."""
+    if USE_TORCH_BLAS and h.shape[0] >= 256:
+        y = _torch.nn.functional.linear(_torch.from_numpy(np.ascontiguousarray(h)),
+                                        _torch.from_numpy(np.ascontiguousarray(w)),
+                                        None if b is None else _torch.from_numpy(np.ascontiguousarray(b)))
+        if relu:
+            y = _torch.relu_(y)
+        return y.numpy()
+    y = h @ w.T
+    if b is not None:
+        y = y + b
+    return np.maximum(y, F32(0)) if relu else y
+
+
+def _matmul_t(h, w):
+    return _affine(h, w, None)
+
+
 def _linear(h, params, name):
-    return h @ params[name + ".weight"].T + params[name + ".bias"]
+    return _affine(h, params[name + ".weight"], params[name + ".bias"])
 
 
 def bf16_round(x):
@@ -86,19 +113,19 @@ def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use
     h32 = None
     for i in range(D):
         w, b = params[f"pts_linears.{i}.weight"], params[f"pts_linears.{i}.bias"]
-        h32 = np.maximum(h @ rnd(w).T + b, F32(0))
+        h32 = _affine(h, rnd(w), b, relu=True)
         h = rnd(h32)
         if i in skips:
             h = np.concatenate([pts_q, h], -1)
     if use_viewdirs:
-        alpha = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
-        feature = rnd(h @ rnd(params["feature_linear.weight"]).T + params["feature_linear.bias"])
+        alpha = _linear(h32, params, "alpha_linear")
+        feature = rnd(_affine(h, rnd(params["feature_linear.weight"]), params["feature_linear.bias"]))
         wv, bv = params["views_linears.0.weight"], params["views_linears.0.bias"]
         W = feature.shape[1]
-        hv = np.maximum(feature @ rnd(wv[:, :W]).T + (input_views @ wv[:, W:].T + bv), F32(0))
-        rgb = hv @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
+        hv = np.maximum(_matmul_t(feature, rnd(wv[:, :W])) + (_matmul_t(input_views, wv[:, W:]) + bv), F32(0))
+        rgb = _linear(hv, params, "rgb_linear")
         return np.concatenate([rgb, alpha], -1).astype(F32)
-    return (h32 @ params["output_linear.weight"].T + params["output_linear.bias"]).astype(F32)
+    return _linear(h32, params, "output_linear").astype(F32)
 
 
 def run_network(pts, viewdirs, params, multires=10, multires_views=4, netchunk=1024 * 64, **net_kw):

@@ -105,6 +105,8 @@ _SIGS = {
                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(RenderOut), C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
+    "plnerf_profile_enable": (C.c_int, [C.c_int]),
+    "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "plnerf_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                             C.c_uint32, C.c_void_p, C.c_void_p]),

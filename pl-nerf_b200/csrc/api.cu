@@ -205,6 +205,11 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   return rc;
 }
 
+int plnerf_profile_enable(int on) { return profile_enable(on); }
+int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_rows) {
+  return profile_read(mlp_ms_sum, mlp_launches, mlp_rows);
+}
+
 int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
   return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
 }

@@ -26,6 +26,9 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "ops.cuh"
 #include "umma.cuh"
@@ -692,6 +695,17 @@ int query_device() {
   return PLNERF_OK;
 }
 
+struct ProfRec { cudaEvent_t e0, e1; int64_t rows; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_evt_pool;
+bool g_prof_on = false;
+std::mutex g_prof_mu;
+
+cudaEvent_t get_event() {
+  if (!g_evt_pool.empty()) { cudaEvent_t e = g_evt_pool.back(); g_evt_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
 int launch_mlp(MlpArgs& a, cudaStream_t st) {
   int rc = query_device();
   if (rc) return rc;
@@ -706,7 +720,10 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   }
   a.n_tiles = ceil_div(a.M, TILE_M);
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
+  ProfRec rec{nullptr, nullptr, a.M};
+  if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
   k_mlp_fwd<<<grid, NUM_THREADS, SL.total, st>>>(a);
+  if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
   PLNERF_LAUNCH_CHECK("k_mlp_fwd");
   return PLNERF_OK;
 }
@@ -809,6 +826,29 @@ int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode,
   PLNERF_CUDA(cudaFuncSetAttribute(k_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
   k_debug_gemm<<<1, 128, smem, st>>>(A, B, N, K, a_mode, lbo, sbo, D);
   PLNERF_LAUNCH_CHECK("k_debug_gemm");
+  return PLNERF_OK;
+}
+
+int profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { g_evt_pool.push_back(r.e0); g_evt_pool.push_back(r.e1); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return PLNERF_OK;
+}
+
+int profile_read(double* ms_sum, int64_t* launches, int64_t* rows) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0; int64_t nr = 0;
+  for (auto& r : g_prof) {
+    PLNERF_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0;
+    PLNERF_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t; nr += r.rows;
+  }
+  if (ms_sum) *ms_sum = ms;
+  if (launches) *launches = (int64_t)g_prof.size();
+  if (rows) *rows = nr;
   return PLNERF_OK;
 }
 

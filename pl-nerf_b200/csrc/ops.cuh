@@ -35,6 +35,8 @@ int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int m
 // NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
                          float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int profile_enable(int on);
+int profile_read(double* ms_sum, int64_t* launches, int64_t* rows);
 int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);
 
 }  // namespace plnerf

@@ -51,6 +51,18 @@ def launch_count():
     return int(L.lib().plnerf_launch_count())
 
 
+def profile_enable(on=True):
+    """Start/stop CUDA-event timing of every fused-MLP launch (bench.py roofline leg)."""
+    L.check(L.lib().plnerf_profile_enable(int(bool(on))))
+
+
+def profile_read():
+    """-> (summed k_mlp_fwd device ms, launches, rows) since profile_enable(True)."""
+    ms, n, rows = C.c_double(0), C.c_int64(0), C.c_int64(0)
+    L.check(L.lib().plnerf_profile_read(C.byref(ms), C.byref(n), C.byref(rows)))
+    return ms.value, n.value, rows.value
+
+
 # ------------------------------------------------------------------------------------------------
 def encode(x, multires):
     """Embedder.embed (run_nerf_helpers.py:53-54): [..., 3] -> [..., 3+6*multires]."""
