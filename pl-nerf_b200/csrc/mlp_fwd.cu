@@ -26,6 +26,8 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -288,6 +290,7 @@ struct MlpArgs {
   int64_t n_tiles;
   float* out; int out_stride;
   int n_stages;
+  int debug_flags;   // bring-up experiments only (PLNERF_DEBUG_FLAGS): 1 = skip weight re-streaming after tile 0
 };
 
 struct SmemLayout {
@@ -356,8 +359,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               const uint32_t bytes = (uint32_t)min(KS_PER_STAGE, total_ks - ks0) * KS_BYTES;
               for (int rep = 0; rep < nsplit; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
+                if ((A.debug_flags & 1) && tile != (int64_t)blockIdx.x) { ptx::mbar_arrive(w_full(slot)); }
+                else {
                 ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
                 ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot));
+                }
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
               }
@@ -718,6 +724,9 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     attr_set = true;
   }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PLNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
+  a.debug_flags = dbg;
   a.n_tiles = ceil_div(a.M, TILE_M);
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
