@@ -373,62 +373,82 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) ==========================================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
-      uint32_t slot = 0, phase = 0;
-      uint32_t uses[2] = {0, 0}, waited[2] = {0, 0};
-      auto wait_epi = [&](int h) {
-        while (waited[h] < uses[h]) { ptx::mbar_wait(a_ready0 + 8u * h, waited[h] & 1); ++waited[h]; }
-      };
-      uint32_t tile_iter = 0;
-      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
-        ptx::mbar_wait(pe_ready, tile_iter & 1);
-        ptx::tc_fence_after();
-        for (int l = 0; l < P.n_layers; ++l) {
-          const LayerPlan& L = P.L[l];
-          const int total_ks = L.n_pe_ks + L.n_h_ks;
-          const uint32_t a_in = tmem + (l > 0 ? a_out_col(l - 1) : COL_A0);
-          const uint32_t a_in_lo = tmem + COL_A1;  // bf16x3 only
-          for (int h = 0; h < L.n_halves; ++h) {
-            wait_epi(h);
-            ptx::tc_fence_after();
-            const uint32_t d = tmem + COL_DA + 128u * h;
-            uint32_t acc = 0;
-            for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
-              const int nks = min(KS_PER_STAGE, total_ks - ks0);
-              for (int rep = 0; rep < nsplit; ++rep) {
-                ptx::mbar_wait(w_full(slot), phase);
-                ptx::tc_fence_after();
-                for (int j = 0; j < nks; ++j) {
-                  const int ks = ks0 + j;
-                  const uint64_t bd = ptx::smem_desc(s_ring + slot * STAGE_BYTES + j * KS_BYTES, 2048, 128);
-                  if (ks < L.n_pe_ks) {
-                    const uint64_t ad_hi = ptx::smem_desc(s_pe_hi + ks * KS_BYTES, 2048, 128);
-                    if (rep == 0) {
-                      ptx::mma_ss(d, ad_hi, bd, idesc, acc); acc = 1;
-                      if (x3) ptx::mma_ss(d, ptx::smem_desc(s_pe_lo + ks * KS_BYTES, 2048, 128), bd, idesc, 1);
-                    } else {
-                      ptx::mma_ss(d, ad_hi, bd, idesc, 1);
+    // ===================== MMA issuer ===========================================================
+    // The whole warp runs this loop with warp-uniform control flow (so addresses and descriptors can
+    // live in uniform registers); one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
+    const uint32_t desc_hi = (uint32_t)(ptx::smem_desc(0, 2048, 128) >> 32);
+    const uint32_t desc_lo_flags = (uint32_t)(ptx::smem_desc(0, 2048, 128) & 0xFFFFFFFFu);  // LBO field
+    auto mk_desc = [&](uint32_t saddr) -> uint64_t {
+      return ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_flags | ((saddr & 0x3FFFFu) >> 4));
+    };
+    uint32_t slot = 0, phase = 0;
+    uint32_t uses0 = 0, uses1 = 0, waited0 = 0, waited1 = 0;
+    uint32_t tile_iter = 0;
+    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+      ptx::mbar_wait(pe_ready, tile_iter & 1);
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int n_pe_ks = P.L[l].n_pe_ks, n_h_ks = P.L[l].n_h_ks, n_halves = P.L[l].n_halves;
+        const int total_ks = n_pe_ks + n_h_ks;
+        const uint32_t a_in = tmem + (l > 0 ? a_out_col(l - 1) : COL_A0);
+        const uint32_t a_in_lo = tmem + COL_A1;  // bf16x3 only
+        for (int h = 0; h < n_halves; ++h) {
+          // accumulator h must have been drained by the epilogue of its previous use
+          if (h == 0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
+          else        { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
+          const uint32_t d = tmem + COL_DA + 128u * h;
+          uint32_t acc = 0;
+          for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
+            const int nks = min(KS_PER_STAGE, total_ks - ks0);
+            const bool is_pe = ks0 < n_pe_ks;              // stages never straddle PE / hidden K-steps
+            const int jh0 = ks0 - n_pe_ks;
+            if (!is_pe && jh0 + nks > 8) {                 // hidden columns >= 128 come from half b
+              while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; }
+            }
+            for (int rep = 0; rep < nsplit; ++rep) {
+              ptx::mbar_wait(w_full(slot), phase);
+              ptx::tc_fence_after();
+              const uint32_t bsm = s_ring + slot * STAGE_BYTES;
+              if (ptx::elect_one()) {
+                if (is_pe) {
+                  const uint32_t asm_hi = s_pe_hi + ks0 * KS_BYTES, asm_lo = s_pe_lo + ks0 * KS_BYTES;
+#pragma unroll
+                  for (int j = 0; j < KS_PER_STAGE; ++j) {
+                    if (j < nks) {
+                      const uint64_t bd = mk_desc(bsm + j * KS_BYTES);
+                      if (rep == 0) {
+                        ptx::mma_ss(d, mk_desc(asm_hi + j * KS_BYTES), bd, idesc, acc | (uint32_t)(j > 0));
+                        if (x3) ptx::mma_ss(d, mk_desc(asm_lo + j * KS_BYTES), bd, idesc, 1);
+                      } else {
+                        ptx::mma_ss(d, mk_desc(asm_hi + j * KS_BYTES), bd, idesc, 1);
+                      }
                     }
-                  } else {
-                    const int jh = ks - L.n_pe_ks;
-                    if (jh >= 8) { wait_epi(1); ptx::tc_fence_after(); }
-                    if (rep == 0) {
-                      ptx::mma_ts(d, a_in + 8u * jh, bd, idesc, acc); acc = 1;
-                      if (x3) ptx::mma_ts(d, a_in_lo + 8u * jh, bd, idesc, 1);
-                    } else {
-                      ptx::mma_ts(d, a_in + 8u * jh, bd, idesc, 1);
+                  }
+                } else {
+                  const uint32_t at = a_in + 8u * jh0, at_lo = a_in_lo + 8u * jh0;
+#pragma unroll
+                  for (int j = 0; j < KS_PER_STAGE; ++j) {
+                    if (j < nks) {
+                      const uint64_t bd = mk_desc(bsm + j * KS_BYTES);
+                      if (rep == 0) {
+                        ptx::mma_ts(d, at + 8u * j, bd, idesc, acc | (uint32_t)(j > 0));
+                        if (x3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
+                      } else {
+                        ptx::mma_ts(d, at + 8u * j, bd, idesc, 1);
+                      }
                     }
                   }
                 }
                 ptx::mma_commit(w_empty(slot));
-                if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
               }
+              __syncwarp();
+              acc = 1;
+              if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
             }
-            ptx::mma_commit(d_full0 + 8u * h);
-            ++uses[h];
           }
+          if (ptx::elect_one()) ptx::mma_commit(d_full0 + 8u * h);
+          __syncwarp();
+          if (h == 0) ++uses0; else ++uses1;
         }
       }
     }

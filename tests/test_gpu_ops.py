@@ -194,7 +194,8 @@ def test_mlp_forward_bf16_vs_emulation(P, name):
     """Fast mode vs an oracle that rounds the same operands to bf16.  Agreement is ~1e-7 of the output
     scale wherever both sides round every activation to the same bf16 value; fp32 summation-order
     differences flip an occasional bf16 rounding (1 ulp = 2^-8 relative on that activation), which
-    shows up as a sparse tail -- so the gate is on quantiles: median 2e-6, 99% within 1e-4, max 5e-3."""
+    shows up as a sparse tail (~1-2% of outputs) -- so the gate is on quantiles: 90% within 1e-6,
+    99% within 5e-4, max 5e-3."""
     g = load_golden(name)
     cfg, kw, pc, pf = case_params(name)
     net = make_net(kw, pc)
@@ -209,7 +210,7 @@ def test_mlp_forward_bf16_vs_emulation(P, name):
     scale = np.abs(ref).max(0, keepdims=True)
     err = np.abs(out - ref) / scale
     qs = np.quantile(err, [0.5, 0.9, 0.99, 0.999, 1.0])
-    assert qs[0] < 2e-6 and qs[2] < 1e-4 and qs[4] < 5e-3, qs
+    assert qs[1] < 1e-6 and qs[2] < 5e-4 and qs[4] < 5e-3, qs
 
 
 @pytest.mark.parametrize("name", ALL)
