@@ -48,7 +48,8 @@ constexpr int MAX_PE_KS = 4;        // input_ch <= 64
 constexpr int PE_TILE_BYTES = MAX_PE_KS * KS_BYTES;   // 16 KB
 constexpr int MAX_CONST_FLOATS = 4096;                // biases + small heads staged in smem
 constexpr int MAX_STAGES = 12;
-constexpr int NUM_THREADS = 256;    // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int NUM_THREADS = 384;    // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int NUM_EPI_THREADS = 256;
 constexpr int MAX_OUT_CH = 8;
 
 enum { EPI_RELU_A = 0, EPI_LINEAR_A = 1, EPI_VIEWS = 2, EPI_RELU_HEAD = 3 };
@@ -294,7 +295,7 @@ struct MlpArgs {
 };
 
 struct SmemLayout {
-  uint32_t pe_hi, pe_lo, ring, consts, bars;  // byte offsets
+  uint32_t pe_hi, pe_lo, ring, consts, xch, bars;  // byte offsets
   uint32_t total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int n_stages) {
@@ -303,22 +304,106 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages) {
   s.pe_lo = PE_TILE_BYTES;
   s.ring = 2 * PE_TILE_BYTES;
   s.consts = s.ring + (uint32_t)n_stages * STAGE_BYTES;
-  s.bars = s.consts + MAX_CONST_FLOATS * 4;
+  s.xch = s.consts + MAX_CONST_FLOATS * 4;
+  s.bars = s.xch + TILE_M * (MAX_OUT_CH + 1) * 4;
   s.total = s.bars + 512;
   return s;
 }
 
+// ---- packed epilogue math -----------------------------------------------------------------------
+// (x0,x1) += (b0,b1) as ONE instruction (Blackwell packed fp32 add)
+__device__ __forceinline__ void add2(float& x0, float& x1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(b0), "f"(b1));
+}
+// {lo, hi} -> bf16x2 with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// Positional encoding of one row -> this thread's panels of the PE tile(s).
+template <bool X3>
+__device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, const SmemLayout& SL, int64_t tile, int row,
+                                            int grp) {
+  const NetPlan& P = A.plan;
+  const int64_t g = tile * TILE_M + row;
+  const int64_t gc = (g < A.M) ? g : (A.M - 1);
+  const int n_panels = 2 * P.pe_ks;
+  const int p_lo = grp * n_panels / 2, p_hi = (grp + 1) * n_panels / 2;   // this column group's panels
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.f;
+  if (A.x_emb) {
+    const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
+#pragma unroll
+    for (int i = 0; i < 64; ++i)
+      if (i >= 8 * p_lo && i < 8 * p_hi && i < P.input_ch) v[i] = xr[i];
+  } else {
+    const int64_t ray = gc / A.S;
+    const float* rp = A.rays + ray * (int64_t)A.stride;
+    const float zz = A.z[gc];
+    float p[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));  // o + d*z, two roundings
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+    if (A.multires > 0) {
+      // frequencies whose outputs land in [8*p_lo, 8*p_hi): element 3+6k.. -> k range
+      const int k_lo = max(0, (8 * p_lo - 3 - 5) / 6), k_hi = min(A.multires - 1, (8 * p_hi - 4) / 6);
+      float f = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        if (k >= k_lo && k <= k_hi) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincosf(p[c] * f, &sn, &cs);
+            v[3 + 6 * k + c] = sn;
+            v[3 + 6 * k + 3 + c] = cs;
+          }
+        }
+        f *= 2.0f;
+      }
+    }
+  }
+#pragma unroll
+  for (int pnl = 0; pnl < 2 * MAX_PE_KS; ++pnl) {
+    if (pnl >= p_lo && pnl < p_hi) {
+      uint4 hi;
+      hi.x = ptx::pack_bf16(v[8 * pnl + 0], v[8 * pnl + 1]); hi.y = ptx::pack_bf16(v[8 * pnl + 2], v[8 * pnl + 3]);
+      hi.z = ptx::pack_bf16(v[8 * pnl + 4], v[8 * pnl + 5]); hi.w = ptx::pack_bf16(v[8 * pnl + 6], v[8 * pnl + 7]);
+      *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
+      if (X3) {
+        float lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) lo[e] = v[8 * pnl + e] - ptx::bf16_round(v[8 * pnl + e]);
+        uint4 l4;
+        l4.x = ptx::pack_bf16(lo[0], lo[1]); l4.y = ptx::pack_bf16(lo[2], lo[3]);
+        l4.z = ptx::pack_bf16(lo[4], lo[5]); l4.w = ptx::pack_bf16(lo[6], lo[7]);
+        *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
+      }
+    }
+  }
+}
+
+template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const NetPlan& P = A.plan;
   const SmemLayout SL = smem_layout(A.n_stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool x3 = (P.precision == PLNERF_PREC_BF16X3);
-  const int nsplit = x3 ? 2 : 1;
+  constexpr int nsplit = X3 ? 2 : 1;
 
   const uint32_t sbase = ptx::smem_u32(smem);
   const uint32_t s_pe_hi = sbase + SL.pe_hi, s_pe_lo = sbase + SL.pe_lo, s_ring = sbase + SL.ring;
   float* consts = reinterpret_cast<float*>(smem + SL.consts);
+  float* xch = reinterpret_cast<float*>(smem + SL.xch);
   const uint32_t s_bars = sbase + SL.bars;
   // barrier map (8 bytes each)
   auto w_full = [&](int s) { return s_bars + 8u * s; };
@@ -331,8 +416,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < A.n_stages; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
     ptx::mbar_init(d_full0, 1); ptx::mbar_init(d_full0 + 8, 1);
-    ptx::mbar_init(a_ready0, 128); ptx::mbar_init(a_ready0 + 8, 128);
-    ptx::mbar_init(pe_ready, 128);
+    ptx::mbar_init(a_ready0, NUM_EPI_THREADS); ptx::mbar_init(a_ready0 + 8, NUM_EPI_THREADS);
+    ptx::mbar_init(pe_ready, NUM_EPI_THREADS);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
@@ -344,7 +429,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 
   constexpr uint32_t COL_DA = 0, COL_A0 = 256, COL_A1 = 384;
   // activation buffer written by the epilogue of layer l (and read by layer l+1)
-  auto a_out_col = [&](int l) -> uint32_t { return x3 ? COL_A0 : ((l & 1) ? COL_A1 : COL_A0); };
+  auto a_out_col = [&](int l) -> uint32_t { return X3 ? COL_A0 : ((l & 1) ? COL_A1 : COL_A0); };
 
   if (warp == 0) {
     // ===================== TMA producer: stream the packed weights through the ring ==============
@@ -361,8 +446,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
                 if ((A.debug_flags & 1) && tile != (int64_t)blockIdx.x) { ptx::mbar_arrive(w_full(slot)); }
                 else {
-                ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
-                ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot));
+                  ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
+                  ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot));
                 }
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
@@ -374,14 +459,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer ===========================================================
-    // The whole warp runs this loop with warp-uniform control flow (so addresses and descriptors can
-    // live in uniform registers); one elected lane issues the tcgen05 instructions.
+    // The whole warp runs this loop with warp-uniform control flow (addresses and descriptors live
+    // in uniform registers); one elected lane issues the tcgen05 instructions.
     const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
-    const uint32_t desc_hi = (uint32_t)(ptx::smem_desc(0, 2048, 128) >> 32);
-    const uint32_t desc_lo_flags = (uint32_t)(ptx::smem_desc(0, 2048, 128) & 0xFFFFFFFFu);  // LBO field
-    auto mk_desc = [&](uint32_t saddr) -> uint64_t {
-      return ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_flags | ((saddr & 0x3FFFFu) >> 4));
-    };
+    const uint64_t desc_base = ptx::smem_desc(0, 2048, 128);
+    const uint32_t desc_hi = (uint32_t)(desc_base >> 32);
+    const uint32_t desc_lo0 = (uint32_t)(desc_base & 0xFFFFFFFFu);  // LBO field, address bits zero
+    auto mk_desc = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+    auto lo_of = [&](uint32_t saddr) -> uint32_t { return desc_lo0 | ((saddr & 0x3FFFFu) >> 4); };
+    constexpr uint32_t KS_DESC = KS_BYTES >> 4;   // descriptor address increment per K-step
     uint32_t slot = 0, phase = 0;
     uint32_t uses0 = 0, uses1 = 0, waited0 = 0, waited1 = 0;
     uint32_t tile_iter = 0;
@@ -405,34 +491,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             if (!is_pe && jh0 + nks > 8) {                 // hidden columns >= 128 come from half b
               while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; }
             }
+#pragma unroll
             for (int rep = 0; rep < nsplit; ++rep) {
               ptx::mbar_wait(w_full(slot), phase);
               ptx::tc_fence_after();
-              const uint32_t bsm = s_ring + slot * STAGE_BYTES;
+              const uint32_t b_lo = lo_of(s_ring + slot * STAGE_BYTES);
               if (ptx::elect_one()) {
                 if (is_pe) {
-                  const uint32_t asm_hi = s_pe_hi + ks0 * KS_BYTES, asm_lo = s_pe_lo + ks0 * KS_BYTES;
+                  const uint32_t a_lo_hi = lo_of(s_pe_hi + ks0 * KS_BYTES), a_lo_lo = lo_of(s_pe_lo + ks0 * KS_BYTES);
 #pragma unroll
                   for (int j = 0; j < KS_PER_STAGE; ++j) {
                     if (j < nks) {
-                      const uint64_t bd = mk_desc(bsm + j * KS_BYTES);
+                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
                       if (rep == 0) {
-                        ptx::mma_ss(d, mk_desc(asm_hi + j * KS_BYTES), bd, idesc, acc | (uint32_t)(j > 0));
-                        if (x3) ptx::mma_ss(d, mk_desc(asm_lo + j * KS_BYTES), bd, idesc, 1);
+                        ptx::mma_ss(d, mk_desc(a_lo_hi + j * KS_DESC), bd, idesc, (j > 0) ? 1u : acc);
+                        if (X3) ptx::mma_ss(d, mk_desc(a_lo_lo + j * KS_DESC), bd, idesc, 1);
                       } else {
-                        ptx::mma_ss(d, mk_desc(asm_hi + j * KS_BYTES), bd, idesc, 1);
+                        ptx::mma_ss(d, mk_desc(a_lo_hi + j * KS_DESC), bd, idesc, 1);
                       }
                     }
                   }
                 } else {
                   const uint32_t at = a_in + 8u * jh0, at_lo = a_in_lo + 8u * jh0;
+                  if (nks == KS_PER_STAGE) {
 #pragma unroll
-                  for (int j = 0; j < KS_PER_STAGE; ++j) {
-                    if (j < nks) {
-                      const uint64_t bd = mk_desc(bsm + j * KS_BYTES);
+                    for (int j = 0; j < KS_PER_STAGE; ++j) {
+                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
                       if (rep == 0) {
-                        ptx::mma_ts(d, at + 8u * j, bd, idesc, acc | (uint32_t)(j > 0));
-                        if (x3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
+                        ptx::mma_ts(d, at + 8u * j, bd, idesc, (j > 0) ? 1u : acc);
+                        if (X3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
+                      } else {
+                        ptx::mma_ts(d, at + 8u * j, bd, idesc, 1);
+                      }
+                    }
+                  } else {
+                    for (int j = 0; j < nks; ++j) {
+                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
+                      if (rep == 0) {
+                        ptx::mma_ts(d, at + 8u * j, bd, idesc, (j > 0) ? 1u : acc);
+                        if (X3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
                       } else {
                         ptx::mma_ts(d, at + 8u * j, bd, idesc, 1);
                       }
@@ -453,70 +550,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps: PE prologue, bias/ReLU/pack, heads, output ==========
-    const int q = warp & 3;
+    // ===================== epilogue warps (8): PE prologue, bias/ReLU/pack, heads, output ========
+    // warp e = warp-4: lane quarter q = e&3 (TMEM lanes 32q..32q+31, one row per thread), column
+    // group grp = e>>2 (chunks 2grp, 2grp+1 of every 128-column half).
+    const int e = warp - 4;
+    const int q = e & 3, grp = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
-    uint32_t seen[2] = {0, 0};
+    uint32_t seen0 = 0, seen1 = 0;
+    int l_pe_last = 0;
+    for (int l = 0; l < P.n_layers; ++l) if (P.L[l].n_pe_ks > 0) l_pe_last = l;
+
+    if ((int64_t)blockIdx.x < A.n_tiles) {
+      pe_prologue<X3>(A, smem, SL, blockIdx.x, row, grp);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(pe_ready);
+    }
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
       const int64_t g = tile * TILE_M + row;
       const bool valid = g < A.M;
       const int64_t gc = valid ? g : (A.M - 1);
-      // ---------------- prologue: positional encoding of this row -> PE tile (smem, bf16 [hi,lo])
-      {
-        float v[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = 0.f;
-        if (A.x_emb) {
-          const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) if (i < P.input_ch) v[i] = xr[i];
-        } else {
-          const int64_t ray = gc / A.S;
-          const float* rp = A.rays + ray * (int64_t)A.stride;
-          const float zz = A.z[gc];
-          float p[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));  // o + d*z, two roundings
-          v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
-          if (A.multires > 0) {
-            float f = 1.0f;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) {
-              if (k < A.multires) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  float s, co;
-                  sincosf(p[c] * f, &s, &co);
-                  v[3 + 6 * k + c] = s;
-                  v[3 + 6 * k + 3 + c] = co;
-                }
-              }
-              f *= 2.0f;
-            }
-          }
-        }
-#pragma unroll
-        for (int pnl = 0; pnl < 2 * MAX_PE_KS; ++pnl) {
-          if (pnl < 2 * P.pe_ks) {
-            uint4 hi;
-            hi.x = ptx::pack_bf16(v[8 * pnl + 0], v[8 * pnl + 1]); hi.y = ptx::pack_bf16(v[8 * pnl + 2], v[8 * pnl + 3]);
-            hi.z = ptx::pack_bf16(v[8 * pnl + 4], v[8 * pnl + 5]); hi.w = ptx::pack_bf16(v[8 * pnl + 6], v[8 * pnl + 7]);
-            *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
-            if (x3) {
-              float lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) lo[e] = v[8 * pnl + e] - ptx::bf16_round(v[8 * pnl + e]);
-              uint4 l4;
-              l4.x = ptx::pack_bf16(lo[0], lo[1]); l4.y = ptx::pack_bf16(lo[2], lo[3]);
-              l4.z = ptx::pack_bf16(lo[4], lo[5]); l4.w = ptx::pack_bf16(lo[6], lo[7]);
-              *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
-            }
-          }
-        }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(pe_ready);
-      }
       float alpha_acc = 0.f;
       float head[MAX_OUT_CH];
 #pragma unroll
@@ -524,81 +577,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       const float* vbrow = A.viewbias ? (A.viewbias + (gc / A.vb_div) * 128) : nullptr;
 
       for (int l = 0; l < P.n_layers; ++l) {
-        const LayerPlan& L = P.L[l];
+        const int epi = P.L[l].epi, flags = P.L[l].flags, n_halves = P.L[l].n_halves, bias_off = P.L[l].bias_off;
         const uint32_t a_out = tmem + lane_addr + a_out_col(l);
         const uint32_t a_out_lo = tmem + lane_addr + COL_A1;
-        bool b_prewaited = false;
-        for (int h = 0; h < L.n_halves; ++h) {
-          if (!(h == 1 && b_prewaited)) { ptx::mbar_wait(d_full0 + 8u * h, seen[h] & 1); ++seen[h]; }
-          if (x3 && h == 0 && L.n_halves == 2) {
-            // bf16x3 keeps ONE activation buffer: half b's MMAs still read it, wait for them too
-            ptx::mbar_wait(d_full0 + 8u, seen[1] & 1); ++seen[1]; b_prewaited = true;
+        for (int h = 0; h < n_halves; ++h) {
+          if (h == 0) {
+            ptx::mbar_wait(d_full0, seen0 & 1); ++seen0;
+            if (X3 && n_halves == 2) {
+              // bf16x3 keeps ONE activation buffer: half b's MMAs still read it, wait for them too
+              ptx::mbar_wait(d_full0 + 8u, seen1 & 1); ++seen1;
+            }
+          } else if (!X3) {
+            ptx::mbar_wait(d_full0 + 8u, seen1 & 1); ++seen1;
           }
           ptx::tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * grp + cc;
+            const int n0 = h * 128 + c * 32;
             uint32_t r[32];
             ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * c, r);
             ptx::tmem_ld_wait();
-            const int n0 = h * 128 + c * 32;
-            float val[32];
-            if (L.epi == EPI_VIEWS) {
+            float* val = reinterpret_cast<float*>(r);
+            if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(vbrow + n0 + i);
-                val[i] = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f);
-                val[i + 1] = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
-                val[i + 2] = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f);
-                val[i + 3] = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+                val[i] = fmaxf(val[i] + b4.x, 0.f); val[i + 1] = fmaxf(val[i + 1] + b4.y, 0.f);
+                val[i + 2] = fmaxf(val[i + 2] + b4.z, 0.f); val[i + 3] = fmaxf(val[i + 3] + b4.w, 0.f);
               }
               const float* rw = consts + P.rgb_w_off + n0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                head[0] = fmaf(val[i], rw[i], head[0]);
-                head[1] = fmaf(val[i], rw[128 + i], head[1]);
-                head[2] = fmaf(val[i], rw[256 + i], head[2]);
+              for (int i = 0; i < 32; i += 4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(rw + i);
+                const float4 w1 = *reinterpret_cast<const float4*>(rw + 128 + i);
+                const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + i);
+                head[0] = fmaf(val[i], w0.x, head[0]); head[0] = fmaf(val[i + 1], w0.y, head[0]);
+                head[0] = fmaf(val[i + 2], w0.z, head[0]); head[0] = fmaf(val[i + 3], w0.w, head[0]);
+                head[1] = fmaf(val[i], w1.x, head[1]); head[1] = fmaf(val[i + 1], w1.y, head[1]);
+                head[1] = fmaf(val[i + 2], w1.z, head[1]); head[1] = fmaf(val[i + 3], w1.w, head[1]);
+                head[2] = fmaf(val[i], w2.x, head[2]); head[2] = fmaf(val[i + 1], w2.y, head[2]);
+                head[2] = fmaf(val[i + 2], w2.z, head[2]); head[2] = fmaf(val[i + 3], w2.w, head[2]);
               }
             } else {
-              const float* bias = consts + L.bias_off + n0;
-              const bool relu = (L.epi != EPI_LINEAR_A);
+              const float* bias = consts + bias_off + n0;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
-                val[i] = __uint_as_float(r[i]) + b4.x;
-                val[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
-                val[i + 2] = __uint_as_float(r[i + 2]) + b4.z;
-                val[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+                add2(val[i], val[i + 1], b4.x, b4.y);
+                add2(val[i + 2], val[i + 3], b4.z, b4.w);
               }
-              if (relu) {
+              uint32_t pk[16];
+              if (!X3 && epi == EPI_RELU_A && flags == 0) {
+                // hot path: ReLU fused into the bf16x2 conversion
 #pragma unroll
-                for (int i = 0; i < 32; ++i) val[i] = fmaxf(val[i], 0.f);
-              }
-              if (L.flags & FLAG_ALPHA) {
-                const float* aw = consts + P.alpha_w_off + n0;
+                for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(val[2 * i], val[2 * i + 1]);
+                ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+              } else {
+                if (epi != EPI_LINEAR_A) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) alpha_acc = fmaf(val[i], aw[i], alpha_acc);
-              }
-              if (L.flags & FLAG_OUTHEAD) {
+                  for (int i = 0; i < 32; ++i) val[i] = fmaxf(val[i], 0.f);
+                }
+                if (flags & FLAG_ALPHA) {
+                  const float* aw = consts + P.alpha_w_off + n0;
 #pragma unroll
-                for (int ch = 0; ch < MAX_OUT_CH; ++ch) {
-                  if (ch < P.out_ch) {
-                    const float* ow = consts + P.out_w_off + ch * 256 + n0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
+                  for (int i = 0; i < 32; i += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(aw + i);
+                    alpha_acc = fmaf(val[i], w4.x, alpha_acc); alpha_acc = fmaf(val[i + 1], w4.y, alpha_acc);
+                    alpha_acc = fmaf(val[i + 2], w4.z, alpha_acc); alpha_acc = fmaf(val[i + 3], w4.w, alpha_acc);
                   }
                 }
-              }
-              if (L.epi != EPI_RELU_HEAD) {
-                uint32_t pk[16];
+                if (flags & FLAG_OUTHEAD) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-                ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
-                if (x3) {
+                  for (int ch = 0; ch < MAX_OUT_CH; ++ch) {
+                    if (ch < P.out_ch) {
+                      const float* ow = consts + P.out_w_off + ch * 256 + n0;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    pk[i] = ptx::pack_bf16(val[2 * i] - ptx::bf16_round(val[2 * i]),
-                                           val[2 * i + 1] - ptx::bf16_round(val[2 * i + 1]));
-                  ptx::tmem_st16(a_out_lo + (uint32_t)(n0 >> 1), pk);
+                      for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
+                    }
+                  }
+                }
+                if (epi != EPI_RELU_HEAD) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+                  ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+                  if (X3) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                      pk[i] = ptx::pack_bf16(val[2 * i] - ptx::bf16_round(val[2 * i]),
+                                             val[2 * i + 1] - ptx::bf16_round(val[2 * i + 1]));
+                    ptx::tmem_st16(a_out_lo + (uint32_t)(n0 >> 1), pk);
+                  }
                 }
               }
             }
@@ -607,18 +676,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           ptx::tc_fence_before();
           ptx::mbar_arrive(a_ready0 + 8u * h);
         }
+        if (l == l_pe_last) {
+          // every MMA that reads the PE tile of this tile has completed (its d_full was waited):
+          // encode the NEXT tile's rows now, overlapped with the remaining layers
+          const int64_t nt = tile + gridDim.x;
+          if (nt < A.n_tiles) {
+            pe_prologue<X3>(A, smem, SL, nt, row, grp);
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(pe_ready);
+          }
+        }
       }
-      if (valid) {
+      // ---- combine the two column groups' partial head sums and write the row
+      if (grp == 1) {
+        float* x = xch + row * (MAX_OUT_CH + 1);
+        x[0] = alpha_acc;
+#pragma unroll
+        for (int c = 0; c < MAX_OUT_CH; ++c) x[1 + c] = head[c];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+      if (grp == 0 && valid) {
+        const float* x = xch + row * (MAX_OUT_CH + 1);
         float* o = A.out + g * (int64_t)A.out_stride;
         if (P.use_viewdirs) {
-          o[0] = head[0] + consts[P.rgb_b_off + 0];
-          o[1] = head[1] + consts[P.rgb_b_off + 1];
-          o[2] = head[2] + consts[P.rgb_b_off + 2];
-          o[3] = alpha_acc + consts[P.alpha_b_off];
+          o[0] = head[0] + x[1] + consts[P.rgb_b_off + 0];
+          o[1] = head[1] + x[2] + consts[P.rgb_b_off + 1];
+          o[2] = head[2] + x[3] + consts[P.rgb_b_off + 2];
+          o[3] = alpha_acc + x[0] + consts[P.alpha_b_off];
         } else {
 #pragma unroll
           for (int ch = 0; ch < MAX_OUT_CH; ++ch)
-            if (ch < P.out_ch) o[ch] = head[ch] + consts[P.out_b_off + ch];
+            if (ch < P.out_ch) o[ch] = head[ch] + x[1 + ch] + consts[P.out_b_off + ch];
         }
       }
     }
@@ -741,7 +829,8 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   const SmemLayout SL = smem_layout(n_stages);
   static bool attr_set = false;
   if (!attr_set) {
-    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     attr_set = true;
   }
   static int dbg = -1;
@@ -751,7 +840,8 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
-  k_mlp_fwd<<<grid, NUM_THREADS, SL.total, st>>>(a);
+  if (a.plan.precision == PLNERF_PREC_BF16X3) k_mlp_fwd<true><<<grid, NUM_THREADS, SL.total, st>>>(a);
+  else k_mlp_fwd<false><<<grid, NUM_THREADS, SL.total, st>>>(a);
   if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
   PLNERF_LAUNCH_CHECK("k_mlp_fwd");
   return PLNERF_OK;
