@@ -126,16 +126,16 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
     V.n_pe_ks = 0; V.n_h_ks = 16; V.n_halves = 1; V.epi = EPI_VIEWS; V.flags = 0;
     V.bias_off = foff; P.views_b_off = foff; foff += 128;
     V.W = p ? p->views_w : nullptr; V.ldw = 256 + d->input_ch_views; V.pe_col0 = -1; V.h_col0 = 0;
-    P.alpha_w_off = foff; foff += 256;
-    P.alpha_b_off = foff; foff += 1;
+    P.alpha_w_off = foff; foff += 256;          // every block starts 16-byte aligned (float4 loads)
+    P.alpha_b_off = foff; foff += 4;
     P.rgb_w_off = foff; foff += 3 * 128;
-    P.rgb_b_off = foff; foff += 3;
+    P.rgb_b_off = foff; foff += 4;
     foff = (foff + 3) & ~3;
     P.const_floats = foff;
     P.dirw_off = foff; foff += 128 * d->input_ch_views;
   } else {
     P.out_w_off = foff; foff += d->output_ch * 256;
-    P.out_b_off = foff; foff += d->output_ch;
+    P.out_b_off = foff; foff += (d->output_ch + 3) & ~3;
     foff = (foff + 3) & ~3;
     P.const_floats = foff;
   }
