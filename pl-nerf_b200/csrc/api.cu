@@ -25,6 +25,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
+int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st);
 
 // workspace carving for render_rays
 struct RenderWs {
@@ -212,6 +213,11 @@ int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_
 
 int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
   return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
+}
+
+// bring-up microbenchmark (not part of the product ABI)
+int plnerf_debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, void* stream) {
+  return plnerf::debug_mma_rate(mode, iters, grid, cycles_out, (cudaStream_t)stream);
 }
 
 // test-only variant with explicit operand mode and descriptor strides (not part of the product ABI)

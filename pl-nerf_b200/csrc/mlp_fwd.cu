@@ -41,13 +41,13 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int KS_BYTES = 4096;      // one K=16 step of one 128-neuron half (2 panels x 128 rows x 16 B)
-constexpr int KS_PER_STAGE = 4;
-constexpr int STAGE_BYTES = KS_PER_STAGE * KS_BYTES;  // 16 KB
+constexpr int KS_PER_STAGE = 8;
+constexpr int STAGE_BYTES = KS_PER_STAGE * KS_BYTES;  // 32 KB
 constexpr int MAX_LAYERS = PLNERF_MAX_DEPTH + 2;
 constexpr int MAX_PE_KS = 4;        // input_ch <= 64
 constexpr int PE_TILE_BYTES = MAX_PE_KS * KS_BYTES;   // 16 KB
 constexpr int MAX_CONST_FLOATS = 4096;                // biases + small heads staged in smem
-constexpr int MAX_STAGES = 12;
+constexpr int MAX_STAGES = 6;
 constexpr int NUM_THREADS = 384;    // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int MAX_OUT_CH = 8;
@@ -80,6 +80,20 @@ struct NetPlan {
   int32_t tail_floats;
   int64_t weight_bytes;  // bf16 stream
 };
+
+// A (layer, half) streams its K-steps in stages of <= KS_PER_STAGE; the PE K-steps (shared-memory A
+// operand) and the hidden K-steps (TMEM A operand) are staged separately so no stage mixes them.
+struct StageInfo { int is_pe, k0, nks; };   // k0 = first K-step of the stage inside its segment
+__host__ __device__ inline int stages_of(int n_pe, int n_h) {
+  return (n_pe + KS_PER_STAGE - 1) / KS_PER_STAGE + (n_h + KS_PER_STAGE - 1) / KS_PER_STAGE;
+}
+__host__ __device__ inline StageInfo stage_info(int n_pe, int n_h, int i) {
+  const int npe_st = (n_pe + KS_PER_STAGE - 1) / KS_PER_STAGE;
+  StageInfo si;
+  if (i < npe_st) { si.is_pe = 1; si.k0 = i * KS_PER_STAGE; si.nks = min(KS_PER_STAGE, n_pe - si.k0); }
+  else { si.is_pe = 0; si.k0 = (i - npe_st) * KS_PER_STAGE; si.nks = min(KS_PER_STAGE, n_h - si.k0); }
+  return si;
+}
 
 // Walks desc -> plan.  Returns 0 or an error code.
 int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params* p, NetPlan* out) {
@@ -174,15 +188,17 @@ __global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ Pa
   }
   if (l >= P.n_layers) return;
   const LayerPlan& L = P.L[l];
-  const int total_ks = L.n_pe_ks + L.n_h_ks;
-  // within a half: stages of <=4 K-steps, each stage = [hi blocks][lo blocks]
-  int ks0 = 0, rep = 0, j = 0;
-  for (;; ks0 += KS_PER_STAGE) {
-    const int nks = min(KS_PER_STAGE, total_ks - ks0);
-    if (blk < nks * nsplit) { rep = blk / nks; j = blk - rep * nks; break; }
-    blk -= nks * nsplit;
+  // within a half: stages (stage_info), each stage = [hi blocks][lo blocks]
+  int rep = 0, ks = 0;
+  for (int st = 0;; ++st) {
+    const StageInfo si = stage_info(L.n_pe_ks, L.n_h_ks, st);
+    if (blk < si.nks * nsplit) {
+      rep = blk / si.nks;
+      ks = (si.is_pe ? 0 : L.n_pe_ks) + si.k0 + (blk - rep * si.nks);
+      break;
+    }
+    blk -= si.nks * nsplit;
   }
-  const int ks = ks0 + j;
   const int u = threadIdx.x;
   const int panel = u >> 7, row = u & 127;
   const int n = h * 128 + row;
@@ -328,6 +344,34 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   return d;
 }
 
+// ---- tight MMA issue: 8 (or 4) consecutive K=16 steps of one 128-neuron half in ONE asm block ------
+// A from TMEM: step j reads columns a + 8j; B from the ring slot: descriptor + j*(4096>>4).
+#define PLNERF_TS_STEP(PRED) \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], [ad], bd, %3, " PRED ";\n\t" \
+  "add.u64 bd, bd, 256;\n\tadd.u32 ad, ad, 8;\n\t"
+#define PLNERF_TS_STEP_X3(PRED) \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], [ad], bd, %3, " PRED ";\n\t" \
+  "tcgen05.mma.cta_group::1.kind::f16 [%0], [al], bd, %3, pt;\n\t" \
+  "add.u64 bd, bd, 256;\n\tadd.u32 ad, ad, 8;\n\tadd.u32 al, al, 8;\n\t"
+#define PLNERF_TS_PROLOG \
+  "{\n\t.reg .pred p, pt;\n\t.reg .b64 bd;\n\t.reg .b32 ad, al;\n\t" \
+  "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\tmov.b64 bd, %2;\n\tmov.b32 ad, %1;\n\tmov.b32 al, %5;\n\t"
+
+template <bool X3PAIR>
+__device__ __forceinline__ void issue_ts8(uint32_t d, uint32_t a, uint32_t a_lo, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (X3PAIR) {
+    asm volatile(PLNERF_TS_PROLOG
+                 PLNERF_TS_STEP_X3("p") PLNERF_TS_STEP_X3("pt") PLNERF_TS_STEP_X3("pt") PLNERF_TS_STEP_X3("pt")
+                 PLNERF_TS_STEP_X3("pt") PLNERF_TS_STEP_X3("pt") PLNERF_TS_STEP_X3("pt") PLNERF_TS_STEP_X3("pt") "}"
+                 ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(a_lo) : "memory");
+  } else {
+    asm volatile(PLNERF_TS_PROLOG
+                 PLNERF_TS_STEP("p") PLNERF_TS_STEP("pt") PLNERF_TS_STEP("pt") PLNERF_TS_STEP("pt")
+                 PLNERF_TS_STEP("pt") PLNERF_TS_STEP("pt") PLNERF_TS_STEP("pt") PLNERF_TS_STEP("pt") "}"
+                 ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(a_lo) : "memory");
+  }
+}
+
 // Positional encoding of one row -> this thread's panels of the PE tile(s).
 template <bool X3>
 __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, const SmemLayout& SL, int64_t tile, int row,
@@ -416,8 +460,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < A.n_stages; ++s) { ptx::mbar_init(w_full(s), 1); ptx::mbar_init(w_empty(s), 1); }
     ptx::mbar_init(d_full0, 1); ptx::mbar_init(d_full0 + 8, 1);
-    ptx::mbar_init(a_ready0, NUM_EPI_THREADS); ptx::mbar_init(a_ready0 + 8, NUM_EPI_THREADS);
-    ptx::mbar_init(pe_ready, NUM_EPI_THREADS);
+    ptx::mbar_init(a_ready0, NUM_EPI_THREADS / 32); ptx::mbar_init(a_ready0 + 8, NUM_EPI_THREADS / 32);
+    ptx::mbar_init(pe_ready, NUM_EPI_THREADS / 32);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
@@ -438,10 +482,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         const uint8_t* src = A.w;
         for (int l = 0; l < P.n_layers; ++l) {
-          const int total_ks = P.L[l].n_pe_ks + P.L[l].n_h_ks;
+          const int nst = stages_of(P.L[l].n_pe_ks, P.L[l].n_h_ks);
           for (int h = 0; h < P.L[l].n_halves; ++h) {
-            for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
-              const uint32_t bytes = (uint32_t)min(KS_PER_STAGE, total_ks - ks0) * KS_BYTES;
+            for (int st = 0; st < nst; ++st) {
+              const uint32_t bytes = (uint32_t)stage_info(P.L[l].n_pe_ks, P.L[l].n_h_ks, st).nks * KS_BYTES;
               for (int rep = 0; rep < nsplit; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
                 if ((A.debug_flags & 1) && tile != (int64_t)blockIdx.x) { ptx::mbar_arrive(w_full(slot)); }
@@ -475,20 +519,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       ptx::mbar_wait(pe_ready, tile_iter & 1);
       for (int l = 0; l < P.n_layers; ++l) {
         const int n_pe_ks = P.L[l].n_pe_ks, n_h_ks = P.L[l].n_h_ks, n_halves = P.L[l].n_halves;
-        const int total_ks = n_pe_ks + n_h_ks;
         const uint32_t a_in = tmem + (l > 0 ? a_out_col(l - 1) : COL_A0);
         const uint32_t a_in_lo = tmem + COL_A1;  // bf16x3 only
         for (int h = 0; h < n_halves; ++h) {
           // accumulator h must have been drained by the epilogue of its previous use
+          if (!(A.debug_flags & 4)) {
           if (h == 0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
           else        { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
+          }
           const uint32_t d = tmem + COL_DA + 128u * h;
           uint32_t acc = 0;
-          for (int ks0 = 0; ks0 < total_ks; ks0 += KS_PER_STAGE) {
-            const int nks = min(KS_PER_STAGE, total_ks - ks0);
-            const bool is_pe = ks0 < n_pe_ks;              // stages never straddle PE / hidden K-steps
-            const int jh0 = ks0 - n_pe_ks;
-            if (!is_pe && jh0 + nks > 8) {                 // hidden columns >= 128 come from half b
+          const int nst = stages_of(n_pe_ks, n_h_ks);
+          for (int st = 0; st < nst; ++st) {
+            const StageInfo si = stage_info(n_pe_ks, n_h_ks, st);
+            const int nks = si.nks, ks0 = si.k0, jh0 = si.k0;
+            const bool is_pe = si.is_pe != 0;
+            if (!is_pe && jh0 + nks > 8 && !(A.debug_flags & 4)) {   // hidden columns >= 128 come from half b
               while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; }
             }
 #pragma unroll
@@ -514,16 +560,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 } else {
                   const uint32_t at = a_in + 8u * jh0, at_lo = a_in_lo + 8u * jh0;
                   if (nks == KS_PER_STAGE) {
-#pragma unroll
-                    for (int j = 0; j < KS_PER_STAGE; ++j) {
-                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
-                      if (rep == 0) {
-                        ptx::mma_ts(d, at + 8u * j, bd, idesc, (j > 0) ? 1u : acc);
-                        if (X3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
-                      } else {
-                        ptx::mma_ts(d, at + 8u * j, bd, idesc, 1);
-                      }
-                    }
+                    if (rep == 0) issue_ts8<X3>(d, at, at_lo, mk_desc(b_lo), idesc, acc);
+                    else issue_ts8<false>(d, at, at_lo, mk_desc(b_lo), idesc, 1);
                   } else {
                     for (int j = 0; j < nks; ++j) {
                       const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
@@ -564,7 +602,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     if ((int64_t)blockIdx.x < A.n_tiles) {
       pe_prologue<X3>(A, smem, SL, blockIdx.x, row, grp);
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(pe_ready);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pe_ready);
     }
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
       const int64_t g = tile * TILE_M + row;
@@ -593,6 +632,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           ptx::tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
+            if (A.debug_flags & 2) break;
             const int c = 2 * grp + cc;
             const int n0 = h * 128 + c * 32;
             uint32_t r[32];
@@ -674,7 +714,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           }
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
-          ptx::mbar_arrive(a_ready0 + 8u * h);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
         }
         if (l == l_pe_last) {
           // every MMA that reads the PE tile of this tile has completed (its d_full was waited):
@@ -683,7 +724,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           if (nt < A.n_tiles) {
             pe_prologue<X3>(A, smem, SL, nt, row, grp);
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(pe_ready);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(pe_ready);
           }
         }
       }
@@ -788,6 +830,52 @@ __global__ void __launch_bounds__(128, 1) k_debug_gemm(const float* __restrict__
     ptx::tmem_ld32(tmem + lane_addr + 32u * c, r);
     ptx::tmem_ld_wait();
     for (int i = 0; i < 32; ++i) Dg[(size_t)row * N + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// debug: raw tcgen05.mma issue/execute rate.  mode 0: TS N=128, 1: TS N=256, 2: SS N=128, 3: SS N=256.
+// One CTA per SM issues `iters` x 16 back-to-back MMAs on garbage operands; reports cycles per MMA.
+// =============================================================================================
+__global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 160 * 1024);
+  const uint32_t bar = ptx::smem_u32(smem + 160 * 1024 + 16);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 1) {
+    const int N = (mode & 1) ? 256 : 128;
+    const bool ss = mode >= 2;
+    const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
+    const uint32_t sb = ptx::smem_u32(smem);
+    const uint32_t lbo = N * 16;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint64_t bd = ptx::smem_desc(sb + 64 * 1024 + (j & 3) * (N * 32), lbo, 128);
+          if (ss) ptx::mma_ss(tmem, ptx::smem_desc(sb + j * 4096, 2048, 128), bd, idesc, j > 0);
+          else ptx::mma_ts(tmem, tmem + 256u + 8u * j, bd, idesc, j > 0);
+        }
+      }
+      __syncwarp();
+    }
+    if (ptx::elect_one()) ptx::mma_commit(bar);
+    __syncwarp();
+    ptx::mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 32) cycles_out[blockIdx.x] = t1 - t0;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -968,6 +1056,15 @@ int profile_read(double* ms_sum, int64_t* launches, int64_t* rows) {
   if (ms_sum) *ms_sum = ms;
   if (launches) *launches = (int64_t)g_prof.size();
   if (rows) *rows = nr;
+  return PLNERF_OK;
+}
+
+int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st) {
+  int rc = query_device();
+  if (rc) return rc;
+  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+  k_debug_mma_rate<<<grid, 128, 160 * 1024 + 64, st>>>(mode, iters, cycles_out);
+  PLNERF_LAUNCH_CHECK("k_debug_mma_rate");
   return PLNERF_OK;
 }
 

@@ -59,5 +59,17 @@ def mlp():
             print(f"{name} {prec}: per-channel max err / scale = {err}  raw[0,0]={raw[0,0]} ref[0,0]={ref[0,0]}", flush=True)
 
 
+def mmarate():
+    for grid in (1, 148):
+        for mode, name in ((0, "TS N=128"), (1, "TS N=256"), (2, "SS N=128"), (3, "SS N=256")):
+            out = torch.zeros(grid, dtype=torch.int64, device="cuda")
+            iters = 200
+            for rep in range(2):
+                L.check(L.lib().plnerf_debug_mma_rate(mode, iters, grid, out.data_ptr(), None))
+                torch.cuda.synchronize()
+            cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
+            print(f"grid={grid} {name}: cycles/MMA mean={cyc.mean():.1f} min={cyc.min():.1f} max={cyc.max():.1f}", flush=True)
+
+
 if __name__ == "__main__":
-    {"gemm": gemm, "mlp": mlp}[sys.argv[1]]()
+    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate}[sys.argv[1]]()
