@@ -108,13 +108,14 @@ _SIGS = {
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "plnerf_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "plnerf_debug_set_trace": (C.c_int, [C.c_void_p]),
     "plnerf_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                             C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 # symbols that include/plnerf_b200.h declares (checked by tests/test_abi.py)
-PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate")]
+PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace")]
 
 
 def lib():

@@ -26,6 +26,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st);
+int debug_set_trace(long long* buf);
 
 // workspace carving for render_rays
 struct RenderWs {
@@ -214,6 +215,9 @@ int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_
 int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
   return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
 }
+
+// debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)
+int plnerf_debug_set_trace(long long* buf) { return plnerf::debug_set_trace(buf); }
 
 // bring-up microbenchmark (not part of the product ABI)
 int plnerf_debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, void* stream) {

@@ -307,11 +307,12 @@ struct MlpArgs {
   int64_t n_tiles;
   float* out; int out_stride;
   int n_stages;
+  long long* trace;  // debug timeline buffer (null in production)
   int debug_flags;   // bring-up experiments only (PLNERF_DEBUG_FLAGS): 1 = skip weight re-streaming after tile 0
 };
 
 struct SmemLayout {
-  uint32_t pe_hi, pe_lo, ring, consts, xch, bars;  // byte offsets
+  uint32_t pe_hi, pe_lo, ring, consts, xch, prog, bars;  // byte offsets
   uint32_t total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int n_stages) {
@@ -321,7 +322,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages) {
   s.ring = 2 * PE_TILE_BYTES;
   s.consts = s.ring + (uint32_t)n_stages * STAGE_BYTES;
   s.xch = s.consts + MAX_CONST_FLOATS * 4;
-  s.bars = s.xch + TILE_M * (MAX_OUT_CH + 1) * 4;
+  s.prog = s.xch + TILE_M * (MAX_OUT_CH + 1) * 4;
+  s.bars = s.prog + 8 * 128;   // flattened MMA stage program (<= 128 entries)
   s.total = s.bars + 512;
   return s;
 }
@@ -436,6 +438,20 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
   }
 }
 
+// debug timeline: (clock, code) pairs for block 0, third tile; region r holds up to 256 events
+#ifdef PLNERF_ENABLE_TRACE
+#define PLNERF_TRACE(region, cnt, code)                                                        \
+  do {                                                                                          \
+    if (A.trace && blockIdx.x == 0 && trace_on && (cnt) < 256) {                               \
+      A.trace[((region) * 256 + (cnt)) * 2] = clock64();                                        \
+      A.trace[((region) * 256 + (cnt)) * 2 + 1] = (code);                                       \
+      ++(cnt);                                                                                  \
+    }                                                                                           \
+  } while (0)
+#else
+#define PLNERF_TRACE(region, cnt, code) do { (void)(cnt); (void)trace_on; } while (0)
+#endif
+
 template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -479,7 +495,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     // ===================== TMA producer: stream the packed weights through the ring ==============
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+      int tcnt = 0;
+      uint32_t tile_iter = 0;
+      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+        const bool trace_on = (tile_iter == 2);
         const uint8_t* src = A.w;
         for (int l = 0; l < P.n_layers; ++l) {
           const int nst = stages_of(P.L[l].n_pe_ks, P.L[l].n_h_ks);
@@ -488,6 +507,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               const uint32_t bytes = (uint32_t)stage_info(P.L[l].n_pe_ks, P.L[l].n_h_ks, st).nks * KS_BYTES;
               for (int rep = 0; rep < nsplit; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
+                PLNERF_TRACE(3, tcnt, 6000 + l * 100 + h * 10 + st);   // slot free, TMA issued
                 if ((A.debug_flags & 1) && tile != (int64_t)blockIdx.x) { ptx::mbar_arrive(w_full(slot)); }
                 else {
                   ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
@@ -503,8 +523,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer ===========================================================
-    // The whole warp runs this loop with warp-uniform control flow (addresses and descriptors live
-    // in uniform registers); one elected lane issues the tcgen05 instructions.
+    // The tensor pipe only buffers ~3-4 MMAs behind the issuing thread (measured), so everything the
+    // thread does between two MMA batches must fit in ~200 cycles or the pipe idles.  The per-tile
+    // control flow is therefore flattened once into a small "program" of stages in shared memory,
+    // and stages that share their dependencies are issued as one batch:
+    //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7     needs a_ready[a](l-1)
+    //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15 needs a_ready[b](l-1)
+    // One elected lane issues; the whole warp follows the (warp-uniform) control flow.
+    enum : uint32_t { F_PE = 1u << 8, F_H = 1u << 9, F_FIRST = 1u << 10, F_LAST = 1u << 11, F_WAIT_A0 = 1u << 16,
+                      F_WAIT_A1 = 1u << 17 };
+    uint2* prog = reinterpret_cast<uint2*>(smem + SL.prog);
+    int n_entries = 0;
+    if (lane == 0) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nh = P.L[l].n_halves;
+        const uint32_t a_col = (l > 0 ? a_out_col(l - 1) : COL_A0);
+        const int nst = stages_of(n_pe, n_h);
+        int batch_first[2] = {-1, -1};   // entry index of the first stage of batch 1 / batch 2
+        int batch_len[2] = {0, 0};
+        for (int h = 0; h < nh; ++h) {
+          for (int st = 0; st < nst; ++st) {
+            const StageInfo si = stage_info(n_pe, n_h, st);
+            uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
+                          (st == nst - 1 ? F_LAST : 0u);
+            const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
+            // batch 2 starts at the first stage that reads hidden columns >= 128 (or at half b)
+            const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
+            if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
+            ++batch_len[bsel];
+            prog[n_entries++] = make_uint2(w0, w1);
+          }
+        }
+        for (int bs = 0; bs < 2; ++bs)
+          if (batch_first[bs] >= 0) prog[batch_first[bs]].x |= (uint32_t)batch_len[bs] << 12;   // bits 12-15
+      }
+    }
+    n_entries = __shfl_sync(0xffffffffu, n_entries, 0);
+    __syncwarp();
+
     const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
     const uint64_t desc_base = ptx::smem_desc(0, 2048, 128);
     const uint32_t desc_hi = (uint32_t)(desc_base >> 32);
@@ -517,74 +573,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     uint32_t tile_iter = 0;
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
       ptx::mbar_wait(pe_ready, tile_iter & 1);
-      for (int l = 0; l < P.n_layers; ++l) {
-        const int n_pe_ks = P.L[l].n_pe_ks, n_h_ks = P.L[l].n_h_ks, n_halves = P.L[l].n_halves;
-        const uint32_t a_in = tmem + (l > 0 ? a_out_col(l - 1) : COL_A0);
-        const uint32_t a_in_lo = tmem + COL_A1;  // bf16x3 only
-        for (int h = 0; h < n_halves; ++h) {
-          // accumulator h must have been drained by the epilogue of its previous use
-          if (!(A.debug_flags & 4)) {
-          if (h == 0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
-          else        { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
+      int i = 0;
+      while (i < n_entries) {
+        const uint32_t bw0 = prog[i].x;
+        const int blen = (bw0 >> 12) & 15;
+        if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
+        if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
+        if (!X3) {   // all weight stages of the batch (<= 4 of the 6 ring slots) must have landed
+          uint32_t s2 = slot, p2 = phase;
+          for (int j = 0; j < blen; ++j) {
+            ptx::mbar_wait(w_full(s2), p2);
+            if (++s2 == (uint32_t)A.n_stages) { s2 = 0; p2 ^= 1; }
           }
-          const uint32_t d = tmem + COL_DA + 128u * h;
-          uint32_t acc = 0;
-          const int nst = stages_of(n_pe_ks, n_h_ks);
-          for (int st = 0; st < nst; ++st) {
-            const StageInfo si = stage_info(n_pe_ks, n_h_ks, st);
-            const int nks = si.nks, ks0 = si.k0, jh0 = si.k0;
-            const bool is_pe = si.is_pe != 0;
-            if (!is_pe && jh0 + nks > 8 && !(A.debug_flags & 4)) {   // hidden columns >= 128 come from half b
-              while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; }
-            }
+        }
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          uint32_t sl = slot, ph = phase;   // private ring cursor of the issuing lane
+          for (int j = 0; j < blen; ++j) {
+            const uint2 e = prog[i + j];
+            const int nks = e.x & 255;
+            const uint32_t d = tmem + COL_DA + ((e.x & F_H) ? 128u : 0u);
+            uint32_t acc = (e.x & F_FIRST) ? 0u : 1u;
 #pragma unroll
             for (int rep = 0; rep < nsplit; ++rep) {
-              ptx::mbar_wait(w_full(slot), phase);
-              ptx::tc_fence_after();
-              const uint32_t b_lo = lo_of(s_ring + slot * STAGE_BYTES);
-              if (ptx::elect_one()) {
-                if (is_pe) {
-                  const uint32_t a_lo_hi = lo_of(s_pe_hi + ks0 * KS_BYTES), a_lo_lo = lo_of(s_pe_lo + ks0 * KS_BYTES);
-#pragma unroll
-                  for (int j = 0; j < KS_PER_STAGE; ++j) {
-                    if (j < nks) {
-                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
-                      if (rep == 0) {
-                        ptx::mma_ss(d, mk_desc(a_lo_hi + j * KS_DESC), bd, idesc, (j > 0) ? 1u : acc);
-                        if (X3) ptx::mma_ss(d, mk_desc(a_lo_lo + j * KS_DESC), bd, idesc, 1);
-                      } else {
-                        ptx::mma_ss(d, mk_desc(a_lo_hi + j * KS_DESC), bd, idesc, 1);
-                      }
-                    }
-                  }
-                } else {
-                  const uint32_t at = a_in + 8u * jh0, at_lo = a_in_lo + 8u * jh0;
-                  if (nks == KS_PER_STAGE) {
-                    if (rep == 0) issue_ts8<X3>(d, at, at_lo, mk_desc(b_lo), idesc, acc);
-                    else issue_ts8<false>(d, at, at_lo, mk_desc(b_lo), idesc, 1);
+              if (X3) { ptx::mbar_wait(w_full(sl), ph); ptx::tc_fence_after(); }
+              const uint32_t b_lo = lo_of(s_ring + sl * STAGE_BYTES);
+              if (e.x & F_PE) {
+                const uint32_t a_lo_hi = lo_of(s_pe_hi + e.y * KS_BYTES), a_lo_lo = lo_of(s_pe_lo + e.y * KS_BYTES);
+                for (int k = 0; k < nks; ++k) {
+                  const uint64_t bd = mk_desc(b_lo + k * KS_DESC);
+                  if (rep == 0) {
+                    ptx::mma_ss(d, mk_desc(a_lo_hi + k * KS_DESC), bd, idesc, (k > 0) ? 1u : acc);
+                    if (X3) ptx::mma_ss(d, mk_desc(a_lo_lo + k * KS_DESC), bd, idesc, 1);
                   } else {
-                    for (int j = 0; j < nks; ++j) {
-                      const uint64_t bd = mk_desc(b_lo + j * KS_DESC);
-                      if (rep == 0) {
-                        ptx::mma_ts(d, at + 8u * j, bd, idesc, (j > 0) ? 1u : acc);
-                        if (X3) ptx::mma_ts(d, at_lo + 8u * j, bd, idesc, 1);
-                      } else {
-                        ptx::mma_ts(d, at + 8u * j, bd, idesc, 1);
-                      }
+                    ptx::mma_ss(d, mk_desc(a_lo_hi + k * KS_DESC), bd, idesc, 1);
+                  }
+                }
+              } else {
+                const uint32_t at = tmem + e.y, at_lo = at + (COL_A1 - COL_A0);
+                if (nks == KS_PER_STAGE) {
+                  if (rep == 0) issue_ts8<X3>(d, at, at_lo, mk_desc(b_lo), idesc, acc);
+                  else issue_ts8<false>(d, at, at_lo, mk_desc(b_lo), idesc, 1);
+                } else {
+                  for (int k = 0; k < nks; ++k) {
+                    const uint64_t bd = mk_desc(b_lo + k * KS_DESC);
+                    if (rep == 0) {
+                      ptx::mma_ts(d, at + 8u * k, bd, idesc, (k > 0) ? 1u : acc);
+                      if (X3) ptx::mma_ts(d, at_lo + 8u * k, bd, idesc, 1);
+                    } else {
+                      ptx::mma_ts(d, at + 8u * k, bd, idesc, 1);
                     }
                   }
                 }
-                ptx::mma_commit(w_empty(slot));
               }
-              __syncwarp();
+              ptx::mma_commit(w_empty(sl));
               acc = 1;
-              if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
+              if (++sl == (uint32_t)A.n_stages) { sl = 0; ph ^= 1; }
             }
+            if (e.x & F_LAST) ptx::mma_commit(d_full0 + ((e.x & F_H) ? 8u : 0u));
           }
-          if (ptx::elect_one()) ptx::mma_commit(d_full0 + 8u * h);
-          __syncwarp();
-          if (h == 0) ++uses0; else ++uses1;
         }
+        __syncwarp();
+        // every lane advances the (warp-uniform) ring cursor and use counters past this batch
+        for (int j = 0; j < blen * nsplit; ++j) { if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; } }
+        for (int j = 0; j < blen; ++j) {
+          const uint32_t w = prog[i + j].x;
+          if (w & F_LAST) { if (w & F_H) ++uses1; else ++uses0; }
+        }
+        i += blen;
       }
     }
   } else if (warp >= 4) {
@@ -605,7 +661,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pe_ready);
     }
-    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    int tcnt = 0;
+    uint32_t tile_iter = 0;
+    for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+      const bool trace_on = (tile_iter == 2) && lane == 0 && q == 0;
       const int64_t g = tile * TILE_M + row;
       const bool valid = g < A.M;
       const int64_t gc = valid ? g : (A.M - 1);
@@ -630,6 +689,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             ptx::mbar_wait(d_full0 + 8u, seen1 & 1); ++seen1;
           }
           ptx::tc_fence_after();
+          PLNERF_TRACE(1 + grp, tcnt, 3000 + l * 10 + h);     // accumulator half observed full
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             if (A.debug_flags & 2) break;
@@ -716,6 +776,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
+          PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
         }
         if (l == l_pe_last) {
           // every MMA that reads the PE tile of this tile has completed (its d_full was waited):
@@ -845,7 +906,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 160 * 1024);
   const uint32_t bar = ptx::smem_u32(smem + 160 * 1024 + 16);
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::fence_mbar_init(); }
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   ptx::fence_proxy_async_smem();
@@ -854,28 +915,58 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp == 1) {
-    const int N = (mode & 1) ? 256 : 128;
-    const bool ss = mode >= 2;
+    const int N = ((mode & 1) && mode < 4) ? 256 : 128;
+    const bool ss = (mode == 2 || mode == 3);
     const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
     const uint32_t sb = ptx::smem_u32(smem);
     const uint32_t lbo = N * 16;
-    long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      if (ptx::elect_one()) {
+    const uint32_t bar2 = bar + 8;   // second barrier for the per-batch commit experiments
+    long long t0 = clock64(), t_issue = 0;
+    if (mode < 4) {
+      for (int it = 0; it < iters; ++it) {
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint64_t bd = ptx::smem_desc(sb + 64 * 1024 + (j & 3) * (N * 32), lbo, 128);
-          if (ss) ptx::mma_ss(tmem, ptx::smem_desc(sb + j * 4096, 2048, 128), bd, idesc, j > 0);
-          else ptx::mma_ts(tmem, tmem + 256u + 8u * j, bd, idesc, j > 0);
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t bd = ptx::smem_desc(sb + 64 * 1024 + (j & 3) * (N * 32), lbo, 128);
+            if (ss) ptx::mma_ss(tmem, ptx::smem_desc(sb + j * 4096, 2048, 128), bd, idesc, j > 0);
+            else ptx::mma_ts(tmem, tmem + 256u + 8u * j, bd, idesc, j > 0);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
+    } else if (mode == 4) {
+      // like the kernel's stage loop: 8 MMAs, commit to a barrier, wait for the PREVIOUS batch's barrier
+      for (int it = 0; it < iters * 2; ++it) {
+        if (ptx::elect_one()) {
+          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
+          ptx::mma_commit(bar2);
+        }
+        __syncwarp();
+        if (it > 0) ptx::mbar_wait(bar2, (it - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      ptx::mbar_wait(bar2, (iters * 2 - 1) & 1);
+    } else {
+      // mode 5: how far ahead of the tensor pipe does the issuing thread run?  (queue depth)
+      for (int it = 0; it < iters; ++it) {
+        long long a0 = clock64();
+        if (ptx::elect_one()) {
+          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
+          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
+        }
+        __syncwarp();
+        long long a1 = clock64();
+        if (ptx::elect_one()) ptx::mma_commit(bar2);
+        __syncwarp();
+        ptx::mbar_wait(bar2, it & 1);
+        t_issue += a1 - a0;
+      }
     }
     if (ptx::elect_one()) ptx::mma_commit(bar);
     __syncwarp();
     ptx::mbar_wait(bar, 0);
     long long t1 = clock64();
-    if (threadIdx.x == 32) cycles_out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 32) cycles_out[blockIdx.x] = (mode == 5) ? t_issue : (t1 - t0);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -897,6 +988,7 @@ int query_device() {
   return PLNERF_OK;
 }
 
+long long* g_trace = nullptr;
 struct ProfRec { cudaEvent_t e0, e1; int64_t rows; };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_evt_pool;
@@ -924,6 +1016,7 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PLNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
   a.debug_flags = dbg;
+  a.trace = g_trace;
   a.n_tiles = ceil_div(a.M, TILE_M);
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
@@ -1035,6 +1128,8 @@ int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode,
   PLNERF_LAUNCH_CHECK("k_debug_gemm");
   return PLNERF_OK;
 }
+
+int debug_set_trace(long long* buf) { g_trace = buf; return PLNERF_OK; }
 
 int profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

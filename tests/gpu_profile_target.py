@@ -22,6 +22,11 @@ ro, rd, K, _ = synth.lego_rays(n, seed=1)
 vd = rd / np.linalg.norm(rd, axis=-1, keepdims=True)
 rays = torch.from_numpy(np.concatenate([ro, rd, np.full((n, 1), 2, np.float32), np.full((n, 1), 6, np.float32), vd], -1)).cuda()
 z = torch.sort(torch.rand(n, S, device="cuda") * 4 + 2, -1)[0]
+trace = None
+if os.environ.get("PLNERF_TRACE"):
+    from plnerf_b200 import _lib as L
+    trace = torch.zeros(4 * 256 * 2, dtype=torch.int64, device="cuda")
+    L.check(L.lib().plnerf_debug_set_trace(trace.data_ptr()))
 with torch.no_grad():
     for i in range(n_launch):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,3 +36,19 @@ with torch.no_grad():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"{prec} launch {i}: {ms:.3f} ms  {n*S*1186816/ms/1e9:.1f} TFLOP/s", flush=True)
+
+if trace is not None:
+    t = trace.cpu().numpy().reshape(4, 256, 2)
+    ev = [(int(c), int(code), r) for r in range(4) for c, code in t[r] if code != 0]
+    ev.sort()
+    t0 = ev[0][0]
+    names = {0: "MMA ", 1: "EPI0", 2: "EPI1", 3: "TMA "}
+    for c, code, r in ev:
+        kind = code // 1000
+        desc = {1: "half start  l=%d h=%d" % ((code % 1000) // 10, code % 10),
+                2: "issue stage l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10),
+                3: "d_full seen l=%d h=%d" % ((code % 1000) // 10, code % 10),
+                4: "arrived     l=%d h=%d" % ((code % 1000) // 10, code % 10),
+                5: "dep ok      l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10),
+                6: "tma issue   l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10)}[kind]
+        print(f"{c - t0:8d}  {names[r]}  {desc}")
