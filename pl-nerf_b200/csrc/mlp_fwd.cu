@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   const uint32_t d_full0 = s_bars + 8u * (2 * MAX_STAGES);      // [2]
   const uint32_t a_ready0 = s_bars + 8u * (2 * MAX_STAGES + 2);  // [2]
   const uint32_t pe_ready = s_bars + 8u * (2 * MAX_STAGES + 4);
+  auto b_full = [&](uint32_t b) { return s_bars + 8u * (2 * MAX_STAGES + 8 + (b & 7u)); };   // batch-level weight barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SL.bars + 8u * (2 * MAX_STAGES + 6));
 
   if (threadIdx.x == 0) {
@@ -478,7 +479,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     ptx::mbar_init(d_full0, 1); ptx::mbar_init(d_full0 + 8, 1);
     ptx::mbar_init(a_ready0, NUM_EPI_THREADS / 32); ptx::mbar_init(a_ready0 + 8, NUM_EPI_THREADS / 32);
     ptx::mbar_init(pe_ready, NUM_EPI_THREADS / 32);
+    for (uint32_t b2 = 0; b2 < 8; ++b2) ptx::mbar_init(b_full(b2), 1);
     ptx::fence_mbar_init();
+  }
+  // ---- flattened per-tile stage program (shared by the TMA producer and the MMA issuer) ----------
+  //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7      needs a_ready[a](l-1)
+  //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15  needs a_ready[b](l-1)
+  // entry.x: bits 0-7 K-steps | F_* flags | bits 12-15 batch length (first entry of a batch only)
+  // entry.y: TMEM column of the A operand (hidden stages) or first PE K-step (PE stages)
+  enum : uint32_t { F_PE = 1u << 8, F_H = 1u << 9, F_FIRST = 1u << 10, F_LAST = 1u << 11, F_WAIT_A0 = 1u << 16,
+                    F_WAIT_A1 = 1u << 17, F_INC0 = 1u << 18, F_INC1 = 1u << 19 };
+  uint2* prog = reinterpret_cast<uint2*>(smem + SL.prog);
+  int* prog_n = reinterpret_cast<int*>(smem + SL.prog + 8 * 127);
+  if (threadIdx.x == 0) {
+    int n_entries = 0;
+    for (int l = 0; l < P.n_layers; ++l) {
+      const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nh = P.L[l].n_halves;
+      const uint32_t a_col = (l > 0 ? (X3 ? 256u : ((((l - 1) & 1) ? 384u : 256u))) : 256u);
+      const int nst = stages_of(n_pe, n_h);
+      int batch_first[2] = {-1, -1};
+      uint32_t batch_len[2] = {0, 0}, batch_inc[2] = {0, 0};
+      for (int h = 0; h < nh; ++h) {
+        for (int st = 0; st < nst; ++st) {
+          const StageInfo si = stage_info(n_pe, n_h, st);
+          uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
+                        (st == nst - 1 ? F_LAST : 0u);
+          const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
+          const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
+          if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
+          ++batch_len[bsel];
+          if (st == nst - 1) batch_inc[bsel] |= h ? F_INC1 : F_INC0;
+          prog[n_entries++] = make_uint2(w0, w1);
+        }
+      }
+      for (int bs = 0; bs < 2; ++bs)
+        if (batch_first[bs] >= 0) prog[batch_first[bs]].x |= (batch_len[bs] << 12) | batch_inc[bs];
+    }
+    *prog_n = n_entries;
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
@@ -486,6 +523,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int n_entries = *prog_n;
 
   constexpr uint32_t COL_DA = 0, COL_A0 = 256, COL_A1 = 384;
   // activation buffer written by the epilogue of layer l (and read by layer l+1)
@@ -494,30 +532,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer: stream the packed weights through the ring ==============
     if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      int tcnt = 0;
-      uint32_t tile_iter = 0;
-      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
-        const bool trace_on = (tile_iter == 2);
+      uint32_t slot = 0, phase = 0, batch = 0;
+      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         const uint8_t* src = A.w;
-        for (int l = 0; l < P.n_layers; ++l) {
-          const int nst = stages_of(P.L[l].n_pe_ks, P.L[l].n_h_ks);
-          for (int h = 0; h < P.L[l].n_halves; ++h) {
-            for (int st = 0; st < nst; ++st) {
-              const uint32_t bytes = (uint32_t)stage_info(P.L[l].n_pe_ks, P.L[l].n_h_ks, st).nks * KS_BYTES;
-              for (int rep = 0; rep < nsplit; ++rep) {
+        const bool copy = !((A.debug_flags & 1) && tile != (int64_t)blockIdx.x);
+        int i = 0;
+        while (i < n_entries) {
+          const int blen = (prog[i].x >> 12) & 15;
+          if (!X3) {
+            // one full-barrier per batch: armed with the batch's total bytes, every stage copy signals it.
+            // 8 batch barriers > ring slots, so a barrier is never re-armed before its previous phase was consumed.
+            uint32_t total = 0;
+            for (int j = 0; j < blen; ++j) total += (prog[i + j].x & 255u) * KS_BYTES;
+            const uint32_t bar = b_full(batch);
+            if (copy) ptx::mbar_arrive_expect_tx(bar, total); else ptx::mbar_arrive(bar);
+            for (int j = 0; j < blen; ++j) {
+              const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
+              ptx::mbar_wait(w_empty(slot), phase ^ 1);
+              if (copy) ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, bar);
+              src += bytes;
+              if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
+            }
+            ++batch;
+          } else {
+            for (int j = 0; j < blen; ++j) {
+              const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
+              for (int rep = 0; rep < 2; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
-                PLNERF_TRACE(3, tcnt, 6000 + l * 100 + h * 10 + st);   // slot free, TMA issued
-                if ((A.debug_flags & 1) && tile != (int64_t)blockIdx.x) { ptx::mbar_arrive(w_full(slot)); }
-                else {
-                  ptx::mbar_arrive_expect_tx(w_full(slot), bytes);
-                  ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot));
-                }
+                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot)); }
+                else ptx::mbar_arrive(w_full(slot));
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
               }
             }
           }
+          i += blen;
         }
       }
     }
@@ -530,37 +579,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7     needs a_ready[a](l-1)
     //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15 needs a_ready[b](l-1)
     // One elected lane issues; the whole warp follows the (warp-uniform) control flow.
-    enum : uint32_t { F_PE = 1u << 8, F_H = 1u << 9, F_FIRST = 1u << 10, F_LAST = 1u << 11, F_WAIT_A0 = 1u << 16,
-                      F_WAIT_A1 = 1u << 17 };
-    uint2* prog = reinterpret_cast<uint2*>(smem + SL.prog);
-    int n_entries = 0;
-    if (lane == 0) {
-      for (int l = 0; l < P.n_layers; ++l) {
-        const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nh = P.L[l].n_halves;
-        const uint32_t a_col = (l > 0 ? a_out_col(l - 1) : COL_A0);
-        const int nst = stages_of(n_pe, n_h);
-        int batch_first[2] = {-1, -1};   // entry index of the first stage of batch 1 / batch 2
-        int batch_len[2] = {0, 0};
-        for (int h = 0; h < nh; ++h) {
-          for (int st = 0; st < nst; ++st) {
-            const StageInfo si = stage_info(n_pe, n_h, st);
-            uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
-                          (st == nst - 1 ? F_LAST : 0u);
-            const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
-            // batch 2 starts at the first stage that reads hidden columns >= 128 (or at half b)
-            const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
-            if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
-            ++batch_len[bsel];
-            prog[n_entries++] = make_uint2(w0, w1);
-          }
-        }
-        for (int bs = 0; bs < 2; ++bs)
-          if (batch_first[bs] >= 0) prog[batch_first[bs]].x |= (uint32_t)batch_len[bs] << 12;   // bits 12-15
-      }
-    }
-    n_entries = __shfl_sync(0xffffffffu, n_entries, 0);
-    __syncwarp();
-
     const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
     const uint64_t desc_base = ptx::smem_desc(0, 2048, 128);
     const uint32_t desc_hi = (uint32_t)(desc_base >> 32);
@@ -568,25 +586,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     auto mk_desc = [&](uint32_t lo) -> uint64_t { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
     auto lo_of = [&](uint32_t saddr) -> uint32_t { return desc_lo0 | ((saddr & 0x3FFFFu) >> 4); };
     constexpr uint32_t KS_DESC = KS_BYTES >> 4;   // descriptor address increment per K-step
-    uint32_t slot = 0, phase = 0;
+    uint32_t slot = 0, phase = 0, batch = 0;
     uint32_t uses0 = 0, uses1 = 0, waited0 = 0, waited1 = 0;
     uint32_t tile_iter = 0;
+    int tcnt = 0;
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+      const bool trace_on = (tile_iter == 2) && lane == 0;
       ptx::mbar_wait(pe_ready, tile_iter & 1);
       int i = 0;
       while (i < n_entries) {
+        PLNERF_TRACE(0, tcnt, 1000 + i);                 // batch loop top
         const uint32_t bw0 = prog[i].x;
         const int blen = (bw0 >> 12) & 15;
         if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
         if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
-        if (!X3) {   // all weight stages of the batch (<= 4 of the 6 ring slots) must have landed
-          uint32_t s2 = slot, p2 = phase;
-          for (int j = 0; j < blen; ++j) {
-            ptx::mbar_wait(w_full(s2), p2);
-            if (++s2 == (uint32_t)A.n_stages) { s2 = 0; p2 ^= 1; }
-          }
+        if (!X3) {   // ONE wait for all weight stages of the batch (<= 4 of the ring slots)
+          ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);
+          ++batch;
         }
         ptx::tc_fence_after();
+        PLNERF_TRACE(0, tcnt, 2000 + i);                 // dependencies + weights ready, issuing batch
         if (ptx::elect_one()) {
           uint32_t sl = slot, ph = phase;   // private ring cursor of the issuing lane
           for (int j = 0; j < blen; ++j) {
@@ -634,12 +653,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           }
         }
         __syncwarp();
+        PLNERF_TRACE(0, tcnt, 5000 + i);                 // issue returned
         // every lane advances the (warp-uniform) ring cursor and use counters past this batch
         for (int j = 0; j < blen * nsplit; ++j) { if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; } }
-        for (int j = 0; j < blen; ++j) {
-          const uint32_t w = prog[i + j].x;
-          if (w & F_LAST) { if (w & F_H) ++uses1; else ++uses0; }
-        }
+        uses0 += (bw0 >> 18) & 1u;
+        uses1 += (bw0 >> 19) & 1u;
         i += blen;
       }
     }
@@ -690,15 +708,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           }
           ptx::tc_fence_after();
           PLNERF_TRACE(1 + grp, tcnt, 3000 + l * 10 + h);     // accumulator half observed full
+          // both 32-column chunks of this warp are requested before the single wait::ld, so the second
+          // TMEM read overlaps the first chunk's math
+          uint32_t r2[2][32];
+          if (!(A.debug_flags & 2)) {
+            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (2 * grp), r2[0]);
+            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (2 * grp + 1), r2[1]);
+            ptx::tmem_ld_wait();
+          }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             if (A.debug_flags & 2) break;
             const int c = 2 * grp + cc;
             const int n0 = h * 128 + c * 32;
-            uint32_t r[32];
-            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * c, r);
-            ptx::tmem_ld_wait();
-            float* val = reinterpret_cast<float*>(r);
+            float* val = reinterpret_cast<float*>(r2[cc]);
             if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {

@@ -45,10 +45,10 @@ if trace is not None:
     names = {0: "MMA ", 1: "EPI0", 2: "EPI1", 3: "TMA "}
     for c, code, r in ev:
         kind = code // 1000
-        desc = {1: "half start  l=%d h=%d" % ((code % 1000) // 10, code % 10),
-                2: "issue stage l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10),
+        desc = {1: "batch top   entry=%d" % (code % 1000),
+                2: "batch issue entry=%d" % (code % 1000),
                 3: "d_full seen l=%d h=%d" % ((code % 1000) // 10, code % 10),
                 4: "arrived     l=%d h=%d" % ((code % 1000) // 10, code % 10),
-                5: "dep ok      l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10),
+                5: "issue ret   entry=%d" % (code % 1000),
                 6: "tma issue   l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10)}[kind]
         print(f"{c - t0:8d}  {names[r]}  {desc}")
