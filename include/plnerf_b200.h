@@ -156,6 +156,16 @@ int plnerf_raw2outputs(const float* raw, int raw_stride, const float* z, const f
                        float* acc_map, float* depth_map, float* weights, float* tau, float* T,
                        void* stream);
 
+/* ---- backward of a8/a9/a10 (what autograd computes through raw2outputs, run_plnerf.py:553-624) ----
+ * Upstream gradients of rgb_map [n,3], depth_map/acc_map/disp_map [n] (any may be NULL) ->
+ * g_raw [n,S,raw_stride] (channels 0-3; further channels are zeroed).  z_vals carry no gradient
+ * (the reference detaches the importance samples, run_plnerf.py:728). */
+int plnerf_raw2outputs_bwd(const float* raw, int raw_stride, const float* z, const float* rays,
+                           int64_t n, int stride, int S, int mode, int color_mode, int white_bkgd,
+                           int farcolorfix, const float* noise, const float* g_rgb_map,
+                           const float* g_depth_map, const float* g_acc_map, const float* g_disp_map,
+                           float* g_raw, void* stream);
+
 /* ---- a11: sample_pdf_reformulation (+pw_linear_sample_*) (run_nerf_helpers.py:340-445) --------
  * z [n,S], weights [n,S+1], tau,T [n,S+2], rays (near/far cols 6,7), u [n,Ni] in [0,1) or NULL
  * (Philox).  -> samples [n,Ni] (unclamped, unsorted), inds [n,Ni] int64 or NULL. */

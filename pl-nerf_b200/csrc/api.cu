@@ -114,6 +114,17 @@ int plnerf_raw2outputs(const float* raw, int raw_stride, const float* z, const f
                           0.f, 0, 0, 0, rgb_map, disp_map, acc_map, depth_map, weights, tau, T, (cudaStream_t)stream);
 }
 
+int plnerf_raw2outputs_bwd(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n, int stride,
+                           int S, int mode, int color_mode, int white_bkgd, int farcolorfix, const float* noise,
+                           const float* g_rgb_map, const float* g_depth_map, const float* g_acc_map,
+                           const float* g_disp_map, float* g_raw, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (raw && z && rays && g_raw)), "raw2outputs_bwd: null argument");
+  PLNERF_CHECK_ARG(raw_stride >= 4 && stride >= 8 && S >= 1, "raw2outputs_bwd: need raw_stride >= 4, stride >= 8, S >= 1");
+  PLNERF_CHECK_ARG(mode == PLNERF_MODE_LINEAR || mode == PLNERF_MODE_CONSTANT, "raw2outputs_bwd: bad mode %d", mode);
+  return launch_composite_bwd(raw, raw_stride, z, rays, n, stride, S, mode, color_mode, white_bkgd, farcolorfix, noise,
+                              g_rgb_map, g_depth_map, g_acc_map, g_disp_map, g_raw, (cudaStream_t)stream);
+}
+
 int plnerf_sample_pdf_pl(const float* z, const float* weights, const float* tau, const float* T, const float* rays,
                          int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray_id_offset,
                          float zero_tol, float epsilon, float* samples, int64_t* inds, void* stream) {

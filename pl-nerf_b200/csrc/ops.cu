@@ -236,6 +236,188 @@ int launch_composite(const float* raw, int raw_stride, const float* z, const flo
 }
 
 // =============================================================================================
+// backward of raw2outputs (what autograd differentiates in the reference):
+// upstream grads of rgb_map/depth_map/acc_map/disp_map -> grad of raw[..., :4].
+//   linear:   dL/da_k = e_k T_k G_k - sum_{j>k} w_j G_j ;  dL/dtau_i = .5 (D_{i-1} dL/da_{i-1} + D_i dL/da_i)
+//   constant: dL/dalpha_i = T_i G_i - (sum_{j>i} w_j G_j) / (1 - alpha_i + 1e-10)
+// with G_j = gC.m_j + gD' zmid_j + gA' (m_j the colour of interval j).  One warp per ray; the forward
+// scan is recomputed, the suffix sum is a reverse warp scan.
+// =============================================================================================
+struct CompositeBwdArgs {
+  const float* raw; int raw_stride;
+  const float* z; const float* rays; int64_t n; int stride; int S;
+  int color_mode, white_bkgd, farcolorfix;
+  const float* noise;
+  const float *g_rgb, *g_depth, *g_acc, *g_disp;   // any may be null
+  float* g_raw;                                      // [n,S,raw_stride]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_composite_bwd(CompositeBwdArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int S = a.S;
+  const int nI = (MODE == PLNERF_MODE_LINEAR) ? S + 1 : S;
+  float* sw = smem + (size_t)wib * 4 * (S + 2);   // w_j
+  float* sx = sw + (S + 2);                        // e_j T_j (linear) / T_j (constant)
+  float* sy = sx + (S + 2);                        // delta_j (interval length * |d|) ; later dL/da_j
+  float* sg = sy + (S + 2);                        // suffix sums of w_j G_j (exclusive)
+  const float* ray = a.rays + r * a.stride;
+  const float dx = ray[3], dy = ray[4], dz = ray[5];
+  const float near = ray[6], far = ray[7];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float* raw = a.raw + r * (int64_t)S * a.raw_stride;
+  const float* z = a.z + r * (int64_t)S;
+  auto sigma_at = [&](int k) -> float {
+    float s = raw[(int64_t)k * a.raw_stride + 3];
+    if (a.noise) s += a.noise[r * (int64_t)S + k];
+    return s;
+  };
+  auto color_at = [&](int k, int c) -> float { return sigmoidf_(raw[(int64_t)k * a.raw_stride + c]); };
+  auto knot = [&](int k) -> float { return k == 0 ? near : (k == S + 1 ? far : z[k - 1]); };
+  auto tau_at = [&](int k) -> float { return k == 0 ? 1e-10f : (k == S + 1 ? 1e10f : fmaxf(sigma_at(k - 1), 0.0f)); };
+
+  // ---- pass 1: forward scan (same arithmetic as k_composite), totals
+  float acc_d = 0.f, acc_w = 0.f;
+  double carry = 1.0;
+  for (int base = 0; base < nI; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < nI;
+    float e = 1.0f, delta = 0.f, zm = 0.f, fac = 0.f;
+    if (valid) {
+      if (MODE == PLNERF_MODE_LINEAR) {
+        const float s0 = knot(i), s1 = knot(i + 1);
+        delta = (s1 - s0) * dnorm;
+        e = expf(-0.5f * (tau_at(i + 1) + tau_at(i)) * delta);
+        fac = 1.0f - e;
+        zm = 0.5f * (s1 + s0);
+      } else {
+        zm = z[i];
+        delta = ((i < S - 1) ? (z[i + 1] - zm) : 1e10f) * dnorm;
+        const float alpha = 1.0f - expf(-fmaxf(sigma_at(i), 0.f) * delta);
+        fac = alpha;
+        e = (1.0f - alpha) + 1e-10f;
+      }
+    }
+    const double incl = warp_incl_scan_mul((double)e, lane) * carry;
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = carry;
+    carry = __shfl_sync(0xffffffffu, incl, 31);
+    if (valid) {
+      const float T = (float)excl;
+      const float w = fac * T;
+      sw[i] = w;
+      sx[i] = (MODE == PLNERF_MODE_LINEAR) ? e * T : T;
+      sy[i] = delta;
+      acc_d += w * zm;
+      acc_w += w;
+    }
+  }
+  acc_d = warp_sum(acc_d); acc_w = warp_sum(acc_w);
+  __syncwarp();
+  // ---- upstream scalars
+  float gC[3] = {0.f, 0.f, 0.f};
+  if (a.g_rgb) { gC[0] = a.g_rgb[r * 3]; gC[1] = a.g_rgb[r * 3 + 1]; gC[2] = a.g_rgb[r * 3 + 2]; }
+  float gD = a.g_depth ? a.g_depth[r] : 0.f;
+  float gA = a.g_acc ? a.g_acc[r] : 0.f;
+  if (a.g_disp) {
+    const float q = acc_d / acc_w;
+    if (q > 1e-10f) {   // disp = 1/q ; below the clamp the output is constant
+      const float gq = -a.g_disp[r] / (q * q);
+      gD += gq / acc_w;
+      gA += -gq * acc_d / (acc_w * acc_w);
+    }
+  }
+  if (a.white_bkgd) gA -= gC[0] + gC[1] + gC[2];
+  // colour of interval / sample j as used by the forward
+  auto mcol = [&](int j, int c) -> float {
+    if (MODE != PLNERF_MODE_LINEAR) return color_at(j, c);
+    const int kl = max(j - 1, 0), kr = min(j, S - 1);
+    if (a.color_mode == PLNERF_COLOR_LEFT) return color_at(kl, c);
+    const float right = (a.farcolorfix && j == S) ? 0.f : color_at(kr, c);
+    return 0.5f * (right + color_at(kl, c));
+  };
+  // ---- pass 2: reverse (suffix) scan of w_j G_j, exclusive
+  float rcarry = 0.f;
+  for (int top = ((nI - 1) / 32) * 32; top >= 0; top -= 32) {
+    const int i = top + lane;
+    float v = 0.f;
+    if (i < nI) {
+      float zm;
+      if (MODE == PLNERF_MODE_LINEAR) zm = 0.5f * (knot(i + 1) + knot(i)); else zm = z[i];
+      const float G = gC[0] * mcol(i, 0) + gC[1] * mcol(i, 1) + gC[2] * mcol(i, 2) + gD * zm + gA;
+      v = sw[i] * G;
+      sg[i] = G;   // stash G_i, replaced below
+    }
+    float incl = v;   // inclusive suffix within the chunk
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    const float suffix_excl = incl - v + rcarry;
+    rcarry += __shfl_sync(0xffffffffu, incl, 0);
+    if (i < nI) {
+      const float G = sg[i];
+      if (MODE == PLNERF_MODE_LINEAR) sy[i] = sy[i] * (sx[i] * G - suffix_excl);   // delta_i * dL/da_i
+      else sg[i] = suffix_excl;                                                    // constant mode: finished in pass 3
+    }
+  }
+  __syncwarp();
+  // ---- pass 3: per-sample gradients
+  float* graw = a.g_raw + r * (int64_t)S * a.raw_stride;
+  for (int i = lane; i < S; i += 32) {
+    float gs = 0.f, gcr[3];
+    const float sraw = sigma_at(i);
+    if (MODE == PLNERF_MODE_LINEAR) {
+      // sample i is knot i+1: dL/dtau = .5 (delta_i dL/da_i + delta_{i+1} dL/da_{i+1})
+      gs = (sraw > 0.f) ? 0.5f * (sy[i] + sy[i + 1]) : 0.f;
+      float cw;   // total weight multiplying c_i
+      if (a.color_mode == PLNERF_COLOR_LEFT) cw = sw[i + 1] + (i == 0 ? sw[0] : 0.f);
+      else cw = 0.5f * (sw[i] + sw[i + 1]) + (i == 0 ? 0.5f * sw[0] : 0.f) + ((i == S - 1 && !a.farcolorfix) ? 0.5f * sw[S] : 0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gcr[c] = cw * gC[c];
+    } else {
+      const float zi = z[i];
+      const float delta = sy[i];
+      const float sg_relu = fmaxf(sraw, 0.f);
+      const float ex = expf(-sg_relu * delta);           // 1 - alpha
+      const float G = gC[0] * color_at(i, 0) + gC[1] * color_at(i, 1) + gC[2] * color_at(i, 2) + gD * zi + gA;
+      const float dLdalpha = sx[i] * G - sg[i] / (ex + 1e-10f);
+      gs = (sraw > 0.f) ? dLdalpha * delta * ex : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gcr[c] = sw[i] * gC[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float col = color_at(i, c);
+      graw[(int64_t)i * a.raw_stride + c] = gcr[c] * col * (1.0f - col);
+    }
+    graw[(int64_t)i * a.raw_stride + 3] = gs;
+    for (int c = 4; c < a.raw_stride; ++c) graw[(int64_t)i * a.raw_stride + c] = 0.f;
+  }
+}
+
+int launch_composite_bwd(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n, int stride,
+                         int S, int mode, int color_mode, int white_bkgd, int farcolorfix, const float* noise,
+                         const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_disp,
+                         float* g_raw, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  CompositeBwdArgs a{raw, raw_stride, z, rays, n, stride, S, color_mode, white_bkgd, farcolorfix, noise,
+                     g_rgb, g_depth, g_acc, g_disp, g_raw};
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * 4 * (S + 2) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("raw2outputs_bwd: N_samples=%d too large", S); return PLNERF_E_UNSUPPORTED; }
+  const unsigned blocks = (unsigned)ceil_div(n, wpb);
+  if (mode == PLNERF_MODE_LINEAR) k_composite_bwd<PLNERF_MODE_LINEAR><<<blocks, wpb * 32, smem, st>>>(a);
+  else k_composite_bwd<PLNERF_MODE_CONSTANT><<<blocks, wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_composite_bwd");
+  return PLNERF_OK;
+}
+
+// =============================================================================================
 // samplers
 // =============================================================================================
 // torch.searchsorted(cdf, u, right=True): ATen's upper-bound loop, reproduced step for step so the

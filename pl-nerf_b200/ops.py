@@ -119,6 +119,25 @@ def raw2outputs(raw, z_vals, rays, mode, color_mode, noise=None, white_bkgd=Fals
     return rgb, disp, acc, w, depth, tau, T
 
 
+def raw2outputs_bwd(raw, z_vals, rays, mode, color_mode, g_rgb=None, g_depth=None, g_acc=None, g_disp=None,
+                    noise=None, white_bkgd=False, farcolorfix=False):
+    """Gradient of raw2outputs w.r.t. raw given upstream grads of (rgb_map, depth_map, acc_map, disp_map)."""
+    raw, z_vals, rays = _f32(raw, "raw"), _f32(z_vals, "z_vals"), _f32(rays, "rays")
+    n, S = z_vals.shape
+    if mode not in ("linear", "constant"):
+        raise ValueError(f"mode must be 'linear' or 'constant', got {mode!r}")
+    opt = lambda t, nm: None if t is None else _f32(t, nm)
+    g_rgb, g_depth, g_acc, g_disp, noise = (opt(g_rgb, "g_rgb"), opt(g_depth, "g_depth"), opt(g_acc, "g_acc"),
+                                            opt(g_disp, "g_disp"), opt(noise, "noise"))
+    g_raw = torch.empty_like(raw)
+    L.check(L.lib().plnerf_raw2outputs_bwd(_p(raw), raw.shape[-1], _p(z_vals), _p(rays), n, rays.shape[1], S,
+                                            L.MODE_LINEAR if mode == "linear" else L.MODE_CONSTANT,
+                                            L.COLOR_MIDPOINT if color_mode == "midpoint" else L.COLOR_LEFT,
+                                            int(bool(white_bkgd)), int(bool(farcolorfix)), _p(noise), _p(g_rgb),
+                                            _p(g_depth), _p(g_acc), _p(g_disp), _p(g_raw), _stream()))
+    return g_raw
+
+
 def sample_pdf_pl(z_vals, weights, tau, T, rays, N_importance, u=None, seed=0, ray_id_offset=0, zero_tol=1e-4,
                   epsilon=1e-3, return_inds=False):
     """sample_pdf_reformulation (run_nerf_helpers.py:364-445) with near/far taken from rays cols 6,7."""

@@ -180,6 +180,21 @@ def run_case(H, R, name, cfg):
             out["weights1"] = r1[3].numpy()
         else:
             np.testing.assert_array_equal(out["rgb_map"], rgb0.numpy())
+    # ---- gradient golden: d(loss)/d(raw0) through the reference's own raw2outputs (torch autograd),
+    # loss = <rgb,Wr> + <depth,Wd> + <acc,Wa> + <disp,Wp> with seeded upstream weights
+    rs = np.random.RandomState(77)
+    up = {"up_rgb": rs.randn(n, 3).astype(np.float32), "up_depth": rs.randn(n).astype(np.float32),
+          "up_acc": rs.randn(n).astype(np.float32), "up_disp": rs.randn(n).astype(np.float32)}
+    raw_req = torch.from_numpy(out["raw0"].copy()).requires_grad_(True)
+    mode_g = "constant" if cfg["constant_init"] else cfg["mode"]
+    rb = torch.from_numpy(out["ray_batch"])
+    rg = R.raw2outputs(raw_req, torch.from_numpy(out["z_vals0"]), rb[:, 6:7], rb[:, 7:8], rb[:, 3:6], mode_g,
+                       cfg["color_mode"], cfg["raw_noise_std"], pytest=True, white_bkgd=cfg["white_bkgd"])
+    loss = (rg[0] * torch.from_numpy(up["up_rgb"])).sum() + (rg[4] * torch.from_numpy(up["up_depth"])).sum() \
+        + (rg[2] * torch.from_numpy(up["up_acc"])).sum() + (rg[1] * torch.from_numpy(up["up_disp"])).sum()
+    loss.backward()
+    out.update(up)
+    out["g_raw0"] = raw_req.grad.numpy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), keys={sorted(out)}")

@@ -93,6 +93,25 @@ def test_raw2outputs_vs_golden(P, name):
         assert max_rel(host(T), g["T0"], 1e-6) < 2e-5
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_raw2outputs_backward_vs_reference_autograd(P, name):
+    """d(loss)/d(raw) through raw2outputs vs torch autograd on the reference's own function (golden):
+    <= 1e-4 of the gradient scale (fp32; (1-e) cancellations and exp make this looser than forward)."""
+    g = load_golden(name)
+    cfg = CASES[name]
+    mode = "constant" if cfg["constant_init"] else cfg["mode"]
+    noise = dev(g["noise0"]) if "noise0" in g else None
+    graw = host(P.raw2outputs_bwd(dev(g["raw0"]), dev(g["z_vals0"]), dev(g["ray_batch"]), mode, cfg["color_mode"],
+                                  g_rgb=dev(g["up_rgb"]), g_depth=dev(g["up_depth"]), g_acc=dev(g["up_acc"]),
+                                  g_disp=dev(g["up_disp"]), noise=noise, white_bkgd=cfg["white_bkgd"]))
+    ref = g["g_raw0"]
+    for c in range(4):
+        scale = np.abs(ref[..., c]).max() + 1e-12
+        err = np.abs(graw[..., c] - ref[..., c]).max() / scale
+        assert err < 1e-4, (c, err)
+    assert np.all(graw[..., 4:] == 0)
+
+
 @pytest.mark.parametrize("name", FINE)
 def test_sampler_indices_bit_exact(P, name):
     """Given the reference's own (z, weights, tau, T, u): searchsorted indices identical, samples 1e-5."""
