@@ -151,7 +151,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     desc = f"{sample} of the 640000 rays per step (chunks are independent; rays/s is chunk-size invariant)"
-    print(json.dumps({
+    OUT.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -301,12 +301,36 @@ def run_ours(args):
                                "sample": f"{reps} x {sample} rays of the same 640000-ray image, numpy/torch-CPU oracle "
                                          f"(oracle/plnerf_oracle.py), {cores} host threads"}
     if rank == 0:
-        print(json.dumps(out))
+        OUT.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """Everything libraries print on fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is
+    written to the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -316,10 +340,11 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per CPU-baseline repetition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr() as OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
