@@ -72,6 +72,23 @@ typedef struct plnerf_net_params {
   const float* output_b;
 } plnerf_net_params;
 
+/* Gradient buffers with the same names / shapes as plnerf_net_params (fp32, accumulated with +=, so
+ * the caller zeroes them or lets them alias param.grad). */
+typedef struct plnerf_net_grads {
+  float* pts_w[PLNERF_MAX_DEPTH];
+  float* pts_b[PLNERF_MAX_DEPTH];
+  float* views_w;
+  float* views_b;
+  float* feature_w;
+  float* feature_b;
+  float* alpha_w;
+  float* alpha_b;
+  float* rgb_w;
+  float* rgb_b;
+  float* output_w;
+  float* output_b;
+} plnerf_net_grads;
+
 /* Everything render_rays() receives besides tensors (run_plnerf.py:627-646). */
 typedef struct plnerf_render_cfg {
   int32_t N_samples;
@@ -139,6 +156,25 @@ size_t plnerf_query_workspace_bytes(const plnerf_net_desc* desc, int64_t n_rays)
 int plnerf_network_query(const plnerf_net_desc* desc, const void* packed, int precision,
                          int multires, int multires_views, const float* rays, int64_t n, int stride,
                          const float* z, int S, float* raw, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- training: what loss.backward() replays through run_network / NeRF.forward (autograd) --------
+ * plnerf_network_query_train = plnerf_network_query (bf16) that additionally stashes every layer's
+ * bf16 activations + ReLU masks (stash: plnerf_train_stash_bytes(desc, n, S) bytes, 1 KiB aligned).
+ * plnerf_network_query_bwd consumes that stash and g_raw = dL/draw [n*S, g_stride>=4] and ADDS the
+ * parameter gradients into `grads` (fp32, reference state_dict layout).  packed_bwd: transposed weight
+ * stream from plnerf_pack_weights_bwd (plnerf_packed_bwd_bytes).  use_viewdirs networks only; the
+ * sample positions carry no gradient (run_plnerf.py:728), so no input gradient is produced. */
+size_t plnerf_train_stash_bytes(const plnerf_net_desc* desc, int64_t n_rays, int S);
+int plnerf_network_query_train(const plnerf_net_desc* desc, const void* packed, int multires,
+                               int multires_views, const float* rays, int64_t n, int stride,
+                               const float* z, int S, float* raw, void* stash, size_t stash_bytes,
+                               void* ws, size_t ws_bytes, void* stream);
+size_t plnerf_packed_bwd_bytes(const plnerf_net_desc* desc);
+int plnerf_pack_weights_bwd(const plnerf_net_desc* desc, const plnerf_net_params* params,
+                            void* packed_bwd, void* stream);
+int plnerf_network_query_bwd(const plnerf_net_desc* desc, const void* packed, const void* packed_bwd,
+                             int64_t n, int S, const float* g_raw, int g_stride, void* stash,
+                             size_t stash_bytes, const plnerf_net_grads* grads, void* stream);
 
 /* ---- a7: NeRF.forward (run_nerf_helpers.py:105-128) on already-embedded rows ------------------
  * x [m, input_ch + input_ch_views] -> out [m,4] (use_viewdirs) or [m,output_ch].

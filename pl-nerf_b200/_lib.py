@@ -36,6 +36,10 @@ class NetParams(C.Structure):
                 ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p), ("output_w", C.c_void_p), ("output_b", C.c_void_p)]
 
 
+class NetGrads(C.Structure):
+    _fields_ = NetParams._fields_
+
+
 class RenderCfg(C.Structure):
     _fields_ = [("N_samples", C.c_int32), ("N_importance", C.c_int32), ("mode", C.c_int32),
                 ("color_mode", C.c_int32), ("white_bkgd", C.c_int32), ("lindisp", C.c_int32),
@@ -88,6 +92,14 @@ _SIGS = {
     "plnerf_network_query": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]),
+    "plnerf_train_stash_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int]),
+    "plnerf_network_query_train": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                             C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plnerf_packed_bwd_bytes": (C.c_size_t, [C.POINTER(NetDesc)]),
+    "plnerf_pack_weights_bwd": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetParams), C.c_void_p, C.c_void_p]),
+    "plnerf_network_query_bwd": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_size_t, C.POINTER(NetGrads), C.c_void_p]),
     "plnerf_mlp_forward": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "plnerf_raw2outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -111,6 +123,8 @@ _SIGS = {
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "plnerf_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "plnerf_debug_umma_gemm_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
+                                            C.c_void_p]),
     "plnerf_debug_set_trace": (C.c_int, [C.c_void_p]),
     "plnerf_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
@@ -118,7 +132,7 @@ _SIGS = {
 }
 
 # symbols that include/plnerf_b200.h declares (checked by tests/test_abi.py)
-PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace")]
+PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace", "plnerf_debug_umma_gemm_mn")]
 
 
 def lib():

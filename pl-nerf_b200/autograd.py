@@ -1,20 +1,138 @@
-"""Autograd bridge for training (loss.backward() through render_rays).
+"""Autograd bridge for training: loss.backward() through render_rays / NeRF.forward.
 
-Round-1 status: the backward kernels (fused MLP backward + compositing backward, SURVEY.md 7
-steps 5/7) are not written yet, so requesting gradients fails loudly instead of silently falling
-back to a PyTorch path.
+Forward = the same sm_100a kernels as inference with the fused MLP in "stash" mode (bf16 activations +
+ReLU masks of every layer written as weight-gradient operand tiles); backward = compositing backward
+(k_composite_bwd), the input-gradient chain (the fused MLP kernel run on W^T), the weight-gradient
+GEMMs (k_wgrad, MN-major tcgen05 operands, TMEM-resident accumulators) and the small heads.
+What is differentiated follows the reference: gradients flow from rgb_map / depth_map /
+acc_map / disp_map (fine and coarse) to both networks' parameters; the importance samples are
+detached (run_plnerf.py:728) and ray inputs carry no gradient.  bf16 tensor-core operands with fp32
+accumulation; use_viewdirs networks only (anything else raises).
 """
+import torch
+
+from . import ops
 
 
-def _no_backward(what):
-    raise NotImplementedError(
-        f"plnerf_b200: {what} was called with gradients enabled, but the sm_100a backward kernels are not "
-        "implemented yet (forward/render-only path is complete). Wrap the call in torch.no_grad().")
+def _names(net):
+    return [k for k, _ in net.named_parameters()]
+
+
+class _RenderRaysFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, rays, *params):
+        net_c, net_f = cfg["net_c"], cfg["net_f"]
+        Ns, Ni = cfg["N_samples"], cfg["N_importance"]
+        mode, cmode = cfg["mode"], cfg["color_mode"]
+        n = rays.shape[0]
+        z0 = ops.stratified_z(rays, Ns, cfg["lindisp"], cfg["perturb"], cfg["t_rand"], cfg["seed"], cfg["ray_id_offset"])
+        raw0, stash0 = ops.network_query_train(net_c, rays, z0)
+        rgb0, disp0, acc0, w0, depth0, tau0, T0 = ops.raw2outputs(raw0, z0, rays, mode, cmode, noise=cfg["noise0"],
+                                                                  white_bkgd=cfg["white_bkgd"],
+                                                                  farcolorfix=cfg["farcolorfix"])
+        ctx.cfg = cfg
+        ctx.n = n
+        if Ni == 0:
+            ctx.save_for_backward(rays, z0, raw0)
+            ctx.stashes = (stash0, None)
+            outs = (rgb0, disp0, acc0, depth0, raw0)
+            ctx.mark_non_differentiable(raw0)
+            return outs
+        if mode == "linear":
+            zs = ops.sample_pdf_pl(z0, w0, tau0, T0, rays, Ni, u=cfg["u"], seed=cfg["seed"],
+                                   ray_id_offset=cfg["ray_id_offset"], zero_tol=cfg["zero_tol"], epsilon=cfg["epsilon"])
+        else:
+            zmid = 0.5 * (z0[..., 1:] + z0[..., :-1])
+            zs = ops.sample_pdf(zmid, w0[..., 1:-1].contiguous(), Ni, u=cfg["u"], seed=cfg["seed"],
+                                ray_id_offset=cfg["ray_id_offset"])
+        z1, z_std = ops.merge_samples(z0, zs, rays)
+        fine = net_f if net_f is not None else net_c
+        raw1, stash1 = ops.network_query_train(fine, rays, z1)
+        rgb, disp, acc, w1, depth, _, _ = ops.raw2outputs(raw1, z1, rays, mode, cmode, noise=cfg["noise1"],
+                                                          white_bkgd=cfg["white_bkgd"], farcolorfix=cfg["farcolorfix"],
+                                                          want_weights=False)
+        ctx.save_for_backward(rays, z0, raw0, z1, raw1)
+        ctx.stashes = (stash0, stash1)
+        ctx.mark_non_differentiable(raw1, z_std)
+        return rgb, disp, acc, depth, raw1, rgb0, disp0, acc0, depth0, z_std
+
+    @staticmethod
+    def backward(ctx, *g):
+        cfg = ctx.cfg
+        net_c, net_f = cfg["net_c"], cfg["net_f"]
+        Ns, Ni = cfg["N_samples"], cfg["N_importance"]
+        mode, cmode = cfg["mode"], cfg["color_mode"]
+        n = ctx.n
+        saved = ctx.saved_tensors
+        rays, z0, raw0 = saved[0], saved[1], saved[2]
+        kw = dict(white_bkgd=cfg["white_bkgd"], farcolorfix=cfg["farcolorfix"])
+        c = lambda t: None if t is None else t.contiguous()
+        grads_c = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net_c.named_parameters()}
+        grads_f = None
+        if Ni == 0:
+            g_rgb, g_disp, g_acc, g_depth = g[0], g[1], g[2], g[3]
+            graw0 = ops.raw2outputs_bwd(raw0, z0, rays, mode, cmode, g_rgb=c(g_rgb), g_depth=c(g_depth), g_acc=c(g_acc),
+                                        g_disp=c(g_disp), noise=cfg["noise0"], **kw)
+            ops.network_query_bwd(net_c, graw0, ctx.stashes[0], n, Ns, grads_c)
+        else:
+            z1, raw1 = saved[3], saved[4]
+            g_rgb, g_disp, g_acc, g_depth, _, g_rgb0, g_disp0, g_acc0, g_depth0, _ = g
+            graw1 = ops.raw2outputs_bwd(raw1, z1, rays, mode, cmode, g_rgb=c(g_rgb), g_depth=c(g_depth), g_acc=c(g_acc),
+                                        g_disp=c(g_disp), noise=cfg["noise1"], **kw)
+            if net_f is not None:
+                grads_f = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net_f.named_parameters()}
+                ops.network_query_bwd(net_f, graw1, ctx.stashes[1], n, Ns + Ni, grads_f)
+            else:
+                ops.network_query_bwd(net_c, graw1, ctx.stashes[1], n, Ns + Ni, grads_c)
+            if any(t is not None for t in (g_rgb0, g_disp0, g_acc0, g_depth0)):
+                graw0 = ops.raw2outputs_bwd(raw0, z0, rays, mode, cmode, g_rgb=c(g_rgb0), g_depth=c(g_depth0),
+                                            g_acc=c(g_acc0), g_disp=c(g_disp0), noise=cfg["noise0"], **kw)
+                ops.network_query_bwd(net_c, graw0, ctx.stashes[0], n, Ns, grads_c)
+        ctx.stashes = None
+        out = [None, None] + [grads_c[k] for k in _names(net_c)]
+        if net_f is not None:
+            out += [grads_f[k] for k in _names(net_f)] if grads_f is not None else [None] * len(_names(net_f))
+        return tuple(out)
+
+
+def render_rays_autograd(ray_batch, network_fn, network_fine, N_samples, N_importance, mode, color_mode, perturb_on,
+                         white_bkgd, lindisp, raw_noise_std, zero_tol, epsilon, farcolorfix, t_rand, u, noise0, noise1,
+                         seed, ray_id_offset, retraw, precision):
+    if precision not in (None, "bf16") or (precision is None and ops.get_precision() != "bf16"):
+        raise NotImplementedError("plnerf_b200: gradients are implemented for precision='bf16' only")
+    if not getattr(network_fn, "use_viewdirs", False):
+        raise NotImplementedError("plnerf_b200: gradients are implemented for use_viewdirs networks only")
+    rays = ray_batch.detach().float().contiguous()
+    n = rays.shape[0]
+    dev = rays.device
+    if raw_noise_std > 0.:   # the backward must see the same draws: make them explicit
+        if noise0 is None:
+            noise0 = torch.randn((n, N_samples), device=dev) * raw_noise_std
+        if noise1 is None and N_importance > 0:
+            noise1 = torch.randn((n, N_samples + N_importance), device=dev) * raw_noise_std
+    cfg = dict(net_c=network_fn, net_f=network_fine if N_importance > 0 else None, N_samples=N_samples,
+               N_importance=N_importance, mode=mode, color_mode=color_mode, perturb=perturb_on, white_bkgd=white_bkgd,
+               lindisp=lindisp, zero_tol=zero_tol, epsilon=epsilon, farcolorfix=farcolorfix, t_rand=t_rand, u=u,
+               noise0=noise0, noise1=noise1, seed=seed, ray_id_offset=ray_id_offset)
+    params = list(network_fn.parameters())
+    if cfg["net_f"] is not None:
+        params += list(cfg["net_f"].parameters())
+    outs = _RenderRaysFn.apply(cfg, rays, *params)
+    if N_importance == 0:
+        rgb, disp, acc, depth, raw = outs
+        ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth}
+        if retraw:
+            ret["raw"] = raw
+        return ret
+    rgb, disp, acc, depth, raw, rgb0, disp0, acc0, depth0, z_std = outs
+    ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "depth_map": depth}
+    if retraw:
+        ret["raw"] = raw
+    ret.update(rgb0=rgb0, disp0=disp0, depth0=depth0, acc0=acc0, z_std=z_std)
+    return ret
 
 
 def mlp_forward_autograd(net, x):
-    _no_backward("NeRF.forward")
-
-
-def render_rays_autograd(*args, **kwargs):
-    _no_backward("render_rays")
+    raise NotImplementedError(
+        "plnerf_b200: NeRF.forward on pre-embedded rows has no backward kernel (gradients flow through render_rays / "
+        "render, whose fused query recomputes the encoding); call it under torch.no_grad().")

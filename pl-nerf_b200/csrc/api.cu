@@ -27,6 +27,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st);
 int debug_set_trace(long long* buf);
+int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 
 // workspace carving for render_rays
 struct RenderWs {
@@ -95,6 +96,28 @@ int plnerf_network_query(const plnerf_net_desc* desc, const void* packed, int pr
   PLNERF_CHECK_ARG(desc, "network_query: null desc");
   return mlp_query(desc, packed, precision, multires, multires_views, rays, n, stride, z, S, raw,
                    desc->use_viewdirs ? 4 : desc->output_ch, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t plnerf_train_stash_bytes(const plnerf_net_desc* desc, int64_t n_rays, int S) { return mlp_train_stash_bytes(desc, n_rays, S); }
+
+int plnerf_network_query_train(const plnerf_net_desc* desc, const void* packed, int multires, int multires_views,
+                               const float* rays, int64_t n, int stride, const float* z, int S, float* raw, void* stash,
+                               size_t stash_bytes, void* ws, size_t ws_bytes, void* stream) {
+  PLNERF_CHECK_ARG(desc, "network_query_train: null desc");
+  return mlp_query_train(desc, packed, multires, multires_views, rays, n, stride, z, S, raw, 4, stash, stash_bytes, ws,
+                         ws_bytes, (cudaStream_t)stream);
+}
+
+size_t plnerf_packed_bwd_bytes(const plnerf_net_desc* desc) { return mlp_packed_bwd_bytes(desc); }
+
+int plnerf_pack_weights_bwd(const plnerf_net_desc* desc, const plnerf_net_params* params, void* packed_bwd, void* stream) {
+  return mlp_pack_bwd(desc, params, packed_bwd, (cudaStream_t)stream);
+}
+
+int plnerf_network_query_bwd(const plnerf_net_desc* desc, const void* packed, const void* packed_bwd, int64_t n, int S,
+                             const float* g_raw, int g_stride, void* stash, size_t stash_bytes,
+                             const plnerf_net_grads* grads, void* stream) {
+  return mlp_query_bwd(desc, packed, packed_bwd, n, S, g_raw, g_stride, stash, stash_bytes, grads, (cudaStream_t)stream);
 }
 
 int plnerf_mlp_forward(const plnerf_net_desc* desc, const void* packed, int precision, const float* x, int64_t m,
@@ -225,6 +248,10 @@ int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_
 
 int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
   return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
+}
+
+int plnerf_debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, void* stream) {
+  return plnerf::debug_umma_gemm_mn(X, Y, N, K, lbo, sbo, D, (cudaStream_t)stream);
 }
 
 // debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)

@@ -63,11 +63,29 @@ struct LayerPlan {
   int8_t flags;
   int8_t pad;
   int32_t bias_off;  // float offset into the tail/const block
+  // training: stash tensor this layer's epilogue writes (forward: its output activations as a
+  // weight-gradient operand; dgrad: its output gradient), relu mask it writes (forward) / applies (dgrad)
+  int16_t stash_idx, mask_idx;
   // packing sources (host/pack kernel only)
   const float* W;
   int32_t ldw;
   int32_t pe_col0;   // source column of the PE part (or -1)
   int32_t h_col0;    // source column of the hidden part (or -1)
+  int32_t transposed;  // dgrad: B'[k][n] = W[n][h_col0 + k]
+};
+
+// Per-tile layout of the training stash (all tensors as MN-major 8x8 core-matrix tiles
+// [m-half(2)][col8(width/8)][m8(8)][8 rows x 8 cols], i.e. exactly the wgrad MMA operand image).
+constexpr int MAX_STASH = 16;
+struct TrainLayout {
+  int32_t n_in, n_dy, n_mask;
+  int32_t in_width[MAX_STASH], in_off[MAX_STASH];     // forward activations (weight-gradient B operands)
+  int32_t dy_width[MAX_STASH], dy_off[MAX_STASH];     // output gradients (weight-gradient A operands)
+  int32_t mask_words[MAX_STASH], mask_off[MAX_STASH]; // relu masks: [word][row] uint32, word offsets
+  int32_t in_tile_bytes, dy_tile_bytes, mask_tile_words;
+  int32_t idx_pe, idx_h0, idx_feat, idx_hv, idx_dir;  // In tensors
+  int32_t dy_h0, dy_feat, dy_views;                    // dY tensors
+  int32_t mask_views;                                  // mask index of the views layer (trunk layer l -> l)
 };
 
 struct NetPlan {
@@ -79,6 +97,8 @@ struct NetPlan {
   int32_t const_floats;  // prefix of the tail staged in shared memory (everything but dirw)
   int32_t tail_floats;
   int64_t weight_bytes;  // bf16 stream
+  int32_t is_dgrad;      // plan describes the backward (input-gradient) chain
+  int32_t D;
 };
 
 // A (layer, half) streams its K-steps in stages of <= KS_PER_STAGE; the PE K-steps (shared-memory A
@@ -109,7 +129,7 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
   memset(&P, 0, sizeof(P));
   P.input_ch = d->input_ch; P.input_ch_views = d->use_viewdirs ? d->input_ch_views : 0;
   P.out_ch = d->use_viewdirs ? 4 : d->output_ch; P.use_viewdirs = d->use_viewdirs;
-  P.pe_ks = (d->input_ch + 15) / 16; P.precision = precision;
+  P.pe_ks = (d->input_ch + 15) / 16; P.precision = precision; P.D = d->D;
   auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
   int nl = 0, foff = 0;
   for (int i = 0; i < d->D; ++i) {
@@ -120,6 +140,7 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
     L.n_halves = 2;
     L.epi = EPI_RELU_A; L.flags = 0;
     L.bias_off = foff; foff += 256;
+    L.stash_idx = (int16_t)(1 + i); L.mask_idx = (int16_t)i;   // In tensors: 0 = PE, 1+l = h_l
     L.W = p ? p->pts_w[i] : nullptr;
     L.ldw = first ? d->input_ch : (skip_in ? 256 + d->input_ch : 256);
     L.pe_col0 = (first || skip_in) ? 0 : -1;
@@ -135,10 +156,12 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
     LayerPlan& F = P.L[nl++];
     F.n_pe_ks = 0; F.n_h_ks = 16; F.n_halves = 2; F.epi = EPI_LINEAR_A; F.flags = 0;
     F.bias_off = foff; foff += 256;
+    F.stash_idx = (int16_t)(1 + d->D); F.mask_idx = -1;
     F.W = p ? p->feature_w : nullptr; F.ldw = 256; F.pe_col0 = -1; F.h_col0 = 0;
     LayerPlan& V = P.L[nl++];
     V.n_pe_ks = 0; V.n_h_ks = 16; V.n_halves = 1; V.epi = EPI_VIEWS; V.flags = 0;
     V.bias_off = foff; P.views_b_off = foff; foff += 128;
+    V.stash_idx = (int16_t)(2 + d->D); V.mask_idx = (int16_t)d->D;
     V.W = p ? p->views_w : nullptr; V.ldw = 256 + d->input_ch_views; V.pe_col0 = -1; V.h_col0 = 0;
     P.alpha_w_off = foff; foff += 256;          // every block starts 16-byte aligned (float4 loads)
     P.alpha_b_off = foff; foff += 4;
@@ -159,6 +182,80 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
   int64_t wb = 0;
   const int nsplit = (precision == PLNERF_PREC_BF16X3) ? 2 : 1;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * (P.L[l].n_pe_ks + P.L[l].n_h_ks) * KS_BYTES * nsplit;
+  P.weight_bytes = wb;
+  return PLNERF_OK;
+}
+
+// Training stash layout for a (viewdirs) network.
+int build_train_layout(const plnerf_net_desc* d, TrainLayout* out) {
+  if (!d->use_viewdirs) { set_error("training (backward) is implemented for use_viewdirs networks only"); return PLNERF_E_UNSUPPORTED; }
+  if (d->D + 4 > MAX_STASH) { set_error("network too deep for the training stash"); return PLNERF_E_UNSUPPORTED; }
+  TrainLayout& T = *out;
+  memset(&T, 0, sizeof(T));
+  const int pe_w = ((d->input_ch + 15) / 16) * 16;
+  int n = 0, off = 0;
+  auto add_in = [&](int w) { T.in_width[n] = w; T.in_off[n] = off; off += w * 256; return n++; };
+  T.idx_pe = add_in(pe_w);
+  T.idx_h0 = n;
+  for (int l = 0; l < d->D; ++l) add_in(256);
+  T.idx_feat = add_in(256);
+  T.idx_hv = add_in(128);
+  T.idx_dir = add_in(32);
+  T.n_in = n; T.in_tile_bytes = off;
+  n = 0; off = 0;
+  auto add_dy = [&](int w) { T.dy_width[n] = w; T.dy_off[n] = off; off += w * 256; return n++; };
+  T.dy_h0 = 0;
+  for (int l = 0; l < d->D; ++l) add_dy(256);
+  T.dy_feat = add_dy(256);
+  T.dy_views = add_dy(128);
+  T.n_dy = n; T.dy_tile_bytes = off;
+  n = 0; off = 0;
+  for (int l = 0; l < d->D; ++l) { T.mask_words[n] = 8; T.mask_off[n] = off; off += 8 * 128; ++n; }
+  T.mask_views = n; T.mask_words[n] = 4; T.mask_off[n] = off; off += 4 * 128; ++n;
+  T.n_mask = n; T.mask_tile_words = off;
+  return PLNERF_OK;
+}
+
+// Input-gradient chain as a plan for the same fused kernel: activations = gradients (bf16, TMEM),
+// weights = W^T.  Layer order: views (128->256, d_feature), feature (256->256, +alpha rank-1, mask D-1),
+// trunk D-1 .. 1 (mask l-1).  Trunk layer 0 needs no input gradient.
+int build_dgrad_plan(const plnerf_net_desc* d, const plnerf_net_params* p, NetPlan* out) {
+  if (!d->use_viewdirs) { set_error("training (backward) is implemented for use_viewdirs networks only"); return PLNERF_E_UNSUPPORTED; }
+  NetPlan fwd;
+  int rc = build_plan(d, PLNERF_PREC_BF16, nullptr, &fwd);
+  if (rc) return rc;
+  NetPlan& P = *out;
+  memset(&P, 0, sizeof(P));
+  P.input_ch = d->input_ch; P.input_ch_views = d->input_ch_views; P.out_ch = 4; P.use_viewdirs = 1;
+  P.pe_ks = 0; P.precision = PLNERF_PREC_BF16; P.is_dgrad = 1; P.D = d->D;
+  auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
+  int nl = 0;
+  {  // views: d_feature = d_hv . W_views[:, :256]
+    LayerPlan& L = P.L[nl++];
+    L.n_pe_ks = 0; L.n_h_ks = 8; L.n_halves = 2; L.epi = EPI_LINEAR_A; L.flags = 0; L.bias_off = 0;
+    L.stash_idx = (int16_t)(d->D); L.mask_idx = -1;                 // dY tensors: l = dY_l, D = dY_feat, D+1 = dY_views
+    L.W = p ? p->views_w : nullptr; L.ldw = 256 + d->input_ch_views; L.pe_col0 = -1; L.h_col0 = 0; L.transposed = 1;
+  }
+  {  // feature: dh_{D-1} = d_feature . W_feat + g_alpha * w_alpha, masked by relu(D-1)
+    LayerPlan& L = P.L[nl++];
+    L.n_pe_ks = 0; L.n_h_ks = 16; L.n_halves = 2; L.epi = EPI_RELU_A; L.flags = FLAG_ALPHA; L.bias_off = 0;
+    L.stash_idx = (int16_t)(d->D - 1); L.mask_idx = (int16_t)(d->D - 1);
+    L.W = p ? p->feature_w : nullptr; L.ldw = 256; L.pe_col0 = -1; L.h_col0 = 0; L.transposed = 1;
+  }
+  for (int l = d->D - 1; l >= 1; --l) {  // trunk layer l: dh_{l-1} = dY_l . W_l[:, hidden part], masked by relu(l-1)
+    LayerPlan& L = P.L[nl++];
+    const bool skip_in = is_skip(l - 1);
+    L.n_pe_ks = 0; L.n_h_ks = 16; L.n_halves = 2; L.epi = EPI_RELU_A; L.flags = 0; L.bias_off = 0;
+    L.stash_idx = (int16_t)(l - 1); L.mask_idx = (int16_t)(l - 1);
+    L.W = p ? p->pts_w[l] : nullptr; L.ldw = skip_in ? 256 + d->input_ch : 256; L.pe_col0 = -1;
+    L.h_col0 = skip_in ? d->input_ch : 0; L.transposed = 1;
+  }
+  P.n_layers = nl;
+  // const block: rgb_w [3][128] and alpha_w [256] (same offsets as the forward plan so the tail is shared)
+  P.alpha_w_off = fwd.alpha_w_off; P.alpha_b_off = fwd.alpha_b_off; P.rgb_w_off = fwd.rgb_w_off; P.rgb_b_off = fwd.rgb_b_off;
+  P.const_floats = fwd.const_floats; P.tail_floats = fwd.tail_floats;
+  int64_t wb = 0;
+  for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * P.L[l].n_h_ks * KS_BYTES;
   P.weight_bytes = wb;
   return PLNERF_OK;
 }
@@ -212,7 +309,8 @@ __global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ Pa
     } else {
       col = L.h_col0 + (ks - L.n_pe_ks) * 16 + panel * 8 + e;
     }
-    v[e] = (col >= 0) ? L.W[(int64_t)n * L.ldw + col] : 0.0f;
+    if (L.transposed) v[e] = L.W[(int64_t)((ks - L.n_pe_ks) * 16 + panel * 8 + e) * L.ldw + L.h_col0 + n];   // B'[n][k] = W[k][col0+n]
+    else v[e] = (col >= 0) ? L.W[(int64_t)n * L.ldw + col] : 0.0f;
     if (rep == 1) v[e] = v[e] - ptx::bf16_round(v[e]);   // lo part
   }
   uint4 q;
@@ -263,7 +361,7 @@ __global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
 __global__ void __launch_bounds__(128) k_viewbias(const float* __restrict__ tail, int views_b_off, int dirw_off,
                                                   int icv, int multires_views, const float* __restrict__ rays,
                                                   int stride, const float* __restrict__ x_emb, int x_ld, int x_col0,
-                                                  int64_t n, float* __restrict__ vb) {
+                                                  int64_t n, float* __restrict__ vb, float* __restrict__ dirpe) {
   __shared__ float emb[64];
   const int64_t r = blockIdx.x;
   if (r >= n) return;
@@ -282,7 +380,9 @@ __global__ void __launch_bounds__(128) k_viewbias(const float* __restrict__ tail
       }
     }
     emb[t] = v;
+    if (dirpe) dirpe[r * 32 + t] = v;
   }
+  if (dirpe && t >= icv && t < 32) dirpe[r * 32 + t] = 0.f;
   __syncthreads();
   float acc = tail[views_b_off + t];
   const float* w = tail + dirw_off + t * icv;
@@ -306,6 +406,13 @@ struct MlpArgs {
   int64_t M;              // total rows
   int64_t n_tiles;
   float* out; int out_stride;
+  // training (MODE 2 = forward + stash, MODE 3 = input-gradient chain)
+  TrainLayout tl;
+  uint8_t* in_stash;       // [tiles][tl.in_tile_bytes]   forward activations
+  uint8_t* dy_stash;       // [tiles][tl.dy_tile_bytes]   output gradients
+  uint32_t* masks;         // [tiles][tl.mask_tile_words] relu masks
+  const float* dirpe;      // [rays][32] fp32 dir encoding (padded), MODE 2
+  const float* g_raw; int g_stride;   // MODE 3: upstream gradient of the network output [rows, >=4]
   int n_stages;
   long long* trace;  // debug timeline buffer (null in production)
   int debug_flags;   // bring-up experiments only (PLNERF_DEBUG_FLAGS): 1 = skip weight re-streaming after tile 0
@@ -375,9 +482,17 @@ __device__ __forceinline__ void issue_ts8(uint32_t d, uint32_t a, uint32_t a_lo,
 }
 
 // Positional encoding of one row -> this thread's panels of the PE tile(s).
-template <bool X3>
+// store 8 consecutive bf16 columns (16 bytes) of row `row` into an MN-major stash tile
+__device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, int col8, uint4 v) {
+  const int mh = row >> 6, m8 = (row & 63) >> 3, i = row & 7;
+  *reinterpret_cast<uint4*>(tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16) = v;
+}
+
+template <int MODE>
 __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, const SmemLayout& SL, int64_t tile, int row,
                                             int grp) {
+  constexpr bool X3 = (MODE == 1);
+  constexpr bool STASH = (MODE == 2);
   const NetPlan& P = A.plan;
   const int64_t g = tile * TILE_M + row;
   const int64_t gc = (g < A.M) ? g : (A.M - 1);
@@ -425,6 +540,8 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
       hi.x = ptx::pack_bf16(v[8 * pnl + 0], v[8 * pnl + 1]); hi.y = ptx::pack_bf16(v[8 * pnl + 2], v[8 * pnl + 3]);
       hi.z = ptx::pack_bf16(v[8 * pnl + 4], v[8 * pnl + 5]); hi.w = ptx::pack_bf16(v[8 * pnl + 6], v[8 * pnl + 7]);
       *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
+      if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
+                              A.tl.in_width[A.tl.idx_pe], row, pnl, hi);
       if (X3) {
         float lo[8];
 #pragma unroll
@@ -436,6 +553,51 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
       }
     }
   }
+  if (STASH) {
+    // the (padded, 32-wide) viewdir encoding of this row's ray as a weight-gradient operand tile:
+    // column group g writes columns [16g, 16g+16)
+    const float* dp = A.dirpe + (gc / A.vb_div) * 32 + 16 * grp;
+    uint8_t* tile_dir = A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_dir];
+#pragma unroll
+    for (int c8 = 0; c8 < 2; ++c8) {
+      uint4 q;
+      q.x = ptx::pack_bf16(dp[8 * c8 + 0], dp[8 * c8 + 1]); q.y = ptx::pack_bf16(dp[8 * c8 + 2], dp[8 * c8 + 3]);
+      q.z = ptx::pack_bf16(dp[8 * c8 + 4], dp[8 * c8 + 5]); q.w = ptx::pack_bf16(dp[8 * c8 + 6], dp[8 * c8 + 7]);
+      stash_store8(tile_dir, 32, row, 2 * grp + c8, q);
+    }
+  }
+}
+
+// Input of the gradient chain: d_hv = (g_rgb . W_rgb) * relu'(views) for this thread's 64 columns
+// -> bf16 A operand in TMEM (cols COL_A1 + n/2) and the dY_views stash tile.
+__device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* consts, uint32_t tmem_lane_a1, int64_t tile,
+                                               int row, int grp) {
+  const NetPlan& P = A.plan;
+  const int64_t g = tile * TILE_M + row;
+  float gr = 0.f, gg = 0.f, gb = 0.f;
+  if (g < A.M) { const float* q = A.g_raw + g * (int64_t)A.g_stride; gr = q[0]; gg = q[1]; gb = q[2]; }
+  const float* rw = consts + P.rgb_w_off;
+  const uint32_t* mk = A.masks + tile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[A.tl.mask_views];
+  uint8_t* tile_dy = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_views];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int n0 = 64 * grp + 32 * cc;
+    const uint32_t m = mk[(n0 >> 5) * 128 + row];
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float v0 = gr * rw[n0 + i] + gg * rw[128 + n0 + i] + gb * rw[256 + n0 + i];
+      float v1 = gr * rw[n0 + i + 1] + gg * rw[128 + n0 + i + 1] + gb * rw[256 + n0 + i + 1];
+      v0 = ((m >> i) & 1u) ? v0 : 0.f;
+      v1 = ((m >> (i + 1)) & 1u) ? v1 : 0.f;
+      pk[i >> 1] = ptx::pack_bf16(v0, v1);
+    }
+    ptx::tmem_st16(tmem_lane_a1 + (uint32_t)(n0 >> 1), pk);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      stash_store8(tile_dy, 128, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+  }
+  ptx::tmem_st_wait();
 }
 
 // debug timeline: (clock, code) pairs for block 0, third tile; region r holds up to 256 events
@@ -452,8 +614,12 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
 #define PLNERF_TRACE(region, cnt, code) do { (void)(cnt); (void)trace_on; } while (0)
 #endif
 
-template <bool X3>
+// MODE 0: bf16 forward, 1: bf16x3 forward, 2: bf16 forward + training stash, 3: input-gradient chain
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constant__ MlpArgs A) {
+  constexpr bool X3 = (MODE == 1);
+  constexpr bool STASH = (MODE == 2);
+  constexpr bool DGRAD = (MODE == 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   const NetPlan& P = A.plan;
   const SmemLayout SL = smem_layout(A.n_stages);
@@ -495,7 +661,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     int n_entries = 0;
     for (int l = 0; l < P.n_layers; ++l) {
       const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nh = P.L[l].n_halves;
-      const uint32_t a_col = (l > 0 ? (X3 ? 256u : ((((l - 1) & 1) ? 384u : 256u))) : 256u);
+      const uint32_t a_col = (l > 0 ? (X3 ? 256u : ((((l - 1) & 1) ? 384u : 256u))) : (DGRAD ? 384u : 256u));
       const int nst = stages_of(n_pe, n_h);
       int batch_first[2] = {-1, -1};
       uint32_t batch_len[2] = {0, 0}, batch_inc[2] = {0, 0};
@@ -673,8 +839,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     int l_pe_last = 0;
     for (int l = 0; l < P.n_layers; ++l) if (P.L[l].n_pe_ks > 0) l_pe_last = l;
 
-    if ((int64_t)blockIdx.x < A.n_tiles) {
-      pe_prologue<X3>(A, smem, SL, blockIdx.x, row, grp);
+    if (!DGRAD && (int64_t)blockIdx.x < A.n_tiles) {
+      pe_prologue<MODE>(A, smem, SL, blockIdx.x, row, grp);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pe_ready);
@@ -691,9 +857,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
       for (int c = 0; c < MAX_OUT_CH; ++c) head[c] = 0.f;
       const float* vbrow = A.viewbias ? (A.viewbias + (gc / A.vb_div) * 128) : nullptr;
+      float g_alpha = 0.f;
+      if (DGRAD) {
+        // the chain's input buffer (A1) is free again: the previous tile's last layer has been drained
+        g_alpha = valid ? A.g_raw[g * (int64_t)A.g_stride + 3] : 0.f;
+        dgrad_prologue(A, consts, tmem + lane_addr + COL_A1, tile, row, grp);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(pe_ready);
+      }
+      uint8_t* in_tile = (STASH) ? A.in_stash + tile * (int64_t)A.tl.in_tile_bytes : nullptr;
+      uint8_t* dy_tile = (DGRAD) ? A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes : nullptr;
+      uint32_t* mask_tile = (STASH || DGRAD) ? A.masks + tile * (int64_t)A.tl.mask_tile_words : nullptr;
 
       for (int l = 0; l < P.n_layers; ++l) {
         const int epi = P.L[l].epi, flags = P.L[l].flags, n_halves = P.L[l].n_halves, bias_off = P.L[l].bias_off;
+        const int stash_idx = P.L[l].stash_idx, mask_idx = P.L[l].mask_idx;
         const uint32_t a_out = tmem + lane_addr + a_out_col(l);
         const uint32_t a_out_lo = tmem + lane_addr + COL_A1;
         for (int h = 0; h < n_halves; ++h) {
@@ -722,12 +901,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             const int c = 2 * grp + cc;
             const int n0 = h * 128 + c * 32;
             float* val = reinterpret_cast<float*>(r2[cc]);
-            if (epi == EPI_VIEWS) {
+            if (DGRAD) {
+              // gradient chain: (+ g_alpha * w_alpha) then relu'(.) of the forward activation, no bias
+              if (flags & FLAG_ALPHA) {
+                const float* aw = consts + P.alpha_w_off + n0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) val[i] = fmaf(g_alpha, aw[i], val[i]);
+              }
+              if (mask_idx >= 0) {
+                const uint32_t m = mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) val[i] = ((m >> i) & 1u) ? val[i] : 0.f;
+              }
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+              ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+              uint8_t* t = dy_tile + A.tl.dy_off[stash_idx];
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+            } else if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(vbrow + n0 + i);
                 val[i] = fmaxf(val[i] + b4.x, 0.f); val[i + 1] = fmaxf(val[i + 1] + b4.y, 0.f);
                 val[i + 2] = fmaxf(val[i + 2] + b4.z, 0.f); val[i + 3] = fmaxf(val[i + 3] + b4.w, 0.f);
+              }
+              if (STASH) {
+                uint32_t m = 0, pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+                mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = m;
+                uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  stash_store8(t, 128, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
               }
               const float* rw = consts + P.rgb_w_off + n0;
 #pragma unroll
@@ -751,7 +962,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 add2(val[i + 2], val[i + 3], b4.z, b4.w);
               }
               uint32_t pk[16];
-              if (!X3 && epi == EPI_RELU_A && flags == 0) {
+              if (!X3 && !STASH && epi == EPI_RELU_A && flags == 0) {
                 // hot path: ReLU fused into the bf16x2 conversion
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(val[2 * i], val[2 * i + 1]);
@@ -784,6 +995,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
                   for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
                   ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+                  if (STASH) {
+                    if (mask_idx >= 0) {
+                      uint32_t m = 0;
+#pragma unroll
+                      for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+                      mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = m;
+                    }
+                    uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                      stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+                  }
                   if (X3) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -801,18 +1024,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
           PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
         }
-        if (l == l_pe_last) {
+        if (!DGRAD && l == l_pe_last) {
           // every MMA that reads the PE tile of this tile has completed (its d_full was waited):
           // encode the NEXT tile's rows now, overlapped with the remaining layers
           const int64_t nt = tile + gridDim.x;
           if (nt < A.n_tiles) {
-            pe_prologue<X3>(A, smem, SL, nt, row, grp);
+            pe_prologue<MODE>(A, smem, SL, nt, row, grp);
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(pe_ready);
           }
         }
       }
+      if (DGRAD) continue;   // the gradient chain's outputs are the dY stash tiles
       // ---- combine the two column groups' partial head sums and write the row
       if (grp == 1) {
         float* x = xch + row * (MAX_OUT_CH + 1);
@@ -921,6 +1145,61 @@ __global__ void __launch_bounds__(128, 1) k_debug_gemm(const float* __restrict__
 }
 
 // =============================================================================================
+// debug: MN-major operands (what the weight-gradient GEMM uses).  D[128, N] = sum_k X[k, m] Y[k, n],
+// X [K,128] and Y [K,N] row-major fp32 (so the contraction index k is the strided one).  Operands are
+// staged as no-swizzle MN-major core matrices: block (mn8, k8) = 8 k-rows x 8 mn-values (mn fastest,
+// 128 contiguous bytes) at ((mn8 * K/8) + k8) * 128; descriptor SBO = (K/8)*128 (MN direction),
+// LBO = 128 (K direction).
+// =============================================================================================
+__global__ void __launch_bounds__(128, 1) k_debug_gemm_mn(const float* __restrict__ Xg, const float* __restrict__ Yg, int N, int K,
+                                                          uint32_t lbo, uint32_t sbo, float* __restrict__ Dg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int k8n = K / 8;
+  uint8_t* sA = smem;                                  // 16 mn8 blocks x k8n x 128 B
+  uint8_t* sB = smem + (size_t)16 * k8n * 128;         // N/8 blocks x k8n x 128 B
+  uint8_t* sBar = sB + (size_t)(N / 8) * k8n * 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 16);
+  const uint32_t bar = ptx::smem_u32(sBar);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  for (int idx = threadIdx.x; idx < K * 128; idx += 128) {
+    const int k = idx / 128, m = idx % 128;
+    reinterpret_cast<__nv_bfloat16*>(sA + ((size_t)(m / 8) * k8n + k / 8) * 128)[(k % 8) * 8 + (m % 8)] = __float2bfloat16_rn(Xg[idx]);
+  }
+  for (int idx = threadIdx.x; idx < K * N; idx += 128) {
+    const int k = idx / N, n = idx % N;
+    reinterpret_cast<__nv_bfloat16*>(sB + ((size_t)(n / 8) * k8n + k / 8) * 128)[(k % 8) * 8 + (n % 8)] = __float2bfloat16_rn(Yg[idx]);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = ptx::idesc_bf16_f32_mn(128, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t ad = ptx::smem_desc(ptx::smem_u32(sA) + ks * 256, lbo, sbo);
+      const uint64_t bd = ptx::smem_desc(ptx::smem_u32(sB) + ks * 256, lbo, sbo);
+      ptx::mma_ss(tmem, ad, bd, idesc, ks > 0);
+    }
+    ptx::mma_commit(bar);
+  }
+  ptx::mbar_wait(bar, 0);
+  ptx::tc_fence_after();
+  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    ptx::tmem_ld32(tmem + lane_addr + 32u * c, r);
+    ptx::tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) Dg[(size_t)threadIdx.x * N + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // debug: raw tcgen05.mma issue/execute rate.  mode 0: TS N=128, 1: TS N=256, 2: SS N=128, 3: SS N=256.
 // One CTA per SM issues `iters` x 16 back-to-back MMAs on garbage operands; reports cycles per MMA.
 // =============================================================================================
@@ -996,6 +1275,175 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// weight gradients:  dW[n, k] += sum_m dY[m, n] * In[m, k]   (contraction over the sample rows m)
+// Both operands are the MN-major stash tiles written by the forward (In) and by the gradient chain
+// (dY), loaded with plain bulk TMA; accumulators stay in tensor memory across all tiles of a CTA and
+// are flushed once with fp32 atomics.  The bias gradient is the same GEMM against a ones operand.
+// A work item = (dY tensor, 128-row half, In tensor); grid = items x splits (tiles strided by split).
+// =============================================================================================
+constexpr int MAX_WG_ITEMS = 40;
+struct WgradItem {
+  int32_t dy_idx, dy_half, in_idx;
+  int32_t ldw, col0, ncols;
+  float* dW;   // dW[(128*dy_half + r) * ldw + col0 + c]
+  float* db;   // db[128*dy_half + r] or null
+};
+struct WgradArgs {
+  WgradItem items[MAX_WG_ITEMS];
+  int32_t n_items, splits;
+  TrainLayout tl;
+  const uint8_t* in_stash;
+  const uint8_t* dy_stash;
+  int64_t n_tiles;
+};
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGE_BYTES = 32768 + 65536;
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__ WgradArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const WgradItem& it = A.items[blockIdx.x / A.splits];
+  const int split = blockIdx.x % A.splits;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wd = A.tl.in_width[it.in_idx];
+  const int Wdy = A.tl.dy_width[it.dy_idx];
+  uint8_t* s_ones = smem + 2 * WG_STAGE_BYTES;
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const uint32_t s_bars = sbase + 2 * WG_STAGE_BYTES + 1024;
+  auto full = [&](int s) { return s_bars + 8u * s; };
+  auto empty = [&](int s) { return s_bars + 16u + 8u * s; };
+  const uint32_t done = s_bars + 32u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * WG_STAGE_BYTES + 1024 + 48);
+  if (threadIdx.x == 0) {
+    for (int s2 = 0; s2 < 2; ++s2) { ptx::mbar_init(full(s2), 1); ptx::mbar_init(empty(s2), 1); }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  for (int i = threadIdx.x; i < 256; i += WG_THREADS) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  int64_t my_tiles = 0;
+  for (int64_t t = split; t < A.n_tiles; t += A.splits) ++my_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int64_t t = split; t < A.n_tiles; t += A.splits) {
+        ptx::mbar_wait(empty(st), ph ^ 1);
+        const uint32_t in_bytes = (uint32_t)Wd * 256u;
+        ptx::mbar_arrive_expect_tx(full(st), 32768u + in_bytes);
+        const uint8_t* dy = A.dy_stash + t * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[it.dy_idx];
+        const uint32_t sdst = sbase + st * WG_STAGE_BYTES;
+        for (int mh = 0; mh < 2; ++mh)
+          ptx::bulk_g2s(sdst + mh * 16384, dy + ((size_t)(mh * (Wdy >> 3) + 16 * it.dy_half)) * 1024, 16384u, full(st));
+        ptx::bulk_g2s(sdst + 32768, A.in_stash + t * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[it.in_idx], in_bytes, full(st));
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::idesc_bf16_f32_mn(128, Wd);
+    const uint32_t idesc_b = ptx::idesc_bf16_f32_mn(128, 16);
+    const uint64_t ones_desc = ptx::smem_desc(ptx::smem_u32(s_ones), 128, 256);
+    uint32_t st = 0, ph = 0, acc = 0;
+    for (int64_t t = split; t < A.n_tiles; t += A.splits) {
+      ptx::mbar_wait(full(st), ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t sa = sbase + st * WG_STAGE_BYTES, sb = sa + 32768;
+        uint32_t a2 = acc;
+        for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t ad = ptx::smem_desc(sa + mh * 16384 + j * 256, 128, 1024);
+            const uint64_t bd = ptx::smem_desc(sb + mh * (Wd >> 3) * 1024 + j * 256, 128, 1024);
+            ptx::mma_ss(tmem, ad, bd, idesc, a2);
+            if (it.db) ptx::mma_ss(tmem + 256u, ad, ones_desc, idesc_b, a2);
+            a2 = 1;
+          }
+        }
+        ptx::mma_commit(empty(st));
+      }
+      __syncwarp();
+      acc = 1;
+      if (++st == 2) { st = 0; ph ^= 1; }
+    }
+    if (ptx::elect_one()) ptx::mma_commit(done);
+    __syncwarp();
+  } else {
+    // flush warps 2..5: TMEM lane quarter = warp % 4
+    if (my_tiles > 0) {
+      ptx::mbar_wait(done, 0);
+      ptx::tc_fence_after();
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+      float* drow = it.dW + (int64_t)(128 * it.dy_half + r) * it.ldw + it.col0;
+      for (int c0 = 0; c0 < Wd; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < it.ncols) atomicAdd(drow + c0 + i, __uint_as_float(v[i]));
+      }
+      if (it.db) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + lane_addr + 256u, v);
+        ptx::tmem_ld_wait();
+        atomicAdd(it.db + 128 * it.dy_half + r, __uint_as_float(v[0]));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+}
+
+// Head gradients on CUDA cores: d alpha_linear = sum_m g_alpha[m] h_{D-1}[m,:], d rgb_linear = sum_m g_rgb[m,:] (x) hv[m,:]
+struct HeadGradArgs {
+  TrainLayout tl; const uint8_t* in_stash; const float* g_raw; int g_stride; int64_t M, n_tiles;
+  int idx_hlast;
+  float *d_alpha_w, *d_alpha_b, *d_rgb_w, *d_rgb_b;
+};
+__global__ void __launch_bounds__(256) k_head_grads(const __grid_constant__ HeadGradArgs A) {
+  __shared__ float sg[128][4];
+  const int tid = threadIdx.x;
+  float acc_a = 0.f, acc_r0 = 0.f, acc_r1 = 0.f, acc_b = 0.f;   // alpha_w[tid]; rgb_w flat idx tid, tid+256; biases (tid<4)
+  auto elem = [&](const uint8_t* tile, int width, int m, int k) -> float {
+    const int mh = m >> 6, m8 = (m & 63) >> 3, i = m & 7;
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(tile + ((size_t)((mh * (width >> 3) + (k >> 3)) * 8 + m8)) * 128 + i * 16);
+    return __bfloat162float(p[k & 7]);
+  };
+  for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < 512; i += 256) {
+      const int m = i >> 2, c = i & 3;
+      const int64_t g = t * 128 + m;
+      sg[m][c] = (g < A.M) ? A.g_raw[g * (int64_t)A.g_stride + c] : 0.f;
+    }
+    __syncthreads();
+    const uint8_t* tile = A.in_stash + t * (int64_t)A.tl.in_tile_bytes;
+    const uint8_t* th = tile + A.tl.in_off[A.idx_hlast];
+    const uint8_t* tv = tile + A.tl.in_off[A.tl.idx_hv];
+    for (int m = 0; m < 128; ++m) acc_a = fmaf(sg[m][3], elem(th, 256, m, tid), acc_a);
+    {
+      const int c = tid >> 7, k = tid & 127;            // flat idx tid -> (c = 0/1, k)
+      for (int m = 0; m < 128; ++m) acc_r0 = fmaf(sg[m][c], elem(tv, 128, m, k), acc_r0);
+      if (tid < 128) for (int m = 0; m < 128; ++m) acc_r1 = fmaf(sg[m][2], elem(tv, 128, m, tid), acc_r1);
+    }
+    if (tid < 4) for (int m = 0; m < 128; ++m) acc_b += sg[m][tid];
+  }
+  atomicAdd(A.d_alpha_w + tid, acc_a);
+  atomicAdd(A.d_rgb_w + tid, acc_r0);
+  if (tid < 128) atomicAdd(A.d_rgb_w + 256 + tid, acc_r1);
+  if (tid < 3) atomicAdd(A.d_rgb_b + tid, acc_b);
+  if (tid == 3) atomicAdd(A.d_alpha_b, acc_b);
+}
+
 int g_num_sms = 0;
 int g_max_smem = 0;
 int query_device() {
@@ -1023,7 +1471,7 @@ cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-int launch_mlp(MlpArgs& a, cudaStream_t st) {
+int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   int rc = query_device();
   if (rc) return rc;
   int n_stages = MAX_STAGES;
@@ -1032,8 +1480,10 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   const SmemLayout SL = smem_layout(n_stages);
   static bool attr_set = false;
   if (!attr_set) {
-    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     attr_set = true;
   }
   static int dbg = -1;
@@ -1044,8 +1494,11 @@ int launch_mlp(MlpArgs& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
-  if (a.plan.precision == PLNERF_PREC_BF16X3) k_mlp_fwd<true><<<grid, NUM_THREADS, SL.total, st>>>(a);
-  else k_mlp_fwd<false><<<grid, NUM_THREADS, SL.total, st>>>(a);
+  if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
+  if (mode == 1) k_mlp_fwd<1><<<grid, NUM_THREADS, SL.total, st>>>(a);
+  else if (mode == 2) k_mlp_fwd<2><<<grid, NUM_THREADS, SL.total, st>>>(a);
+  else if (mode == 3) k_mlp_fwd<3><<<grid, NUM_THREADS, SL.total, st>>>(a);
+  else k_mlp_fwd<0><<<grid, NUM_THREADS, SL.total, st>>>(a);
   if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
   PLNERF_LAUNCH_CHECK("k_mlp_fwd");
   return PLNERF_OK;
@@ -1087,7 +1540,7 @@ size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays) {
 
 static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int precision, MlpArgs& a, int64_t vb_rows,
                           int multires_views, const float* rays, int stride, const float* x_emb, int x_ld, void* ws,
-                          size_t ws_bytes, cudaStream_t st) {
+                          size_t ws_bytes, cudaStream_t st, int mode = -1, float* dirpe_out = nullptr) {
   int rc = build_plan(d, precision, nullptr, &a.plan);
   if (rc) return rc;
   PLNERF_CHECK_ARG(packed && ((uintptr_t)packed & 15) == 0, "packed weights null or misaligned");
@@ -1099,11 +1552,11 @@ static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int prec
     if (!ws || ws_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes); return PLNERF_E_WORKSPACE; }
     float* vb = static_cast<float*>(ws);
     k_viewbias<<<(unsigned)vb_rows, 128, 0, st>>>(a.tail, a.plan.views_b_off, a.plan.dirw_off, d->input_ch_views, multires_views,
-                                                  rays, stride, x_emb, x_ld, d->input_ch, vb_rows, vb);
+                                                  rays, stride, x_emb, x_ld, d->input_ch, vb_rows, vb, dirpe_out);
     PLNERF_LAUNCH_CHECK("k_viewbias");
     a.viewbias = vb;
   }
-  return launch_mlp(a, st);
+  return launch_mlp(a, st, mode);
 }
 
 int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
@@ -1174,6 +1627,157 @@ int profile_read(double* ms_sum, int64_t* launches, int64_t* rows) {
   if (ms_sum) *ms_sum = ms;
   if (launches) *launches = (int64_t)g_prof.size();
   if (rows) *rows = nr;
+  return PLNERF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training entry points
+// ---------------------------------------------------------------------------------------------
+struct StashPtrs { uint8_t* in; uint8_t* dy; uint32_t* masks; float* dirpe; size_t total; };
+static StashPtrs carve_stash(const TrainLayout& tl, int64_t rows, int64_t n_rays, uint8_t* base) {
+  const int64_t tiles = ceil_div(rows, TILE_M);
+  auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  StashPtrs s;
+  size_t off = 0;
+  s.in = base + off; off += up((size_t)tiles * tl.in_tile_bytes);
+  s.dy = base + off; off += up((size_t)tiles * tl.dy_tile_bytes);
+  s.masks = reinterpret_cast<uint32_t*>(base + off); off += up((size_t)tiles * tl.mask_tile_words * 4);
+  s.dirpe = reinterpret_cast<float*>(base + off); off += up((size_t)n_rays * 32 * 4);
+  s.total = off;
+  return s;
+}
+
+size_t mlp_train_stash_bytes(const plnerf_net_desc* d, int64_t n_rays, int S) {
+  TrainLayout tl;
+  if (!d || build_train_layout(d, &tl)) return 0;
+  return carve_stash(tl, n_rays * S, n_rays, nullptr).total;
+}
+
+int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, int multires_views, const float* rays,
+                    int64_t n, int stride, const float* z, int S, float* raw, int raw_stride, void* stash,
+                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PLNERF_CHECK_ARG(d && rays && z && raw && stash, "network_query_train: null argument");
+  PLNERF_CHECK_ARG(n >= 0 && S > 0 && stride >= 11, "network_query_train: bad sizes (rays need a viewdir)");
+  if (n == 0) return PLNERF_OK;
+  PLNERF_CHECK_ARG(((uintptr_t)stash & 1023) == 0, "network_query_train: stash must be 1024-byte aligned");
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = build_train_layout(d, &a.tl);
+  if (rc) return rc;
+  const StashPtrs sp = carve_stash(a.tl, n * S, n, static_cast<uint8_t*>(stash));
+  if (stash_bytes < sp.total) { set_error("training stash too small: need %zu bytes, got %zu", sp.total, stash_bytes); return PLNERF_E_WORKSPACE; }
+  const int want_ic = multires < 0 ? 3 : 3 + 6 * multires;
+  const int want_icv = multires_views < 0 ? 3 : 3 + 6 * multires_views;
+  PLNERF_CHECK_ARG(want_ic == d->input_ch && want_icv == d->input_ch_views && multires <= 10,
+                   "network_query_train: multires/multires_views do not match the network");
+  a.rays = rays; a.stride = stride; a.z = z; a.S = S; a.multires = multires;
+  a.vb_div = S; a.M = n * S; a.out = raw; a.out_stride = raw_stride;
+  a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = sp.dirpe;
+  return run_mlp_common(d, packed, PLNERF_PREC_BF16, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st, 2, sp.dirpe);
+}
+
+size_t mlp_packed_bwd_bytes(const plnerf_net_desc* d) {
+  NetPlan P;
+  if (!d || build_dgrad_plan(d, nullptr, &P)) return 0;
+  return (size_t)P.weight_bytes;
+}
+
+int mlp_pack_bwd(const plnerf_net_desc* d, const plnerf_net_params* p, void* packed, cudaStream_t st) {
+  PLNERF_CHECK_ARG(d && p && packed, "pack_weights_bwd: null argument");
+  PLNERF_CHECK_ARG(((uintptr_t)packed & 15) == 0, "pack_weights_bwd: buffer must be 16-byte aligned");
+  PackArgs a;
+  int rc = build_dgrad_plan(d, p, &a.plan);
+  if (rc) return rc;
+  a.dst = static_cast<uint8_t*>(packed);
+  a.tail = nullptr;
+  a.prm = *p;
+  k_pack_weights<<<(unsigned)(a.plan.weight_bytes / KS_BYTES), 256, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_pack_weights(bwd)");
+  return PLNERF_OK;
+}
+
+int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* packed_bwd, int64_t n, int S,
+                  const float* g_raw, int g_stride, void* stash, size_t stash_bytes, const plnerf_net_grads* g,
+                  cudaStream_t st) {
+  PLNERF_CHECK_ARG(d && packed_fwd && packed_bwd && g_raw && stash && g, "network_query_bwd: null argument");
+  PLNERF_CHECK_ARG(n >= 0 && S > 0 && g_stride >= 4, "network_query_bwd: bad sizes");
+  if (n == 0) return PLNERF_OK;
+  int rc = query_device();
+  if (rc) return rc;
+  NetPlan fwd;
+  rc = build_plan(d, PLNERF_PREC_BF16, nullptr, &fwd);
+  if (rc) return rc;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  rc = build_train_layout(d, &a.tl);
+  if (rc) return rc;
+  rc = build_dgrad_plan(d, nullptr, &a.plan);
+  if (rc) return rc;
+  const StashPtrs sp = carve_stash(a.tl, n * S, n, static_cast<uint8_t*>(stash));
+  if (stash_bytes < sp.total) { set_error("training stash too small: need %zu bytes, got %zu", sp.total, stash_bytes); return PLNERF_E_WORKSPACE; }
+  for (int i = 0; i < d->D; ++i) PLNERF_CHECK_ARG(g->pts_w[i] && g->pts_b[i], "network_query_bwd: missing gradient buffer for pts_linears.%d", i);
+  PLNERF_CHECK_ARG(g->views_w && g->views_b && g->feature_w && g->feature_b && g->alpha_w && g->alpha_b && g->rgb_w && g->rgb_b,
+                   "network_query_bwd: missing head gradient buffers");
+  // (1) input-gradient chain -> dY stash
+  a.w = static_cast<const uint8_t*>(packed_bwd);
+  a.tail = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed_fwd) + fwd.weight_bytes);
+  a.S = S; a.vb_div = S; a.M = n * S;
+  a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = sp.dirpe;
+  a.g_raw = g_raw; a.g_stride = g_stride;
+  rc = launch_mlp(a, st, 3);
+  if (rc) return rc;
+  // (2) weight gradients
+  WgradArgs w;
+  memset(&w, 0, sizeof(w));
+  w.tl = a.tl; w.in_stash = sp.in; w.dy_stash = sp.dy; w.n_tiles = ceil_div(n * S, TILE_M);
+  int ni = 0;
+  auto add = [&](int dy_idx, int halves, int in_idx, float* dW, int ldw, int col0, int ncols, float* db) {
+    for (int h = 0; h < halves; ++h) {
+      WgradItem& it = w.items[ni++];
+      it.dy_idx = dy_idx; it.dy_half = h; it.in_idx = in_idx; it.dW = dW; it.ldw = ldw; it.col0 = col0; it.ncols = ncols; it.db = db;
+    }
+  };
+  auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
+  const TrainLayout& T = a.tl;
+  for (int i = 0; i < d->D; ++i) {
+    const bool first = (i == 0), skip_in = (i > 0) && is_skip(i - 1);
+    if (first) add(T.dy_h0 + i, 2, T.idx_pe, g->pts_w[i], d->input_ch, 0, d->input_ch, g->pts_b[i]);
+    else if (skip_in) {
+      add(T.dy_h0 + i, 2, T.idx_pe, g->pts_w[i], 256 + d->input_ch, 0, d->input_ch, nullptr);
+      add(T.dy_h0 + i, 2, T.idx_h0 + i - 1, g->pts_w[i], 256 + d->input_ch, d->input_ch, 256, g->pts_b[i]);
+    } else add(T.dy_h0 + i, 2, T.idx_h0 + i - 1, g->pts_w[i], 256, 0, 256, g->pts_b[i]);
+  }
+  add(T.dy_feat, 2, T.idx_h0 + d->D - 1, g->feature_w, 256, 0, 256, g->feature_b);
+  add(T.dy_views, 1, T.idx_feat, g->views_w, 256 + d->input_ch_views, 0, 256, g->views_b);
+  add(T.dy_views, 1, T.idx_dir, g->views_w, 256 + d->input_ch_views, 256, d->input_ch_views, nullptr);
+  w.n_items = ni;
+  w.splits = g_num_sms / ni > 0 ? g_num_sms / ni : 1;
+  if ((int64_t)w.splits > w.n_tiles) w.splits = (int)w.n_tiles;
+  static bool wattr = false;
+  const size_t wsmem = 2 * WG_STAGE_BYTES + 1024 + 64;
+  if (!wattr) { PLNERF_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); wattr = true; }
+  k_wgrad<<<(unsigned)(ni * w.splits), WG_THREADS, wsmem, st>>>(w);
+  PLNERF_LAUNCH_CHECK("k_wgrad");
+  // (3) alpha / rgb heads
+  HeadGradArgs hg;
+  hg.tl = a.tl; hg.in_stash = sp.in; hg.g_raw = g_raw; hg.g_stride = g_stride; hg.M = n * S; hg.n_tiles = w.n_tiles;
+  hg.idx_hlast = T.idx_h0 + d->D - 1;
+  hg.d_alpha_w = g->alpha_w; hg.d_alpha_b = g->alpha_b; hg.d_rgb_w = g->rgb_w; hg.d_rgb_b = g->rgb_b;
+  const unsigned hgrid = (unsigned)(hg.n_tiles < 2 * g_num_sms ? hg.n_tiles : 2 * g_num_sms);
+  k_head_grads<<<hgrid, 256, 0, st>>>(hg);
+  PLNERF_LAUNCH_CHECK("k_head_grads");
+  return PLNERF_OK;
+}
+
+int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st) {
+  PLNERF_CHECK_ARG(X && Y && D, "debug_umma_gemm_mn: null argument");
+  PLNERF_CHECK_ARG(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 128, "debug_umma_gemm_mn: bad N/K");
+  int rc = query_device();
+  if (rc) return rc;
+  const size_t smem = (size_t)(16 + N / 8) * (K / 8) * 128 + 64;
+  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+  k_debug_gemm_mn<<<1, 128, smem, st>>>(X, Y, N, K, lbo, sbo, D);
+  PLNERF_LAUNCH_CHECK("k_debug_gemm_mn");
   return PLNERF_OK;
 }
 

@@ -39,6 +39,15 @@ int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int m
 // NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
                          float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t mlp_train_stash_bytes(const plnerf_net_desc* d, int64_t n_rays, int S);
+int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, int multires_views, const float* rays,
+                    int64_t n, int stride, const float* z, int S, float* raw, int raw_stride, void* stash,
+                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t mlp_packed_bwd_bytes(const plnerf_net_desc* d);
+int mlp_pack_bwd(const plnerf_net_desc* d, const plnerf_net_params* p, void* packed, cudaStream_t st);
+int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* packed_bwd, int64_t n, int S,
+                  const float* g_raw, int g_stride, void* stash, size_t stash_bytes, const plnerf_net_grads* g,
+                  cudaStream_t st);
 int profile_enable(int on);
 int profile_read(double* ms_sum, int64_t* launches, int64_t* rows);
 int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);

@@ -92,6 +92,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same, with both operands MN-major (the contraction index is the strided one): a_major[15]=1, b_major[16]=1
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int M, int N) {
+  return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
+}
+
 // ---- MMA (issued by ONE thread) ------------------------------------------------------------------
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

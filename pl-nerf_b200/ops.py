@@ -249,6 +249,91 @@ class PackedNet:
         return self.buf[prec]
 
 
+def _fill_params(struct, desc, tensors, keep):
+    """Fill a NetParams / NetGrads ctypes struct from a {state_dict name: tensor} mapping."""
+    def ptr(name):
+        t = tensors[name]
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"{name}: expected a contiguous float32 tensor")
+        keep.append(t)
+        return t.data_ptr()
+    for i in range(desc.D):
+        struct.pts_w[i] = ptr(f"pts_linears.{i}.weight")
+        struct.pts_b[i] = ptr(f"pts_linears.{i}.bias")
+    if desc.use_viewdirs:
+        for f, nme in (("views_w", "views_linears.0.weight"), ("views_b", "views_linears.0.bias"),
+                       ("feature_w", "feature_linear.weight"), ("feature_b", "feature_linear.bias"),
+                       ("alpha_w", "alpha_linear.weight"), ("alpha_b", "alpha_linear.bias"),
+                       ("rgb_w", "rgb_linear.weight"), ("rgb_b", "rgb_linear.bias")):
+            setattr(struct, f, ptr(nme))
+    else:
+        struct.output_w = ptr("output_linear.weight")
+        struct.output_b = ptr("output_linear.bias")
+
+
+def packed_bwd_of(net):
+    """Transposed (input-gradient) weight stream of a network, cached like PackedNet."""
+    pk = packed_of(net)
+    ver = pk._versions(net)
+    cache = net.__dict__.setdefault("_plnerf_packed_bwd", {})
+    if cache.get("ver") == ver:
+        return cache["buf"]
+    nbytes = L.lib().plnerf_packed_bwd_bytes(C.byref(pk.desc))
+    if nbytes == 0:
+        L.check(-2)
+    first = next(net.parameters())
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
+    prm = L.NetParams()
+    keep = []
+    _fill_params(prm, pk.desc, {k: v.detach().float().contiguous() for k, v in net.named_parameters()}, keep)
+    L.check(L.lib().plnerf_pack_weights_bwd(C.byref(pk.desc), C.byref(prm), _p(buf), _stream()))
+    cache["ver"], cache["buf"] = ver, buf
+    return buf
+
+
+def network_query_train(net, rays, z_vals):
+    """run_network forward that also stashes what the backward needs.  -> (raw [n,S,4], stash)."""
+    rays, z_vals = _f32(rays, "rays"), _f32(z_vals, "z_vals")
+    pk = packed_of(net)
+    buf = pk.get(net, "bf16")
+    n, S = z_vals.shape
+    raw = torch.empty((n, S, 4), device=rays.device)
+    sb = L.lib().plnerf_train_stash_bytes(C.byref(pk.desc), n, S)
+    if sb == 0:
+        L.check(-2)
+    if sb > 64 * 2 ** 30:
+        raise RuntimeError(f"plnerf_b200: training stash for {n} rays x {S} samples would need {sb / 2**30:.1f} GiB; "
+                           "use a smaller ray batch / chunk for calls that require gradients")
+    stash = torch.empty(sb + 1024, dtype=torch.uint8, device=rays.device)
+    off = (-stash.data_ptr()) % 1024
+    wsb = L.lib().plnerf_query_workspace_bytes(C.byref(pk.desc), n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=rays.device)
+    mr = _multires_of(pk.desc.input_ch)
+    mrv = _multires_of(pk.desc.input_ch_views)
+    L.check(L.lib().plnerf_network_query_train(C.byref(pk.desc), _p(buf), mr, mrv, _p(rays), n, rays.shape[1],
+                                                _p(z_vals), S, _p(raw), C.c_void_p(stash.data_ptr() + off), sb,
+                                                _p(ws), wsb, _stream()))
+    return raw, (stash, off, sb)
+
+
+def network_query_bwd(net, g_raw, stash, n, S, grads=None):
+    """Parameter gradients of one network query.  g_raw [n,S,>=4].  Returns {state_dict name: grad} (fp32);
+    `grads` may supply zero-initialised / accumulating buffers."""
+    stash_t, off, sb = stash
+    g_raw = _f32(g_raw, "g_raw")
+    pk = packed_of(net)
+    buf = pk.get(net, "bf16")
+    bwd = packed_bwd_of(net)
+    if grads is None:
+        grads = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net.named_parameters()}
+    gs = L.NetGrads()
+    keep = []
+    _fill_params(gs, pk.desc, grads, keep)
+    L.check(L.lib().plnerf_network_query_bwd(C.byref(pk.desc), _p(buf), _p(bwd), n, S, _p(g_raw), g_raw.shape[-1],
+                                              C.c_void_p(stash_t.data_ptr() + off), sb, C.byref(gs), _stream()))
+    return grads
+
+
 def packed_of(net):
     """Per-module PackedNet cache stored on the module itself."""
     pk = net.__dict__.get("_plnerf_packed")

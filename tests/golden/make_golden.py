@@ -195,6 +195,24 @@ def run_case(H, R, name, cfg):
     loss.backward()
     out.update(up)
     out["g_raw0"] = raw_req.grad.numpy()
+    # ---- training-loss gradient golden (viewdirs + fine cases): the reference's own loss
+    # img2mse(rgb, target) + img2mse(rgb0, target) (run_plnerf.py:1290-1297) back-propagated through the
+    # unmodified reference; stored per parameter as L2 norm + first 256 entries (full tensors are 4.8 MB)
+    if cfg["use_viewdirs"] and Ni > 0:
+        tgt = torch.from_numpy(np.random.RandomState(99).rand(n, 3).astype(np.float32))
+        for p_ in list(net_c.parameters()) + list(net_f.parameters()):
+            p_.grad = None
+        rgb_t, disp_t, acc_t, ex_t = R.render(Hh, Ww, K, chunk=32768, rays=rays_t, ndc=cfg["ndc"], near=cfg["near"],
+                                               far=cfg["far"], use_viewdirs=True, **common)
+        loss_t = H.img2mse(rgb_t, tgt) + H.img2mse(ex_t["rgb0"], tgt)
+        loss_t.backward()
+        out["train_target"] = tgt.numpy()
+        out["train_loss"] = np.float32(loss_t.item())
+        for tag, net in (("c", net_c), ("f", net_f)):
+            for k_, p_ in net.named_parameters():
+                g_ = p_.grad.detach().numpy().ravel()
+                out[f"gnorm_{tag}.{k_}"] = np.float32(np.linalg.norm(g_))
+                out[f"ghead_{tag}.{k_}"] = g_[:256].copy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), keys={sorted(out)}")

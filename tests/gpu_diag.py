@@ -59,6 +59,23 @@ def mlp():
             print(f"{name} {prec}: per-channel max err / scale = {err}  raw[0,0]={raw[0,0]} ref[0,0]={ref[0,0]}", flush=True)
 
 
+def gemm_mn():
+    rs = np.random.RandomState(0)
+    for N, K in ((128, 16), (256, 64), (64, 128), (32, 128)):
+        for (lbo, sbo) in ((128, (K // 8) * 128),):
+            X = rs.randn(K, 128).astype(np.float32)
+            Y = rs.randn(K, N).astype(np.float32)
+            ref = O.bf16_round(X).astype(np.float64).T @ O.bf16_round(Y).astype(np.float64)
+            D = torch.zeros((128, N), device="cuda")
+            dX, dY = dev(X), dev(Y)
+            rc = L.lib().plnerf_debug_umma_gemm_mn(dX.data_ptr(), dY.data_ptr(), N, K, lbo, sbo, D.data_ptr(), None)
+            torch.cuda.synchronize()
+            out = D.cpu().numpy()
+            err = np.abs(out - ref).max() / np.abs(ref).max()
+            print(f"MN-major N={N} K={K} lbo={lbo} sbo={sbo} rc={rc} relerr={err:.3e} out[0,:3]={out[0,:3]} ref[0,:3]={ref[0,:3]}",
+                  flush=True)
+
+
 def mmarate():
     for grid in (1, 148):
         for mode, name in ((0, "TS N=128"), (1, "TS N=256"), (2, "SS N=128"), (3, "SS N=256"),
@@ -73,4 +90,4 @@ def mmarate():
 
 
 if __name__ == "__main__":
-    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate}[sys.argv[1]]()
+    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate, "gemm_mn": gemm_mn}[sys.argv[1]]()

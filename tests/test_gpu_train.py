@@ -1,0 +1,129 @@
+"""GPU tests of the training path (autograd through render_rays): compositing backward, the
+input-gradient chain, the weight-gradient GEMMs and the heads, all through the C ABI.
+
+Gradient GEMMs use bf16 tensor-core operands with fp32 accumulation (activations and output gradients
+are rounded to bf16 once), so parameter gradients are compared tensor-wise: relative Frobenius error
+<= 3e-2 and cosine similarity >= 0.999 against fp32 PyTorch autograd / the reference's own backward."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import plnerf_oracle as O
+from util import CASES, case_params, load_golden, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_net(kw, params, requires_grad=True):
+    from plnerf_b200.run_nerf_helpers import NeRF
+    net = NeRF(D=kw["D"], W=kw["W"], input_ch=kw["input_ch"], input_ch_views=kw["input_ch_views"],
+               output_ch=kw["output_ch"], skips=list(kw["skips"]), use_viewdirs=kw["use_viewdirs"])
+    net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in params.items()})
+    net = net.cuda()
+    for p in net.parameters():
+        p.requires_grad_(requires_grad)
+    return net
+
+
+def torch_ref_query(net, rays, z):
+    """fp32 PyTorch restatement of run_network + NeRF.forward (run_plnerf.py:78-92,
+    run_nerf_helpers.py:105-128) on the module's own nn.Linear layers -- test-side checker only."""
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    def emb(x, L):
+        outs = [x]
+        for k in range(L):
+            outs += [torch.sin(x * 2.0 ** k), torch.cos(x * 2.0 ** k)]
+        return torch.cat(outs, -1)
+    x = emb(pts.reshape(-1, 3), 10)
+    vd = emb(rays[:, None, -3:].expand(pts.shape).reshape(-1, 3), 4)
+    h = x
+    for i, l in enumerate(net.pts_linears):
+        h = F.relu(l(h))
+        if i in net.skips:
+            h = torch.cat([x, h], -1)
+    alpha = net.alpha_linear(h)
+    feat = net.feature_linear(h)
+    hv = F.relu(net.views_linears[0](torch.cat([feat, vd], -1)))
+    rgb = net.rgb_linear(hv)
+    return torch.cat([rgb, alpha], -1).reshape(z.shape[0], z.shape[1], 4)
+
+
+def cmp_grads(got, ref, tol=3e-2, what=""):
+    for k in ref:
+        a, b = got[k].double().flatten(), ref[k].double().flatten()
+        nb = b.norm().item()
+        if nb == 0:
+            assert a.norm().item() == 0, (what, k)
+            continue
+        rel = (a - b).norm().item() / nb
+        cos = torch.dot(a, b).item() / (a.norm().item() * nb + 1e-300)
+        assert rel < tol and cos > 0.999, (what, k, rel, cos)
+
+
+@pytest.mark.parametrize("n,S", [(40, 96), (3, 64), (257, 192)])
+def test_network_query_backward_vs_torch_autograd(n, S):
+    from plnerf_b200 import ops
+    cfg, kw, pc, pf = case_params("lego_linear_mid")
+    net = make_net(kw, pc)
+    rs = np.random.RandomState(n)
+    g = load_golden("lego_linear_mid")
+    rb = np.tile(g["ray_batch"], (n // g["ray_batch"].shape[0] + 1, 1))[:n]
+    rays = dev(rb)
+    z = torch.sort(torch.rand(n, S, device="cuda") * 4 + 2, -1)[0]
+    g_raw = dev(rs.randn(n, S, 4).astype(np.float32))
+    with torch.no_grad():
+        raw, stash = ops.network_query_train(net, rays, z)
+        raw_nograd = ops.network_query(net, rays, z, precision="bf16")
+        grads = ops.network_query_bwd(net, g_raw, stash, n, S)
+    assert torch.equal(raw, raw_nograd)          # the stash mode must not change the forward result
+    ref_raw = torch_ref_query(net, rays, z)
+    (ref_raw * g_raw).sum().backward()
+    ref = {k: p.grad for k, p in net.named_parameters()}
+    cmp_grads(grads, ref, what=f"n={n},S={S}")
+
+
+@pytest.mark.parametrize("name", ["lego_linear_mid", "lego_constant", "llff_ndc_linear", "llff_ndc_constant"])
+def test_training_loss_gradients_vs_reference(name):
+    """loss = mse(rgb, tgt) + mse(rgb0, tgt) through render() with the reference's pytest draws:
+    loss value and every parameter gradient (norm + first 256 entries) vs the unmodified reference."""
+    from plnerf_b200 import run_plnerf as RP
+    g = load_golden(name)
+    cfg, kw, pc, pf = case_params(name)
+    net_c, net_f = make_net(kw, pc), make_net(kw, pf)
+    Hh, Ww, focal = g["hwf"]
+    rays = torch.stack([dev(g["rays_o"]), dev(g["rays_d"])])
+    rgb, disp, acc, extras = RP.render(int(Hh), int(Ww), g["K"], chunk=1024 * 32, rays=rays, ndc=cfg["ndc"],
+                                       near=cfg["near"], far=cfg["far"], use_viewdirs=True, network_query_fn=None,
+                                       network_fn=net_c, network_fine=net_f, N_samples=cfg["Ns"],
+                                       N_importance=cfg["Ni"], perturb=1.0, raw_noise_std=cfg["raw_noise_std"],
+                                       white_bkgd=cfg["white_bkgd"], mode=cfg["mode"], color_mode=cfg["color_mode"],
+                                       lindisp=cfg["lindisp"], pytest=True, retraw=True,
+                                       constant_init=cfg["constant_init"])
+    assert rgb.requires_grad and extras["rgb0"].requires_grad and not extras["raw"].requires_grad
+    tgt = dev(g["train_target"])
+    loss = torch.mean((rgb - tgt) ** 2) + torch.mean((extras["rgb0"] - tgt) ** 2)
+    assert abs(loss.item() - float(g["train_loss"])) / float(g["train_loss"]) < 1e-2     # bf16 forward
+    loss.backward()
+    for tag, net in (("c", net_c), ("f", net_f)):
+        for k, p in net.named_parameters():
+            ref_norm = float(g[f"gnorm_{tag}.{k}"])
+            got = p.grad.flatten()
+            assert abs(got.norm().item() - ref_norm) / ref_norm < 5e-2, (tag, k, got.norm().item(), ref_norm)
+            head = dev(g[f"ghead_{tag}.{k}"]).double()
+            a = got[:head.numel()].double()
+            rel = (a - head).norm().item() / (head.norm().item() + 1e-300)
+            assert rel < 6e-2, (tag, k, rel)
+
+
+def test_gradients_need_viewdirs_and_bf16():
+    from plnerf_b200 import run_plnerf as RP
+    cfg, kw, pc, pf = case_params("coarse_only")
+    net = make_net(kw, pc)
+    g = load_golden("coarse_only")
+    with pytest.raises(NotImplementedError):
+        RP.render_rays(dev(g["ray_batch"]), net, None, 64, "linear", "midpoint", perturb=1.0)
