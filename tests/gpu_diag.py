@@ -90,4 +90,38 @@ def mmarate():
 
 
 if __name__ == "__main__":
-    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate, "gemm_mn": gemm_mn}[sys.argv[1]]()
+    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate, "gemm_mn": gemm_mn, "train": lambda: None}[sys.argv[1]]()
+
+
+def train_diag():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_train as T
+    from util import case_params, load_golden
+    n, S = 40, 96
+    cfg, kw, pc, pf = case_params("lego_linear_mid")
+    net = T.make_net(kw, pc)
+    rs = np.random.RandomState(n)
+    g = load_golden("lego_linear_mid")
+    rb = np.tile(g["ray_batch"], (n // g["ray_batch"].shape[0] + 1, 1))[:n]
+    rays = dev(rb)
+    z = torch.sort(torch.rand(n, S, device="cuda") * 4 + 2, -1)[0]
+    g_raw = dev(rs.randn(n, S, 4).astype(np.float32))
+    with torch.no_grad():
+        raw, stash = ops.network_query_train(net, rays, z)
+        grads = ops.network_query_bwd(net, g_raw, stash, n, S)
+    emu = T.emulated_backward(net, rays, z, g_raw)
+    for k, p in net.named_parameters():
+        a, b = grads[k].double().flatten(), emu[k].double().flatten()
+        rel = (a - b).norm().item() / b.norm().item()
+        print(f"EMU {k:28s} rel={rel:.5f}", flush=True)
+    ref_raw = T.torch_ref_query(net, rays, z)
+    (ref_raw * g_raw).sum().backward()
+    for k, p in net.named_parameters():
+        a, b = grads[k].double().flatten(), p.grad.double().flatten()
+        rel = (a - b).norm().item() / b.norm().item()
+        cos = torch.dot(a, b).item() / (a.norm().item() * b.norm().item() + 1e-300)
+        print(f"{k:28s} rel={rel:.4f} cos={cos:.6f} |ref|={b.norm().item():.4e} |got|={a.norm().item():.4e}", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "train":
+    train_diag()

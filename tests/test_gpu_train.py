@@ -53,6 +53,64 @@ def torch_ref_query(net, rays, z):
     return torch.cat([rgb, alpha], -1).reshape(z.shape[0], z.shape[1], 4)
 
 
+def bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def emulated_backward(net, rays, z, g_raw):
+    """The kernels' arithmetic restated in PyTorch (fp32 matmuls on bf16-ROUNDED operands): forward
+    activations, output gradients and GEMM weights are rounded to bf16 exactly where the sm_100a path
+    rounds them; biases, heads and the viewdir columns stay fp32.  Returns {param name: grad}."""
+    D = net.D
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    def emb(x, L):
+        outs = [x]
+        for k in range(L):
+            outs += [torch.sin(x * 2.0 ** k), torch.cos(x * 2.0 ** k)]
+        return torch.cat(outs, -1)
+    x = bf16(emb(pts.reshape(-1, 3), 10))
+    vd = emb(rays[:, None, -3:].expand(pts.shape).reshape(-1, 3), 4)
+    W = {k: v.detach() for k, v in net.named_parameters()}
+    ic = x.shape[1]
+    ins, masks = [], []
+    h = x
+    for i in range(D):
+        w, b = W[f"pts_linears.{i}.weight"], W[f"pts_linears.{i}.bias"]
+        ins.append(h)
+        h32 = F.relu(h @ bf16(w).t() + b)
+        masks.append(h32 > 0)
+        a = bf16(h32)
+        h = torch.cat([x, a], -1) if i in net.skips else a
+        last = a
+    feat = bf16(last @ bf16(W["feature_linear.weight"]).t() + W["feature_linear.bias"])
+    wv, bv = W["views_linears.0.weight"], W["views_linears.0.bias"]
+    hv32 = F.relu(feat @ bf16(wv[:, :256]).t() + (vd @ wv[:, 256:].t() + bv))
+    mask_v = hv32 > 0
+    hv = bf16(hv32)
+    g = g_raw.reshape(-1, 4)
+    g_rgb, g_alpha = g[:, :3], g[:, 3:4]
+    grads = {}
+    grads["rgb_linear.weight"] = g_rgb.t() @ hv
+    grads["rgb_linear.bias"] = g_rgb.sum(0)
+    grads["alpha_linear.weight"] = g_alpha.t() @ last
+    grads["alpha_linear.bias"] = g_alpha.sum(0)
+    d_hv = bf16((g_rgb @ W["rgb_linear.weight"]) * mask_v)
+    grads["views_linears.0.weight"] = torch.cat([d_hv.t() @ feat, d_hv.t() @ bf16(vd)], -1)
+    grads["views_linears.0.bias"] = d_hv.sum(0)
+    d_feat = bf16(d_hv @ bf16(wv[:, :256]))
+    grads["feature_linear.weight"] = d_feat.t() @ last
+    grads["feature_linear.bias"] = d_feat.sum(0)
+    dy = bf16((d_feat @ bf16(W["feature_linear.weight"]) + g_alpha * W["alpha_linear.weight"]) * masks[D - 1])
+    for i in range(D - 1, -1, -1):
+        grads[f"pts_linears.{i}.weight"] = dy.t() @ ins[i]
+        grads[f"pts_linears.{i}.bias"] = dy.sum(0)
+        if i > 0:
+            w = W[f"pts_linears.{i}.weight"]
+            wh = w[:, ic:] if (i - 1) in net.skips else w
+            dy = bf16((dy @ bf16(wh)) * masks[i - 1])
+    return grads
+
+
 def cmp_grads(got, ref, tol=3e-2, what=""):
     for k in ref:
         a, b = got[k].double().flatten(), ref[k].double().flatten()
@@ -81,10 +139,18 @@ def test_network_query_backward_vs_torch_autograd(n, S):
         raw_nograd = ops.network_query(net, rays, z, precision="bf16")
         grads = ops.network_query_bwd(net, g_raw, stash, n, S)
     assert torch.equal(raw, raw_nograd)          # the stash mode must not change the forward result
+    # (a) against the same arithmetic restated in PyTorch (bf16-rounded operands): tight
+    emu = emulated_backward(net, rays, z, g_raw)
+    cmp_grads(grads, emu, tol=5e-3, what=f"emulation n={n},S={S}")
+    # (b) against pure fp32 autograd: bf16 operand rounding accumulates over the 9 chained GEMMs of the
+    # gradient chain (measured ~2% at the heads' side, ~10% at layer 0 for N(0,1) upstream gradients)
     ref_raw = torch_ref_query(net, rays, z)
     (ref_raw * g_raw).sum().backward()
     ref = {k: p.grad for k, p in net.named_parameters()}
-    cmp_grads(grads, ref, what=f"n={n},S={S}")
+    for k in ref:
+        a, b = grads[k].double().flatten(), ref[k].double().flatten()
+        cos = torch.dot(a, b).item() / (a.norm().item() * b.norm().item() + 1e-300)
+        assert cos > 0.99 and abs(a.norm().item() / b.norm().item() - 1) < 0.05, (k, cos)
 
 
 @pytest.mark.parametrize("name", ["lego_linear_mid", "lego_constant", "llff_ndc_linear", "llff_ndc_constant"])
