@@ -161,6 +161,69 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def train_leg(args, dev, rank, world, ro, rd, K):
+    """Secondary number: training iterations/s of the reference loop's step (run_plnerf.py:1283-1303) on the
+    blender_linear.txt shape (N_rand=1024 rays per rank, N_samples=128, N_importance=64): stash-mode forward,
+    loss, backward (compositing bwd + gradient chain + weight-gradient GEMMs), ONE flat NCCL all-reduce of both
+    networks' gradients, two fused Adam steps.  Weak scaling: global batch = 1024 x ranks."""
+    import torch
+    import torch.distributed as dist
+    from plnerf_b200 import run_plnerf as RP, synth
+    from plnerf_b200 import dist as PD
+    from plnerf_b200.run_nerf_helpers import NeRF
+    N_rand, Ns, Ni, iters, warm = 1024, 128, 64, 30, 5
+
+    def mk(seed):
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy())
+                             for k, v in synth.nerf_params(seed, density_boost=False, **NET_KW).items()})
+        return net.to(dev)
+    net_c, net_f = mk(11), mk(12)
+    bucket = PD.FlatGradBucket([net_c, net_f])
+    opt_f = torch.optim.Adam(net_f.parameters(), lr=5e-4, fused=True)
+    opt_c = torch.optim.Adam(net_c.parameters(), lr=5e-4, fused=True)
+    ro_t, rd_t = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    target_img = torch.rand(H * W, 3, device=dev, generator=gen)
+
+    def step():
+        idx = torch.randint(0, H * W, (N_rand,), device=dev, generator=gen)
+        rays = torch.stack([ro_t[idx], rd_t[idx]])
+        rgb, disp, acc, extras = RP.render(H, W, K, chunk=CHUNK, rays=rays, ndc=False, near=2., far=6.,
+                                           use_viewdirs=True, network_query_fn=None, network_fn=net_c,
+                                           network_fine=net_f, N_samples=Ns, N_importance=Ni, perturb=1.0,
+                                           white_bkgd=True, mode="linear", color_mode="midpoint", retraw=True)
+        tgt = target_img[idx]
+        loss = torch.mean((rgb - tgt) ** 2) + torch.mean((extras["rgb0"] - tgt) ** 2)
+        bucket.zero_()
+        loss.backward()
+        bucket.allreduce_mean()
+        opt_f.step(); opt_c.step()
+        return loss
+
+    for _ in range(warm):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / iters
+    rows = N_rand * (2 * Ns + Ni)
+    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "rays_per_iter_global": N_rand * world,
+            "algorithmic_tflops_per_gpu": rows * 3489024 / ms / 1e9, "final_loss": float(loss.item()),
+            "config": f"N_rand={N_rand}/rank, N_samples={Ns}, N_importance={Ni}, linear/midpoint, viewdirs, white_bkgd, "
+                      f"bf16 tensor-core operands, 2x fused Adam, 1 flat all-reduce ({bucket.flat.numel() * 4} B) per step"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -285,6 +348,8 @@ def run_ours(args):
                      "algorithmic_flop_per_launch": mlp_rows * FLOP_PER_EVAL / max(1, mlp_n)},
         "clocks": clocks,
     }
+    if not args.no_train:
+        out["train"] = train_leg(args, dev, rank, world, ro, rd, K)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)
@@ -339,6 +404,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PLNERF_PRECISION", "bf16"), choices=["bf16", "bf16x3"])
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per CPU-baseline repetition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step timing")
     args = ap.parse_args()
     with StdoutToStderr() as OUT:
         if args.impl == "reference":
