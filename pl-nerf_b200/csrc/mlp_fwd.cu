@@ -764,12 +764,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         PLNERF_TRACE(0, tcnt, 1000 + i);                 // batch loop top
         const uint32_t bw0 = prog[i].x;
         const int blen = (bw0 >> 12) & 15;
-        if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
-        if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
-        if (!X3) {   // ONE wait for all weight stages of the batch (<= 4 of the ring slots)
-          ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);
+        if (!X3) {   // ONE wait for all weight stages of the batch (<= 4 of the ring slots); weights land long
+          ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);   // before the activations, so this wait goes first
           ++batch;
         }
+        if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
+        if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
         ptx::tc_fence_after();
         PLNERF_TRACE(0, tcnt, 2000 + i);                 // dependencies + weights ready, issuing batch
         if (ptx::elect_one()) {
@@ -821,7 +821,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         __syncwarp();
         PLNERF_TRACE(0, tcnt, 5000 + i);                 // issue returned
         // every lane advances the (warp-uniform) ring cursor and use counters past this batch
-        for (int j = 0; j < blen * nsplit; ++j) { if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; } }
+        slot += (uint32_t)(blen * nsplit);
+        while (slot >= (uint32_t)A.n_stages) { slot -= (uint32_t)A.n_stages; phase ^= 1; }
         uses0 += (bw0 >> 18) & 1u;
         uses1 += (bw0 >> 19) & 1u;
         i += blen;

@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (r >= a.n) return;
   const int S = a.S, Ni = a.Ni;
-  float* zc = smem + (size_t)wib * (S + 2 * Ni);
+  int np2s = 1;
+  while (np2s < Ni) np2s <<= 1;
+  float* zc = smem + (size_t)wib * (S + Ni + np2s);
   float* xs = zc + S;
   float* xsorted = xs + Ni;
   const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
@@ -615,21 +617,28 @@ __global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
     v = warp_sum(v);
     if (lane == 0) a.z_std[r] = sqrtf(__fdiv_rn(v, (float)Ni));
   }
-  // rank sort (stable): rank_k = #{m: x_m < x_k or (x_m == x_k and m < k)}; NaNs sort last
-  for (int k = lane; k < Ni; k += 32) {
-    const float x = xs[k];
-    int rank = 0;
-    if (x == x) {
-      for (int m = 0; m < Ni; ++m) {
-        const float y = xs[m];
-        rank += (y < x) || (y == x && m < k);
-      }
-    } else {
-      for (int m = 0; m < Ni; ++m) { const float y = xs[m]; rank += (y == y) || (m < k); }
-    }
-    xsorted[rank] = x;
-  }
+  // in-warp bitonic sort of the clamped samples (padded to a power of two with keys that sort last).  The output is the sorted multiset, like torch.sort.
+  int np2 = 1;
+  while (np2 < Ni) np2 <<= 1;
+  for (int k = lane; k < np2; k += 32) xsorted[k] = (k < Ni) ? xs[k] : __int_as_float(0x7fffffff);   // pad key: sorts after everything
   __syncwarp();
+  auto gt = [](float p, float q) {   // total order: numbers < NaNs (like torch.sort) < pad keys
+    const bool pn = (p != p), qn = (q != q);
+    if (pn || qn) return pn && (!qn || __float_as_int(p) > __float_as_int(q));
+    return p > q;
+  };
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (np2 >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));       // index with the `stride` bit clear
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const float p = xsorted[lo], q = xsorted[hi];
+        if (gt(p, q) == up) { xsorted[lo] = q; xsorted[hi] = p; }
+      }
+      __syncwarp();
+    }
+  }
   float* out = a.z_out + r * (int64_t)(S + Ni);
   for (int i = lane; i < S; i += 32) {  // coarse i lands after every sample strictly smaller
     const float v = zc[i];
@@ -651,7 +660,9 @@ int launch_merge(const float* z, const float* samples, const float* rays, int64_
   if (n == 0) return PLNERF_OK;
   MergeArgs a{z, samples, rays, n, stride, S, Ni, z_out, z_std};
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * (S + 2 * Ni) * sizeof(float);
+  int np2 = 1;
+  while (np2 < Ni) np2 <<= 1;
+  const size_t smem = (size_t)wpb * (S + Ni + np2) * sizeof(float);
   if (smem > 48 * 1024) { set_error("merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
   k_merge<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_merge");
