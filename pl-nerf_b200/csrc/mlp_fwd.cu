@@ -48,8 +48,11 @@ constexpr int MAX_PE_KS = 4;        // input_ch <= 64
 constexpr int PE_TILE_BYTES = MAX_PE_KS * KS_BYTES;   // 16 KB
 constexpr int MAX_CONST_FLOATS = 4096;                // biases + small heads staged in smem
 constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 384;    // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 epilogue
-constexpr int NUM_EPI_THREADS = 256;
+constexpr int NGRP = 4;               // epilogue column groups: each owns 4/NGRP of the 32-column chunks of a half
+constexpr int CHUNKS_PER_GRP = 4 / NGRP;
+constexpr int NUM_EPI_THREADS = 128 * NGRP;
+constexpr int FIRST_EPI_WARP = 2;
+constexpr int NUM_THREADS = 32 * FIRST_EPI_WARP + NUM_EPI_THREADS;   // warps: 0 TMA producer (+TMEM alloc), 1 MMA issuer, 2.. epilogue
 constexpr int MAX_OUT_CH = 8;
 
 enum { EPI_RELU_A = 0, EPI_LINEAR_A = 1, EPI_VIEWS = 2, EPI_RELU_HEAD = 3 };
@@ -429,7 +432,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n_stages) {
   s.ring = 2 * PE_TILE_BYTES;
   s.consts = s.ring + (uint32_t)n_stages * STAGE_BYTES;
   s.xch = s.consts + MAX_CONST_FLOATS * 4;
-  s.prog = s.xch + TILE_M * (MAX_OUT_CH + 1) * 4;
+  s.prog = s.xch + (NGRP - 1) * TILE_M * (MAX_OUT_CH + 1) * 4;
   s.bars = s.prog + 8 * 128;   // flattened MMA stage program (<= 128 entries)
   s.total = s.bars + 512;
   return s;
@@ -497,79 +500,62 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
   const int64_t g = tile * TILE_M + row;
   const int64_t gc = (g < A.M) ? g : (A.M - 1);
   const int n_panels = 2 * P.pe_ks;
-  const int p_lo = grp * n_panels / 2, p_hi = (grp + 1) * n_panels / 2;   // this column group's panels
-  float v[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = 0.f;
+  const int p_lo = grp * n_panels / NGRP, p_hi = (grp + 1) * n_panels / NGRP;   // this column group's panels
+  float p[3] = {0.f, 0.f, 0.f};
+  const float* xr = nullptr;
   if (A.x_emb) {
-    const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
-#pragma unroll
-    for (int i = 0; i < 64; ++i)
-      if (i >= 8 * p_lo && i < 8 * p_hi && i < P.input_ch) v[i] = xr[i];
+    xr = A.x_emb + gc * (int64_t)A.x_ld;
   } else {
     const int64_t ray = gc / A.S;
     const float* rp = A.rays + ray * (int64_t)A.stride;
     const float zz = A.z[gc];
-    float p[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));  // o + d*z, two roundings
-    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
-    if (A.multires > 0) {
-      // frequencies whose outputs land in [8*p_lo, 8*p_hi): element 3+6k.. -> k range
-      const int k_lo = max(0, (8 * p_lo - 3 - 5) / 6), k_hi = min(A.multires - 1, (8 * p_hi - 4) / 6);
-      float f = 1.0f;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        if (k >= k_lo && k <= k_hi) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn, cs;
-            sincosf(p[c] * f, &sn, &cs);
-            v[3 + 6 * k + c] = sn;
-            v[3 + 6 * k + 3 + c] = cs;
-          }
-        }
-        f *= 2.0f;
-      }
-    }
   }
+  // element idx of the encoding: [x,y,z, sin(2^0 p), cos(2^0 p), sin(2^1 p), ...] (run_nerf_helpers.py:45-48)
+  auto elem = [&](int idx) -> float {
+    if (idx >= P.input_ch) return 0.f;
+    if (xr) return xr[idx];
+    if (idx < 3) return p[idx];
+    const int t = idx - 3, k = t / 6, r = t - 6 * k, c = (r >= 3) ? r - 3 : r;
+    const float a = p[c] * __int_as_float((127 + k) << 23);   // exact power-of-two scale
+    return (r >= 3) ? cosf(a) : sinf(a);
+  };
+  for (int pnl = p_lo; pnl < p_hi; ++pnl) {
+    float v[8];
 #pragma unroll
-  for (int pnl = 0; pnl < 2 * MAX_PE_KS; ++pnl) {
-    if (pnl >= p_lo && pnl < p_hi) {
-      uint4 hi;
-      hi.x = ptx::pack_bf16(v[8 * pnl + 0], v[8 * pnl + 1]); hi.y = ptx::pack_bf16(v[8 * pnl + 2], v[8 * pnl + 3]);
-      hi.z = ptx::pack_bf16(v[8 * pnl + 4], v[8 * pnl + 5]); hi.w = ptx::pack_bf16(v[8 * pnl + 6], v[8 * pnl + 7]);
-      *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
-      if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
-                              A.tl.in_width[A.tl.idx_pe], row, pnl, hi);
-      if (X3) {
-        float lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) lo[e] = v[8 * pnl + e] - ptx::bf16_round(v[8 * pnl + e]);
-        uint4 l4;
-        l4.x = ptx::pack_bf16(lo[0], lo[1]); l4.y = ptx::pack_bf16(lo[2], lo[3]);
-        l4.z = ptx::pack_bf16(lo[4], lo[5]); l4.w = ptx::pack_bf16(lo[6], lo[7]);
-        *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
-      }
+    for (int e = 0; e < 8; ++e) v[e] = elem(8 * pnl + e);
+    uint4 hi;
+    hi.x = ptx::pack_bf16(v[0], v[1]); hi.y = ptx::pack_bf16(v[2], v[3]);
+    hi.z = ptx::pack_bf16(v[4], v[5]); hi.w = ptx::pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(smem + SL.pe_hi + pnl * 2048 + row * 16) = hi;
+    if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
+                            A.tl.in_width[A.tl.idx_pe], row, pnl, hi);
+    if (X3) {
+      uint4 l4;
+      l4.x = ptx::pack_bf16(v[0] - ptx::bf16_round(v[0]), v[1] - ptx::bf16_round(v[1]));
+      l4.y = ptx::pack_bf16(v[2] - ptx::bf16_round(v[2]), v[3] - ptx::bf16_round(v[3]));
+      l4.z = ptx::pack_bf16(v[4] - ptx::bf16_round(v[4]), v[5] - ptx::bf16_round(v[5]));
+      l4.w = ptx::pack_bf16(v[6] - ptx::bf16_round(v[6]), v[7] - ptx::bf16_round(v[7]));
+      *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
     }
   }
   if (STASH) {
     // the (padded, 32-wide) viewdir encoding of this row's ray as a weight-gradient operand tile:
-    // column group g writes columns [16g, 16g+16)
-    const float* dp = A.dirpe + (gc / A.vb_div) * 32 + 16 * grp;
+    // column group g writes its share of the four 8-column blocks
+    const float* dp = A.dirpe + (gc / A.vb_div) * 32;
     uint8_t* tile_dir = A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_dir];
-#pragma unroll
-    for (int c8 = 0; c8 < 2; ++c8) {
+    for (int c8 = grp * 4 / NGRP; c8 < (grp + 1) * 4 / NGRP; ++c8) {
       uint4 q;
       q.x = ptx::pack_bf16(dp[8 * c8 + 0], dp[8 * c8 + 1]); q.y = ptx::pack_bf16(dp[8 * c8 + 2], dp[8 * c8 + 3]);
       q.z = ptx::pack_bf16(dp[8 * c8 + 4], dp[8 * c8 + 5]); q.w = ptx::pack_bf16(dp[8 * c8 + 6], dp[8 * c8 + 7]);
-      stash_store8(tile_dir, 32, row, 2 * grp + c8, q);
+      stash_store8(tile_dir, 32, row, c8, q);
     }
   }
 }
 
-// Input of the gradient chain: d_hv = (g_rgb . W_rgb) * relu'(views) for this thread's 64 columns
-// -> bf16 A operand in TMEM (cols COL_A1 + n/2) and the dY_views stash tile.
+// Input of the gradient chain: d_hv = (g_rgb . W_rgb) * relu'(views) for this thread's columns
+// -> bf16 A operand in TMEM (cols COL_A1 + n/2) and the dY_views stash tile (128 columns over the column groups).
 __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* consts, uint32_t tmem_lane_a1, int64_t tile,
                                                int row, int grp) {
   const NetPlan& P = A.plan;
@@ -579,9 +565,8 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
   const float* rw = consts + P.rgb_w_off;
   const uint32_t* mk = A.masks + tile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[A.tl.mask_views];
   uint8_t* tile_dy = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_views];
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int n0 = 64 * grp + 32 * cc;
+  for (int cc = grp * CHUNKS_PER_GRP; cc < (grp + 1) * CHUNKS_PER_GRP; ++cc) {
+    const int n0 = 32 * cc;
     const uint32_t m = mk[(n0 >> 5) * 128 + row];
     uint32_t pk[16];
 #pragma unroll
@@ -683,7 +668,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     }
     *prog_n = n_entries;
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
   ptx::tc_fence_before();
   __syncthreads();
@@ -756,18 +741,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     uint32_t uses0 = 0, uses1 = 0, waited0 = 0, waited1 = 0;
     uint32_t tile_iter = 0;
     int tcnt = 0;
+    // the weights of a batch always land long before its activations: their barrier is waited right after
+    // the PREVIOUS batch was issued (while the tensor pipe is still busy), never on the critical path
+    uint32_t bw0 = prog[0].x;
+    if (!X3 && (int64_t)blockIdx.x < A.n_tiles) ptx::mbar_wait(b_full(0), 0);
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
       const bool trace_on = (tile_iter == 2) && lane == 0;
       ptx::mbar_wait(pe_ready, tile_iter & 1);
       int i = 0;
       while (i < n_entries) {
         PLNERF_TRACE(0, tcnt, 1000 + i);                 // batch loop top
-        const uint32_t bw0 = prog[i].x;
         const int blen = (bw0 >> 12) & 15;
-        if (!X3) {   // ONE wait for all weight stages of the batch (<= 4 of the ring slots); weights land long
-          ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);   // before the activations, so this wait goes first
-          ++batch;
-        }
         if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
         if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
         ptx::tc_fence_after();
@@ -826,14 +810,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         uses0 += (bw0 >> 18) & 1u;
         uses1 += (bw0 >> 19) & 1u;
         i += blen;
+        ++batch;
+        {
+          const bool more = (i < n_entries) || (tile + (int64_t)gridDim.x < A.n_tiles);
+          if (more) {
+            bw0 = prog[(i < n_entries) ? i : 0].x;
+            if (!X3) ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);
+          }
+        }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue warps (8): PE prologue, bias/ReLU/pack, heads, output ========
-    // warp e = warp-4: lane quarter q = e&3 (TMEM lanes 32q..32q+31, one row per thread), column
-    // group grp = e>>2 (chunks 2grp, 2grp+1 of every 128-column half).
-    const int e = warp - 4;
-    const int q = e & 3, grp = e >> 2;
+    // lane quarter q = warp % 4 (TMEM lanes 32q..32q+31, one row per thread), column group grp = (warp-2)/4
+    // owns CHUNKS_PER_GRP 32-column chunks of every 128-column half.
+    const int e = warp - FIRST_EPI_WARP;
+    const int q = warp & 3, grp = e >> 2;   // TMEM lane quarter = hardware warp id % 4; grp in [0, NGRP)
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     uint32_t seen0 = 0, seen1 = 0;
@@ -888,18 +880,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           }
           ptx::tc_fence_after();
           PLNERF_TRACE(1 + grp, tcnt, 3000 + l * 10 + h);     // accumulator half observed full
-          // both 32-column chunks of this warp are requested before the single wait::ld, so the second
-          // TMEM read overlaps the first chunk's math
-          uint32_t r2[2][32];
+          // all 32-column chunks of this warp are requested before the single wait::ld
+          uint32_t r2[CHUNKS_PER_GRP][32];
           if (!(A.debug_flags & 2)) {
-            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (2 * grp), r2[0]);
-            ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (2 * grp + 1), r2[1]);
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc)
+              ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (CHUNKS_PER_GRP * grp + cc), r2[cc]);
             ptx::tmem_ld_wait();
           }
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc) {
             if (A.debug_flags & 2) break;
-            const int c = 2 * grp + cc;
+            const int c = CHUNKS_PER_GRP * grp + cc;
             const int n0 = h * 128 + c * 32;
             float* val = reinterpret_cast<float*>(r2[cc]);
             if (DGRAD) {
@@ -1038,33 +1030,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         }
       }
       if (DGRAD) continue;   // the gradient chain's outputs are the dY stash tiles
-      // ---- combine the two column groups' partial head sums and write the row
-      if (grp == 1) {
-        float* x = xch + row * (MAX_OUT_CH + 1);
+      // ---- combine the column groups' partial head sums and write the row
+      if (grp > 0) {
+        float* x = xch + ((grp - 1) * TILE_M + row) * (MAX_OUT_CH + 1);
         x[0] = alpha_acc;
 #pragma unroll
         for (int c = 0; c < MAX_OUT_CH; ++c) x[1 + c] = head[c];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
-      if (grp == 0 && valid) {
-        const float* x = xch + row * (MAX_OUT_CH + 1);
-        float* o = A.out + g * (int64_t)A.out_stride;
-        if (P.use_viewdirs) {
-          o[0] = head[0] + x[1] + consts[P.rgb_b_off + 0];
-          o[1] = head[1] + x[2] + consts[P.rgb_b_off + 1];
-          o[2] = head[2] + x[3] + consts[P.rgb_b_off + 2];
-          o[3] = alpha_acc + x[0] + consts[P.alpha_b_off];
-        } else {
+      if (grp == 0) {
 #pragma unroll
-          for (int ch = 0; ch < MAX_OUT_CH; ++ch)
-            if (ch < P.out_ch) o[ch] = head[ch] + x[1 + ch] + consts[P.out_b_off + ch];
+        for (int g2 = 1; g2 < NGRP; ++g2) {
+          const float* x = xch + ((g2 - 1) * TILE_M + row) * (MAX_OUT_CH + 1);
+          alpha_acc += x[0];
+#pragma unroll
+          for (int c = 0; c < MAX_OUT_CH; ++c) head[c] += x[1 + c];
+        }
+        if (valid) {
+          float* o = A.out + g * (int64_t)A.out_stride;
+          if (P.use_viewdirs) {
+            o[0] = head[0] + consts[P.rgb_b_off + 0];
+            o[1] = head[1] + consts[P.rgb_b_off + 1];
+            o[2] = head[2] + consts[P.rgb_b_off + 2];
+            o[3] = alpha_acc + consts[P.alpha_b_off];
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < MAX_OUT_CH; ++ch)
+              if (ch < P.out_ch) o[ch] = head[ch] + consts[P.out_b_off + ch];
+          }
         }
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");   // xch is reused by the next tile
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
 // =============================================================================================
