@@ -51,8 +51,8 @@ constexpr int MAX_STAGES = 6;
 constexpr int NGRP = 4;               // epilogue column groups: each owns 4/NGRP of the 32-column chunks of a half
 constexpr int CHUNKS_PER_GRP = 4 / NGRP;
 constexpr int NUM_EPI_THREADS = 128 * NGRP;
-constexpr int FIRST_EPI_WARP = 3;
-constexpr int NUM_THREADS = 32 * FIRST_EPI_WARP + NUM_EPI_THREADS;   // warps: 0 TMA producer (+TMEM alloc), 1-2 MMA issuers (half a / half b), 3.. epilogue
+constexpr int FIRST_EPI_WARP = 2;
+constexpr int NUM_THREADS = 32 * FIRST_EPI_WARP + NUM_EPI_THREADS;   // warps: 0 TMA producer (+TMEM alloc), 1 MMA issuer, 2.. epilogue
 constexpr int MAX_OUT_CH = 8;
 
 enum { EPI_RELU_A = 0, EPI_LINEAR_A = 1, EPI_VIEWS = 2, EPI_RELU_HEAD = 3 };
@@ -634,9 +634,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     ptx::fence_mbar_init();
   }
   // ---- flattened per-tile stage program (shared by the TMA producer and the MMA issuer) ----------
-  //   batch 0 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7   needs a_ready[a](l-1)      issuer A
-  //   batch 1 of layer l: (l,a) hidden K-steps 8-15                   needs a_ready[b](l-1)      issuer A
-  //   batch 2 of layer l: [(l,b) PE] (l,b) hidden 0-7, 8-15            needs both                 issuer B
+  //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7      needs a_ready[a](l-1)
+  //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15  needs a_ready[b](l-1)
   // entry.x: bits 0-7 K-steps | F_* flags | bits 12-15 batch length (first entry of a batch only)
   // entry.y: TMEM column of the A operand (hidden stages) or first PE K-step (PE stages)
   enum : uint32_t { F_PE = 1u << 8, F_H = 1u << 9, F_FIRST = 1u << 10, F_LAST = 1u << 11, F_WAIT_A0 = 1u << 16,
@@ -649,27 +648,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nh = P.L[l].n_halves;
       const uint32_t a_col = (l > 0 ? (X3 ? 256u : ((((l - 1) & 1) ? 384u : 256u))) : (DGRAD ? 384u : 256u));
       const int nst = stages_of(n_pe, n_h);
-      int batch_first[3] = {-1, -1, -1};
-      uint32_t batch_len[3] = {0, 0, 0}, batch_inc[3] = {0, 0, 0};
+      int batch_first[2] = {-1, -1};
+      uint32_t batch_len[2] = {0, 0}, batch_inc[2] = {0, 0};
       for (int h = 0; h < nh; ++h) {
         for (int st = 0; st < nst; ++st) {
           const StageInfo si = stage_info(n_pe, n_h, st);
           uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
                         (st == nst - 1 ? F_LAST : 0u);
           const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
-          // batch 0: half a, operands from columns < 128 (needs a_ready[a]); batch 1: half a, columns >= 128
-          // (needs a_ready[b]); batch 2: half b (needs both: its accumulator and all columns)
-          const int bsel = (h == 1) ? 2 : ((!si.is_pe && si.k0 + si.nks > 8) ? 1 : 0);
-          if (batch_first[bsel] < 0) {
-            batch_first[bsel] = n_entries;
-            w0 |= (bsel == 0) ? F_WAIT_A0 : ((bsel == 1) ? F_WAIT_A1 : (F_WAIT_A0 | F_WAIT_A1));
-          }
+          const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
+          if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
           ++batch_len[bsel];
           if (st == nst - 1) batch_inc[bsel] |= h ? F_INC1 : F_INC0;
           prog[n_entries++] = make_uint2(w0, w1);
         }
       }
-      for (int bs = 0; bs < 3; ++bs)
+      for (int bs = 0; bs < 2; ++bs)
         if (batch_first[bs] >= 0) prog[batch_first[bs]].x |= (batch_len[bs] << 12) | batch_inc[bs];
     }
     *prog_n = n_entries;
@@ -727,15 +721,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers ==========================================================
-    // Issuing one N=128 MMA costs the issuing thread ~50 cycles (measured) against 64 cycles of tensor-pipe
-    // time, so a single issuer can never run ahead of the pipe and every wait it performs idles the pipe.
-    // Two issuers share the work by accumulator: warp 1 issues every half-a stage, warp 2 every half-b stage;
-    // each accumulator is written by one thread only, cross-issuer ordering is carried by the mbarriers.
-    const bool issuer_b = (warp == 2);
-    // Both walk the same flattened stage program (built above); stages that share their dependencies are
-    // issued as one batch.  One elected lane issues; the whole warp follows the warp-uniform control flow.
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===========================================================
+    // The tensor pipe only buffers ~3-4 MMAs behind the issuing thread (measured), so everything the
+    // thread does between two MMA batches must fit in ~200 cycles or the pipe idles.  The per-tile
+    // control flow is therefore flattened once into a small "program" of stages in shared memory,
+    // and stages that share their dependencies are issued as one batch:
+    //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7     needs a_ready[a](l-1)
+    //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15 needs a_ready[b](l-1)
+    // One elected lane issues; the whole warp follows the (warp-uniform) control flow.
     const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
     const uint64_t desc_base = ptx::smem_desc(0, 2048, 128);
     const uint32_t desc_hi = (uint32_t)(desc_base >> 32);
@@ -747,25 +741,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     uint32_t uses0 = 0, uses1 = 0, waited0 = 0, waited1 = 0;
     uint32_t tile_iter = 0;
     int tcnt = 0;
+    // the weights of a batch always land long before its activations: their barrier is waited right after
+    // the PREVIOUS batch was issued (while the tensor pipe is still busy), never on the critical path
+    uint32_t bw0 = prog[0].x;
+    if (!X3 && (int64_t)blockIdx.x < A.n_tiles) ptx::mbar_wait(b_full(0), 0);
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
-      const bool trace_on = (tile_iter == 2) && lane == 0 && !issuer_b;
+      const bool trace_on = (tile_iter == 2) && lane == 0;
       ptx::mbar_wait(pe_ready, tile_iter & 1);
       int i = 0;
       while (i < n_entries) {
-        const uint32_t bw0 = prog[i].x;
-        const int blen = (bw0 >> 12) & 15;
-        const bool mine = (((bw0 & F_H) != 0) == issuer_b);
-        if (!mine) {   // the other issuer's batch: only advance the shared cursors
-          slot += (uint32_t)(blen * nsplit);
-          while (slot >= (uint32_t)A.n_stages) { slot -= (uint32_t)A.n_stages; phase ^= 1; }
-          uses0 += (bw0 >> 18) & 1u;
-          uses1 += (bw0 >> 19) & 1u;
-          i += blen;
-          ++batch;
-          continue;
-        }
         PLNERF_TRACE(0, tcnt, 1000 + i);                 // batch loop top
-        if (!X3) ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);   // weights: land long before the activations
+        const int blen = (bw0 >> 12) & 15;
         if (bw0 & F_WAIT_A0) { while (waited0 < uses0) { ptx::mbar_wait(a_ready0, waited0 & 1); ++waited0; } }
         if (bw0 & F_WAIT_A1) { while (waited1 < uses1) { ptx::mbar_wait(a_ready0 + 8u, waited1 & 1); ++waited1; } }
         ptx::tc_fence_after();
@@ -825,6 +811,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         uses1 += (bw0 >> 19) & 1u;
         i += blen;
         ++batch;
+        {
+          const bool more = (i < n_entries) || (tile + (int64_t)gridDim.x < A.n_tiles);
+          if (more) {
+            bw0 = prog[(i < n_entries) ? i : 0].x;
+            if (!X3) ptx::mbar_wait(b_full(batch), (batch >> 3) & 1u);
+          }
+        }
       }
     }
   } else if (warp >= FIRST_EPI_WARP) {
@@ -1217,7 +1210,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 160 * 1024);
   const uint32_t bar = ptx::smem_u32(smem + 160 * 1024 + 16);
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::mbar_init(bar + 16, 1); ptx::fence_mbar_init(); }
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::fence_mbar_init(); }
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   ptx::fence_proxy_async_smem();
@@ -1257,22 +1250,6 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
         ptx::tc_fence_after();
       }
       ptx::mbar_wait(bar2, (iters * 2 - 1) & 1);
-    } else if (mode == 6 || mode == 7) {
-      // does tcgen05.commit hold the issuing thread?  time (8 MMAs + 1 or 2 commits) with an idle pipe at start
-      const uint32_t bar3 = bar + 16;
-      for (int it = 0; it < iters; ++it) {
-        long long a0 = clock64();
-        if (ptx::elect_one()) {
-          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
-          ptx::mma_commit(bar2);
-          if (mode == 7) ptx::mma_commit(bar3);
-        }
-        __syncwarp();
-        long long a1 = clock64();
-        ptx::mbar_wait(bar2, it & 1);
-        if (mode == 7) ptx::mbar_wait(bar3, it & 1);
-        t_issue += a1 - a0;
-      }
     } else {
       // mode 5: how far ahead of the tensor pipe does the issuing thread run?  (queue depth)
       for (int it = 0; it < iters; ++it) {
@@ -1293,7 +1270,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
     __syncwarp();
     ptx::mbar_wait(bar, 0);
     long long t1 = clock64();
-    if (threadIdx.x == 32) cycles_out[blockIdx.x] = (mode >= 5) ? t_issue * (mode == 5 ? 1 : 2) : (t1 - t0);
+    if (threadIdx.x == 32) cycles_out[blockIdx.x] = (mode == 5) ? t_issue : (t1 - t0);
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -79,9 +79,7 @@ def gemm_mn():
 def mmarate():
     for grid in (1, 148):
         for mode, name in ((0, "TS N=128"), (1, "TS N=256"), (2, "SS N=128"), (3, "SS N=256"),
-                           (4, "TS N=128, 8/batch + commit + wait(prev)"), (5, "TS N=128 issue-return time of 16 MMAs"),
-                           (6, "TS N=128: cycles for [8 MMAs + 1 commit] to return, per MMA"),
-                           (7, "TS N=128: cycles for [8 MMAs + 2 commits] to return, per MMA")):
+                           (4, "TS N=128, 8/batch + commit + wait(prev)"), (5, "TS N=128 issue-return time of 16 MMAs")):
             out = torch.zeros(grid, dtype=torch.int64, device="cuda")
             iters = 200
             for rep in range(2):
