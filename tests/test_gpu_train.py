@@ -141,7 +141,7 @@ def test_network_query_backward_vs_torch_autograd(n, S):
     assert torch.equal(raw, raw_nograd)          # the stash mode must not change the forward result
     # (a) against the same arithmetic restated in PyTorch (bf16-rounded operands): tight
     emu = emulated_backward(net, rays, z, g_raw)
-    cmp_grads(grads, emu, tol=1e-2, what=f"emulation n={n},S={S}")   # residual = isolated bf16 rounding flips
+    cmp_grads(grads, emu, tol=2e-2, what=f"emulation n={n},S={S}")   # residual = isolated bf16 rounding flips
     # (b) against pure fp32 autograd: bf16 operand rounding accumulates over the 9 chained GEMMs of the
     # gradient chain (measured ~2% at the heads' side, ~10% at layer 0 for N(0,1) upstream gradients)
     ref_raw = torch_ref_query(net, rays, z)
