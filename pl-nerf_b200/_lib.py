@@ -9,7 +9,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libplnerf_b200.so")
+# PLNERF_LIB: developer override (e.g. a -DPLNERF_ENABLE_TRACE build of the same sources); never a fallback
+LIB_PATH = os.environ.get("PLNERF_LIB") or os.path.join(HERE, "libplnerf_b200.so")
 SOURCES = ["ops.cu", "mlp_fwd.cu", "api.cu"]
 HEADERS = ["common.cuh", "ops.cuh", "umma.cuh", os.path.join("..", "..", "include", "plnerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
