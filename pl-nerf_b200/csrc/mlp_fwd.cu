@@ -102,6 +102,12 @@ struct NetPlan {
   int64_t weight_bytes;  // bf16 stream
   int32_t is_dgrad;      // plan describes the backward (input-gradient) chain
   int32_t D;
+  // k_mlp2 only (PLNERF_PREC_BF16): after the fp32 tail, one 4 KB "bias K-step" block per (layer, 128-neuron half)
+  // of every layer whose bias is a per-neuron constant: B-operand image with columns 0,1,2 = bf16 hi/mid/lo parts of
+  // the bias (exact fp32 split); multiplied by a constant ones A operand it adds the bias inside the tensor pipe.
+  int64_t bias_blocks_off;     // byte offset from the start of the packed buffer (16-byte aligned), 0 = none
+  int32_t bias_block_idx[MAX_LAYERS];   // first block of layer l, or -1
+  int32_t n_bias_blocks;
 };
 
 // A (layer, half) streams its K-steps in stages of <= KS_PER_STAGE; the PE K-steps (shared-memory A
@@ -186,6 +192,12 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
   const int nsplit = (precision == PLNERF_PREC_BF16X3) ? 2 : 1;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * (P.L[l].n_pe_ks + P.L[l].n_h_ks) * KS_BYTES * nsplit;
   P.weight_bytes = wb;
+  P.n_bias_blocks = 0;
+  for (int l = 0; l < nl; ++l) {
+    if (precision == PLNERF_PREC_BF16 && P.L[l].epi != EPI_VIEWS) { P.bias_block_idx[l] = P.n_bias_blocks; P.n_bias_blocks += P.L[l].n_halves; }
+    else P.bias_block_idx[l] = -1;
+  }
+  P.bias_blocks_off = (precision == PLNERF_PREC_BF16) ? ((wb + (int64_t)P.tail_floats * 4 + 15) & ~(int64_t)15) : 0;
   return PLNERF_OK;
 }
 
@@ -257,6 +269,7 @@ int build_dgrad_plan(const plnerf_net_desc* d, const plnerf_net_params* p, NetPl
   // const block: rgb_w [3][128] and alpha_w [256] (same offsets as the forward plan so the tail is shared)
   P.alpha_w_off = fwd.alpha_w_off; P.alpha_b_off = fwd.alpha_b_off; P.rgb_w_off = fwd.rgb_w_off; P.rgb_b_off = fwd.rgb_b_off;
   P.const_floats = fwd.const_floats; P.tail_floats = fwd.tail_floats;
+  for (int l = 0; l < MAX_LAYERS; ++l) P.bias_block_idx[l] = -1;
   int64_t wb = 0;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * P.L[l].n_h_ks * KS_BYTES;
   P.weight_bytes = wb;
@@ -355,6 +368,27 @@ __global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
     }
   }
   a.tail[i] = v;
+}
+
+// one block (256 threads) per bias block: thread u -> 16-byte unit (panel = u/128, row = u%128)
+__global__ void __launch_bounds__(256) k_pack_bias(const __grid_constant__ PackArgs a) {
+  const NetPlan& P = a.plan;
+  int l = 0;
+  for (; l < P.n_layers; ++l)
+    if (P.bias_block_idx[l] >= 0 && (int)blockIdx.x >= P.bias_block_idx[l] && (int)blockIdx.x < P.bias_block_idx[l] + P.L[l].n_halves) break;
+  if (l >= P.n_layers) return;
+  const int h = blockIdx.x - P.bias_block_idx[l];
+  const int u = threadIdx.x, panel = u >> 7, row = u & 127;
+  const int trunk_layers = P.use_viewdirs ? P.n_layers - 2 : P.n_layers;
+  const float* b = (l < trunk_layers) ? a.prm.pts_b[l] : a.prm.feature_b;
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  if (panel == 0) {
+    const float v = b[h * 128 + row];
+    const float hi = ptx::bf16_round(v), mid = ptx::bf16_round(v - hi);
+    q.x = ptx::pack_bf16(hi, mid);                      // columns 0,1,2 = hi, mid, lo: the three bf16 terms sum to the
+    q.y = ptx::pack_bf16((v - hi) - mid, 0.f);          // fp32 bias exactly (3 x 8 mantissa bits)
+  }
+  *reinterpret_cast<uint4*>(a.dst + P.bias_blocks_off + (int64_t)blockIdx.x * KS_BYTES + (size_t)u * 16) = q;
 }
 
 // =============================================================================================
@@ -1068,6 +1102,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
+#include "mlp_fwd2.cuh"
+
 // =============================================================================================
 // debug: single tile GEMM  D[128,N] = A[128,K] * B[N,K]^T  through the same primitives
 // (N in {128,256}, K % 16 == 0, K <= 256).  a_mode 0 = A from shared memory panels (SS),
@@ -1205,20 +1241,55 @@ __global__ void __launch_bounds__(128, 1) k_debug_gemm_mn(const float* __restric
 // debug: raw tcgen05.mma issue/execute rate.  mode 0: TS N=128, 1: TS N=256, 2: SS N=128, 3: SS N=256.
 // One CTA per SM issues `iters` x 16 back-to-back MMAs on garbage operands; reports cycles per MMA.
 // =============================================================================================
-__global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, long long* cycles_out) {
+__global__ void __launch_bounds__(640, 1) k_debug_mma_rate(int mode, int iters, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 160 * 1024);
   const uint32_t bar = ptx::smem_u32(smem + 160 * 1024 + 16);
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::fence_mbar_init(); }
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::mbar_init(bar + 16, 1); ptx::fence_mbar_init(); }
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (warp == 1) {
+  if (warp >= 4) {
+    // mode 13/14: extra warps polling an mbarrier (what the epilogue warps of the fused kernels do while they wait)
+    ptx::mbar_wait(bar + 16, 0);
+  } else if (mode >= 20) {
+    // CUDA-core conversion throughput (all 4 warps): 20 = cvt.rn.relu.bf16x2.f32, 21 = max + integer round-half-up + PRMT,
+    // 22 = packed fp32 add (baseline), 23 = cvt.rn.bf16x2.f32 (no relu).  Reports cycles per warp-level "pair" operation.
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (float)(threadIdx.x * 32 + i) * 1.0001f - 1000.f;
+    uint32_t sink = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t d;
+        if (mode == 20) {
+          d = pack_bf16_relu(v[2 * i], v[2 * i + 1]);
+        } else if (mode == 23) {
+          d = ptx::pack_bf16(v[2 * i], v[2 * i + 1]);
+        } else if (mode == 21) {
+          const uint32_t a = __float_as_uint(fmaxf(v[2 * i], 0.f)) + 0x8000u, b = __float_as_uint(fmaxf(v[2 * i + 1], 0.f)) + 0x8000u;
+          d = __byte_perm(a, b, 0x7632);
+        } else {
+          float x = v[2 * i], y = v[2 * i + 1];
+          add2(x, y, 1.5f, 2.5f);
+          d = __float_as_uint(x) ^ __float_as_uint(y);
+        }
+        sink ^= d;
+        v[2 * i] = __uint_as_float(__float_as_uint(v[2 * i]) ^ (d & 1u));   // keep the chain data-dependent but cheap
+      }
+    }
+    const long long t1 = clock64();
+    if (sink == 0x12345678u) cycles_out[0] = 0;
+    if (threadIdx.x == 32) cycles_out[blockIdx.x] = t1 - t0;
+  } else if (warp == 1) {
     const int N = ((mode & 1) && mode < 4) ? 256 : 128;
     const bool ss = (mode == 2 || mode == 3);
     const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
@@ -1234,6 +1305,29 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
             const uint64_t bd = ptx::smem_desc(sb + 64 * 1024 + (j & 3) * (N * 32), lbo, 128);
             if (ss) ptx::mma_ss(tmem, ptx::smem_desc(sb + j * 4096, 2048, 128), bd, idesc, j > 0);
             else ptx::mma_ts(tmem, tmem + 256u + 8u * j, bd, idesc, j > 0);
+          }
+        }
+        __syncwarp();
+      }
+    } else if (mode >= 6 && mode <= 14) {
+      // SS-form operand-layout experiments (rate only, operands are garbage):
+      //  6: N=256 no swizzle   7: N=256 A+B SWIZZLE_128B   8: N=256 A swizzled only   9: N=256 B swizzled only
+      // 10: N=128 A+B SWIZZLE_128B   11: N=256 no swizzle, A fixed (same 4 KB every MMA)   12: N=256 no swizzle, B fixed
+      const int N = (mode == 10) ? 128 : 256;
+      const bool a_sw = (mode == 7 || mode == 8 || mode == 10), b_sw = (mode == 7 || mode == 9 || mode == 10);
+      const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
+      const uint32_t sb = ptx::smem_u32(smem);
+      auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) -> uint64_t {
+        return ptx::smem_desc(addr, lbo, sbo) | ((uint64_t)layout << 61);
+      };
+      for (int it = 0; it < iters; ++it) {
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ja = (mode == 11) ? 0 : j, jb = (mode == 12) ? 0 : (j & 3);
+            const uint64_t ad = a_sw ? desc(sb + (ja >> 2) * 16384 + (ja & 3) * 32, 16, 1024, 2) : desc(sb + ja * 4096, 2048, 128, 0);
+            const uint64_t bd = b_sw ? desc(sb + 64 * 1024 + jb * 32, 16, 1024, 2) : desc(sb + 64 * 1024 + jb * (N * 32), N * 16, 128, 0);
+            ptx::mma_ss(tmem, ad, bd, idesc, j > 0);
           }
         }
         __syncwarp();
@@ -1271,6 +1365,7 @@ __global__ void __launch_bounds__(128, 1) k_debug_mma_rate(int mode, int iters, 
     ptx::mbar_wait(bar, 0);
     long long t1 = clock64();
     if (threadIdx.x == 32) cycles_out[blockIdx.x] = (mode == 5) ? t_issue : (t1 - t0);
+    if (threadIdx.x == 32) ptx::mbar_arrive(bar + 16);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1473,9 +1568,58 @@ cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
+// bf16 inference goes through k_mlp2 (two tiles in flight per CTA, SS operands); PLNERF_MLP_KERNEL=v1 selects the
+// first-generation kernel, PLNERF_MLP_CTA=1|2 the CTA-pair mode (developer A/B switches, both are CUDA paths).
+int launch_mlp2(MlpArgs& a, cudaStream_t st, int kcta) {
+  const v2::Smem2 SL = v2::smem2_layout(kcta, a.plan.const_floats - v2::head_const_off(a.plan), g_max_smem);
+  if (SL.n_stages < 2) { set_error("k_mlp2: not enough shared memory for the weight ring"); return PLNERF_E_UNSUPPORTED; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PLNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } a.debug_flags = dbg; }
+  a.n_stages = g_max_smem;   // k_mlp2 derives its shared-memory layout from the same inputs as the host
+  a.trace = g_trace;
+  a.n_tiles = ceil_div(a.M, (int64_t)TILE_M * kcta);   // units of 128*kcta rows
+  const int64_t groups_max = g_num_sms / kcta;
+  const unsigned groups = (unsigned)((a.n_tiles < groups_max) ? a.n_tiles : groups_max);
+  ProfRec rec{nullptr, nullptr, a.M};
+  if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
+  if (kcta == 1) {
+    v2::k_mlp2<1><<<groups, v2::THREADS, SL.total, st>>>(a);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(groups * 2); cfg.blockDim = dim3(v2::THREADS); cfg.dynamicSmemBytes = SL.total; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, v2::k_mlp2<2>, a);
+    if (e != cudaSuccess) return cuda_fail(e, "k_mlp2<2> launch");
+  }
+  if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
+  PLNERF_LAUNCH_CHECK("k_mlp2");
+  return PLNERF_OK;
+}
+
 int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   int rc = query_device();
   if (rc) return rc;
+  {
+    static int use_v2 = -1, kcta = 1;
+    if (use_v2 < 0) {
+      const char* e = getenv("PLNERF_MLP_KERNEL");
+      use_v2 = (e && !strcmp(e, "v1")) ? 0 : 1;
+      const char* c = getenv("PLNERF_MLP_CTA");
+      kcta = (c && atoi(c) == 2) ? 2 : 1;
+    }
+    const int m = (mode < 0) ? ((a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0) : mode;
+    if (use_v2 && m == 0) return launch_mlp2(a, st, kcta);
+  }
   int n_stages = MAX_STAGES;
   while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
   a.n_stages = n_stages;
@@ -1512,6 +1656,7 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
 size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision) {
   NetPlan P;
   if (build_plan(d, precision, nullptr, &P)) return 0;
+  if (P.n_bias_blocks > 0) return (size_t)P.bias_blocks_off + (size_t)P.n_bias_blocks * KS_BYTES;
   return (size_t)P.weight_bytes + (size_t)P.tail_floats * 4;
 }
 
@@ -1532,6 +1677,10 @@ int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision
   PLNERF_LAUNCH_CHECK("k_pack_weights");
   k_pack_tail<<<(unsigned)ceil_div(a.plan.tail_floats, 256), 256, 0, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_pack_tail");
+  if (a.plan.n_bias_blocks > 0) {
+    k_pack_bias<<<(unsigned)a.plan.n_bias_blocks, 256, 0, st>>>(a);
+    PLNERF_LAUNCH_CHECK("k_pack_bias");
+  }
   return PLNERF_OK;
 }
 
@@ -1787,7 +1936,8 @@ int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStr
   int rc = query_device();
   if (rc) return rc;
   PLNERF_CUDA(cudaFuncSetAttribute(k_debug_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-  k_debug_mma_rate<<<grid, 128, 160 * 1024 + 64, st>>>(mode, iters, cycles_out);
+  const int threads = (mode == 13) ? 640 : (mode == 14 ? 256 : 128);   // 13: 16 polling warps, 14: 4 polling warps
+  k_debug_mma_rate<<<grid, threads, 160 * 1024 + 64, st>>>(mode, iters, cycles_out);
   PLNERF_LAUNCH_CHECK("k_debug_mma_rate");
   return PLNERF_OK;
 }

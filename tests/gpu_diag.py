@@ -76,6 +76,30 @@ def gemm_mn():
                   flush=True)
 
 
+def mmarate2():
+    for mode, name in ((3, "SS N=256 none (old loop)"), (6, "SS N=256 none"), (7, "SS N=256 A+B sw128"), (8, "SS N=256 A sw128"),
+                       (9, "SS N=256 B sw128"), (10, "SS N=128 A+B sw128"), (11, "SS N=256 none, A fixed"), (12, "SS N=256 none, B fixed"),
+                       (13, "SS N=256 none + 16 warps polling an mbarrier"), (14, "SS N=256 none + 4 warps polling")):
+        out = torch.zeros(148, dtype=torch.int64, device="cuda")
+        iters = 200
+        for rep in range(2):
+            L.check(L.lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
+            torch.cuda.synchronize()
+        cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
+        print(f"{name}: cycles/MMA mean={cyc.mean():.1f} min={cyc.min():.1f} max={cyc.max():.1f}", flush=True)
+
+
+def alurate():
+    for mode, name in ((20, "cvt.rn.relu.bf16x2.f32"), (23, "cvt.rn.bf16x2.f32"), (21, "fmax+iadd round-half-up + prmt"), (22, "add.f32x2")):
+        out = torch.zeros(148, dtype=torch.int64, device="cuda")
+        iters = 2000
+        for rep in range(2):
+            L.check(L.lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
+            torch.cuda.synchronize()
+        cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
+        print(f"{name}: cycles per pair-op per warp (4 warps/SM, 1 per SMSP) = {cyc.mean():.2f}", flush=True)
+
+
 def mmarate():
     for grid in (1, 148):
         for mode, name in ((0, "TS N=128"), (1, "TS N=256"), (2, "SS N=128"), (3, "SS N=256"),
@@ -90,7 +114,7 @@ def mmarate():
 
 
 if __name__ == "__main__":
-    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate, "gemm_mn": gemm_mn, "train": lambda: None}[sys.argv[1]]()
+    {"gemm": gemm, "mlp": mlp, "mmarate": mmarate, "mmarate2": mmarate2, "alurate": alurate, "gemm_mn": gemm_mn, "train": lambda: None}[sys.argv[1]]()
 
 
 def train_diag():

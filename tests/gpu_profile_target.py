@@ -38,13 +38,24 @@ with torch.no_grad():
         print(f"{prec} launch {i}: {ms:.3f} ms  {n*S*1186816/ms/1e9:.1f} TFLOP/s", flush=True)
 
 if trace is not None:
-    t = trace.cpu().numpy().reshape(4, 256, 2)
+    tt = trace.cpu().numpy()
+    if tt[-1] > 0:
+        print(f"kernel: {tt[-2]} SM cycles in {tt[-1]} ns -> {tt[-2] / tt[-1]:.3f} GHz; cycles per tile = {tt[-2] / (n * S / 128 / 148):.0f}")
+    tt[-2:] = 0
+    t = tt.reshape(4, 256, 2)
     ev = [(int(c), int(code), r) for r in range(4) for c, code in t[r] if code != 0]
     ev.sort()
     t0 = ev[0][0]
     names = {0: "MMA ", 1: "EPI0", 2: "EPI1", 3: "TMA "}
     for c, code, r in ev:
         kind = code // 1000
+        if os.environ.get("PLNERF_MLP_KERNEL") != "v1":
+            sub = code % 1000
+            l, t, st = sub // 100, (sub % 100) // 50, sub % 50
+            what = {1: "slot ready (a_ready seen)", 2: "stage full seen, issuing", 3: "d_full seen", 4: "a_ready signalled",
+                    6: "stage empty seen, TMA issue", 7: "tmem loaded", 8: "activations stored", 9: "issue returned", 10: "d_full committed", 11: "item top"}[kind]
+            print(f"{c - t0:8d}  {names[r]}  l={l} slot={t} st={st:2d}  {what}")
+            continue
         desc = {1: "batch top   entry=%d" % (code % 1000),
                 2: "batch issue entry=%d" % (code % 1000),
                 3: "d_full seen l=%d h=%d" % ((code % 1000) // 10, code % 10),
