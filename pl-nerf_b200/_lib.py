@@ -127,13 +127,14 @@ _SIGS = {
     "plnerf_debug_umma_gemm_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
                                             C.c_void_p]),
     "plnerf_debug_set_trace": (C.c_int, [C.c_void_p]),
+    "plnerf_debug_set_mlp_kernel": (C.c_int, [C.c_int, C.c_int]),
     "plnerf_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                             C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 # symbols that include/plnerf_b200.h declares (checked by tests/test_abi.py)
-PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace", "plnerf_debug_umma_gemm_mn")]
+PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace", "plnerf_debug_umma_gemm_mn", "plnerf_debug_set_mlp_kernel")]
 
 
 def lib():

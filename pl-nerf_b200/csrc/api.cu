@@ -27,6 +27,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st);
 int debug_set_trace(long long* buf);
+int debug_set_mlp_kernel(int variant, int cta);
 int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 
 // workspace carving for render_rays
@@ -256,6 +257,9 @@ int plnerf_debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint
 
 // debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)
 int plnerf_debug_set_trace(long long* buf) { return plnerf::debug_set_trace(buf); }
+
+// bf16 inference kernel selector: variant 1 = k_mlp_fwd (default), 2 = k_mlp2 with cta = 1 | 2 (not part of the product ABI)
+int plnerf_debug_set_mlp_kernel(int variant, int cta) { return plnerf::debug_set_mlp_kernel(variant, cta); }
 
 // bring-up microbenchmark (not part of the product ABI)
 int plnerf_debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, void* stream) {

@@ -51,8 +51,10 @@ constexpr int MAX_STAGES = 6;
 constexpr int NGRP = 4;               // epilogue column groups: each owns 4/NGRP of the 32-column chunks of a half
 constexpr int CHUNKS_PER_GRP = 4 / NGRP;
 constexpr int NUM_EPI_THREADS = 128 * NGRP;
-constexpr int FIRST_EPI_WARP = 2;
-constexpr int NUM_THREADS = 32 * FIRST_EPI_WARP + NUM_EPI_THREADS;   // warps: 0 TMA producer (+TMEM alloc), 1 MMA issuer, 2.. epilogue
+// warps 0..15 epilogue, then the TMA producer (+TMEM alloc) and the MMA issuer: the SM's warp arbiter prefers the
+// HIGHEST warp id, so the two latency-critical single-thread roles sit above the epilogue warps they share SMSPs with
+constexpr int WARP_TMA = NUM_EPI_THREADS / 32, WARP_MMA = WARP_TMA + 1;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 constexpr int MAX_OUT_CH = 8;
 
 enum { EPI_RELU_A = 0, EPI_LINEAR_A = 1, EPI_VIEWS = 2, EPI_RELU_HEAD = 3 };
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     }
     *prog_n = n_entries;
   }
-  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  if (warp == WARP_TMA) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
   ptx::tc_fence_before();
   __syncthreads();
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   // activation buffer written by the epilogue of layer l (and read by layer l+1)
   auto a_out_col = [&](int l) -> uint32_t { return X3 ? COL_A0 : ((l & 1) ? COL_A1 : COL_A0); };
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ===================== TMA producer: stream the packed weights through the ring ==============
     if (lane == 0) {
       uint32_t slot = 0, phase = 0, batch = 0;
@@ -755,7 +757,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer ===========================================================
     // The tensor pipe only buffers ~3-4 MMAs behind the issuing thread (measured), so everything the
     // thread does between two MMA batches must fit in ~200 cycles or the pipe idles.  The per-tile
@@ -854,12 +856,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         }
       }
     }
-  } else if (warp >= FIRST_EPI_WARP) {
+  } else {
     // ===================== epilogue warps (8): PE prologue, bias/ReLU/pack, heads, output ========
     // lane quarter q = warp % 4 (TMEM lanes 32q..32q+31, one row per thread), column group grp = (warp-2)/4
     // owns CHUNKS_PER_GRP 32-column chunks of every 128-column half.
-    const int e = warp - FIRST_EPI_WARP;
-    const int q = warp & 3, grp = e >> 2;   // TMEM lane quarter = hardware warp id % 4; grp in [0, NGRP)
+    const int q = warp & 3, grp = warp >> 2;   // TMEM lane quarter = hardware warp id % 4; grp in [0, NGRP)
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     uint32_t seen0 = 0, seen1 = 0;
@@ -1099,7 +1100,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+  if (warp == WARP_TMA) ptx::tmem_dealloc(tmem, 512);
 }
 
 #include "mlp_fwd2.cuh"
@@ -1543,6 +1544,7 @@ __global__ void __launch_bounds__(256) k_head_grads(const __grid_constant__ Head
 
 int g_num_sms = 0;
 int g_max_smem = 0;
+int g_mlp_variant = -1, g_mlp_cta = 2;   // bf16 inference kernel: 1 = k_mlp_fwd, 2 = k_mlp2 (single CTA or CTA pair)
 int query_device() {
   if (g_num_sms) return PLNERF_OK;
   int dev = 0;
@@ -1568,8 +1570,8 @@ cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-// bf16 inference goes through k_mlp2 (two tiles in flight per CTA, SS operands); PLNERF_MLP_KERNEL=v1 selects the
-// first-generation kernel, PLNERF_MLP_CTA=1|2 the CTA-pair mode (developer A/B switches, both are CUDA paths).
+// k_mlp2 (two tiles in flight per CTA, SS operands, optional CTA pairs): experimental alternative to k_mlp_fwd for bf16
+// inference, selected by PLNERF_MLP_KERNEL=v2 / plnerf_debug_set_mlp_kernel (both are CUDA paths on the same packed weights).
 int launch_mlp2(MlpArgs& a, cudaStream_t st, int kcta) {
   const v2::Smem2 SL = v2::smem2_layout(kcta, a.plan.const_floats - v2::head_const_off(a.plan), g_max_smem);
   if (SL.n_stages < 2) { set_error("k_mlp2: not enough shared memory for the weight ring"); return PLNERF_E_UNSUPPORTED; }
@@ -1610,15 +1612,16 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   int rc = query_device();
   if (rc) return rc;
   {
-    static int use_v2 = -1, kcta = 1;
-    if (use_v2 < 0) {
+    if (g_mlp_variant < 0) {
+      // default: the first-generation kernel (faster today); PLNERF_MLP_KERNEL=v2 [PLNERF_MLP_CTA=1|2]
+      // or plnerf_debug_set_mlp_kernel() select k_mlp2
       const char* e = getenv("PLNERF_MLP_KERNEL");
-      use_v2 = (e && !strcmp(e, "v1")) ? 0 : 1;
+      g_mlp_variant = (e && !strcmp(e, "v2")) ? 2 : 1;
       const char* c = getenv("PLNERF_MLP_CTA");
-      kcta = (c && atoi(c) == 2) ? 2 : 1;
+      g_mlp_cta = (c && atoi(c) == 1) ? 1 : 2;
     }
     const int m = (mode < 0) ? ((a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0) : mode;
-    if (use_v2 && m == 0) return launch_mlp2(a, st, kcta);
+    if (g_mlp_variant == 2 && m == 0) return launch_mlp2(a, st, g_mlp_cta);
   }
   int n_stages = MAX_STAGES;
   while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
@@ -1757,6 +1760,12 @@ int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode,
 }
 
 int debug_set_trace(long long* buf) { g_trace = buf; return PLNERF_OK; }
+
+int debug_set_mlp_kernel(int variant, int cta) {
+  PLNERF_CHECK_ARG((variant == 1 || variant == 2) && (cta == 1 || cta == 2), "debug_set_mlp_kernel: variant in {1,2}, cta in {1,2}");
+  g_mlp_variant = variant; g_mlp_cta = cta;
+  return PLNERF_OK;
+}
 
 int profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);

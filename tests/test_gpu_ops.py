@@ -232,6 +232,37 @@ def test_mlp_forward_bf16_vs_emulation(P, name):
     assert qs[1] < 1e-6 and qs[2] < 5e-4 and qs[4] < 5e-3, qs
 
 
+@pytest.mark.parametrize("cta", [1, 2])
+@pytest.mark.parametrize("name", ["lego_linear_mid", "lego_left_noise_lindisp"])
+def test_mlp2_kernel_variants(P, name, cta):
+    """k_mlp2 (two tiles in flight, SS operands, bias K-step; single CTA and CTA pair) against the same bf16-emulating
+    oracle and quantile gate as the default kernel, on embedded rows and through the fused-PE query."""
+    from plnerf_b200 import _lib as L
+    if name not in ALL:
+        pytest.skip("golden case not present")
+    g = load_golden(name)
+    cfg, kw, pc, pf = case_params(name)
+    net = make_net(kw, pc)
+    pts = g["pts0"].reshape(-1, 3)
+    emb = O.embed(pts, 10)
+    if cfg["use_viewdirs"]:
+        vd = np.broadcast_to(g["ray_batch"][:, None, -3:], g["pts0"].shape).reshape(-1, 3)
+        emb = np.concatenate([emb, O.embed(vd, 4)], -1)
+    ref = O.nerf_forward(pc, emb, emulate_bf16=True, **oracle_net_kw(kw))
+    L.check(L.lib().plnerf_debug_set_mlp_kernel(2, cta))
+    try:
+        with torch.no_grad():
+            out = host(P.mlp_forward(net, dev(emb), precision="bf16"))
+            raw = host(P.network_query(net, dev(g["ray_batch"]), dev(g["z_vals0"]), precision="bf16"))
+    finally:
+        L.check(L.lib().plnerf_debug_set_mlp_kernel(1, 2))
+    ref = ref[:, :out.shape[1]]
+    scale = np.abs(ref).max(0, keepdims=True)
+    for got in (out, raw.reshape(out.shape)):
+        qs = np.quantile(np.abs(got - ref) / scale, [0.5, 0.9, 0.99, 0.999, 1.0])
+        assert qs[1] < 2e-6 and qs[2] < 5e-4 and qs[4] < 5e-3, qs
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_network_query_fused_pe(P, name):
     """Fused query (PE computed in-kernel from rays and depths) vs the reference's raw0, bf16x3."""
