@@ -108,6 +108,79 @@ __device__ __forceinline__ double warp_incl_scan_mul(double v, int lane) {
 }
 #endif
 
+#ifdef __CUDACC__
+// ---- positional-encoding angles --------------------------------------------------------------------
+// The encoding needs sin/cos of p * 2^k for k = 0..L-1 (run_nerf_helpers.py:45-48).  Scaling by 2^k is exact in
+// fp32, so the reference's argument is the real number p * 2^k.  pe_turns() converts p once to a 32-bit fixed-point
+// fraction of a full turn, U = frac(p / 2pi) * 2^32 (fp64 multiply: 2^-32 turns absolute error); the angle of octave k
+// is then the EXACT left shift U << k (mod 1 turn), and pe_sin / pe_cos evaluate it with the SFU on [-pi, pi), where
+// sin.approx / cos.approx are accurate to 2^-21.4 absolute.  Total error <= ~1e-6 absolute at k = 9 (shifted
+// conversion error 2^-23 turns + SFU), i.e. the fp32-reference encoding to within the 1e-4 parity budget of the
+// network outputs, at ~6 instructions per sin/cos pair instead of ~60 for two precise sinf/cosf calls.
+__device__ __forceinline__ uint32_t pe_turns(float p) {
+  const double t = (double)p * 0.15915494309189535;          // p / (2 pi)
+  return (uint32_t)(long long)(t * 4294967296.0);             // two's-complement wrap = fraction mod 1
+}
+__device__ __forceinline__ float pe_angle(uint32_t turns, int k) {
+  return (float)(int32_t)(turns << k) * 1.4629180792671596e-9f;   // 2 pi / 2^32: radians in [-pi, pi)
+}
+__device__ __forceinline__ float pe_sin(uint32_t turns, int k) { return __sinf(pe_angle(turns, k)); }
+__device__ __forceinline__ float pe_cos(uint32_t turns, int k) { return __cosf(pe_angle(turns, k)); }
+
+// Elements [16*G, 16*G + 16) of the 3 + 6*L wide encoding [x, y, z, sin(2^0 p), cos(2^0 p), sin(2^1 p), ...] of one point,
+// fully unrolled for a compile-time group G (no dynamic indexing, no integer division, one angle per sin/cos pair that
+// falls into the group): out[e] = element 16*G + e, zero beyond n_ch.
+// Per coordinate, the LOWEST octave the group touches is evaluated exactly (shifted turn fraction + SFU); the group's
+// higher octaves (at most 3 more) follow from the double-angle recurrence sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a
+// on the FMA pipe -- the SFU / conversion pipe (16 lanes per clock per SM) is what bounds the encoding.  Each doubling
+// multiplies the absolute error by 3-4: <= 2e-5 at the end of a group -- invisible after the bf16 rounding of the
+// operand (RECUR = true, bf16 modes) but not for the hi+lo split mode, which evaluates every octave exactly (RECUR = false).
+template <int G, bool RECUR>
+__device__ __forceinline__ void pe_group16(const float (&p)[3], const uint32_t (&turns)[3], int n_ch, float (&out)[16]) {
+  constexpr int i_lo = (16 * G < 3) ? 3 : 16 * G, i_hi = 16 * G + 15;
+  constexpr int k_lo = (i_lo - 3) / 6, k_hi = (i_hi - 3) / 6;                 // octaves touched by elements [i_lo, i_hi]
+  float sn[3][k_hi - k_lo + 1], cs[3][k_hi - k_lo + 1];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // first octave whose sin or cos of coordinate c falls into the group
+    const int k0 = (3 + 6 * k_lo + 3 + c >= i_lo) ? k_lo : k_lo + 1;   // cos(c, k_lo) index = 3 + 6 k_lo + 3 + c
+#pragma unroll
+    for (int k = k_lo; k <= k_hi; ++k) {
+      if (k < k0) { sn[c][k - k_lo] = 0.f; cs[c][k - k_lo] = 0.f; }
+      else if (k == k0 || !RECUR) {
+        const float ang = pe_angle(turns[c], k);
+        sn[c][k - k_lo] = __sinf(ang); cs[c][k - k_lo] = __cosf(ang);
+      } else {
+        const float s1 = sn[c][k - 1 - k_lo], c1 = cs[c][k - 1 - k_lo];
+        sn[c][k - k_lo] = 2.f * s1 * c1;
+        cs[c][k - k_lo] = fmaf(-2.f * s1, s1, 1.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int idx = 16 * G + e;
+    float v;
+    if (idx < 3) {
+      v = p[idx];
+    } else {
+      const int t = idx - 3, k = t / 6, r = t % 6, c = r % 3;      // compile-time after unrolling
+      v = (r >= 3) ? cs[c][k - k_lo] : sn[c][k - k_lo];
+    }
+    out[e] = (idx < n_ch) ? v : 0.f;
+  }
+}
+template <bool RECUR>
+__device__ __forceinline__ void pe_group16(int g, const float (&p)[3], const uint32_t (&turns)[3], int n_ch, float (&out)[16]) {
+  switch (g) {
+    case 0: pe_group16<0, RECUR>(p, turns, n_ch, out); break;
+    case 1: pe_group16<1, RECUR>(p, turns, n_ch, out); break;
+    case 2: pe_group16<2, RECUR>(p, turns, n_ch, out); break;
+    default: pe_group16<3, RECUR>(p, turns, n_ch, out); break;
+  }
+}
+#endif
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace plnerf

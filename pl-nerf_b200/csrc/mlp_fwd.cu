@@ -529,7 +529,7 @@ __device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, 
 
 template <int MODE>
 __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, const SmemLayout& SL, int64_t tile, int row,
-                                            int grp) {
+                                            int grp, const float* p_pre = nullptr) {
   constexpr bool X3 = (MODE == 1);
   constexpr bool STASH = (MODE == 2);
   const NetPlan& P = A.plan;
@@ -541,6 +541,8 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
   const float* xr = nullptr;
   if (A.x_emb) {
     xr = A.x_emb + gc * (int64_t)A.x_ld;
+  } else if (p_pre) {
+    p[0] = p_pre[0]; p[1] = p_pre[1]; p[2] = p_pre[2];     // sample position fetched earlier in the tile (see the epilogue loop)
   } else {
     const int64_t ray = gc / A.S;
     const float* rp = A.rays + ray * (int64_t)A.stride;
@@ -548,19 +550,23 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
 #pragma unroll
     for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));  // o + d*z, two roundings
   }
+  const uint32_t turns[3] = {pe_turns(p[0]), pe_turns(p[1]), pe_turns(p[2])};
   // element idx of the encoding: [x,y,z, sin(2^0 p), cos(2^0 p), sin(2^1 p), ...] (run_nerf_helpers.py:45-48)
   auto elem = [&](int idx) -> float {
     if (idx >= P.input_ch) return 0.f;
     if (xr) return xr[idx];
     if (idx < 3) return p[idx];
     const int t = idx - 3, k = t / 6, r = t - 6 * k, c = (r >= 3) ? r - 3 : r;
-    const float a = p[c] * __int_as_float((127 + k) << 23);   // exact power-of-two scale
-    return (r >= 3) ? cosf(a) : sinf(a);
+    return (r >= 3) ? pe_cos(turns[c], k) : pe_sin(turns[c], k);   // angle p * 2^k as an exact shift of p's turn fraction
   };
+  // fast path: 63-wide encoding computed in-kernel, 4 column groups of two panels each -> one fully unrolled 16-element group
+  const bool fast16 = !X3 && (xr == nullptr) && (n_panels == 8) && (NGRP == 4);   // (the split mode is register-bound: generic path)
+  float v16[16];
+  if (fast16) pe_group16<false>(grp, p, turns, P.input_ch, v16);
   for (int pnl = p_lo; pnl < p_hi; ++pnl) {
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = elem(8 * pnl + e);
+    for (int e = 0; e < 8; ++e) v[e] = fast16 ? v16[(pnl == p_lo ? 0 : 8) + e] : elem(8 * pnl + e);
     uint4 hi;
     hi.x = ptx::pack_bf16(v[0], v[1]); hi.y = ptx::pack_bf16(v[2], v[3]);
     hi.z = ptx::pack_bf16(v[4], v[5]); hi.w = ptx::pack_bf16(v[6], v[7]);
@@ -866,6 +872,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     uint32_t seen0 = 0, seen1 = 0;
     int l_pe_last = 0;
     for (int l = 0; l < P.n_layers; ++l) if (P.L[l].n_pe_ks > 0) l_pe_last = l;
+    float pe_pos[3] = {0.f, 0.f, 0.f}, pre_od[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pre_z = 0.f;
 
     if (!DGRAD && (int64_t)blockIdx.x < A.n_tiles) {
       pe_prologue<MODE>(A, smem, SL, blockIdx.x, row, grp);
@@ -1052,15 +1059,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
           PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
         }
+        // The next tile's depths / ray rows are a cold DRAM read (~2000+ cycles): the loads are issued after layer 0's
+        // epilogue, consumed (o + d*z) after layer 1's, and only the cheap encoding itself is left for l_pe_last --
+        // otherwise that latency sits between two layers' epilogues and idles the tensor pipe.
+        if (!DGRAD && !X3 && !A.x_emb && l_pe_last >= 2) {
+          const int64_t nt = tile + gridDim.x;
+          if (nt < A.n_tiles) {
+            if (l == 0) {
+              const int64_t gn = nt * TILE_M + row, gcn = (gn < A.M) ? gn : (A.M - 1);
+              const float* rp = A.rays + (gcn / A.S) * (int64_t)A.stride;
+              pre_z = A.z[gcn];
+#pragma unroll
+              for (int c = 0; c < 6; ++c) pre_od[c] = rp[c];
+            } else if (l == 1) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) pe_pos[c] = __fadd_rn(pre_od[c], __fmul_rn(pre_od[3 + c], pre_z));  // o + d*z, two roundings
+            }
+          }
+        }
         if (!DGRAD && l == l_pe_last) {
           // every MMA that reads the PE tile of this tile has completed (its d_full was waited):
           // encode the NEXT tile's rows now, overlapped with the remaining layers
           const int64_t nt = tile + gridDim.x;
           if (nt < A.n_tiles) {
-            pe_prologue<MODE>(A, smem, SL, nt, row, grp);
+            PLNERF_TRACE(1 + grp, tcnt, 7000);
+            pe_prologue<MODE>(A, smem, SL, nt, row, grp, (!X3 && !A.x_emb && l_pe_last >= 2) ? pe_pos : nullptr);
+            PLNERF_TRACE(1 + grp, tcnt, 7001);
             ptx::fence_proxy_async_smem();
+            PLNERF_TRACE(1 + grp, tcnt, 7002);
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(pe_ready);
+            PLNERF_TRACE(1 + grp, tcnt, 7003);
           }
         }
       }

@@ -303,13 +303,13 @@ __device__ __forceinline__ void pe_rows(const MlpArgs& A, uint8_t* pe_panels, in
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = __fadd_rn(rp[k], __fmul_rn(rp[3 + k], zz));  // o + d*z, two roundings (run_plnerf.py:707)
   }
+  const uint32_t turns[3] = {pe_turns(p[0]), pe_turns(p[1]), pe_turns(p[2])};
   auto elem = [&](int idx) -> float {
     if (idx >= P.input_ch) return 0.f;
     if (xr) return xr[idx];
     if (idx < 3) return p[idx];
     const int t = idx - 3, k = t / 6, r = t - 6 * k, cc = (r >= 3) ? r - 3 : r;
-    const float a = p[cc] * __int_as_float((127 + k) << 23);   // exact power-of-two scale (run_nerf_helpers.py:45-48)
-    return (r >= 3) ? cosf(a) : sinf(a);
+    return (r >= 3) ? pe_cos(turns[cc], k) : pe_sin(turns[cc], k);   // run_nerf_helpers.py:45-48; common.cuh pe_turns
   };
   for (int pnl = p_lo; pnl < p_hi; ++pnl) {
     float v[8];

@@ -61,5 +61,6 @@ if trace is not None:
                 3: "d_full seen l=%d h=%d" % ((code % 1000) // 10, code % 10),
                 4: "arrived     l=%d h=%d" % ((code % 1000) // 10, code % 10),
                 5: "issue ret   entry=%d" % (code % 1000),
-                6: "tma issue   l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10)}[kind]
+                6: "tma issue   l=%d h=%d st=%d" % ((code % 1000) // 100, (code % 100) // 10, code % 10),
+                7: "pe step %d" % (code % 1000)}[kind]
         print(f"{c - t0:8d}  {names[r]}  {desc}")

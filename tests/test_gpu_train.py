@@ -132,7 +132,7 @@ def test_network_query_backward_vs_torch_autograd(n, S):
     g = load_golden("lego_linear_mid")
     rb = np.tile(g["ray_batch"], (n // g["ray_batch"].shape[0] + 1, 1))[:n]
     rays = dev(rb)
-    z = torch.sort(torch.rand(n, S, device="cuda") * 4 + 2, -1)[0]
+    z = dev(np.sort(rs.rand(n, S).astype(np.float32) * 4 + 2, -1))      # seeded: the tolerances below are per-sample-set
     g_raw = dev(rs.randn(n, S, 4).astype(np.float32))
     with torch.no_grad():
         raw, stash = ops.network_query_train(net, rays, z)
