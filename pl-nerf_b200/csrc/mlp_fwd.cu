@@ -397,36 +397,53 @@ __global__ void __launch_bounds__(256) k_pack_bias(const __grid_constant__ PackA
 // per-ray view bias:  vb[r][n] = views_b[n] + sum_j Wv[n][256+j] * gamma_dir(viewdir_r)_j   (fp32)
 // (the viewdir columns of views_linears[0], run_nerf_helpers.py:117-121, are constant per ray)
 // =============================================================================================
+constexpr int VB_RAYS = 4;   // rays per block iteration
 __global__ void __launch_bounds__(128) k_viewbias(const float* __restrict__ tail, int views_b_off, int dirw_off,
                                                   int icv, int multires_views, const float* __restrict__ rays,
                                                   int stride, const float* __restrict__ x_emb, int x_ld, int x_col0,
                                                   int64_t n, float* __restrict__ vb, float* __restrict__ dirpe) {
-  __shared__ float emb[64];
-  const int64_t r = blockIdx.x;
-  if (r >= n) return;
+  // thread t owns output neuron t: its icv weights live in registers for the whole (grid-strided) ray loop
+  __shared__ float emb[VB_RAYS][64];
   const int t = threadIdx.x;
-  if (t < icv) {
-    float v;
-    if (x_emb) {
-      v = x_emb[r * (int64_t)x_ld + x_col0 + t];
-    } else {
-      const float* vd = rays + r * (int64_t)stride + (stride - 3);
-      if (multires_views < 0 || t < 3) v = vd[t % 3];
-      else {
-        const int k = (t - 3) / 6, rem = (t - 3) % 6;
-        const float a = vd[rem % 3] * exp2f((float)k);
-        v = (rem < 3) ? sinf(a) : cosf(a);
+  float w[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) w[j] = (j < icv) ? tail[dirw_off + t * icv + j] : 0.f;
+  const float b = tail[views_b_off + t];
+  for (int64_t r0 = (int64_t)blockIdx.x * VB_RAYS; r0 < n; r0 += (int64_t)gridDim.x * VB_RAYS) {
+    // the rays' direction encodings: thread (rr, j) = (t / 32, t % 32) and (t / 32, 32 + t % 32)
+    for (int e = t; e < VB_RAYS * 64; e += 128) {
+      const int rr = e >> 6, j = e & 63;
+      const int64_t r = r0 + rr;
+      float v = 0.f;
+      if (r < n && j < icv) {
+        if (x_emb) {
+          v = x_emb[r * (int64_t)x_ld + x_col0 + j];
+        } else {
+          const float* vd = rays + r * (int64_t)stride + (stride - 3);
+          if (multires_views < 0 || j < 3) v = vd[j % 3];
+          else {
+            const int k = (j - 3) / 6, rem = (j - 3) % 6;
+            const float a = vd[rem % 3] * exp2f((float)k);
+            v = (rem < 3) ? sinf(a) : cosf(a);
+          }
+        }
+      }
+      emb[rr][j] = v;
+      if (dirpe && r < n && j < 32) dirpe[r * 32 + j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < VB_RAYS; ++rr) {
+      const int64_t r = r0 + rr;
+      if (r < n) {
+        float acc = b;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if (j < icv) acc = fmaf(w[j], emb[rr][j], acc);
+        vb[r * 128 + t] = acc;
       }
     }
-    emb[t] = v;
-    if (dirpe) dirpe[r * 32 + t] = v;
+    __syncthreads();
   }
-  if (dirpe && t >= icv && t < 32) dirpe[r * 32 + t] = 0.f;
-  __syncthreads();
-  float acc = tail[views_b_off + t];
-  const float* w = tail + dirw_off + t * icv;
-  for (int j = 0; j < icv; ++j) acc = fmaf(w[j], emb[j], acc);
-  vb[r * 128 + t] = acc;
 }
 
 // =============================================================================================
@@ -1724,7 +1741,9 @@ size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays) {
 static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int precision, MlpArgs& a, int64_t vb_rows,
                           int multires_views, const float* rays, int stride, const float* x_emb, int x_ld, void* ws,
                           size_t ws_bytes, cudaStream_t st, int mode = -1, float* dirpe_out = nullptr) {
-  int rc = build_plan(d, precision, nullptr, &a.plan);
+  int rc = query_device();
+  if (rc) return rc;
+  rc = build_plan(d, precision, nullptr, &a.plan);
   if (rc) return rc;
   PLNERF_CHECK_ARG(packed && ((uintptr_t)packed & 15) == 0, "packed weights null or misaligned");
   a.w = static_cast<const uint8_t*>(packed);
@@ -1734,7 +1753,8 @@ static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int prec
     const size_t need = (size_t)vb_rows * 128 * sizeof(float);
     if (!ws || ws_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes); return PLNERF_E_WORKSPACE; }
     float* vb = static_cast<float*>(ws);
-    k_viewbias<<<(unsigned)vb_rows, 128, 0, st>>>(a.tail, a.plan.views_b_off, a.plan.dirw_off, d->input_ch_views, multires_views,
+    const int64_t vb_blocks = ceil_div(vb_rows, VB_RAYS);
+    k_viewbias<<<(unsigned)(vb_blocks < 8 * g_num_sms ? vb_blocks : 8 * g_num_sms), 128, 0, st>>>(a.tail, a.plan.views_b_off, a.plan.dirw_off, d->input_ch_views, multires_views,
                                                   rays, stride, x_emb, x_ld, d->input_ch, vb_rows, vb, dirpe_out);
     PLNERF_LAUNCH_CHECK("k_viewbias");
     a.viewbias = vb;

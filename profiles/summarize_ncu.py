@@ -24,7 +24,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 srows = list(csv.reader(io.StringIO(src)))
 hi = [i for i, r in enumerate(srows) if "# Samples" in r]
 if hi:
-    hdr = srows[hi[0]]; data = [r for r in srows[hi[0] + 1:] if len(r) == len(hdr)]
+    hdr = srows[hi[0]]; data = [r for r in srows[hi[0] + 1:] if len(r) == len(hdr) and r[hdr.index('# Samples')].isdigit()]
     iS, iSrc, iEx = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
     tot = sum(int(r[iS]) for r in data) or 1
     texec = sum(int(r[iEx]) for r in data)
