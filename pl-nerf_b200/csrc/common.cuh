@@ -112,14 +112,29 @@ __device__ __forceinline__ double warp_incl_scan_mul(double v, int lane) {
 // ---- positional-encoding angles --------------------------------------------------------------------
 // The encoding needs sin/cos of p * 2^k for k = 0..L-1 (run_nerf_helpers.py:45-48).  Scaling by 2^k is exact in
 // fp32, so the reference's argument is the real number p * 2^k.  pe_turns() converts p once to a 32-bit fixed-point
-// fraction of a full turn, U = frac(p / 2pi) * 2^32 (fp64 multiply: 2^-32 turns absolute error); the angle of octave k
+// fraction of a full turn, U = frac(p / 2pi) * 2^32 (64x24-bit integer product: 2^-32 turns absolute error); the angle of octave k
 // is then the EXACT left shift U << k (mod 1 turn), and pe_sin / pe_cos evaluate it with the SFU on [-pi, pi), where
 // sin.approx / cos.approx are accurate to 2^-21.4 absolute.  Total error <= ~1e-6 absolute at k = 9 (shifted
 // conversion error 2^-23 turns + SFU), i.e. the fp32-reference encoding to within the 1e-4 parity budget of the
 // network outputs, at ~6 instructions per sin/cos pair instead of ~60 for two precise sinf/cosf calls.
 __device__ __forceinline__ uint32_t pe_turns(float p) {
-  const double t = (double)p * 0.15915494309189535;          // p / (2 pi)
-  return (uint32_t)(long long)(t * 4294967296.0);             // two's-complement wrap = fraction mod 1
+  // integer-only: p = +-m * 2^(e-150); frac(|p| / 2pi) * 2^32 = (m * C) >> (182 - e) mod 2^32 with C = 2^64 / (2 pi)
+  // (truncation error < 2^-32 turns).  No fp64: the double-precision multiply / 64-bit convert pair costs this kernel's
+  // 16 epilogue warps ~3000 cycles per tile on B200.
+  const uint32_t bits = __float_as_uint(p);
+  uint32_t e = (bits >> 23) & 255u;
+  const uint32_t m = (bits & 0x7FFFFFu) | (e ? 0x800000u : 0u);
+  if (e == 0) e = 1;
+  const unsigned long long C = 0x28BE60DB9391054AULL;
+  const unsigned long long lo = (unsigned long long)m * C;          // low 64 bits of the 88-bit product
+  const unsigned long long hi = __umul64hi((unsigned long long)m, C);
+  const int sh = 182 - (int)e;                                       // right shift of the 128-bit value hi:lo
+  uint32_t u;
+  if (sh >= 96) u = 0u;
+  else if (sh >= 64) u = (uint32_t)(hi >> (sh - 64));
+  else if (sh > 0) u = (uint32_t)((lo >> sh) | (hi << (64 - sh)));
+  else u = (uint32_t)(lo << (-sh));                                  // |p| >= 2^32: only the low product bits matter
+  return (bits >> 31) ? (0u - u) : u;
 }
 __device__ __forceinline__ float pe_angle(uint32_t turns, int k) {
   return (float)(int32_t)(turns << k) * 1.4629180792671596e-9f;   // 2 pi / 2^32: radians in [-pi, pi)

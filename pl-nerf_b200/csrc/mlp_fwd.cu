@@ -621,6 +621,7 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
                                             int grp, const float* p_pre = nullptr) {
   constexpr bool X3 = (MODE == 1);
   constexpr bool STASH = (MODE == 2);
+  if (A.debug_flags & 8) return;   // bring-up experiment: no encoding at all (garbage inputs)
   const NetPlan& P = A.plan;
   const int64_t g = tile * TILE_M + row;
   const int64_t gc = (g < A.M) ? g : (A.M - 1);
@@ -648,14 +649,25 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
     const int t = idx - 3, k = t / 6, r = t - 6 * k, c = (r >= 3) ? r - 3 : r;
     return (r >= 3) ? pe_cos(turns[c], k) : pe_sin(turns[c], k);   // angle p * 2^k as an exact shift of p's turn fraction
   };
-  // fast path: 63-wide encoding computed in-kernel, 4 column groups of two panels each -> one fully unrolled 16-element group
-  const bool fast16 = !X3 && (xr == nullptr) && (n_panels == 8) && (NGRP == 4);   // (the split mode is register-bound: generic path)
-  float v16[16];
-  if (fast16) pe_group16<false>(grp, p, turns, P.input_ch, v16);
+  // fast path: 63-wide encoding computed in-kernel, 4 column groups of two panels each -> one fully unrolled 16-element
+  // group whose values never leave registers (this kernel leaves ~3 KB of L1: a local-memory array costs L2 round trips)
+  if (!X3 && (xr == nullptr) && (n_panels == 8) && (NGRP == 4)) {
+    float v16[16];
+    pe_group16<false>(grp, p, turns, P.input_ch, v16);
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      uint4 hi;
+      hi.x = ptx::pack_bf16(v16[8 * h2 + 0], v16[8 * h2 + 1]); hi.y = ptx::pack_bf16(v16[8 * h2 + 2], v16[8 * h2 + 3]);
+      hi.z = ptx::pack_bf16(v16[8 * h2 + 4], v16[8 * h2 + 5]); hi.w = ptx::pack_bf16(v16[8 * h2 + 6], v16[8 * h2 + 7]);
+      *reinterpret_cast<uint4*>(smem + SL.pe_hi + (p_lo + h2) * 2048 + row * 16) = hi;
+      if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
+                              A.tl.in_width[A.tl.idx_pe], row, p_lo + h2, hi);
+    }
+  } else
   for (int pnl = p_lo; pnl < p_hi; ++pnl) {
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fast16 ? v16[(pnl == p_lo ? 0 : 8) + e] : elem(8 * pnl + e);
+    for (int e = 0; e < 8; ++e) v[e] = elem(8 * pnl + e);
     uint4 hi;
     hi.x = ptx::pack_bf16(v[0], v[1]); hi.y = ptx::pack_bf16(v[2], v[3]);
     hi.z = ptx::pack_bf16(v[4], v[5]); hi.w = ptx::pack_bf16(v[6], v[7]);
@@ -1766,6 +1778,7 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   }
   int n_stages = MAX_STAGES;
   while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
+  { static int force = -1; if (force < 0) { const char* e = getenv("PLNERF_STAGES"); force = e ? atoi(e) : 0; } if (force >= 2 && force < n_stages) n_stages = force; }
   a.n_stages = n_stages;
   const SmemLayout SL = smem_layout(n_stages);
   static bool attr_set = false;

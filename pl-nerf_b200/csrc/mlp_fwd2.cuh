@@ -311,6 +311,19 @@ __device__ __forceinline__ void pe_rows(const MlpArgs& A, uint8_t* pe_panels, in
     const int t = idx - 3, k = t / 6, r = t - 6 * k, cc = (r >= 3) ? r - 3 : r;
     return (r >= 3) ? pe_cos(turns[cc], k) : pe_sin(turns[cc], k);   // run_nerf_helpers.py:45-48; common.cuh pe_turns
   };
+  if (xr == nullptr && n_panels == 8) {
+    // 63-wide encoding: one fully unrolled 16-element group per thread, values stay in registers (common.cuh)
+    float v16[16];
+    pe_group16<false>(c, p, turns, P.input_ch, v16);
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      uint4 q;
+      q.x = ptx::pack_bf16(v16[8 * h2 + 0], v16[8 * h2 + 1]); q.y = ptx::pack_bf16(v16[8 * h2 + 2], v16[8 * h2 + 3]);
+      q.z = ptx::pack_bf16(v16[8 * h2 + 4], v16[8 * h2 + 5]); q.w = ptx::pack_bf16(v16[8 * h2 + 6], v16[8 * h2 + 7]);
+      *reinterpret_cast<uint4*>(pe_panels + (p_lo + h2) * 2048 + row * 16) = q;
+    }
+    return;
+  }
   for (int pnl = p_lo; pnl < p_hi; ++pnl) {
     float v[8];
 #pragma unroll
