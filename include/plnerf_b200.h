@@ -134,6 +134,18 @@ uint64_t plnerf_launch_count(void);
  * x [n,3] -> out [n, 3+6*multires]  (multires < 0: copy). */
 int plnerf_encode(const float* x, int64_t n, int multires, float* out, void* stream);
 
+/* ---- f-1 (next row): ray generation and packing done by render(), run_plnerf.py:138-164 ----------
+ * get_rays (run_nerf_helpers.py:162-171) from a pose c2w [3, >=4] (row stride c2w_ld), or the given
+ * rays_o / rays_d [n,3] when c2w == NULL; viewdirs = d/|d| taken before NDC (:145-150, from c2w even
+ * when c2w_staticcam supplies origins and directions); ndc_rays (:184-201) with the near plane
+ * ndc_near (render() passes 1.0) and the scalar factors ndc_cx = -1/(W/(2 focal)), ndc_cy =
+ * -1/(H/(2 focal)) the caller computed in double; near/far columns.  out [n, 8 | 11] row-major with
+ * row stride `stride` floats.  n = H*W when c2w != NULL. */
+int plnerf_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                     const float* c2w_staticcam, int c2w_staticcam_ld, const float* rays_o,
+                     const float* rays_d, int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near,
+                     float near, float far, int use_viewdirs, float* out, int stride, void* stream);
+
 /* ---- a3 (first part): stratified depths, render_rays (run_plnerf.py:683-705) -----------------
  * rays [n, stride] (cols 6,7 = near, far).  t_rand [n,Ns] explicit jitter in [0,1) or NULL;
  * with t_rand == NULL, perturb != 0 draws Philox(seed, ray id, sample) jitter. */

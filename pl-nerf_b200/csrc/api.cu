@@ -255,6 +255,19 @@ int plnerf_debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint
   return plnerf::debug_umma_gemm_mn(X, Y, N, K, lbo, sbo, D, (cudaStream_t)stream);
 }
 
+int plnerf_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                     const float* c2w_staticcam, int c2w_staticcam_ld, const float* rays_o, const float* rays_d,
+                     int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far,
+                     int use_viewdirs, float* out, int stride, void* stream) {
+  PLNERF_CHECK_ARG(out && n >= 0, "pack_rays: null output or negative size");
+  PLNERF_CHECK_ARG(c2w || (rays_o && rays_d), "pack_rays: need a pose or rays_o/rays_d");
+  PLNERF_CHECK_ARG(!c2w || (H > 0 && W > 0 && n == (int64_t)H * W && c2w_ld >= 4), "pack_rays: with a pose, n must be H*W and c2w_ld >= 4");
+  PLNERF_CHECK_ARG(!c2w_staticcam || (c2w && c2w_staticcam_ld >= 4), "pack_rays: c2w_staticcam needs c2w");
+  PLNERF_CHECK_ARG(stride >= (use_viewdirs ? 11 : 8), "pack_rays: row stride too small");
+  return launch_pack_rays(H, W, fx, fy, cx, cy, c2w, c2w_ld, c2w_staticcam, c2w_staticcam_ld, rays_o, rays_d, n, ndc, ndc_cx,
+                          ndc_cy, ndc_near, near, far, use_viewdirs, out, stride, (cudaStream_t)stream);
+}
+
 // debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)
 int plnerf_debug_set_trace(long long* buf) { return plnerf::debug_set_trace(buf); }
 

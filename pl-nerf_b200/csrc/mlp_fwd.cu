@@ -470,24 +470,33 @@ struct MlpArgs {
   const float* dirpe;      // [rays][32] fp32 dir encoding (padded), MODE 2
   const float* g_raw; int g_stride;   // MODE 3: upstream gradient of the network output [rows, >=4]
   int n_stages;
+  int slot_bytes;          // ring slot size (STAGE_BYTES, or SLOT_BYTES_BIAS when the layer biases are added by the tensor pipe)
+  int bias_mma;            // 1: every biased layer's (layer, half) ends with a bias K-step (ones operand x packed bias block)
   long long* trace;  // debug timeline buffer (null in production)
   int debug_flags;   // bring-up experiments only (PLNERF_DEBUG_FLAGS): 1 = skip weight re-streaming after tile 0
 };
 
 struct SmemLayout {
-  uint32_t pe_hi, pe_lo, ring, consts, xch, prog, prog2, bars;  // byte offsets
+  uint32_t pe_hi, pe_lo, ring, consts, xch, prog, prog2, ones, vb, bars;  // byte offsets
   uint32_t total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n_stages) {
+// A ring slot holds one 32 KB weight stage; with the bias K-step enabled (bf16 forward) it is 36 KB: the 4 KB bias block
+// of the (layer, half) the stage completes rides behind its 8 K-steps.
+constexpr int SLOT_BYTES_BIAS = STAGE_BYTES + KS_BYTES;
+constexpr int VB_SMEM_RAYS = 3;
+__host__ __device__ inline SmemLayout smem_layout(int n_stages, int slot_bytes) {
   SmemLayout s;
   s.pe_hi = 0;
   s.pe_lo = PE_TILE_BYTES;
   s.ring = 2 * PE_TILE_BYTES;
-  s.consts = s.ring + (uint32_t)n_stages * STAGE_BYTES;
+  s.consts = s.ring + (uint32_t)n_stages * (uint32_t)slot_bytes;
   s.xch = s.consts + MAX_CONST_FLOATS * 4;
   s.prog = s.xch + (NGRP - 1) * TILE_M * (MAX_OUT_CH + 1) * 4;
   s.prog2 = s.prog + 8 * 128;  // flattened MMA stage program (<= 128 entries)
-  s.bars = s.prog2 + 16 * 128; // the same program, pre-decoded for the asm issue loop (16 bytes per stage)
+  s.ones = s.prog2 + 16 * 128; // the same program, pre-decoded for the asm issue loop (16 bytes per stage)
+  const bool extra = (slot_bytes != STAGE_BYTES);
+  s.vb = s.ones + (extra ? KS_BYTES : 0);   // constant A operand of the bias K-step: panel 0 = [1,1,1,0,0,0,0,0] per row, panel 1 = 0
+  s.bars = s.vb + (extra ? VB_SMEM_RAYS * 128 * 4 : 0);   // the tile's per-ray view-bias rows (<= 3 rays per 128 samples)
   s.total = s.bars + 512;
   return s;
 }
@@ -553,9 +562,11 @@ __device__ __forceinline__ void issue_ts8(uint32_t d, uint32_t a, uint32_t a_lo,
 // Ring / dependency state of the issuing thread, carried across tiles.
 struct IssueState { uint32_t slot, batch, uses0, uses1, waited0, waited1, pend0, pend1; };
 // Flags of a program entry: 1 first-of-accumulator, 2 shared-memory A, 4 commit accumulator-full, 8 / 16 batch waits for
-// a_ready[a] / a_ready[b], 32 first entry of a batch, 64 / 128 the batch completes accumulator half a / b, bits 8-15 K-steps.
+// a_ready[a] / a_ready[b], 32 first entry of a batch, 64 / 128 the batch completes accumulator half a / b, bits 8-15 K-steps,
+// 65536 a bias K-step follows (shared-memory ones operand x the bias block at byte 32768 of the ring slot).
 __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, uint32_t n_entries, uint32_t idesc, uint64_t ring_desc,
-                                           uint32_t desc_hi, uint32_t wempty0, uint32_t n_stages, uint32_t bfull0, uint32_t aready0) {
+                                           uint32_t desc_hi, uint32_t wempty0, uint32_t n_stages, uint32_t bfull0, uint32_t aready0,
+                                           uint32_t slot16, uint32_t ones_lo) {
   asm volatile(
       "{\n\t.reg .pred p, p2, pacc, pt, ppe, pl;\n\t"
       ".reg .b32 sl, n, pa, ed, ea, ef, eb, t, k, wb, bt, u0, u1, w0, w1, q0, q1;\n\t.reg .b64 bd, so, ad;\n\t"
@@ -582,7 +593,7 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "NA1:\n\t"
       "tcgen05.fence::after_thread_sync;\n\t"
       "NOBATCH:\n\t"
-      "mul.wide.u32 so, sl, 2048;\n\tadd.u64 bd, so, %10;\n\t"
+      "mul.wide.u32 so, sl, %17;\n\tadd.u64 bd, so, %10;\n\t"
       "and.b32 t, ef, 1;\n\tsetp.eq.b32 pacc, t, 0;\n\t"
       "and.b32 t, ef, 2;\n\tsetp.ne.b32 ppe, t, 0;\n\t"
       "@ppe bra PE;\n\t"
@@ -596,6 +607,10 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "setp.eq.b32 pacc, sl, sl;\n\tadd.u64 ad, ad, 256;\n\tadd.u64 bd, bd, 256;\n\t"
       "sub.u32 k, k, 1;\n\tsetp.ne.b32 p, k, 0;\n\t@p bra PEL;\n\t"
       "COMMIT:\n\t"
+      "and.b32 t, ef, 65536;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOBIAS;\n\t"
+      "add.u64 bd, so, %10;\n\tadd.u64 bd, bd, 2048;\n\tmov.b64 ad, {%18, %12};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [ed], ad, bd, %11, pt;\n\t"
+      "NOBIAS:\n\t"
       "shl.b32 wb, sl, 3;\n\tadd.u32 wb, wb, %13;\n\t"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [wb];\n\t"
       "and.b32 t, ef, 4;\n\tsetp.ne.b32 pl, t, 0;\n\t"
@@ -605,7 +620,8 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "mov.b32 %0, sl;\n\tmov.b32 %1, bt;\n\tmov.b32 %2, u0;\n\tmov.b32 %3, u1;\n\tmov.b32 %4, w0;\n\tmov.b32 %5, w1;\n\t"
       "mov.b32 %6, q0;\n\tmov.b32 %7, q1;\n\t}"
       : "+r"(st.slot), "+r"(st.batch), "+r"(st.uses0), "+r"(st.uses1), "+r"(st.waited0), "+r"(st.waited1), "+r"(st.pend0), "+r"(st.pend1)
-      : "r"(prog_addr), "r"(n_entries), "l"(ring_desc), "r"(idesc), "r"(desc_hi), "r"(wempty0), "r"(n_stages), "r"(bfull0), "r"(aready0)
+      : "r"(prog_addr), "r"(n_entries), "l"(ring_desc), "r"(idesc), "r"(desc_hi), "r"(wempty0), "r"(n_stages), "r"(bfull0), "r"(aready0),
+        "r"(slot16), "r"(ones_lo)
       : "memory");
 }
 
@@ -750,7 +766,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   constexpr bool DGRAD = (MODE == 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   const NetPlan& P = A.plan;
-  const SmemLayout SL = smem_layout(A.n_stages);
+  const SmemLayout SL = smem_layout(A.n_stages, A.slot_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nsplit = X3 ? 2 : 1;
 
@@ -798,6 +814,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           const StageInfo si = stage_info(n_pe, n_h, st);
           uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
                         (st == nst - 1 ? F_LAST : 0u);
+          if (A.bias_mma && st == nst - 1 && P.bias_block_idx[l] >= 0) w0 |= (uint32_t)(P.bias_block_idx[l] + h + 1) << 20;   // bias K-step
           const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
           const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
           if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
@@ -813,6 +830,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   }
   if (warp == WARP_TMA) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
+  if (A.bias_mma)
+  for (int i = threadIdx.x; i < KS_BYTES / 16; i += NUM_THREADS)     // bf16 1.0 = 0x3F80
+    reinterpret_cast<uint4*>(smem + SL.ones)[i] = (i < 128) ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -837,13 +858,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             // one full-barrier per batch: armed with the batch's total bytes, every stage copy signals it.
             // 8 batch barriers > ring slots, so a barrier is never re-armed before its previous phase was consumed.
             uint32_t total = 0;
-            for (int j = 0; j < blen; ++j) total += (prog[i + j].x & 255u) * KS_BYTES;
+            for (int j = 0; j < blen; ++j) total += (prog[i + j].x & 255u) * KS_BYTES + (((prog[i + j].x >> 20) & 255u) ? KS_BYTES : 0u);
             const uint32_t bar = b_full(batch);
             if (copy) ptx::mbar_arrive_expect_tx(bar, total); else ptx::mbar_arrive(bar);
             for (int j = 0; j < blen; ++j) {
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               ptx::mbar_wait(w_empty(slot), phase ^ 1);
-              if (copy) ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, bar);
+              if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes, src, bytes, bar);
+              const uint32_t bidx = (prog[i + j].x >> 20) & 255u;     // bias block behind the stage's 8 K-steps
+              if (bidx) {
+                if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes + STAGE_BYTES, A.w + P.bias_blocks_off + (size_t)(bidx - 1) * KS_BYTES, KS_BYTES, bar);
+              }
               src += bytes;
               if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
             }
@@ -853,7 +878,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               for (int rep = 0; rep < 2; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
-                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * STAGE_BYTES, src, bytes, w_full(slot)); }
+                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes, src, bytes, w_full(slot)); }
                 else ptx::mbar_arrive(w_full(slot));
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
@@ -892,7 +917,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       const uint2 e = prog[n];
       const uint32_t fl = ((e.x & F_FIRST) ? 1u : 0u) | ((e.x & F_PE) ? 2u : 0u) | ((e.x & F_LAST) ? 4u : 0u) | ((e.x & 255u) << 8) |
                           ((e.x & F_WAIT_A0) ? 8u : 0u) | ((e.x & F_WAIT_A1) ? 16u : 0u) | (((e.x >> 12) & 15u) ? 32u : 0u) |
-                          ((e.x & F_INC0) ? 64u : 0u) | ((e.x & F_INC1) ? 128u : 0u);
+                          ((e.x & F_INC0) ? 64u : 0u) | ((e.x & F_INC1) ? 128u : 0u) | (((e.x >> 20) & 255u) ? 65536u : 0u);
       prog2[n] = make_uint4(tmem + COL_DA + ((e.x & F_H) ? 128u : 0u), (e.x & F_PE) ? lo_of(s_pe_hi + e.y * KS_BYTES) : tmem + e.y, fl,
                             d_full0 + ((e.x & F_H) ? 8u : 0u));
     }
@@ -906,7 +931,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         ptx::mbar_wait(pe_ready, tile_iter & 1);
         ptx::tc_fence_after();
         if (ptx::elect_one())
-          issue_tile(st, sbase + SL.prog2, (uint32_t)n_entries, idesc, ring_desc, desc_hi, w_empty(0), (uint32_t)A.n_stages, b_full(0), a_ready0);
+          issue_tile(st, sbase + SL.prog2, (uint32_t)n_entries, idesc, ring_desc, desc_hi, w_empty(0), (uint32_t)A.n_stages, b_full(0), a_ready0,
+                     (uint32_t)A.slot_bytes >> 4, lo_of(sbase + SL.ones));
         __syncwarp();
         // the state lives in the elected lane; elect.sync of a converged warp picks the same lane every time
       }
@@ -932,7 +958,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
             for (int rep = 0; rep < nsplit; ++rep) {
               if (X3) { ptx::mbar_wait(w_full(sl), ph); ptx::tc_fence_after(); }
-              const uint32_t b_lo = lo_of(s_ring + sl * STAGE_BYTES);
+              const uint32_t b_lo = lo_of(s_ring + sl * (uint32_t)A.slot_bytes);
               if (e.x & F_PE) {
                 const uint32_t a_lo_hi = lo_of(s_pe_hi + e.y * KS_BYTES), a_lo_lo = lo_of(s_pe_lo + e.y * KS_BYTES);
                 for (int k = 0; k < nks; ++k) {
@@ -1016,6 +1042,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
       for (int c = 0; c < MAX_OUT_CH; ++c) head[c] = 0.f;
       const float* vbrow = A.viewbias ? (A.viewbias + (gc / A.vb_div) * 128) : nullptr;
+      // The views layer's epilogue is the tile's last link; with ~3 KB of L1 left its per-ray bias rows would come from L2
+      // (~600 cycles on the critical path).  They are copied to shared memory asynchronously at the start of the tile.
+      const bool vb_smem = !DGRAD && A.bias_mma && A.viewbias && A.vb_div >= 64;
+      const int64_t vb_ray0 = (tile * TILE_M) / A.vb_div;
+      if (vb_smem && threadIdx.x < VB_SMEM_RAYS * 128) {
+        const int64_t last_row = (tile * TILE_M + TILE_M - 1 < A.M) ? tile * TILE_M + TILE_M - 1 : A.M - 1;
+        int64_t ray = vb_ray0 + (threadIdx.x >> 7);
+        if (ray > last_row / A.vb_div) ray = last_row / A.vb_div;
+        const uint32_t dst = sbase + SL.vb + 4u * threadIdx.x;
+        const float* srcp = A.viewbias + ray * 128 + (threadIdx.x & 127);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(srcp) : "memory");
+      }
+      if (vb_smem) asm volatile("cp.async.commit_group;" ::: "memory");
       float g_alpha = 0.f;
       if (DGRAD) {
         // the chain's input buffer (A1) is free again: the previous tile's last layer has been drained
@@ -1034,6 +1073,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         const int stash_idx = P.L[l].stash_idx, mask_idx = P.L[l].mask_idx;
         const uint32_t a_out = tmem + lane_addr + a_out_col(l);
         const uint32_t a_out_lo = tmem + lane_addr + COL_A1;
+        if (vb_smem && epi == EPI_VIEWS) {
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");     // rows were fetched by other threads
+        }
         for (int h = 0; h < n_halves; ++h) {
           if (h == 0) {
             ptx::mbar_wait(d_full0, seen0 & 1); ++seen0;
@@ -1083,7 +1126,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             } else if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(vbrow + n0 + i);
+                const float4 b4 = vb_smem ? *reinterpret_cast<const float4*>(smem + SL.vb + (((gc / A.vb_div) - vb_ray0) * 128 + n0 + i) * 4)
+                                          : *reinterpret_cast<const float4*>(vbrow + n0 + i);
                 val[i] = fmaxf(val[i] + b4.x, 0.f); val[i + 1] = fmaxf(val[i + 1] + b4.y, 0.f);
                 val[i + 2] = fmaxf(val[i + 2] + b4.z, 0.f); val[i + 3] = fmaxf(val[i + 3] + b4.w, 0.f);
               }
@@ -1113,12 +1157,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 head[2] = fmaf(val[i + 2], w2.z, head[2]); head[2] = fmaf(val[i + 3], w2.w, head[2]);
               }
             } else {
-              const float* bias = consts + bias_off + n0;
+              if (!(A.bias_mma && P.bias_block_idx[l] >= 0)) {      // else: added by the tensor pipe (bias K-step)
+                const float* bias = consts + bias_off + n0;
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
-                add2(val[i], val[i + 1], b4.x, b4.y);
-                add2(val[i + 2], val[i + 3], b4.z, b4.w);
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
+                  add2(val[i], val[i + 1], b4.x, b4.y);
+                  add2(val[i + 2], val[i + 3], b4.z, b4.w);
+                }
               }
               uint32_t pk[16];
               if (!X3 && !STASH && epi == EPI_RELU_A && flags == 0) {
@@ -1776,11 +1822,15 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
     const int m = (mode < 0) ? ((a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0) : mode;
     if (g_mlp_variant == 2 && m == 0) return launch_mlp2(a, st, g_mlp_cta);
   }
-  int n_stages = MAX_STAGES;
-  while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
+  if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
+  // bf16 forward (inference and stash mode must agree bit for bit): biases added by the tensor pipe, 36 KB ring slots
+  a.bias_mma = ((mode == 0 || mode == 2) && a.plan.n_bias_blocks > 0 && !getenv("PLNERF_NO_BIAS_MMA")) ? 1 : 0;
+  a.slot_bytes = a.bias_mma ? SLOT_BYTES_BIAS : STAGE_BYTES;
+  int n_stages = a.bias_mma ? 4 : MAX_STAGES;
+  while (n_stages > 2 && (int)smem_layout(n_stages, a.slot_bytes).total > g_max_smem) --n_stages;
   { static int force = -1; if (force < 0) { const char* e = getenv("PLNERF_STAGES"); force = e ? atoi(e) : 0; } if (force >= 2 && force < n_stages) n_stages = force; }
   a.n_stages = n_stages;
-  const SmemLayout SL = smem_layout(n_stages);
+  const SmemLayout SL = smem_layout(n_stages, a.slot_bytes);
   static bool attr_set = false;
   if (!attr_set) {
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));

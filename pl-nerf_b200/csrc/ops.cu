@@ -685,4 +685,88 @@ int launch_stratified_z(const float* rays, int64_t n, int stride, int Ns, int li
   return PLNERF_OK;
 }
 
+// =============================================================================================
+// f-1: ray generation + packing.  One thread per ray does what render() spends ~15 full-image torch ops on
+// (run_plnerf.py:138-164): get_rays from a camera pose (run_nerf_helpers.py:162-171) or a given (o, d) pair,
+// viewdirs = d / |d| taken BEFORE the NDC warp (:145-150), ndc_rays (:184-201), and the [o, d, near, far, viewdir]
+// row.  Every operation is a separately rounded fp32 op in the reference's order (no FMA contraction).
+// =============================================================================================
+struct PackRaysArgs {
+  int H, W;
+  float fx, fy, cx, cy;         // K[0][0], K[1][1], K[0][2], K[1][2] rounded to fp32 like torch does with python scalars
+  const float* c2w; int c2w_ld;         // [3, >=4] pose (rows strided by c2w_ld) or null
+  const float* c2w_static; int c2w_static_ld;   // optional: origins/directions from this pose, viewdirs from c2w
+  const float* rays_o; const float* rays_d;     // [n,3] each, used when c2w == null
+  int64_t n;
+  int ndc, use_viewdirs;
+  float ndc_cx, ndc_cy;         // fl32(-1/(W/(2 focal))), fl32(-1/(H/(2 focal)))  (python float64 arithmetic, then fp32)
+  float ndc_near;               // the near plane passed to ndc_rays (1.0 in render())
+  float near, far;
+  float* out; int stride;       // [n, 8 | 11]
+};
+
+__device__ __forceinline__ void pose_ray(const float* c2w, int ld, float dx, float dy, float dz, float (&o)[3], float (&d)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // torch.sum(dirs[..., None, :] * c2w[:3,:3], -1): three rounded products, summed left to right
+    d[c] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w[c * ld + 0]), __fmul_rn(dy, c2w[c * ld + 1])), __fmul_rn(dz, c2w[c * ld + 2]));
+    o[c] = c2w[c * ld + 3];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pack_rays(const PackRaysArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n) return;
+  float o[3], d[3], vd[3] = {0.f, 0.f, 0.f};
+  if (a.c2w) {
+    const float i = (float)(r % a.W), j = (float)(r / a.W);          // torch.linspace(0, W-1, W) is exact on integers
+    const float dx = __fdiv_rn(__fsub_rn(i, a.cx), a.fx);
+    const float dy = -__fdiv_rn(__fsub_rn(j, a.cy), a.fy);
+    pose_ray(a.c2w, a.c2w_ld, dx, dy, -1.f, o, d);
+    if (a.use_viewdirs) { vd[0] = d[0]; vd[1] = d[1]; vd[2] = d[2]; }
+    if (a.c2w_static) pose_ray(a.c2w_static, a.c2w_static_ld, dx, dy, -1.f, o, d);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { o[c] = a.rays_o[r * 3 + c]; d[c] = a.rays_d[r * 3 + c]; }
+    if (a.use_viewdirs) { vd[0] = d[0]; vd[1] = d[1]; vd[2] = d[2]; }
+  }
+  if (a.use_viewdirs) {
+    // torch.norm(dim=-1): sqrt of the fp32 sum of squares
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vd[0], vd[0]), __fmul_rn(vd[1], vd[1])), __fmul_rn(vd[2], vd[2])));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vd[c] = __fdiv_rn(vd[c], nrm);
+  }
+  if (a.ndc) {
+    const float t = __fdiv_rn(-__fadd_rn(a.ndc_near, o[2]), d[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = __fadd_rn(o[c], __fmul_rn(t, d[c]));
+    const float o0 = __fdiv_rn(__fmul_rn(a.ndc_cx, o[0]), o[2]);
+    const float o1 = __fdiv_rn(__fmul_rn(a.ndc_cy, o[1]), o[2]);
+    const float o2 = __fadd_rn(1.f, __fdiv_rn(__fmul_rn(2.f, a.ndc_near), o[2]));
+    const float d0 = __fmul_rn(a.ndc_cx, __fsub_rn(__fdiv_rn(d[0], d[2]), __fdiv_rn(o[0], o[2])));
+    const float d1 = __fmul_rn(a.ndc_cy, __fsub_rn(__fdiv_rn(d[1], d[2]), __fdiv_rn(o[1], o[2])));
+    const float d2 = __fdiv_rn(__fmul_rn(-2.f, a.ndc_near), o[2]);
+    o[0] = o0; o[1] = o1; o[2] = o2; d[0] = d0; d[1] = d1; d[2] = d2;
+  }
+  float* row = a.out + r * (int64_t)a.stride;
+  row[0] = o[0]; row[1] = o[1]; row[2] = o[2]; row[3] = d[0]; row[4] = d[1]; row[5] = d[2];
+  row[6] = a.near; row[7] = a.far;
+  if (a.use_viewdirs) { row[8] = vd[0]; row[9] = vd[1]; row[10] = vd[2]; }
+}
+
+int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d, int64_t n,
+                     int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far, int use_viewdirs,
+                     float* out, int stride, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  PackRaysArgs a;
+  a.H = H; a.W = W; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.c2w = c2w; a.c2w_ld = c2w_ld;
+  a.c2w_static = c2w_static; a.c2w_static_ld = c2w_static_ld; a.rays_o = rays_o; a.rays_d = rays_d; a.n = n;
+  a.ndc = ndc; a.use_viewdirs = use_viewdirs; a.ndc_cx = ndc_cx; a.ndc_cy = ndc_cy; a.ndc_near = ndc_near;
+  a.near = near; a.far = far; a.out = out; a.stride = stride;
+  k_pack_rays<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_pack_rays");
+  return PLNERF_OK;
+}
+
 }  // namespace plnerf

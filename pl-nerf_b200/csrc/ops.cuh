@@ -28,6 +28,11 @@ int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const 
 int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                  int Ni, float* z_out, float* z_std, cudaStream_t st);
 
+int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d, int64_t n,
+                     int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far, int use_viewdirs,
+                     float* out, int stride, cudaStream_t st);
+
 // ---- fused MLP (mlp_fwd.cu) ----------------------------------------------------------------
 size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision);
 int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision, void* packed, cudaStream_t st);

@@ -75,6 +75,31 @@ def encode(x, multires):
     return out.reshape(*shp[:-1], od)
 
 
+def pack_rays(H, W, K, c2w=None, rays=None, ndc=True, near=0., far=1., use_viewdirs=False, c2w_staticcam=None):
+    """The ray generation + packing of render() (run_plnerf.py:138-164) as one kernel: get_rays from a pose (or the given
+    (rays_o, rays_d)), viewdirs before NDC, ndc_rays(H, W, K[0][0], 1., ...), near/far columns.
+    Returns (packed [n, 8|11] fp32, shape of rays_d) -- `shape` is what render() reshapes its outputs to."""
+    fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    ndc_cx, ndc_cy = -1. / (W / (2. * fx)), -1. / (H / (2. * fx))          # python float64 arithmetic like the reference
+    if c2w is not None:
+        c2w = _f32(c2w, "c2w")
+        dev, n, sh = c2w.device, H * W, (H, W, 3)
+        ro = rd = None
+        if c2w_staticcam is not None:
+            c2w_staticcam = _f32(c2w_staticcam, "c2w_staticcam")
+    else:
+        ro, rd = _f32(rays[0], "rays_o"), _f32(rays[1], "rays_d")
+        sh = tuple(rd.shape)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        dev, n = rd.device, rd.shape[0]
+    out = torch.empty((n, 11 if use_viewdirs else 8), device=dev, dtype=torch.float32)
+    L.check(L.lib().plnerf_pack_rays(int(H), int(W), fx, fy, cx, cy, _p(c2w), 0 if c2w is None else c2w.stride(0),
+                                      _p(c2w_staticcam), 0 if c2w_staticcam is None else c2w_staticcam.stride(0),
+                                      _p(ro), _p(rd), n, int(bool(ndc)), ndc_cx, ndc_cy, 1.0, float(near), float(far),
+                                      int(bool(use_viewdirs)), _p(out), out.shape[1], _stream()))
+    return out, sh
+
+
 def stratified_z(rays, N_samples, lindisp=False, perturb=True, t_rand=None, seed=0, ray_id_offset=0):
     """render_rays' depth sampling (run_plnerf.py:683-705).  rays [n, >=8]."""
     rays = _f32(rays, "rays")

@@ -163,25 +163,10 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """run_plnerf.py:110-175: same arguments, returns [rgb_map, disp_map, acc_map, extras]."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, K, c2w)
-    else:
-        rays_o, rays_d = rays
-    if use_viewdirs:
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
-    sh = rays_d.shape
-    if ndc:
-        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-    rays = torch.cat([rays_o, rays_d, near, far], -1)
-    if use_viewdirs:
-        rays = torch.cat([rays, viewdirs], -1)
+    # ray generation, viewdirs (before NDC), ndc_rays and the [o, d, near, far, viewdir] packing: one kernel
+    # (plnerf_pack_rays) instead of ~15 full-image torch ops (run_plnerf.py:138-164)
+    rays, sh = ops.pack_rays(H, W, K, c2w=c2w, rays=rays, ndc=ndc, near=near, far=far, use_viewdirs=use_viewdirs,
+                             c2w_staticcam=c2w_staticcam)
     all_ret = batchify_rays(rays, chunk, **kwargs)
     for k in all_ret:
         k_sh = list(sh[:-1]) + list(all_ret[k].shape[1:])

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import plnerf_oracle as O
-from util import CASES, case_params, load_golden, max_rel, oracle_net_kw
+from util import CASES, case_params, load_golden, max_rel, oracle_net_kw, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -360,3 +360,64 @@ def test_philox_draws_invariant_to_chunking(P):
     z0 = O.stratified_z(g["ray_batch"][:, 6:7], g["ray_batch"][:, 7:8], 64, None)
     assert np.all(zs >= 2.0) and np.all(zs <= 6.0) and np.all(np.diff(zs, axis=-1) >= 0)
     assert np.abs(zs - z0).max() < (6 - 2) / 63
+
+
+# ------------------------------------------------------------------------------------------------
+# f-1: ray generation + packing (render(), run_plnerf.py:138-164)
+# ------------------------------------------------------------------------------------------------
+def _torch_pack(H, W, K, c2w=None, rays=None, ndc=True, near=0., far=1., use_viewdirs=False, c2w_staticcam=None):
+    """render()'s packing restated with the reference's own torch ops on the CPU."""
+    from plnerf_b200.run_nerf_helpers import get_rays, ndc_rays
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w)
+    else:
+        rays_o, rays_d = rays
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    rays_o, rays_d = torch.reshape(rays_o, [-1, 3]).float(), torch.reshape(rays_d, [-1, 3]).float()
+    nr, fr = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    out = torch.cat([rays_o, rays_d, nr, fr], -1)
+    return torch.cat([out, viewdirs], -1) if use_viewdirs else out
+
+
+@pytest.mark.parametrize("case", ["lego_pose", "llff_pose_ndc", "given_rays", "given_rays_ndc_noview", "staticcam"])
+def test_pack_rays_vs_torch(P, case):
+    """plnerf_pack_rays against the reference's get_rays / viewdir normalisation / ndc_rays / cat sequence (torch, CPU):
+    every fp32 operation is rounded separately in the same order, so the packed rows agree to the last bit or two."""
+    rs = np.random.RandomState(5)
+    if case.startswith("llff") or "ndc" in case:
+        H, W, focal = 30, 40, 32.5
+    else:
+        H, W, focal = 25, 33, 41.25
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    pose = lambda th: torch.from_numpy(synth.pose_spherical(th, -30.0, 4.0)[:3, :4].astype(np.float32).copy())
+    kw = dict(ndc=False, near=2.0, far=6.0, use_viewdirs=True)
+    c2w = rays = static = None
+    if case == "lego_pose":
+        c2w = pose(40.0)
+    elif case == "llff_pose_ndc":
+        c2w = torch.from_numpy(np.concatenate([np.eye(3, dtype=np.float32) + 0.05 * rs.randn(3, 3).astype(np.float32),
+                                               0.1 * rs.randn(3, 1).astype(np.float32)], 1))
+        kw = dict(ndc=True, near=0.0, far=1.0, use_viewdirs=True)
+    elif case.startswith("given_rays"):
+        o = rs.randn(77, 3).astype(np.float32)
+        d = rs.randn(77, 3).astype(np.float32); d[:, 2] = -np.abs(d[:, 2]) - 0.5
+        rays = (torch.from_numpy(o), torch.from_numpy(d))
+        if case == "given_rays_ndc_noview":
+            kw = dict(ndc=True, near=0.0, far=1.0, use_viewdirs=False)
+    else:
+        c2w, static = pose(40.0), pose(-75.0)
+    ref = _torch_pack(H, W, K, c2w=c2w, rays=rays, c2w_staticcam=static, **kw).numpy()
+    got, sh = P.pack_rays(H, W, K, c2w=None if c2w is None else c2w.cuda(), rays=None if rays is None else (rays[0].cuda(), rays[1].cuda()),
+                          c2w_staticcam=None if static is None else static.cuda(), **kw)
+    got = host(got)
+    assert got.shape == ref.shape and tuple(sh)[-1] == 3
+    np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)
+    assert (got == ref).mean() > 0.95          # almost everything is bit-identical (torch.norm's reduction order is the exception)
