@@ -362,6 +362,25 @@ def run_ours(args):
             oracle_render(ro[idx], rd[idx], K, pc, pf)
             reps += 1
         dt = time.perf_counter() - t0
+        # PSNR of the CUDA path against the CPU port on the SAME rays and the SAME random draws (the "PSNR vs ref" half of
+        # BASELINE.json's metric): identical images would be +inf dB; bf16 operands land around 60-70 dB.
+        try:
+            rs = np.random.RandomState(0)
+            t_rand = rs.rand(sample, N_SAMPLES).astype(np.float32)
+            u = rs.rand(sample, N_IMPORTANCE).astype(np.float32)
+            ref_img = oracle_render(ro[idx], rd[idx], K, pc, pf)          # same seed -> same t_rand / u as above
+            with torch.no_grad():
+                r = torch.stack([torch.from_numpy(ro[idx]), torch.from_numpy(rd[idx])]).to(dev)
+                kw2 = dict(kwargs); kw2.pop("seed", None)
+                rgb_g, _, _, ex_g = RP.render(H, W, K, chunk=CHUNK, rays=r, ndc=False, near=2., far=6., use_viewdirs=True,
+                                              t_rand=torch.from_numpy(t_rand).to(dev), u=torch.from_numpy(u).to(dev), **kw2)
+            mse = float(np.mean((rgb_g.cpu().numpy().astype(np.float64) - ref_img["rgb_map"]) ** 2))
+            dmax = float(np.abs(ex_g["depth_map"].cpu().numpy() - ref_img["depth_map"]).max())
+            out["psnr_vs_reference"] = {"psnr_db": (-10.0 * np.log10(mse)) if mse > 0 else float("inf"), "rgb_mse": mse,
+                                        "max_abs_depth_err": dmax, "rays": int(sample), "precision": args.precision,
+                                        "reference": "oracle/plnerf_oracle.py (fp32 CPU port pinned to the reference), same rays and draws"}
+        except Exception as e:  # the timing lines above must survive a failure of this extra
+            out["psnr_vs_reference"] = {"error": repr(e)}
         out["cpu_baseline"] = {"value": sample * reps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
                                "sample": f"{reps} x {sample} rays of the same 640000-ray image, numpy/torch-CPU oracle "
                                          f"(oracle/plnerf_oracle.py), {cores} host threads"}
