@@ -190,6 +190,9 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
   P.tail_floats = (foff + 3) & ~3;
   P.n_layers = nl;
   if (P.const_floats > MAX_CONST_FLOATS) { set_error("const block too large"); return PLNERF_E_UNSUPPORTED; }
+  // issue_tile relies on it: hidden K-steps come in full stages of KS_PER_STAGE, PE K-steps fit one stage
+  for (int l = 0; l < nl; ++l)
+    if (P.L[l].n_h_ks % KS_PER_STAGE != 0 || P.L[l].n_pe_ks > MAX_PE_KS) { set_error("unsupported layer shape"); return PLNERF_E_UNSUPPORTED; }
   int64_t wb = 0;
   const int nsplit = (precision == PLNERF_PREC_BF16X3) ? 2 : 1;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * (P.L[l].n_pe_ks + P.L[l].n_h_ks) * KS_BYTES * nsplit;
@@ -1824,7 +1827,9 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   }
   if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
   // bf16 forward (inference and stash mode must agree bit for bit): biases added by the tensor pipe, 36 KB ring slots
-  a.bias_mma = ((mode == 0 || mode == 2) && a.plan.n_bias_blocks > 0 && !getenv("PLNERF_NO_BIAS_MMA")) ? 1 : 0;
+  static int no_bias_mma = -1;     // developer A/B switch: keep the layer biases in the epilogue (32 KB ring slots)
+  if (no_bias_mma < 0) no_bias_mma = getenv("PLNERF_NO_BIAS_MMA") ? 1 : 0;
+  a.bias_mma = ((mode == 0 || mode == 2) && a.plan.n_bias_blocks > 0 && !no_bias_mma) ? 1 : 0;
   a.slot_bytes = a.bias_mma ? SLOT_BYTES_BIAS : STAGE_BYTES;
   int n_stages = a.bias_mma ? 4 : MAX_STAGES;
   while (n_stages > 2 && (int)smem_layout(n_stages, a.slot_bytes).total > g_max_smem) --n_stages;
