@@ -628,6 +628,91 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       : "memory");
 }
 
+// The same interpreter for the hi+lo split mode (bf16x3): a stage occupies TWO ring slots (hi weights, then lo weights),
+// each with its own full barrier; slot 1 issues A_hi*B_hi + A_lo*B_hi per K-step, slot 2 A_hi*B_lo.  A_lo sits 128 TMEM
+// columns (or PE_TILE_BYTES of shared memory) behind A_hi.  No batch barriers in this mode.
+struct IssueStateX3 { uint32_t slot, phase, uses0, uses1, waited0, waited1, pend0, pend1; };
+#define PLNERF_X3_TS2(PRED) \
+  "tcgen05.mma.cta_group::1.kind::f16 [ed], [ea], bd, %11, " PRED ";\n\t" \
+  "tcgen05.mma.cta_group::1.kind::f16 [ed], [el], bd, %11, pt;\n\t" \
+  "add.u64 bd, bd, 256;\n\tadd.u32 ea, ea, 8;\n\tadd.u32 el, el, 8;\n\t"
+#define PLNERF_X3_TS1 \
+  "tcgen05.mma.cta_group::1.kind::f16 [ed], [ea], bd, %11, pt;\n\t" \
+  "add.u64 bd, bd, 256;\n\tadd.u32 ea, ea, 8;\n\t"
+#define PLNERF_X3_SLOT_WAIT(L) \
+  "shl.b32 wb, sl, 3;\n\tadd.u32 wb, wb, %13;\n\t" \
+  L ":\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [wb], ph;\n\t@!p bra " L ";\n\t" \
+  "tcgen05.fence::after_thread_sync;\n\t" \
+  "mul.wide.u32 so, sl, 2048;\n\tadd.u64 bd, so, %10;\n\t"
+#define PLNERF_X3_SLOT_DONE \
+  "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [wb+48];\n\t" \
+  "add.u32 sl, sl, 1;\n\tsetp.eq.u32 p, sl, %14;\n\t@p mov.b32 sl, 0;\n\t@p xor.b32 ph, ph, 1;\n\t"
+static_assert(MAX_STAGES == 6 && STAGE_BYTES == 32768 && PE_TILE_BYTES == 16384, "issue_tile_x3 hard-codes barrier / slot / PE strides");
+__device__ __forceinline__ void issue_tile_x3(IssueStateX3& st, uint32_t prog_addr, uint32_t n_entries, uint32_t idesc, uint64_t ring_desc,
+                                              uint32_t desc_hi, uint32_t wfull0, uint32_t n_stages, uint32_t aready0) {
+  asm volatile(
+      "{\n\t.reg .pred p, p2, pacc, pt, ppe, pl;\n\t"
+      ".reg .b32 sl, ph, n, pa, ed, ea, el, e0, ef, eb, t, k, wb, u0, u1, w0, w1, q0, q1;\n\t.reg .b64 bd, so, ad, al;\n\t"
+      "mov.b32 sl, %0;\n\tmov.b32 ph, %1;\n\tmov.b32 u0, %2;\n\tmov.b32 u1, %3;\n\tmov.b32 w0, %4;\n\tmov.b32 w1, %5;\n\t"
+      "mov.b32 q0, %6;\n\tmov.b32 q1, %7;\n\t"
+      "mov.b32 n, %9;\n\tmov.b32 pa, %8;\n\tsetp.eq.b32 pt, sl, sl;\n\t"
+      "LOOP:\n\t"
+      "ld.shared.v4.u32 {ed, e0, ef, eb}, [pa];\n\t"
+      "and.b32 t, ef, 32;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOBATCH;\n\t"
+      "add.u32 u0, u0, q0;\n\tadd.u32 u1, u1, q1;\n\t"
+      "shr.u32 q0, ef, 6;\n\tand.b32 q0, q0, 1;\n\tshr.u32 q1, ef, 7;\n\tand.b32 q1, q1, 1;\n\t"
+      "and.b32 t, ef, 8;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NA0;\n\t"
+      "LA0:\n\tsetp.ge.u32 p2, w0, u0;\n\t@p2 bra NA0;\n\tand.b32 t, w0, 1;\n\t"
+      "WA0:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%15], t;\n\t@!p bra WA0;\n\tadd.u32 w0, w0, 1;\n\tbra LA0;\n\t"
+      "NA0:\n\t"
+      "and.b32 t, ef, 16;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NA1;\n\t"
+      "LA1:\n\tsetp.ge.u32 p2, w1, u1;\n\t@p2 bra NA1;\n\tand.b32 t, w1, 1;\n\t"
+      "WA1:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%15+8], t;\n\t@!p bra WA1;\n\tadd.u32 w1, w1, 1;\n\tbra LA1;\n\t"
+      "NA1:\n\t"
+      "NOBATCH:\n\t"
+      "and.b32 t, ef, 1;\n\tsetp.eq.b32 pacc, t, 0;\n\t"
+      "and.b32 t, ef, 2;\n\tsetp.ne.b32 ppe, t, 0;\n\t"
+      // ---------------- ring slot 1 of the stage: hi weights
+      PLNERF_X3_SLOT_WAIT("S0")
+      "@ppe bra PE0;\n\t"
+      "mov.b32 ea, e0;\n\tadd.u32 el, e0, 128;\n\t"
+      PLNERF_X3_TS2("pacc") PLNERF_X3_TS2("pt") PLNERF_X3_TS2("pt") PLNERF_X3_TS2("pt")
+      PLNERF_X3_TS2("pt") PLNERF_X3_TS2("pt") PLNERF_X3_TS2("pt") PLNERF_X3_TS2("pt")
+      "bra C0;\n\t"
+      "PE0:\n\t"
+      "mov.b64 ad, {e0, %12};\n\tadd.u64 al, ad, 1024;\n\tshr.u32 k, ef, 8;\n\tand.b32 k, k, 255;\n\t"
+      "PEL0:\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [ed], ad, bd, %11, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [ed], al, bd, %11, pt;\n\t"
+      "setp.eq.b32 pacc, sl, sl;\n\tadd.u64 ad, ad, 256;\n\tadd.u64 al, al, 256;\n\tadd.u64 bd, bd, 256;\n\t"
+      "sub.u32 k, k, 1;\n\tsetp.ne.b32 p, k, 0;\n\t@p bra PEL0;\n\t"
+      "C0:\n\t"
+      PLNERF_X3_SLOT_DONE
+      // ---------------- ring slot 2 of the stage: lo weights
+      PLNERF_X3_SLOT_WAIT("S1")
+      "@ppe bra PE1;\n\t"
+      "mov.b32 ea, e0;\n\t"
+      PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1 PLNERF_X3_TS1
+      "bra C1;\n\t"
+      "PE1:\n\t"
+      "mov.b64 ad, {e0, %12};\n\tshr.u32 k, ef, 8;\n\tand.b32 k, k, 255;\n\t"
+      "PEL1:\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [ed], ad, bd, %11, pt;\n\t"
+      "add.u64 ad, ad, 256;\n\tadd.u64 bd, bd, 256;\n\t"
+      "sub.u32 k, k, 1;\n\tsetp.ne.b32 p, k, 0;\n\t@p bra PEL1;\n\t"
+      "C1:\n\t"
+      "and.b32 t, ef, 4;\n\tsetp.ne.b32 pl, t, 0;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [wb+48];\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n\t"
+      "add.u32 sl, sl, 1;\n\tsetp.eq.u32 p, sl, %14;\n\t@p mov.b32 sl, 0;\n\t@p xor.b32 ph, ph, 1;\n\t"
+      "add.u32 pa, pa, 16;\n\tsub.u32 n, n, 1;\n\tsetp.ne.b32 p, n, 0;\n\t@p bra LOOP;\n\t"
+      "mov.b32 %0, sl;\n\tmov.b32 %1, ph;\n\tmov.b32 %2, u0;\n\tmov.b32 %3, u1;\n\tmov.b32 %4, w0;\n\tmov.b32 %5, w1;\n\t"
+      "mov.b32 %6, q0;\n\tmov.b32 %7, q1;\n\t}"
+      : "+r"(st.slot), "+r"(st.phase), "+r"(st.uses0), "+r"(st.uses1), "+r"(st.waited0), "+r"(st.waited1), "+r"(st.pend0), "+r"(st.pend1)
+      : "r"(prog_addr), "r"(n_entries), "l"(ring_desc), "r"(idesc), "r"(desc_hi), "r"(wfull0), "r"(n_stages), "r"(aready0)
+      : "memory");
+}
+
 // Positional encoding of one row -> this thread's panels of the PE tile(s).
 // store 8 consecutive bf16 columns (16 bytes) of row `row` into an MN-major stash tile
 __device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, int col8, uint4 v) {
@@ -670,7 +755,7 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
   };
   // fast path: 63-wide encoding computed in-kernel, 4 column groups of two panels each -> one fully unrolled 16-element
   // group whose values never leave registers (this kernel leaves ~3 KB of L1: a local-memory array costs L2 round trips)
-  if (!X3 && (xr == nullptr) && (n_panels == 8) && (NGRP == 4)) {
+  if (!X3 && (xr == nullptr) && (n_panels == 8) && (NGRP == 4)) {   // (the split mode measured slower with this path: register-bound)
     float v16[16];
     pe_group16<false>(grp, p, turns, P.input_ch, v16);
 #pragma unroll
@@ -679,6 +764,14 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
       hi.x = ptx::pack_bf16(v16[8 * h2 + 0], v16[8 * h2 + 1]); hi.y = ptx::pack_bf16(v16[8 * h2 + 2], v16[8 * h2 + 3]);
       hi.z = ptx::pack_bf16(v16[8 * h2 + 4], v16[8 * h2 + 5]); hi.w = ptx::pack_bf16(v16[8 * h2 + 6], v16[8 * h2 + 7]);
       *reinterpret_cast<uint4*>(smem + SL.pe_hi + (p_lo + h2) * 2048 + row * 16) = hi;
+      if (X3) {
+        uint4 l4;
+        l4.x = ptx::pack_bf16(v16[8 * h2 + 0] - ptx::bf16_round(v16[8 * h2 + 0]), v16[8 * h2 + 1] - ptx::bf16_round(v16[8 * h2 + 1]));
+        l4.y = ptx::pack_bf16(v16[8 * h2 + 2] - ptx::bf16_round(v16[8 * h2 + 2]), v16[8 * h2 + 3] - ptx::bf16_round(v16[8 * h2 + 3]));
+        l4.z = ptx::pack_bf16(v16[8 * h2 + 4] - ptx::bf16_round(v16[8 * h2 + 4]), v16[8 * h2 + 5] - ptx::bf16_round(v16[8 * h2 + 5]));
+        l4.w = ptx::pack_bf16(v16[8 * h2 + 6] - ptx::bf16_round(v16[8 * h2 + 6]), v16[8 * h2 + 7] - ptx::bf16_round(v16[8 * h2 + 7]));
+        *reinterpret_cast<uint4*>(smem + SL.pe_lo + (p_lo + h2) * 2048 + row * 16) = l4;
+      }
       if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
                               A.tl.in_width[A.tl.idx_pe], row, p_lo + h2, hi);
     }
@@ -938,6 +1031,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                      (uint32_t)A.slot_bytes >> 4, lo_of(sbase + SL.ones));
         __syncwarp();
         // the state lives in the elected lane; elect.sync of a converged warp picks the same lane every time
+      }
+    } else if (!(A.debug_flags & 16)) {
+      // hi+lo split mode: same one-call-per-tile structure (issue_tile_x3); debug flag 16 selects the C++ loop below
+      IssueStateX3 st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
+        ptx::mbar_wait(pe_ready, tile_iter & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one())
+          issue_tile_x3(st, sbase + SL.prog2, (uint32_t)n_entries, idesc, ring_desc, desc_hi, w_full(0), (uint32_t)A.n_stages, a_ready0);
+        __syncwarp();
       }
     } else
     for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
