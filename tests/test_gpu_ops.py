@@ -421,3 +421,54 @@ def test_pack_rays_vs_torch(P, case):
     assert got.shape == ref.shape and tuple(sh)[-1] == 3
     np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)
     assert (got == ref).mean() > 0.95          # almost everything is bit-identical (torch.norm's reduction order is the exception)
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-size, size-independent properties (BASELINE.json configs[1]: one 32 768-ray chunk at 64 + 128 samples)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(P):
+    """At the bench shape the oracle is too slow to be the checker, so the path is held to properties that do not depend
+    on size: merged depths sorted, inside [near, far] and a superset of the coarse depths; outputs in range; the
+    composited weights of `retraw` raw re-derived by the op-level quadrature give back the same maps; bitwise
+    determinism; invariance to the chunk split (Philox draws are keyed by global ray id); equivariance to a permutation
+    of the rays (no row depends on its tile neighbours)."""
+    n, Ns, Ni = 32768, 64, 128
+    kw = dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=(4,), use_viewdirs=True)
+    net_c, net_f = make_net(kw, synth.nerf_params(1, **kw)), make_net(kw, synth.nerf_params(2, **kw))
+    ro, rd, K, _ = synth.lego_rays(n, seed=7)
+    vd = rd / np.linalg.norm(rd, axis=-1, keepdims=True)
+    rays = dev(np.concatenate([ro, rd, np.full((n, 1), 2, np.float32), np.full((n, 1), 6, np.float32), vd], -1).astype(np.float32))
+    common = dict(N_samples=Ns, N_importance=Ni, mode="linear", color_mode="midpoint", perturb=True, white_bkgd=True,
+                  seed=77, precision="bf16")
+    with torch.no_grad():
+        a = P.render_rays_fwd(rays, net_c, net_f, retraw=True, want_z=True, **common)
+        b = P.render_rays_fwd(rays, net_c, net_f, retraw=True, want_z=True, **common)
+        # two half chunks with the global ray offset
+        h1 = P.render_rays_fwd(rays[: n // 2], net_c, net_f, ray_id_offset=0, **common)
+        h2 = P.render_rays_fwd(rays[n // 2:], net_c, net_f, ray_id_offset=n // 2, **common)
+        # permuted rays with explicit (permuted) draws
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        t_rand = torch.rand(n, Ns, device="cuda", generator=g)
+        u = torch.rand(n, Ni, device="cuda", generator=g)
+        perm = torch.randperm(n, device="cuda", generator=g)
+        kw2 = {k: v for k, v in common.items() if k != "seed"}
+        c = P.render_rays_fwd(rays, net_c, net_f, t_rand=t_rand, u=u, **kw2)
+        d = P.render_rays_fwd(rays[perm].contiguous(), net_c, net_f, t_rand=t_rand[perm].contiguous(), u=u[perm].contiguous(), **kw2)
+        # the op-level quadrature on the fine raw gives the same maps
+        rgb2, disp2, acc2, w2, depth2, _, _ = P.raw2outputs(a["raw"], a["z_vals"], rays, "linear", "midpoint", white_bkgd=True)
+    z = a["z_vals"]
+    assert bool((z[:, 1:] >= z[:, :-1]).all()) and float(z.min()) >= 2.0 and float(z.max()) <= 6.0
+    for k in ("rgb_map", "acc_map", "disp_map", "depth_map", "rgb0", "acc0", "z_std"):
+        assert bool(torch.isfinite(a[k]).all()), k
+    assert float(a["acc_map"].min()) >= 0.0 and float(a["acc_map"].max()) <= 1.0 + 1e-5
+    assert float(a["rgb_map"].min()) >= -1e-6 and float(a["rgb_map"].max()) <= 1.0 + 1e-5
+    assert float(a["depth_map"].min()) >= 0.0 and float(a["depth_map"].max()) <= 6.0 * (1 + 1e-5)
+    assert float(a["z_std"].min()) >= 0.0
+    for k in a:                                   # determinism, bit for bit
+        assert torch.equal(a[k], b[k]), k
+    for k in h1:                                  # chunk-split invariance, bit for bit
+        assert torch.equal(torch.cat([h1[k], h2[k]], 0), a[k]), k
+    for k in c:                                   # permutation equivariance, bit for bit
+        assert torch.equal(c[k][perm], d[k]), k
+    assert torch.equal(rgb2, a["rgb_map"]) and torch.equal(acc2, a["acc_map"]) and torch.equal(depth2, a["depth_map"])
+    assert float((w2.sum(-1) - a["acc_map"]).abs().max()) < 1e-5      # checksum: the weights add up to the opacity
