@@ -67,7 +67,7 @@ class _RenderRaysFn(torch.autograd.Function):
         rays, z0, raw0 = saved[0], saved[1], saved[2]
         kw = dict(white_bkgd=cfg["white_bkgd"], farcolorfix=cfg["farcolorfix"])
         c = lambda t: None if t is None else t.contiguous()
-        grads_c = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net_c.named_parameters()}
+        grads_c = ops.zero_grads_like(net_c)      # one flat zeroed buffer per network (one fill kernel, not 24)
         grads_f = None
         if Ni == 0:
             g_rgb, g_disp, g_acc, g_depth = g[0], g[1], g[2], g[3]
@@ -80,7 +80,7 @@ class _RenderRaysFn(torch.autograd.Function):
             graw1 = ops.raw2outputs_bwd(raw1, z1, rays, mode, cmode, g_rgb=c(g_rgb), g_depth=c(g_depth), g_acc=c(g_acc),
                                         g_disp=c(g_disp), noise=cfg["noise1"], **kw)
             if net_f is not None:
-                grads_f = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net_f.named_parameters()}
+                grads_f = ops.zero_grads_like(net_f)
                 ops.network_query_bwd(net_f, graw1, ctx.stashes[1], n, Ns + Ni, grads_f)
             else:
                 ops.network_query_bwd(net_c, graw1, ctx.stashes[1], n, Ns + Ni, grads_c)

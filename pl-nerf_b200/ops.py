@@ -341,6 +341,18 @@ def network_query_train(net, rays, z_vals):
     return raw, (stash, off, sb)
 
 
+def zero_grads_like(net):
+    """{state_dict name: zeroed fp32 gradient} as views of ONE flat buffer (the weight-gradient kernels accumulate with
+    atomics, so the buffers must start at zero; a fill kernel per parameter is 24 launches per network and step)."""
+    params = list(net.named_parameters())
+    flat = torch.zeros(sum(p.numel() for _, p in params), device=params[0][1].device, dtype=torch.float32)
+    out, off = {}, 0
+    for k, p in params:
+        out[k] = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    return out
+
+
 def network_query_bwd(net, g_raw, stash, n, S, grads=None):
     """Parameter gradients of one network query.  g_raw [n,S,>=4].  Returns {state_dict name: grad} (fp32);
     `grads` may supply zero-initialised / accumulating buffers."""
@@ -350,7 +362,7 @@ def network_query_bwd(net, g_raw, stash, n, S, grads=None):
     buf = pk.get(net, "bf16")
     bwd = packed_bwd_of(net)
     if grads is None:
-        grads = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in net.named_parameters()}
+        grads = zero_grads_like(net)
     gs = L.NetGrads()
     keep = []
     _fill_params(gs, pk.desc, grads, keep)
