@@ -764,14 +764,6 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
       hi.x = ptx::pack_bf16(v16[8 * h2 + 0], v16[8 * h2 + 1]); hi.y = ptx::pack_bf16(v16[8 * h2 + 2], v16[8 * h2 + 3]);
       hi.z = ptx::pack_bf16(v16[8 * h2 + 4], v16[8 * h2 + 5]); hi.w = ptx::pack_bf16(v16[8 * h2 + 6], v16[8 * h2 + 7]);
       *reinterpret_cast<uint4*>(smem + SL.pe_hi + (p_lo + h2) * 2048 + row * 16) = hi;
-      if (X3) {
-        uint4 l4;
-        l4.x = ptx::pack_bf16(v16[8 * h2 + 0] - ptx::bf16_round(v16[8 * h2 + 0]), v16[8 * h2 + 1] - ptx::bf16_round(v16[8 * h2 + 1]));
-        l4.y = ptx::pack_bf16(v16[8 * h2 + 2] - ptx::bf16_round(v16[8 * h2 + 2]), v16[8 * h2 + 3] - ptx::bf16_round(v16[8 * h2 + 3]));
-        l4.z = ptx::pack_bf16(v16[8 * h2 + 4] - ptx::bf16_round(v16[8 * h2 + 4]), v16[8 * h2 + 5] - ptx::bf16_round(v16[8 * h2 + 5]));
-        l4.w = ptx::pack_bf16(v16[8 * h2 + 6] - ptx::bf16_round(v16[8 * h2 + 6]), v16[8 * h2 + 7] - ptx::bf16_round(v16[8 * h2 + 7]));
-        *reinterpret_cast<uint4*>(smem + SL.pe_lo + (p_lo + h2) * 2048 + row * 16) = l4;
-      }
       if (STASH) stash_store8(A.in_stash + tile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[A.tl.idx_pe],
                               A.tl.in_width[A.tl.idx_pe], row, p_lo + h2, hi);
     }
