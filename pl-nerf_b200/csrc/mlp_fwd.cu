@@ -1805,36 +1805,76 @@ struct HeadGradArgs {
   float *d_alpha_w, *d_alpha_b, *d_rgb_w, *d_rgb_b;
 };
 __global__ void __launch_bounds__(256) k_head_grads(const __grid_constant__ HeadGradArgs A) {
-  __shared__ float sg[128][4];
-  const int tid = threadIdx.x;
-  float acc_a = 0.f, acc_r0 = 0.f, acc_r1 = 0.f, acc_b = 0.f;   // alpha_w[tid]; rgb_w flat idx tid, tid+256; biases (tid<4)
-  auto elem = [&](const uint8_t* tile, int width, int m, int k) -> float {
-    const int mh = m >> 6, m8 = (m & 63) >> 3, i = m & 7;
-    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(tile + ((size_t)((mh * (width >> 3) + (k >> 3)) * 8 + m8)) * 128 + i * 16);
-    return __bfloat162float(p[k & 7]);
+  // The stash tiles are MN-major 8x8 core matrices: 128 contiguous bytes = 8 rows x 8 columns (16 bytes per row).
+  // Lane = (row-in-group i = lane % 8, column group jj = lane / 8): a warp reads four whole 128-byte blocks per step
+  // (fully coalesced), every thread keeps 8 column partial sums over its rows, the 8 lanes of a column group are
+  // reduced by shuffles at the end.  Warp w owns column groups 4w..4w+3: 8 warps cover h_last's 32 groups (alpha head),
+  // warps 0-3 the 16 groups of the views layer output (rgb head).
+  __shared__ __align__(16) float sg[128][4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i = lane & 7, j8 = 4 * warp + (lane >> 3);          // row within an 8-row group, column group
+  float acc_a[8], acc_r[3][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { acc_a[c] = 0.f; acc_r[0][c] = 0.f; acc_r[1][c] = 0.f; acc_r[2][c] = 0.f; }
+  float acc_b = 0.f;                                             // bias sums: thread tid < 4 -> g column tid
+  auto unpack8 = [](const uint4& q, float (&v)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u); }
   };
   for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < 512; i += 256) {
-      const int m = i >> 2, c = i & 3;
+    for (int e = tid; e < 512; e += 256) {
+      const int m = e >> 2, c = e & 3;
       const int64_t g = t * 128 + m;
       sg[m][c] = (g < A.M) ? A.g_raw[g * (int64_t)A.g_stride + c] : 0.f;
     }
     __syncthreads();
     const uint8_t* tile = A.in_stash + t * (int64_t)A.tl.in_tile_bytes;
-    const uint8_t* th = tile + A.tl.in_off[A.idx_hlast];
-    const uint8_t* tv = tile + A.tl.in_off[A.tl.idx_hv];
-    for (int m = 0; m < 128; ++m) acc_a = fmaf(sg[m][3], elem(th, 256, m, tid), acc_a);
-    {
-      const int c = tid >> 7, k = tid & 127;            // flat idx tid -> (c = 0/1, k)
-      for (int m = 0; m < 128; ++m) acc_r0 = fmaf(sg[m][c], elem(tv, 128, m, k), acc_r0);
-      if (tid < 128) for (int m = 0; m < 128; ++m) acc_r1 = fmaf(sg[m][2], elem(tv, 128, m, tid), acc_r1);
+    const uint8_t* th = tile + A.tl.in_off[A.idx_hlast];         // [mh(2)][col8(32)][m8(8)][8 rows x 16 B]
+    const uint8_t* tv = tile + A.tl.in_off[A.tl.idx_hv];         // [mh(2)][col8(16)][m8(8)][8 rows x 16 B]
+#pragma unroll 4
+    for (int s8 = 0; s8 < 16; ++s8) {
+      const int mh = s8 >> 3, m8 = s8 & 7, m = mh * 64 + m8 * 8 + i;
+      const float4 g4 = *reinterpret_cast<const float4*>(&sg[m][0]);
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(th + ((size_t)((mh * 32 + j8) * 8 + m8)) * 128 + i * 16), v);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc_a[c] = fmaf(g4.w, v[c], acc_a[c]);
+      if (warp < 4) {
+        unpack8(*reinterpret_cast<const uint4*>(tv + ((size_t)((mh * 16 + j8) * 8 + m8)) * 128 + i * 16), v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc_r[0][c] = fmaf(g4.x, v[c], acc_r[0][c]);
+          acc_r[1][c] = fmaf(g4.y, v[c], acc_r[1][c]);
+          acc_r[2][c] = fmaf(g4.z, v[c], acc_r[2][c]);
+        }
+      }
     }
     if (tid < 4) for (int m = 0; m < 128; ++m) acc_b += sg[m][tid];
   }
-  atomicAdd(A.d_alpha_w + tid, acc_a);
-  atomicAdd(A.d_rgb_w + tid, acc_r0);
-  if (tid < 128) atomicAdd(A.d_rgb_w + 256 + tid, acc_r1);
+  // reduce over the 8 row lanes of each column group (lanes differing in bits 0-2), then one atomic per column
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      acc_a[c] += __shfl_xor_sync(0xffffffffu, acc_a[c], o);
+      acc_r[0][c] += __shfl_xor_sync(0xffffffffu, acc_r[0][c], o);
+      acc_r[1][c] += __shfl_xor_sync(0xffffffffu, acc_r[1][c], o);
+      acc_r[2][c] += __shfl_xor_sync(0xffffffffu, acc_r[2][c], o);
+    }
+  }
+  if (i == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      atomicAdd(A.d_alpha_w + 8 * j8 + c, acc_a[c]);
+      if (warp < 4) {
+        atomicAdd(A.d_rgb_w + 8 * j8 + c, acc_r[0][c]);
+        atomicAdd(A.d_rgb_w + 128 + 8 * j8 + c, acc_r[1][c]);
+        atomicAdd(A.d_rgb_w + 256 + 8 * j8 + c, acc_r[2][c]);
+      }
+    }
+  }
   if (tid < 3) atomicAdd(A.d_rgb_b + tid, acc_b);
   if (tid == 3) atomicAdd(A.d_alpha_b, acc_b);
 }
@@ -2230,7 +2270,10 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   hg.tl = a.tl; hg.in_stash = sp.in; hg.g_raw = g_raw; hg.g_stride = g_stride; hg.M = n * S; hg.n_tiles = w.n_tiles;
   hg.idx_hlast = T.idx_h0 + d->D - 1;
   hg.d_alpha_w = g->alpha_w; hg.d_alpha_b = g->alpha_b; hg.d_rgb_w = g->rgb_w; hg.d_rgb_b = g->rgb_b;
-  const unsigned hgrid = (unsigned)(hg.n_tiles < 2 * g_num_sms ? hg.n_tiles : 2 * g_num_sms);
+  // blocks: the kernel is latency-shaped per tile (more blocks help) until the final atomics on the 640 shared addresses
+  // start to queue (measured on 1536 tiles: 296 blocks 127 us, 592 blocks 98 us, 1184 blocks 128 us)
+  const int64_t hmax = 4 * (int64_t)g_num_sms;
+  const unsigned hgrid = (unsigned)(hg.n_tiles < hmax ? hg.n_tiles : hmax);
   k_head_grads<<<hgrid, 256, 0, st>>>(hg);
   PLNERF_LAUNCH_CHECK("k_head_grads");
   return PLNERF_OK;
