@@ -1153,6 +1153,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(srcp) : "memory");
       }
       if (vb_smem) asm volatile("cp.async.commit_group;" ::: "memory");
+      // this row's staged bias row (hoisted: the 64-bit division must not sit in the views epilogue's inner loop)
+      const float* vb_srow = reinterpret_cast<const float*>(smem + SL.vb) + (vb_smem ? (int)((gc / A.vb_div) - vb_ray0) * 128 : 0);
       float g_alpha = 0.f;
       if (DGRAD) {
         // the chain's input buffer (A1) is free again: the previous tile's last layer has been drained
@@ -1195,6 +1197,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (CHUNKS_PER_GRP * grp + cc), r2[cc]);
             ptx::tmem_ld_wait();
           }
+          // a layer that writes no activations (views / last trunk layer of a no-viewdirs net) hands its accumulator half
+          // back as soon as the values are in registers: its head math is then off the next tile's critical path
+          const bool early_arrive = !DGRAD && (epi == EPI_VIEWS || epi == EPI_RELU_HEAD);
+          if (early_arrive) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
+          }
 #pragma unroll
           for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc) {
             if (A.debug_flags & 2) break;
@@ -1224,8 +1234,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             } else if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = vb_smem ? *reinterpret_cast<const float4*>(smem + SL.vb + (((gc / A.vb_div) - vb_ray0) * 128 + n0 + i) * 4)
-                                          : *reinterpret_cast<const float4*>(vbrow + n0 + i);
+                const float4 b4 = *reinterpret_cast<const float4*>((vb_smem ? vb_srow : vbrow) + n0 + i);
                 val[i] = fmaxf(val[i] + b4.x, 0.f); val[i + 1] = fmaxf(val[i + 1] + b4.y, 0.f);
                 val[i + 2] = fmaxf(val[i + 2] + b4.z, 0.f); val[i + 3] = fmaxf(val[i + 3] + b4.w, 0.f);
               }
@@ -1275,25 +1284,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
                   for (int i = 0; i < 32; ++i) val[i] = fmaxf(val[i], 0.f);
                 }
-                if (flags & FLAG_ALPHA) {
-                  const float* aw = consts + P.alpha_w_off + n0;
-#pragma unroll
-                  for (int i = 0; i < 32; i += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(aw + i);
-                    alpha_acc = fmaf(val[i], w4.x, alpha_acc); alpha_acc = fmaf(val[i + 1], w4.y, alpha_acc);
-                    alpha_acc = fmaf(val[i + 2], w4.z, alpha_acc); alpha_acc = fmaf(val[i + 3], w4.w, alpha_acc);
-                  }
-                }
-                if (flags & FLAG_OUTHEAD) {
-#pragma unroll
-                  for (int ch = 0; ch < MAX_OUT_CH; ++ch) {
-                    if (ch < P.out_ch) {
-                      const float* ow = consts + P.out_w_off + ch * 256 + n0;
-#pragma unroll
-                      for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
-                    }
-                  }
-                }
+                // (the alpha / output heads read these relu'd fp32 values AFTER the slot has been handed back, below)
                 if (epi != EPI_RELU_HEAD) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
@@ -1321,11 +1312,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               }
             }
           }
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
+          if (!early_arrive) {
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
+          }
           PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
+          // heads with tiny N, off the layer-to-layer critical chain: the relu'd fp32 values are still in registers
+          if (!DGRAD && !(A.debug_flags & 2) && epi != EPI_VIEWS && (flags & (FLAG_ALPHA | FLAG_OUTHEAD))) {
+            static_assert(CHUNKS_PER_GRP == 1, "deferred heads assume one chunk per warp and half");
+            const float* val = reinterpret_cast<const float*>(r2[0]);
+            const int n0 = h * 128 + grp * 32;
+            if (flags & FLAG_ALPHA) {
+              const float* aw = consts + P.alpha_w_off + n0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(aw + i);
+                alpha_acc = fmaf(val[i], w4.x, alpha_acc); alpha_acc = fmaf(val[i + 1], w4.y, alpha_acc);
+                alpha_acc = fmaf(val[i + 2], w4.z, alpha_acc); alpha_acc = fmaf(val[i + 3], w4.w, alpha_acc);
+              }
+            }
+            if (flags & FLAG_OUTHEAD) {
+#pragma unroll
+              for (int ch = 0; ch < MAX_OUT_CH; ++ch) {
+                if (ch < P.out_ch) {
+                  const float* ow = consts + P.out_w_off + ch * 256 + n0;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
+                }
+              }
+            }
+          }
         }
         // The next tile's depths / ray rows are a cold DRAM read (~2000+ cycles): the loads are issued after layer 0's
         // epilogue, consumed (o + d*z) after layer 1's, and only the cheap encoding itself is left for l_pe_last --
