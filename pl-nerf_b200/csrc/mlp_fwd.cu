@@ -1274,10 +1274,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 }
               }
               uint32_t pk[16];
-              if (!X3 && !STASH && epi == EPI_RELU_A && flags == 0) {
-                // hot path: ReLU fused into the bf16x2 conversion
+              if (!X3 && !STASH && epi == EPI_RELU_A) {
+                // hot path: ReLU fused into the bf16x2 conversion (a head flagged on this layer re-applies the ReLU to
+                // the fp32 values after the slot has been handed back)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(val[2 * i], val[2 * i + 1]);
+                ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
+              } else if (!X3 && !STASH && epi == EPI_LINEAR_A && flags == 0) {
+                // linear layer (feature_linear): plain conversion
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
                 ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
               } else {
                 if (epi != EPI_LINEAR_A) {
@@ -1319,7 +1325,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             if (lane == 0) ptx::mbar_arrive(a_ready0 + 8u * h);
           }
           PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
-          // heads with tiny N, off the layer-to-layer critical chain: the relu'd fp32 values are still in registers
+          // heads with tiny N, off the layer-to-layer critical chain: the fp32 values are still in registers (both heads
+          // sit behind a ReLU layer; the hot path above did not apply it in place, so it is (re-)applied here)
           if (!DGRAD && !(A.debug_flags & 2) && epi != EPI_VIEWS && (flags & (FLAG_ALPHA | FLAG_OUTHEAD))) {
             static_assert(CHUNKS_PER_GRP == 1, "deferred heads assume one chunk per warp and half");
             const float* val = reinterpret_cast<const float*>(r2[0]);
@@ -1329,8 +1336,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(aw + i);
-                alpha_acc = fmaf(val[i], w4.x, alpha_acc); alpha_acc = fmaf(val[i + 1], w4.y, alpha_acc);
-                alpha_acc = fmaf(val[i + 2], w4.z, alpha_acc); alpha_acc = fmaf(val[i + 3], w4.w, alpha_acc);
+                alpha_acc = fmaf(fmaxf(val[i], 0.f), w4.x, alpha_acc); alpha_acc = fmaf(fmaxf(val[i + 1], 0.f), w4.y, alpha_acc);
+                alpha_acc = fmaf(fmaxf(val[i + 2], 0.f), w4.z, alpha_acc); alpha_acc = fmaf(fmaxf(val[i + 3], 0.f), w4.w, alpha_acc);
               }
             }
             if (flags & FLAG_OUTHEAD) {
@@ -1339,7 +1346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 if (ch < P.out_ch) {
                   const float* ow = consts + P.out_w_off + ch * 256 + n0;
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) head[ch] = fmaf(val[i], ow[i], head[ch]);
+                  for (int i = 0; i < 32; ++i) head[ch] = fmaf(fmaxf(val[i], 0.f), ow[i], head[ch]);
                 }
               }
             }
