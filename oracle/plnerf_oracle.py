@@ -142,6 +142,31 @@ def run_network(pts, viewdirs, params, multires=10, multires_views=4, netchunk=1
     return out.reshape(list(pts.shape[:-1]) + [out.shape[-1]])
 
 
+def extract_fields(axes, params, multires=10, multires_views=4, block=64, **net_kw):
+    """Density grid of the mesh extractor -- nerf_extract_mesh.py:531-562 (extract_fields) with its
+    own run_network (:80-95, per-point viewdirs).
+
+    ``axes`` = (X, Y, Z): the three ``torch.linspace(bound_min[k], bound_max[k], resolution)`` coordinate
+    vectors (passed in so that the oracle, the reference and the CUDA path see identical coordinates).
+    The grid is walked in ``block``-sized sub-cubes (N = 64, :532-535), each sub-cube's points are the
+    'ij' meshgrid of its coordinate slices (:542-543), the view directions are all-zero rows (:545),
+    and the stored value is relu(raw[..., 3]) (:555,:561).  Returns u [len(X), len(Y), len(Z)] float32."""
+    X, Y, Z = (_f(a) for a in axes)
+    u = np.zeros((len(X), len(Y), len(Z)), F32)
+    for x0 in range(0, len(X), block):
+        for y0 in range(0, len(Y), block):
+            for z0 in range(0, len(Z), block):
+                xs, ys, zs = X[x0:x0 + block], Y[y0:y0 + block], Z[z0:z0 + block]
+                xx, yy, zz = np.meshgrid(xs, ys, zs, indexing="ij")
+                pts = np.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1).astype(F32)
+                emb = embed(pts, multires)
+                if net_kw.get("use_viewdirs", True):
+                    emb = np.concatenate([emb, embed(np.zeros_like(pts), multires_views)], -1)
+                val = nerf_forward(params, emb, **net_kw).reshape(len(xs), len(ys), len(zs), -1)
+                u[x0:x0 + len(xs), y0:y0 + len(ys), z0:z0 + len(zs)] = np.maximum(val[..., 3], F32(0))
+    return u
+
+
 # --------------------------------------------------------------------------------------------
 # Quadrature -- run_plnerf.py:504-624
 # --------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ The directory is named ``pl-nerf_b200`` (not importable by the ``import`` statem
 Public surface (mirrors the reference's two hot-path modules):
   plnerf_b200.run_plnerf        render, batchify_rays, render_rays, raw2outputs, run_network, ...
   plnerf_b200.run_nerf_helpers  NeRF, get_embedder, sample_pdf, sample_pdf_reformulation, ...
+  plnerf_b200.nerf_extract_mesh extract_fields (density grid of the mesh extractor), extract_iso_level
   plnerf_b200.ops               torch-tensor wrappers over the C ABI (include/plnerf_b200.h)
   plnerf_b200.dist              ray sharding + gradient all-reduce helpers (one process per GPU)
   plnerf_b200.synth             synthetic lego/LLFF-shaped rays and seeded NeRF parameters
@@ -22,7 +23,7 @@ def build(force=False, verbose=False):
 
 def __getattr__(name):
     # torch-dependent submodules are imported lazily so that `synth` / `build` work without torch
-    if name in ("ops", "run_plnerf", "run_nerf_helpers", "dist", "autograd"):
+    if name in ("ops", "run_plnerf", "run_nerf_helpers", "dist", "autograd", "nerf_extract_mesh"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("render", "render_rays", "batchify_rays", "raw2outputs", "install"):

@@ -194,6 +194,10 @@ def install(ref_run_plnerf, include_helpers=True):
         for name in _PATCHED_HELPERS:
             saved[name] = getattr(ref_run_plnerf, name, None)
             setattr(ref_run_plnerf, name, getattr(helpers, name))
+    if hasattr(ref_run_plnerf, "extract_fields"):   # nerf_extract_mesh.py carries its own copy of the path + the grid query
+        from . import nerf_extract_mesh
+        saved["extract_fields"] = ref_run_plnerf.extract_fields
+        ref_run_plnerf.extract_fields = nerf_extract_mesh.extract_fields
     return saved
 
 
