@@ -146,6 +146,15 @@ int plnerf_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const
                      const float* rays_d, int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near,
                      float near, float far, int use_viewdirs, float* out, int stride, void* stream);
 
+/* ---- f-2 (next row): the training loop's per-iteration ray selection, run_plnerf.py:1259-1280 ----
+ * The reference builds get_rays for the WHOLE image (H*W*6 floats), a [H*W,2] coordinate grid, then
+ * gathers the N_rand chosen pixels.  Here the rays of the chosen pixels only: pix [n] int64 flat pixel
+ * ids (row*W + col, each in [0, H*W); the caller guarantees the range), same arithmetic per ray as
+ * plnerf_pack_rays with a pose, so out[i] is bit-identical to row pix[i] of the full-image packing. */
+int plnerf_pack_pixel_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                           const int64_t* pix, int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near,
+                           float near, float far, int use_viewdirs, float* out, int stride, void* stream);
+
 /* ---- a3 (first part): stratified depths, render_rays (run_plnerf.py:683-705) -----------------
  * rays [n, stride] (cols 6,7 = near, far).  t_rand [n,Ns] explicit jitter in [0,1) or NULL;
  * with t_rand == NULL, perturb != 0 draws Philox(seed, ray id, sample) jitter. */

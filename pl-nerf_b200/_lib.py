@@ -88,6 +88,9 @@ _SIGS = {
     "plnerf_pack_rays": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
                                    C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "plnerf_pack_pixel_rays": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "plnerf_stratified_z": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "plnerf_packed_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int]),

@@ -264,8 +264,18 @@ int plnerf_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const
   PLNERF_CHECK_ARG(!c2w || (H > 0 && W > 0 && n == (int64_t)H * W && c2w_ld >= 4), "pack_rays: with a pose, n must be H*W and c2w_ld >= 4");
   PLNERF_CHECK_ARG(!c2w_staticcam || (c2w && c2w_staticcam_ld >= 4), "pack_rays: c2w_staticcam needs c2w");
   PLNERF_CHECK_ARG(stride >= (use_viewdirs ? 11 : 8), "pack_rays: row stride too small");
-  return launch_pack_rays(H, W, fx, fy, cx, cy, c2w, c2w_ld, c2w_staticcam, c2w_staticcam_ld, rays_o, rays_d, n, ndc, ndc_cx,
-                          ndc_cy, ndc_near, near, far, use_viewdirs, out, stride, (cudaStream_t)stream);
+  return launch_pack_rays(H, W, fx, fy, cx, cy, c2w, c2w_ld, c2w_staticcam, c2w_staticcam_ld, rays_o, rays_d, nullptr, n, ndc,
+                          ndc_cx, ndc_cy, ndc_near, near, far, use_viewdirs, out, stride, (cudaStream_t)stream);
+}
+
+int plnerf_pack_pixel_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
+                           const int64_t* pix, int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near,
+                           float far, int use_viewdirs, float* out, int stride, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (out && pix && c2w)), "pack_pixel_rays: null argument");
+  PLNERF_CHECK_ARG(H > 0 && W > 0 && c2w_ld >= 4, "pack_pixel_rays: need H, W > 0 and c2w_ld >= 4");
+  PLNERF_CHECK_ARG(stride >= (use_viewdirs ? 11 : 8), "pack_pixel_rays: row stride too small");
+  return launch_pack_rays(H, W, fx, fy, cx, cy, c2w, c2w_ld, nullptr, 0, nullptr, nullptr, pix, n, ndc, ndc_cx, ndc_cy,
+                          ndc_near, near, far, use_viewdirs, out, stride, (cudaStream_t)stream);
 }
 
 // debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)

@@ -697,6 +697,7 @@ struct PackRaysArgs {
   const float* c2w; int c2w_ld;         // [3, >=4] pose (rows strided by c2w_ld) or null
   const float* c2w_static; int c2w_static_ld;   // optional: origins/directions from this pose, viewdirs from c2w
   const float* rays_o; const float* rays_d;     // [n,3] each, used when c2w == null
+  const int64_t* pix;           // optional [n] flat pixel ids (row*W + col) with a pose: rays of those pixels only; null = all H*W in order
   int64_t n;
   int ndc, use_viewdirs;
   float ndc_cx, ndc_cy;         // fl32(-1/(W/(2 focal))), fl32(-1/(H/(2 focal)))  (python float64 arithmetic, then fp32)
@@ -719,7 +720,8 @@ __global__ void __launch_bounds__(256) k_pack_rays(const PackRaysArgs a) {
   if (r >= a.n) return;
   float o[3], d[3], vd[3] = {0.f, 0.f, 0.f};
   if (a.c2w) {
-    const float i = (float)(r % a.W), j = (float)(r / a.W);          // torch.linspace(0, W-1, W) is exact on integers
+    const int64_t px = a.pix ? a.pix[r] : r;
+    const float i = (float)(px % a.W), j = (float)(px / a.W);        // torch.linspace(0, W-1, W) is exact on integers
     const float dx = __fdiv_rn(__fsub_rn(i, a.cx), a.fx);
     const float dy = -__fdiv_rn(__fsub_rn(j, a.cy), a.fy);
     pose_ray(a.c2w, a.c2w_ld, dx, dy, -1.f, o, d);
@@ -755,13 +757,14 @@ __global__ void __launch_bounds__(256) k_pack_rays(const PackRaysArgs a) {
 }
 
 int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
-                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d, int64_t n,
+                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d,
+                     const int64_t* pix, int64_t n,
                      int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far, int use_viewdirs,
                      float* out, int stride, cudaStream_t st) {
   if (n == 0) return PLNERF_OK;
   PackRaysArgs a;
   a.H = H; a.W = W; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.c2w = c2w; a.c2w_ld = c2w_ld;
-  a.c2w_static = c2w_static; a.c2w_static_ld = c2w_static_ld; a.rays_o = rays_o; a.rays_d = rays_d; a.n = n;
+  a.c2w_static = c2w_static; a.c2w_static_ld = c2w_static_ld; a.rays_o = rays_o; a.rays_d = rays_d; a.pix = pix; a.n = n;
   a.ndc = ndc; a.use_viewdirs = use_viewdirs; a.ndc_cx = ndc_cx; a.ndc_cy = ndc_cy; a.ndc_near = ndc_near;
   a.near = near; a.far = far; a.out = out; a.stride = stride;
   k_pack_rays<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a);

@@ -29,7 +29,8 @@ int launch_merge(const float* z, const float* samples, const float* rays, int64_
                  int Ni, float* z_out, float* z_std, cudaStream_t st);
 
 int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
-                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d, int64_t n,
+                     const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d,
+                     const int64_t* pix, int64_t n,
                      int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far, int use_viewdirs,
                      float* out, int stride, cudaStream_t st);
 

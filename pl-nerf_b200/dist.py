@@ -90,6 +90,14 @@ class FlatGradBucket:
             self.flat.div_(ws)
         return self.flat
 
+    def allreduce_sum(self):
+        """SUM over ranks, no division: for steps whose local loss gradient is already scaled by the GLOBAL batch
+        size (train.TrainStep)."""
+        rank, ws = world()
+        if ws > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return self.flat
+
 
 def allreduce_gradients(bucket):
     return bucket.allreduce_mean()

@@ -100,6 +100,25 @@ def pack_rays(H, W, K, c2w=None, rays=None, ndc=True, near=0., far=1., use_viewd
     return out, sh
 
 
+def pack_pixel_rays(H, W, K, c2w, pix, ndc=True, near=0., far=1., use_viewdirs=False):
+    """The training loop's per-iteration ray selection (run_plnerf.py:1259-1280) followed by render()'s packing
+    (:145-164) as one kernel: packed rays [n, 8|11] of the pixels ``pix`` (int64 flat ids row*W + col) of the
+    camera ``c2w`` -- row i is bit-identical to row pix[i] of ``pack_rays(H, W, K, c2w=c2w, ...)``; the full
+    image's rays and the [H*W, 2] coordinate grid are never built."""
+    fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    ndc_cx, ndc_cy = -1. / (W / (2. * fx)), -1. / (H / (2. * fx))
+    c2w = _f32(c2w, "c2w")
+    if not pix.is_cuda or pix.dtype != torch.int64 or pix.dim() != 1:
+        raise RuntimeError("pack_pixel_rays: pix must be a 1-D int64 CUDA tensor")
+    pix = pix.contiguous()
+    n = pix.shape[0]
+    out = torch.empty((n, 11 if use_viewdirs else 8), device=c2w.device, dtype=torch.float32)
+    L.check(L.lib().plnerf_pack_pixel_rays(int(H), int(W), fx, fy, cx, cy, _p(c2w), c2w.stride(0), _p(pix), n,
+                                            int(bool(ndc)), ndc_cx, ndc_cy, 1.0, float(near), float(far),
+                                            int(bool(use_viewdirs)), _p(out), out.shape[1], _stream()))
+    return out
+
+
 def stratified_z(rays, N_samples, lindisp=False, perturb=True, t_rand=None, seed=0, ray_id_offset=0):
     """render_rays' depth sampling (run_plnerf.py:683-705).  rays [n, >=8]."""
     rays = _f32(rays, "rays")

@@ -1,0 +1,137 @@
+"""One optimisation step of the reference's training loop with the per-iteration host work moved to the
+device (reference: run_plnerf.py:1253-1315, the ``no_batching`` branch).
+
+What the reference does every iteration around ``render()`` and what replaces it here:
+
+* ``get_rays`` for the whole image + a ``[H*W, 2]`` coordinate grid + ``np.random.choice(H*W, N_rand,
+  replace=False)`` on the host + three fancy-index gathers (:1259-1280)  ->  ``sample_pixels`` (a device-side
+  permutation, same "N_rand distinct pixels, uniform, random order" law) and ``ops.pack_pixel_rays`` (ONE kernel
+  that generates and packs the rays of the chosen pixels only);
+* ``img2mse`` twice + autograd through the loss (:1289-1299)  ->  the loss gradient ``2 (rgb - target) / (3 B)``
+  is formed directly and handed to ``torch.autograd.backward`` on the two rendered maps; the loss value stays on
+  the device (no ``.item()`` in the step);
+* ``optimizer.zero_grad()`` x2, ``optimizer.step()`` x2 (:1286-1303)  ->  both networks' gradients alias ONE flat
+  buffer (``dist.FlatGradBucket``: one fill, one NCCL all-reduce when several ranks train) and ONE fused
+  multi-tensor Adam updates all 48 parameter tensors;
+* the learning-rate decay loop (:1307-1315) is kept as is, including the reference's quirk that the coarse group
+  is assigned the *fine* rate;
+* ``retraw=True`` (:1284) is not requested: the only reader (``trans``, :1291) is unused.
+
+Data parallel: every rank draws the SAME global pixel batch (same generator seed), renders the
+contiguous shard ``dist.shard_bounds(N_rand)`` of it with ``ray_id_offset`` = the shard's first global ray, scales
+its loss gradient by the GLOBAL batch size and sums gradients over ranks -- the W-rank job is the 1-rank job.
+
+CUDA only; gradients need ``use_viewdirs`` networks and ``precision='bf16'`` (see autograd.py).
+"""
+import torch
+
+from . import dist as pdist
+from . import ops
+from . import run_plnerf as RP
+
+
+def crop_window(H, W, precrop_frac):
+    """(row0, col0, rows, cols) of the centre crop used for the first ``precrop_iters`` iterations
+    (run_plnerf.py:1262-1270): rows H//2-dH .. H//2+dH-1, cols W//2-dW .. W//2+dW-1."""
+    dH = int(H // 2 * precrop_frac)
+    dW = int(W // 2 * precrop_frac)
+    return H // 2 - dH, W // 2 - dW, 2 * dH, 2 * dW
+
+
+def sample_pixels(H, W, N_rand, device, generator=None, precrop_frac=None):
+    """N_rand distinct pixels of an H x W image (or of its centre crop), uniformly, in random order -- the law of
+    ``np.random.choice(coords.shape[0], size=[N_rand], replace=False)`` (run_plnerf.py:1276) -- as int64 flat ids
+    row*W + col on ``device``.  No host round trip: a device permutation of the window's pixel count."""
+    r0, c0, rows, cols = (0, 0, H, W) if precrop_frac is None else crop_window(H, W, precrop_frac)
+    if N_rand > rows * cols:
+        raise ValueError(f"cannot take {N_rand} distinct pixels from a {rows} x {cols} window")   # np.random.choice raises too
+    k = torch.randperm(rows * cols, device=device, generator=generator)[:N_rand]
+    if (r0, c0, rows, cols) == (0, 0, H, W):
+        return k
+    return (r0 + torch.div(k, cols, rounding_mode="floor")) * W + (c0 + k % cols)
+
+
+def decayed_lrate(lrate, lrate_decay, global_step, decay_rate=0.1):
+    """run_plnerf.py:1307-1309: lrate * 0.1 ** (global_step / (lrate_decay * 1000))."""
+    return lrate * (decay_rate ** (global_step / (lrate_decay * 1000)))
+
+
+class TrainStep:
+    """Callable optimisation step.  ``render_kwargs`` is the reference's ``render_kwargs_train`` dict
+    (run_plnerf.py:475-487: network_fn, network_fine, N_samples, N_importance, perturb, white_bkgd, raw_noise_std,
+    mode, color_mode, [lindisp], plus use_viewdirs / ndc / near / far which ``render`` consumes itself)."""
+
+    def __init__(self, H, W, K, render_kwargs, N_rand=1024, chunk=1024 * 32, lrate=5e-4, coarse_lrate=5e-4,
+                 lrate_decay=250, precrop_iters=0, precrop_frac=.5, constant_init=0, seed=0):
+        kw = dict(render_kwargs)
+        self.H, self.W, self.K = int(H), int(W), K
+        self.N_rand, self.chunk = int(N_rand), int(chunk)
+        self.use_viewdirs = bool(kw.pop("use_viewdirs", False))
+        self.ndc = bool(kw.pop("ndc", True))
+        self.near, self.far = float(kw.pop("near", 0.)), float(kw.pop("far", 1.))
+        for k in ("network_query_fn", "retraw", "constant_init", "verbose"):   # set per step below / unused
+            kw.pop(k, None)
+        self.net_c, self.net_f = kw["network_fn"], kw.get("network_fine")
+        self.render_kwargs = kw
+        self.lrate, self.coarse_lrate, self.lrate_decay = lrate, coarse_lrate, lrate_decay
+        self.precrop_iters, self.precrop_frac, self.constant_init = precrop_iters, precrop_frac, constant_init
+        self.device = next(self.net_c.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("plnerf_b200: the NeRF modules must live on a CUDA device (no CPU fallback)")
+        nets = [n for n in (self.net_f, self.net_c) if n is not None]
+        self.bucket = pdist.FlatGradBucket(nets)
+        groups = []
+        if self.net_f is not None:
+            groups.append({"params": list(self.net_f.parameters()), "lr": lrate})
+            groups.append({"params": list(self.net_c.parameters()), "lr": coarse_lrate})
+        else:
+            groups.append({"params": list(self.net_c.parameters()), "lr": coarse_lrate})
+        if len(groups) == 2 and lrate == coarse_lrate:      # one multi-tensor launch instead of two
+            groups = [{"params": groups[0]["params"] + groups[1]["params"], "lr": lrate}]
+        self.optimizer = torch.optim.Adam(groups, lr=lrate, betas=(0.9, 0.999), fused=True)
+        # the same stream of pixel draws on every rank (the shard is taken after the draw)
+        self.generator = torch.Generator(device=self.device)
+        self.generator.manual_seed(int(seed))
+
+    def pixels(self, i):
+        """The global pixel batch of iteration i (precrop window for the first precrop_iters iterations)."""
+        frac = self.precrop_frac if i < self.precrop_iters else None
+        return sample_pixels(self.H, self.W, self.N_rand, self.device, self.generator, frac)
+
+    def __call__(self, target, pose, i, global_step=None, pix=None):
+        """target [H, W, 3] (or [H*W, 3]) device image, pose = c2w [3|4, 4], i = iteration number (drives precrop /
+        constant_init exactly like the reference's loop variable).  Returns {"loss", "img_loss", "img_loss0", "pix"}
+        as device tensors (the loss values are detached scalars; nothing is synchronised).  With several ranks each
+        loss value is this rank's share of the global mean (their sum over ranks is the reference's loss)."""
+        global_step = i if global_step is None else global_step
+        if pix is None:
+            pix = self.pixels(i)
+        B = pix.shape[0]
+        lo, hi = pdist.shard_bounds(B)
+        local = pix[lo:hi]
+        rays = ops.pack_pixel_rays(self.H, self.W, self.K, pose, local, ndc=self.ndc, near=self.near, far=self.far,
+                                   use_viewdirs=self.use_viewdirs)
+        target_s = target.reshape(-1, 3)[local]
+        self.bucket.zero_()
+        with torch.enable_grad():
+            ret = RP.batchify_rays(rays, self.chunk, ray_id_offset=lo, retraw=False,
+                                   constant_init=i < self.constant_init, **self.render_kwargs)
+        rgb, rgb0 = ret["rgb_map"], ret.get("rgb0")
+        scale = 2.0 / (3.0 * B)                                  # d mean((x - t)^2) / dx over the GLOBAL batch
+        d = rgb.detach() - target_s
+        outs, grads = [rgb], [d * scale]
+        img_loss = (d * d).sum() / (3.0 * B)
+        img_loss0 = None
+        if rgb0 is not None:
+            d0 = rgb0.detach() - target_s
+            outs.append(rgb0)
+            grads.append(d0 * scale)
+            img_loss0 = (d0 * d0).sum() / (3.0 * B)
+        torch.autograd.backward(outs, grads)
+        self.bucket.allreduce_sum()
+        self.optimizer.step()
+        new_lrate = decayed_lrate(self.lrate, self.lrate_decay, global_step)
+        for g in self.optimizer.param_groups:                    # both groups get the fine rate (Appendix B.1)
+            g["lr"] = new_lrate
+        loss = img_loss if img_loss0 is None else img_loss + img_loss0
+        return {"loss": loss, "img_loss": img_loss, "img_loss0": img_loss0, "pix": pix}

@@ -59,6 +59,20 @@ def _worker(rank, ws, port, q):
         assert calls["n"] == 1
         want = sum(range(1, ws + 1)) / ws
         assert all(torch.all(p.grad == want) for p in net.parameters())
+        # sum-only variant (train.TrainStep scales its local loss gradient by the GLOBAL batch size)
+        for p in net.parameters():
+            p.grad.fill_(float(rank + 1))
+        bucket.allreduce_sum()
+        assert all(torch.all(p.grad == float(sum(range(1, ws + 1)))) for p in net.parameters())
+
+        # TrainStep's batch split: every rank draws the same global pixel batch, takes its contiguous shard
+        import plnerf_b200.train as T
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(7)
+        pix = T.sample_pixels(40, 50, 101, "cpu", gen)
+        lo3, hi3 = D.shard_bounds(pix.shape[0])
+        gathered = D.gather_rays(pix[lo3:hi3].float(), pix.shape[0])
+        assert torch.equal(gathered, pix.float())          # same draw everywhere, shards tile it in order
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
