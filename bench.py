@@ -224,6 +224,44 @@ def train_leg(args, dev, rank, world, ro, rd, K):
                       f"bf16 tensor-core operands, 2x fused Adam, 1 flat all-reduce ({bucket.flat.numel() * 4} B) per step"}
 
 
+def train_step_leg(dev, K):
+    """Extra (1 GPU only): the same training shape through plnerf_b200.train.TrainStep -- pixel draw, ray generation of
+    the chosen pixels, loss gradient, one flat gradient buffer and ONE fused Adam all on the device,
+    against train_leg's reference-loop-shaped step above."""
+    import torch
+    from plnerf_b200 import synth, train as T
+    from plnerf_b200.run_nerf_helpers import NeRF
+    N_rand, Ns, Ni, iters, warm = 1024, 128, 64, 30, 5
+
+    def mk(seed):
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy())
+                             for k, v in synth.nerf_params(seed, density_boost=False, **NET_KW).items()})
+        return net.to(dev)
+    net_c, net_f = mk(11), mk(12)
+    kw = dict(network_query_fn=None, network_fn=net_c, network_fine=net_f, N_samples=Ns, N_importance=Ni, perturb=1.0,
+              white_bkgd=True, raw_noise_std=0., mode="linear", color_mode="midpoint", use_viewdirs=True, ndc=False,
+              near=2., far=6.)
+    step = T.TrainStep(H, W, K, kw, N_rand=N_rand, chunk=CHUNK, lrate=5e-4, coarse_lrate=5e-4, lrate_decay=500, seed=1234)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
+    target = torch.rand(H, W, 3, device=dev, generator=gen)
+    pose = torch.from_numpy(synth.pose_spherical(-180.0, -30.0, 4.0)[:3, :4].astype(np.float32).copy()).to(dev)
+    for i in range(warm):
+        step(target, pose, i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warm, warm + iters):
+        out = step(target, pose, i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()),
+            "config": "plnerf_b200.train.TrainStep, same shape as `train`: device-side pixel draw (randperm of H*W) + "
+                      "pack_pixel_rays, direct loss gradient, 1 flat gradient buffer, 1 fused Adam over both networks"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -350,6 +388,11 @@ def run_ours(args):
     }
     if not args.no_train:
         out["train"] = train_leg(args, dev, rank, world, ro, rd, K)
+        if world == 1:
+            try:
+                out["train"]["device_side_step"] = train_step_leg(dev, K)
+            except Exception as e:  # an extra: the lines above must survive its failure
+                out["train"]["device_side_step"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)

@@ -69,8 +69,9 @@ class TrainStep:
         self.use_viewdirs = bool(kw.pop("use_viewdirs", False))
         self.ndc = bool(kw.pop("ndc", True))
         self.near, self.far = float(kw.pop("near", 0.)), float(kw.pop("far", 1.))
-        for k in ("network_query_fn", "retraw", "constant_init", "verbose"):   # set per step below / unused
+        for k in ("retraw", "constant_init", "verbose"):   # set per step below / unused
             kw.pop(k, None)
+        kw.setdefault("network_query_fn", None)            # positional in render_rays; the query is fused
         self.net_c, self.net_f = kw["network_fn"], kw.get("network_fine")
         self.render_kwargs = kw
         self.lrate, self.coarse_lrate, self.lrate_decay = lrate, coarse_lrate, lrate_decay
