@@ -399,6 +399,17 @@ def packed_of(net):
     return pk
 
 
+def invalidate_packed(net):
+    """Forget the packed copies of a network whose parameters were modified through an alias (e.g. a flat buffer
+    that the optimizer updates in place): the parameters' own version counters do not move in that case."""
+    pk = net.__dict__.get("_plnerf_packed")
+    if pk is not None:
+        pk.version.clear()
+    cache = net.__dict__.get("_plnerf_packed_bwd")
+    if cache is not None:
+        cache.pop("ver", None)
+
+
 def _multires_of(ch):
     if ch == 3:
         return -1

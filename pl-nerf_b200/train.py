@@ -4,15 +4,16 @@ device (reference: run_plnerf.py:1253-1315, the ``no_batching`` 
 What the reference does every iteration around ``render()`` and what replaces it here:
 
 * ``get_rays`` for the whole image + a ``[H*W, 2]`` coordinate grid + ``np.random.choice(H*W, N_rand,
-  replace=False)`` on the host + three fancy-index gathers (:1259-1280)  ->  ``sample_pixels`` (a device-side
-  permutation, same "N_rand distinct pixels, uniform, random order" law) and ``ops.pack_pixel_rays`` (ONE kernel
-  that generates and packs the rays of the chosen pixels only);
+  replace=False)`` on the host + three fancy-index gathers (:1259-1280)  ->  ``PixelSampler`` (device-side draws with
+  the same "N_rand distinct pixels, uniform, random order" law, 64 iterations per batched draw) and
+  ``ops.pack_pixel_rays`` (ONE kernel that generates and packs the rays of the chosen pixels only);
 * ``img2mse`` twice + autograd through the loss (:1289-1299)  ->  the loss gradient ``2 (rgb - target) / (3 B)``
   is formed directly and handed to ``torch.autograd.backward`` on the two rendered maps; the loss value stays on
   the device (no ``.item()`` in the step);
 * ``optimizer.zero_grad()`` x2, ``optimizer.step()`` x2 (:1286-1303)  ->  both networks' gradients alias ONE flat
-  buffer (``dist.FlatGradBucket``: one fill, one NCCL all-reduce when several ranks train) and ONE fused
-  multi-tensor Adam updates all 48 parameter tensors;
+  buffer (``dist.FlatGradBucket``: one fill, one NCCL all-reduce when several ranks train), the parameters alias a
+  second flat buffer, and ONE fused Adam launch updates the two flat segments (fine, coarse) instead of 48 tensors
+  (measured 33 us instead of 111 us);
 * the learning-rate decay loop (:1307-1315) is kept as is, including the reference's quirk that the coarse group
   is assigned the *fine* rate (SURVEY.md Appendix B.1);
 * ``retraw=True`` (:1284) is not requested: the only reader (``trans``, :1291) is unused.
@@ -38,17 +39,70 @@ def crop_window(H, W, precrop_frac):
     return H // 2 - dH, W // 2 - dW, 2 * dH, 2 * dW
 
 
+def _window(H, W, precrop_frac):
+    return (0, 0, H, W) if precrop_frac is None else crop_window(H, W, precrop_frac)
+
+
+def _to_flat_ids(k, H, W, window):
+    r0, c0, rows, cols = window
+    if window == (0, 0, H, W):
+        return k
+    return (r0 + torch.div(k, cols, rounding_mode="floor")) * W + (c0 + k % cols)
+
+
+def distinct_draws(n_items, n_draws, n_rows, device, generator=None):
+    """[n_rows, n_draws] int64: every row is n_draws DISTINCT items of range(n_items), uniformly, in random order.
+
+    Large windows (n_items >= 64 n_draws): each row is the first n_draws distinct values of 2 n_draws i.i.d. uniform
+    draws -- the first-occurrence subsequence of an i.i.d. stream is exactly a uniform sample without replacement in
+    random order; more than n_draws repeats among 2 n_draws draws from >= 64 n_draws items has probability < 8^-n_draws
+    (the missing slots would then repeat item 0).  All rows are produced by one batched stable sort + scan with fixed
+    shapes (no host round trip).  Small windows: a batched permutation (argsort of uniform keys)."""
+    if n_draws > n_items:
+        raise ValueError(f"cannot take {n_draws} distinct items from {n_items}")   # np.random.choice raises too
+    if n_items < 64 * n_draws:
+        keys = torch.rand((n_rows, n_items), device=device, generator=generator)
+        return torch.argsort(keys, dim=1)[:, :n_draws].contiguous()
+    m = 2 * n_draws
+    c = torch.randint(0, n_items, (n_rows, m), device=device, generator=generator)
+    vals, order = torch.sort(c, dim=1, stable=True)
+    dup_sorted = torch.zeros((n_rows, m), dtype=torch.bool, device=device)
+    dup_sorted[:, 1:] = vals[:, 1:] == vals[:, :-1]               # stable sort: the later draw of an equal pair is the repeat
+    keep = torch.ones((n_rows, m), dtype=torch.bool, device=device)
+    keep.scatter_(1, order, ~dup_sorted)                           # back to draw order
+    pos = torch.cumsum(keep, 1) - 1
+    slot = torch.where(keep & (pos < n_draws), pos, torch.full_like(pos, n_draws))   # column n_draws = discard
+    out = torch.zeros((n_rows, n_draws + 1), dtype=torch.int64, device=device)
+    out.scatter_(1, slot, c)
+    return out[:, :n_draws].contiguous()
+
+
 def sample_pixels(H, W, N_rand, device, generator=None, precrop_frac=None):
     """N_rand distinct pixels of an H x W image (or of its centre crop), uniformly, in random order -- the law of
     ``np.random.choice(coords.shape[0], size=[N_rand], replace=False)`` (run_plnerf.py:1276) -- as int64 flat ids
-    row*W + col on ``device``.  No host round trip: a device permutation of the window's pixel count."""
-    r0, c0, rows, cols = (0, 0, H, W) if precrop_frac is None else crop_window(H, W, precrop_frac)
-    if N_rand > rows * cols:
-        raise ValueError(f"cannot take {N_rand} distinct pixels from a {rows} x {cols} window")   # np.random.choice raises too
-    k = torch.randperm(rows * cols, device=device, generator=generator)[:N_rand]
-    if (r0, c0, rows, cols) == (0, 0, H, W):
-        return k
-    return (r0 + torch.div(k, cols, rounding_mode="floor")) * W + (c0 + k % cols)
+    row*W + col on ``device``.  No host round trip."""
+    window = _window(H, W, precrop_frac)
+    k = distinct_draws(window[2] * window[3], N_rand, 1, device, generator)[0]
+    return _to_flat_ids(k, H, W, window)
+
+
+class PixelSampler:
+    """The pixel batches of consecutive iterations, drawn ``block`` iterations at a time: one batched draw costs about
+    as much as a single one (a dozen small launches, ~130 us on a B200), so the per-iteration cost drops to a slice.
+    A block never mixes windows: it is redrawn when the crop window changes (end of the precrop phase)."""
+
+    def __init__(self, H, W, N_rand, device, generator=None, block=64):
+        self.H, self.W, self.N_rand, self.device, self.generator, self.block = H, W, N_rand, device, generator, block
+        self._window, self._buf, self._next = None, None, 0
+
+    def next(self, precrop_frac=None):
+        window = _window(self.H, self.W, precrop_frac)
+        if self._buf is None or window != self._window or self._next >= self._buf.shape[0]:
+            k = distinct_draws(window[2] * window[3], self.N_rand, self.block, self.device, self.generator)
+            self._buf, self._window, self._next = _to_flat_ids(k, self.H, self.W, window), window, 0
+        row = self._buf[self._next]
+        self._next += 1
+        return row
 
 
 def decayed_lrate(lrate, lrate_decay, global_step, decay_rate=0.1):
@@ -56,10 +110,29 @@ def decayed_lrate(lrate, lrate_decay, global_step, decay_rate=0.1):
     return lrate * (decay_rate ** (global_step / (lrate_decay * 1000)))
 
 
+def alias_parameters_flat(params):
+    """Move the storage of ``params`` into ONE flat fp32 buffer: every ``p.data`` becomes a view of it (values kept,
+    ``state_dict`` / ``load_state_dict`` keep working through the views).  An in-place update of the flat buffer
+    does not move the views' version counters -- callers must ``ops.invalidate_packed(net)`` afterwards."""
+    dev = params[0].device
+    flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        n = p.numel()
+        view = flat[off:off + n].view_as(p)
+        view.copy_(p.data)
+        p.data = view
+        off += n
+    return flat
+
+
 class TrainStep:
     """Callable optimisation step.  ``render_kwargs`` is the reference's ``render_kwargs_train`` dict
     (run_plnerf.py:475-487: network_fn, network_fine, N_samples, N_importance, perturb, white_bkgd, raw_noise_std,
-    mode, color_mode, [lindisp], plus use_viewdirs / ndc / near / far which ``render`` consumes itself)."""
+    mode, color_mode, [lindisp], plus use_viewdirs / ndc / near / far which ``render`` consumes itself).
+
+    Construct it after the networks are on their device: the constructor re-homes their parameters into one flat
+    buffer (``alias_parameters_flat``); a later ``net.to(...)`` would break that aliasing."""
 
     def __init__(self, H, W, K, render_kwargs, N_rand=1024, chunk=1024 * 32, lrate=5e-4, coarse_lrate=5e-4,
                  lrate_decay=250, precrop_iters=0, precrop_frac=.5, constant_init=0, seed=0):
@@ -77,27 +150,33 @@ class TrainStep:
         self.lrate, self.coarse_lrate, self.lrate_decay = lrate, coarse_lrate, lrate_decay
         self.precrop_iters, self.precrop_frac, self.constant_init = precrop_iters, precrop_frac, constant_init
         self.device = next(self.net_c.parameters()).device
-        if self.device.type != "cuda":
-            raise RuntimeError("plnerf_b200: the NeRF modules must live on a CUDA device (no CPU fallback)")
-        nets = [n for n in (self.net_f, self.net_c) if n is not None]
-        self.bucket = pdist.FlatGradBucket(nets)
-        groups = []
-        if self.net_f is not None:
-            groups.append({"params": list(self.net_f.parameters()), "lr": lrate})
-            groups.append({"params": list(self.net_c.parameters()), "lr": coarse_lrate})
-        else:
-            groups.append({"params": list(self.net_c.parameters()), "lr": coarse_lrate})
-        if len(groups) == 2 and lrate == coarse_lrate:      # one multi-tensor launch instead of two
-            groups = [{"params": groups[0]["params"] + groups[1]["params"], "lr": lrate}]
-        self.optimizer = torch.optim.Adam(groups, lr=lrate, betas=(0.9, 0.999), fused=True)
+        self._check_device()
+        self.nets = [n for n in (self.net_f, self.net_c) if n is not None]
+        self.bucket = pdist.FlatGradBucket(self.nets)
+        self.flat_params = alias_parameters_flat(self.bucket.params)
+        # one optimizer "parameter" per network = a segment of the flat buffers (fine first, like the bucket)
+        segs, off = [], 0
+        for net, lr in zip(self.nets, [lrate, coarse_lrate] if self.net_f is not None else [coarse_lrate]):
+            n = sum(p.numel() for p in net.parameters() if p.requires_grad)
+            seg = torch.nn.Parameter(self.flat_params[off:off + n])
+            seg.grad = self.bucket.flat[off:off + n]
+            segs.append({"params": [seg], "lr": lr})
+            off += n
+        if len(segs) == 2 and lrate == coarse_lrate:        # one param group -> one fused launch over both segments
+            segs = [{"params": segs[0]["params"] + segs[1]["params"], "lr": lrate}]
+        self.optimizer = torch.optim.Adam(segs, lr=lrate, betas=(0.9, 0.999), fused=True)
         # the same stream of pixel draws on every rank (the shard is taken after the draw)
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(int(seed))
+        self.sampler = PixelSampler(self.H, self.W, self.N_rand, self.device, self.generator)
+
+    def _check_device(self):
+        if self.device.type != "cuda":
+            raise RuntimeError("plnerf_b200: the NeRF modules must live on a CUDA device (no CPU fallback)")
 
     def pixels(self, i):
         """The global pixel batch of iteration i (precrop window for the first precrop_iters iterations)."""
-        frac = self.precrop_frac if i < self.precrop_iters else None
-        return sample_pixels(self.H, self.W, self.N_rand, self.device, self.generator, frac)
+        return self.sampler.next(self.precrop_frac if i < self.precrop_iters else None)
 
     def __call__(self, target, pose, i, global_step=None, pix=None):
         """target [H, W, 3] (or [H*W, 3]) device image, pose = c2w [3|4, 4], i = iteration number (drives precrop /
@@ -131,6 +210,8 @@ class TrainStep:
         torch.autograd.backward(outs, grads)
         self.bucket.allreduce_sum()
         self.optimizer.step()
+        for net in self.nets:          # the update went through the flat alias: the views' version counters did not move
+            ops.invalidate_packed(net)
         new_lrate = decayed_lrate(self.lrate, self.lrate_decay, global_step)
         for g in self.optimizer.param_groups:                    # both groups get the fine rate (Appendix B.1)
             g["lr"] = new_lrate

@@ -66,3 +66,147 @@ def test_train_step_needs_cuda_models():
     net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         T.TrainStep(8, 8, np.eye(3), dict(network_fn=net, network_fine=net, N_samples=8, N_importance=8))
+
+
+@pytest.mark.parametrize("n_items,n_draws", [(100, 37), (64 * 16, 16), (640000, 1024)])
+def test_distinct_draws_rows_are_distinct_and_in_range(n_items, n_draws):
+    """Both branches (batched permutation for small windows, first-occurrence-distinct draws for large ones)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(11)
+    k = T.distinct_draws(n_items, n_draws, 5, "cpu", gen)
+    assert k.shape == (5, n_draws) and k.dtype == torch.int64
+    assert int(k.min()) >= 0 and int(k.max()) < n_items
+    for row in k:
+        assert torch.unique(row).numel() == n_draws
+    assert not torch.equal(k[0], k[1])
+    with pytest.raises(ValueError):
+        T.distinct_draws(10, 11, 1, "cpu", gen)
+
+
+def test_distinct_draws_large_window_law():
+    """Large-window branch: uniform over items (chi-square) and the FIRST-occurrence order of the underlying draws
+    is kept (a row is the de-duplicated prefix of its own i.i.d. stream)."""
+    n_items, n_draws, rows = 64 * 8, 8, 6000
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(2)
+    k = T.distinct_draws(n_items, n_draws, rows, "cpu", gen)
+    counts = np.bincount(k.numpy().ravel(), minlength=n_items)
+    exp = rows * n_draws / n_items
+    chi2 = ((counts - exp) ** 2 / exp).sum()
+    assert chi2 < 1.3 * n_items, chi2                    # dof = 511, sigma = 32: 1.3x is ~5 sigma
+    # replay: the same generator state gives the same i.i.d. draws; de-duplicate them on the host
+    gen.manual_seed(2)
+    c = torch.randint(0, n_items, (rows, 2 * n_draws), device="cpu", generator=gen).numpy()
+    for r in (0, 1, 17, rows - 1):
+        seen, want = set(), []
+        for v in c[r]:
+            if v not in seen:
+                seen.add(v)
+                want.append(v)
+        assert k[r].tolist() == want[:n_draws]
+
+
+def test_pixel_sampler_blocks_and_window_change():
+    H, W, N = 40, 50, 16
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(9)
+    s = T.PixelSampler(H, W, N, "cpu", gen, block=4)
+    r0, c0, rows, cols = T.crop_window(H, W, 0.5)
+    seen = []
+    for i in range(11):
+        frac = 0.5 if i < 3 else None                    # the precrop phase ends inside the first block
+        pix = s.next(frac)
+        assert pix.shape == (N,) and torch.unique(pix).numel() == N
+        r, c = pix // W, pix % W
+        if frac is not None:
+            assert int(r.min()) >= r0 and int(r.max()) < r0 + rows and int(c.min()) >= c0 and int(c.max()) < c0 + cols
+        seen.append(pix)
+    assert any(int((p // W).min()) < r0 or int((p // W).max()) >= r0 + rows for p in seen[3:])   # full image afterwards
+    assert len({tuple(p.tolist()) for p in seen}) == len(seen)
+    gen.manual_seed(9)
+    s2 = T.PixelSampler(H, W, N, "cpu", gen, block=4)
+    assert all(torch.equal(s2.next(0.5 if i < 3 else None), seen[i]) for i in range(11))         # reproducible
+
+
+def test_alias_parameters_flat_keeps_values_and_state_dict():
+    from plnerf_b200.run_nerf_helpers import NeRF
+    net = NeRF(D=2, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[], use_viewdirs=True)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    params = list(net.parameters())
+    flat = T.alias_parameters_flat(params)
+    assert flat.numel() == sum(p.numel() for p in params)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k])
+    flat.mul_(2.0)                                       # an update through the alias is seen by every parameter
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k] * 2.0)
+    net.load_state_dict(before)                          # and loading writes through the views into the flat buffer
+    off = 0
+    for p in params:
+        assert torch.equal(flat[off:off + p.numel()].view_as(p), p.data)
+        off += p.numel()
+    assert torch.equal(flat[:params[0].numel()].view_as(params[0]), before["pts_linears.0.weight"])
+
+
+def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
+    """The step's own bookkeeping -- pixel batch -> targets, direct loss gradient, flat gradient buffer, ONE fused Adam
+    over flat parameter segments, learning-rate decay with the reference's coarse-gets-fine-rate quirk, packed-copy
+    invalidation -- against the reference loop's sequence (img2mse x2 -> backward -> optimizer.step x2 -> lr loop,
+    run_plnerf.py:1286-1315) with two stock Adam optimisers.  The renderer and the ray kernel are replaced by small
+    differentiable torch stand-ins (this test has no GPU; the real kernels are held to the same sequence in
+    tests/test_ztrain_step.py), so the two runs must agree bit for bit."""
+    from plnerf_b200 import ops, run_plnerf as RP
+    from plnerf_b200.run_nerf_helpers import NeRF
+    H = W = 16
+
+    def fake_pack(H, W, K, pose, pix, ndc, near, far, use_viewdirs):
+        r = torch.zeros(pix.shape[0], 11)
+        r[:, 0], r[:, 1] = (pix % W).float() / W, (pix // W).float() / H
+        return r
+
+    def fake_batchify(rays, chunk, ray_id_offset=0, retraw=False, constant_init=False, network_query_fn="unset", **kw):
+        assert network_query_fn is None and retraw is False
+        x = torch.cat([rays[:, :3]] * 21, -1)
+        return {"rgb_map": torch.sigmoid(kw["network_fine"].pts_linears[0](x)[:, :3]),
+                "rgb0": torch.sigmoid(kw["network_fn"].pts_linears[0](x)[:, :3])}
+    invalidated = []
+    monkeypatch.setattr(ops, "pack_pixel_rays", fake_pack)
+    monkeypatch.setattr(RP, "batchify_rays", fake_batchify)
+    monkeypatch.setattr(ops, "invalidate_packed", lambda net: invalidated.append(net))
+
+    class HostOnlyStep(T.TrainStep):
+        def _check_device(self):       # the stand-ins above run on the host
+            pass
+
+    mk = lambda: NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    for coarse_lrate, n_groups in ((5e-4, 1), (1e-4, 2)):
+        torch.manual_seed(0)
+        net_c, net_f, ref_c, ref_f = mk(), mk(), mk(), mk()
+        ref_c.load_state_dict(net_c.state_dict())
+        ref_f.load_state_dict(net_f.state_dict())
+        kw = dict(network_fn=net_c, network_fine=net_f, N_samples=8, N_importance=8, perturb=1., white_bkgd=True,
+                  raw_noise_std=0., mode="linear", color_mode="midpoint", use_viewdirs=True, ndc=False, near=2., far=6.)
+        step = HostOnlyStep(H, W, np.eye(3), kw, N_rand=64, precrop_iters=2, constant_init=1, lrate=5e-4,
+                            coarse_lrate=coarse_lrate, lrate_decay=500)
+        assert len(step.optimizer.param_groups) == n_groups
+        opt = torch.optim.Adam(ref_f.parameters(), lr=5e-4, betas=(0.9, 0.999))
+        opt_c = torch.optim.Adam(ref_c.parameters(), lr=coarse_lrate, betas=(0.9, 0.999))
+        target = torch.rand(H, W, 3)
+        for i in range(4):
+            out = step(target, torch.eye(4)[:3], i)
+            pix = out["pix"]
+            tgt = target.reshape(-1, 3)[pix]
+            r = fake_batchify(fake_pack(H, W, None, None, pix, False, 2., 6., True), 1, network_query_fn=None,
+                              network_fn=ref_c, network_fine=ref_f)
+            opt.zero_grad(); opt_c.zero_grad()
+            loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2)
+            loss.backward()
+            opt.step(); opt_c.step()
+            new_lrate = 5e-4 * (0.1 ** (i / (500 * 1000)))
+            for g in opt.param_groups + opt_c.param_groups:     # run_plnerf.py:1310-1315 (both get the fine rate)
+                g["lr"] = new_lrate
+            assert float(out["loss"]) == pytest.approx(float(loss.detach()), rel=1e-6)
+            for a, b in zip(list(net_f.parameters()) + list(net_c.parameters()),
+                            list(ref_f.parameters()) + list(ref_c.parameters())):
+                assert torch.equal(a.data, b.data)
+        assert len(invalidated) >= 8
