@@ -258,8 +258,8 @@ def train_step_leg(dev, K):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()),
-            "config": "plnerf_b200.train.TrainStep, same shape as `train`: device-side pixel draw (randperm of H*W) + "
-                      "pack_pixel_rays, direct loss gradient, 1 flat gradient buffer, 1 fused Adam over both networks"}
+            "config": "plnerf_b200.train.TrainStep, same shape as `train`: device-side pixel draws (64 iterations per batched draw) + "
+                      "pack_pixel_rays, direct loss gradient, flat gradient + parameter buffers, 1 fused Adam launch"}
 
 
 def run_ours(args):
