@@ -43,28 +43,55 @@ def grid_columns(xs, Y, Z, stride):
     return cols, Z.expand(n, Z.numel()).contiguous()
 
 
-def query_density_grid(model, X, Y, Z, precision=None, out=None):
-    """relu(sigma) of ``model`` on the grid X x Y x Z ('ij' order): device tensor [len(X), len(Y), len(Z)] fp32.
+_copy_streams = {}
 
-    X, Y, Z: 1-D float32 coordinate vectors (any device; copied to the model's device)."""
+
+def _copy_stream(dev):
+    """One side stream per device for the slab-by-slab device->host copies of extract_fields."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=key)
+    return _copy_streams[key]
+
+
+def query_density_grid(model, X, Y, Z, precision=None, out=None, host_out=None):
+    """relu(sigma) of ``model`` on the grid X x Y x Z ('ij' order), fp32 [len(X), len(Y), len(Z)].
+
+    X, Y, Z: 1-D float32 coordinate vectors (any device; copied to the model's device).  Result: the device tensor
+    ``out`` (allocated if None) -- or, when a pinned host tensor ``host_out`` is given, that tensor: every finished
+    slab is copied to it on a side stream while the next slab's kernel runs, and the call returns after the last copy."""
     dev = next(model.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("plnerf_b200: the NeRF module must live on a CUDA device (no CPU fallback)")
     X, Y, Z = (torch.as_tensor(a, dtype=torch.float32).reshape(-1).to(dev) for a in (X, Y, Z))
     nx, ny, nz = X.numel(), Y.numel(), Z.numel()
-    if out is None:
+    if host_out is None and out is None:
         out = torch.empty((nx, ny, nz), device=dev, dtype=torch.float32)
+    result = out if host_out is None else host_out
     if nx == 0 or ny == 0 or nz == 0:
-        return out
+        return result
     stride = 11 if model.use_viewdirs else 8
+    copy_stream = None if host_out is None else _copy_stream(dev)
     # one slab of whole x-planes per launch
     planes = max(1, _ROWS_PER_LAUNCH // (ny * nz))
     for x0 in range(0, nx, planes):
         xs = X[x0:x0 + planes]
         cols, depths = grid_columns(xs, Y, Z, stride)
         raw = ops.network_query(model, cols, depths, precision=precision)
-        torch.clamp(raw[..., 3].reshape(xs.numel(), ny, nz), min=0., out=out[x0:x0 + xs.numel()])
-    return out
+        sigma = raw[..., 3].reshape(xs.numel(), ny, nz)
+        if host_out is None:
+            torch.clamp(sigma, min=0., out=out[x0:x0 + xs.numel()])
+            continue
+        slab = torch.clamp(sigma, min=0.)
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            host_out[x0:x0 + xs.numel()].copy_(slab, non_blocking=True)
+        slab.record_stream(copy_stream)          # the allocator must not hand the slab out again before the copy ran
+    if copy_stream is not None:
+        copy_stream.synchronize()
+    return result
 
 
 def extract_fields(bound_min, bound_max, resolution, query_func, model, precision=None):
@@ -72,11 +99,16 @@ def extract_fields(bound_min, bound_max, resolution, query_func, model, precisio
 
     ``query_func`` is accepted for signature compatibility (the reference passes ``network_query_fn``); the
     positional-encoding widths are read from ``model.input_ch / input_ch_views`` and the query is fused into the
-    MLP kernel, as in ``render_rays``."""
+    MLP kernel, as in ``render_rays``.  The returned array lives in pinned host memory that the slabs were copied
+    into while the following slabs were being computed."""
     X, Y, Z = (_axis(bound_min[k], bound_max[k], resolution) for k in range(3))
+    if next(model.parameters()).device.type != "cuda":
+        raise RuntimeError("plnerf_b200: the NeRF module must live on a CUDA device (no CPU fallback)")
+    R = int(resolution)
+    host = torch.empty((R, R, R), dtype=torch.float32, pin_memory=True)
     with torch.no_grad():
-        u = query_density_grid(model, X, Y, Z, precision=precision)
-    return u.cpu().numpy()
+        query_density_grid(model, X, Y, Z, precision=precision, host_out=host)
+    return host.numpy()
 
 
 def extract_iso_level(density, threshold=25):
