@@ -10,6 +10,7 @@ kernels behind the C ABI.  ``install(module)`` rebinds these names inside an imp
 import numpy as np
 import torch
 
+from . import nerf_extract_mesh
 from . import ops
 from . import run_nerf_helpers as helpers
 from .run_nerf_helpers import get_rays, ndc_rays
@@ -195,7 +196,6 @@ def install(ref_run_plnerf, include_helpers=True):
             saved[name] = getattr(ref_run_plnerf, name, None)
             setattr(ref_run_plnerf, name, getattr(helpers, name))
     if hasattr(ref_run_plnerf, "extract_fields"):   # nerf_extract_mesh.py carries its own copy of the path + the grid query
-        from . import nerf_extract_mesh
         saved["extract_fields"] = ref_run_plnerf.extract_fields
         ref_run_plnerf.extract_fields = nerf_extract_mesh.extract_fields
     return saved
