@@ -7,9 +7,11 @@ What the reference does every iteration around ``render()`` and what replaces it
   replace=False)`` on the host + three fancy-index gathers (:1259-1280)  ->  ``PixelSampler`` (device-side draws with
   the same "N_rand distinct pixels, uniform, random order" law, 64 iterations per batched draw) and
   ``ops.pack_pixel_rays`` (ONE kernel that generates and packs the rays of the chosen pixels only);
-* ``img2mse`` twice + autograd through the loss (:1289-1299)  ->  the loss gradient ``2 (rgb - target) / (3 B)``
-  is formed directly and handed to ``torch.autograd.backward`` on the two rendered maps; the loss value stays on
-  the device (no ``.item()`` in the step);
+* ``img2mse`` twice + ``loss.backward()`` (:1289-1299)  ->  the loss gradient ``2 (rgb - target) / (3 B)`` is formed
+  directly and the forward (stash mode) and backward kernels are called back to back, the weight-gradient kernels
+  accumulating straight into the flat gradient buffer -- no autograd graph, no per-parameter AccumulateGrad add
+  (48 small launches per step), no zero placeholders for the unused map gradients; the loss value stays on the
+  device (no ``.item()`` in the step);
 * ``optimizer.zero_grad()`` x2, ``optimizer.step()`` x2 (:1286-1303)  ->  both networks' gradients alias ONE flat
   buffer (``dist.FlatGradBucket``: one fill, one NCCL all-reduce when several ranks train), the parameters alias a
   second flat buffer, and ONE fused Adam launch updates the two flat segments (fine, coarse) instead of 48 tensors
@@ -26,6 +28,7 @@ CUDA only; gradients need ``use_viewdirs`` networks and ``precision='bf16'`` (se
 """
 import torch
 
+from . import autograd as AG
 from . import dist as pdist
 from . import ops
 from . import run_plnerf as RP
@@ -165,6 +168,16 @@ class TrainStep:
         if len(segs) == 2 and lrate == coarse_lrate:        # one param group -> one fused launch over both segments
             segs = [{"params": segs[0]["params"] + segs[1]["params"], "lr": lrate}]
         self.optimizer = torch.optim.Adam(segs, lr=lrate, betas=(0.9, 0.999), fused=True)
+        # {state_dict name: view of the flat gradient buffer} per network: what the weight-gradient kernels add into
+        self._grads = {net: {k: p.grad for k, p in net.named_parameters()} for net in self.nets}
+        self._direct = not any(kw.get(k) is not None for k in ("t_rand", "u", "noise0", "noise1")) and not kw.get("pytest")
+        if self._direct:
+            if not all(getattr(n, "use_viewdirs", False) for n in self.nets):
+                raise NotImplementedError("plnerf_b200: gradients are implemented for use_viewdirs networks only")
+            if kw.get("precision") not in (None, "bf16") or (kw.get("precision") is None and ops.get_precision() != "bf16"):
+                raise NotImplementedError("plnerf_b200: gradients are implemented for precision='bf16' only")
+            if not all(p.requires_grad for n in self.nets for p in n.parameters()):
+                raise NotImplementedError("plnerf_b200: TrainStep trains every parameter of both networks")
         # the same stream of pixel draws on every rank (the shard is taken after the draw)
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(int(seed))
@@ -177,6 +190,61 @@ class TrainStep:
     def pixels(self, i):
         """The global pixel batch of iteration i (precrop window for the first precrop_iters iterations)."""
         return self.sampler.next(self.precrop_frac if i < self.precrop_iters else None)
+
+    def _forward_backward_direct(self, rays, target_s, scale, ray0, constant_init):
+        """Forward (stash mode) and backward kernels called back to back, the weight-gradient kernels accumulating
+        straight into the flat gradient buffer: no autograd graph, no per-parameter AccumulateGrad add (48 launches
+        per step through ``loss.backward()``), no zero-filled placeholders for the unused map gradients.
+        Returns (sum of squared errors of rgb_map, of rgb0 | None) of these rays."""
+        kw = self.render_kwargs
+        Ns, Ni = int(kw["N_samples"]), int(kw.get("N_importance", 0))
+        std = float(kw.get("raw_noise_std", 0.))
+        sq = sq0 = None
+        with torch.no_grad():
+            for c0 in range(0, rays.shape[0], self.chunk):
+                r = rays[c0:c0 + self.chunk]
+                n = r.shape[0]
+                cfg = dict(net_c=self.net_c, net_f=self.net_f if Ni > 0 else None, N_samples=Ns, N_importance=Ni,
+                           mode="constant" if constant_init else kw["mode"], color_mode=kw["color_mode"],
+                           perturb=kw.get("perturb", 0.) > 0., white_bkgd=bool(kw.get("white_bkgd", False)),
+                           lindisp=bool(kw.get("lindisp", False)), zero_tol=kw.get("zero_tol", 1e-4),
+                           epsilon=kw.get("epsilon", 1e-3), farcolorfix=bool(kw.get("farcolorfix", False)), t_rand=None,
+                           u=None, noise0=torch.randn((n, Ns), device=r.device) * std if std > 0. else None,
+                           noise1=torch.randn((n, Ns + Ni), device=r.device) * std if (std > 0. and Ni > 0) else None,
+                           seed=kw["seed"] if kw.get("seed") is not None else RP._next_seed(), ray_id_offset=ray0 + c0)
+                if Ni > 0 and not cfg["perturb"]:      # det=True: the reference's linspace u (see render_rays)
+                    cfg["u"] = torch.linspace(0., 1., steps=Ni, device=r.device).expand(n, Ni).contiguous()
+                outs, saved, stashes = AG.forward_stashed(cfg, r)
+                t = target_s[c0:c0 + n]
+                d = outs[0] - t
+                sq = (d * d).sum() if sq is None else sq + (d * d).sum()
+                g_main = (d * scale, None, None, None)
+                if Ni > 0:
+                    d0 = outs[5] - t
+                    sq0 = (d0 * d0).sum() if sq0 is None else sq0 + (d0 * d0).sum()
+                    AG.backward_stashed(cfg, saved, stashes, g_main, (d0 * scale, None, None, None),
+                                        self._grads[self.net_c], self._grads.get(self.net_f))
+                else:
+                    AG.backward_stashed(cfg, saved, stashes, None, g_main, self._grads[self.net_c], None)
+        return sq, sq0
+
+    def _forward_backward_autograd(self, rays, target_s, scale, ray0, constant_init):
+        """The same step through render_rays' autograd.Function (used when explicit draws / the pytest hook are asked
+        for in the render kwargs)."""
+        with torch.enable_grad():
+            ret = RP.batchify_rays(rays, self.chunk, ray_id_offset=ray0, retraw=False, constant_init=constant_init,
+                                   **self.render_kwargs)
+        rgb, rgb0 = ret["rgb_map"], ret.get("rgb0")
+        d = rgb.detach() - target_s
+        outs, grads = [rgb], [d * scale]
+        sq, sq0 = (d * d).sum(), None
+        if rgb0 is not None:
+            d0 = rgb0.detach() - target_s
+            outs.append(rgb0)
+            grads.append(d0 * scale)
+            sq0 = (d0 * d0).sum()
+        torch.autograd.backward(outs, grads)
+        return sq, sq0
 
     def __call__(self, target, pose, i, global_step=None, pix=None):
         """target [H, W, 3] (or [H*W, 3]) device image, pose = c2w [3|4, 4], i = iteration number (drives precrop /
@@ -193,21 +261,13 @@ class TrainStep:
                                    use_viewdirs=self.use_viewdirs)
         target_s = target.reshape(-1, 3)[local]
         self.bucket.zero_()
-        with torch.enable_grad():
-            ret = RP.batchify_rays(rays, self.chunk, ray_id_offset=lo, retraw=False,
-                                   constant_init=i < self.constant_init, **self.render_kwargs)
-        rgb, rgb0 = ret["rgb_map"], ret.get("rgb0")
         scale = 2.0 / (3.0 * B)                                  # d mean((x - t)^2) / dx over the GLOBAL batch
-        d = rgb.detach() - target_s
-        outs, grads = [rgb], [d * scale]
-        img_loss = (d * d).sum() / (3.0 * B)
-        img_loss0 = None
-        if rgb0 is not None:
-            d0 = rgb0.detach() - target_s
-            outs.append(rgb0)
-            grads.append(d0 * scale)
-            img_loss0 = (d0 * d0).sum() / (3.0 * B)
-        torch.autograd.backward(outs, grads)
+        if self._direct:
+            sq, sq0 = self._forward_backward_direct(rays, target_s, scale, lo, i < self.constant_init)
+        else:
+            sq, sq0 = self._forward_backward_autograd(rays, target_s, scale, lo, i < self.constant_init)
+        img_loss = sq / (3.0 * B)
+        img_loss0 = None if sq0 is None else sq0 / (3.0 * B)
         self.bucket.allreduce_sum()
         self.optimizer.step()
         for net in self.nets:          # the update went through the flat alias: the views' version counters did not move

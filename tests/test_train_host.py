@@ -164,14 +164,35 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
         r[:, 0], r[:, 1] = (pix % W).float() / W, (pix // W).float() / H
         return r
 
-    def fake_batchify(rays, chunk, ray_id_offset=0, retraw=False, constant_init=False, network_query_fn="unset", **kw):
+    def fake_batchify(rays, chunk, ray_id_offset=0, retraw=False, constant_init=False, network_query_fn="unset",
+                      pytest=False, **kw):
         assert network_query_fn is None and retraw is False
         x = torch.cat([rays[:, :3]] * 21, -1)
         return {"rgb_map": torch.sigmoid(kw["network_fine"].pts_linears[0](x)[:, :3]),
                 "rgb0": torch.sigmoid(kw["network_fn"].pts_linears[0](x)[:, :3])}
+    # stand-ins for the kernel pair of the direct path (autograd.forward_stashed / backward_stashed): same outs layout,
+    # parameter gradients ACCUMULATED into the dicts the step hands over
+    def fake_forward(cfg, rays):
+        with torch.enable_grad():
+            r = fake_batchify(rays, 1, network_query_fn=None, network_fn=cfg["net_c"], network_fine=cfg["net_f"])
+        z = torch.zeros(rays.shape[0])
+        outs = (r["rgb_map"].detach(), z, z, z, None, r["rgb0"].detach(), z, z, z, z)
+        return outs, (r["rgb_map"], r["rgb0"]), (None, None)
+
+    def fake_backward(cfg, saved, stashes, g_fine, g_coarse, grads_c, grads_f):
+        assert g_fine[1:] == (None, None, None) and g_coarse[1:] == (None, None, None)
+        for out, g, net, grads in ((saved[0], g_fine[0], cfg["net_f"], grads_f), (saved[1], g_coarse[0], cfg["net_c"], grads_c)):
+            names = [k for k, _ in net.named_parameters()]
+            got = torch.autograd.grad(out, list(net.parameters()), g, allow_unused=True)
+            for k, gk in zip(names, got):
+                if gk is not None:
+                    grads[k].add_(gk)
+    from plnerf_b200 import autograd as AG
     invalidated = []
     monkeypatch.setattr(ops, "pack_pixel_rays", fake_pack)
     monkeypatch.setattr(RP, "batchify_rays", fake_batchify)
+    monkeypatch.setattr(AG, "forward_stashed", fake_forward)
+    monkeypatch.setattr(AG, "backward_stashed", fake_backward)
     monkeypatch.setattr(ops, "invalidate_packed", lambda net: invalidated.append(net))
 
     class HostOnlyStep(T.TrainStep):
@@ -179,16 +200,18 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
             pass
 
     mk = lambda: NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
-    for coarse_lrate, n_groups in ((5e-4, 1), (1e-4, 2)):
+    for coarse_lrate, n_groups, extra in ((5e-4, 1, {}), (1e-4, 2, {}), (5e-4, 1, {"pytest": True})):
         torch.manual_seed(0)
         net_c, net_f, ref_c, ref_f = mk(), mk(), mk(), mk()
         ref_c.load_state_dict(net_c.state_dict())
         ref_f.load_state_dict(net_f.state_dict())
         kw = dict(network_fn=net_c, network_fine=net_f, N_samples=8, N_importance=8, perturb=1., white_bkgd=True,
-                  raw_noise_std=0., mode="linear", color_mode="midpoint", use_viewdirs=True, ndc=False, near=2., far=6.)
+                  raw_noise_std=0., mode="linear", color_mode="midpoint", use_viewdirs=True, ndc=False, near=2., far=6.,
+                  **extra)
         step = HostOnlyStep(H, W, np.eye(3), kw, N_rand=64, precrop_iters=2, constant_init=1, lrate=5e-4,
                             coarse_lrate=coarse_lrate, lrate_decay=500)
         assert len(step.optimizer.param_groups) == n_groups
+        assert step._direct == (not extra)        # explicit draws / the pytest hook go through render_rays' autograd.Function
         opt = torch.optim.Adam(ref_f.parameters(), lr=5e-4, betas=(0.9, 0.999))
         opt_c = torch.optim.Adam(ref_c.parameters(), lr=coarse_lrate, betas=(0.9, 0.999))
         target = torch.rand(H, W, 3)
@@ -210,3 +233,4 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
                             list(ref_f.parameters()) + list(ref_c.parameters())):
                 assert torch.equal(a.data, b.data)
         assert len(invalidated) >= 8
+    assert len(invalidated) == 3 * 4 * 2
