@@ -259,7 +259,7 @@ def train_step_leg(dev, K):
     ms = e0.elapsed_time(e1) / iters
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()),
             "config": "plnerf_b200.train.TrainStep, same shape as `train`: device-side pixel draws (64 iterations per batched draw) + "
-                      "pack_pixel_rays, direct loss gradient, flat gradient + parameter buffers, 1 fused Adam launch"}
+                      "pack_pixel_rays, direct loss gradient, forward/backward kernels called without an autograd graph into flat gradient + parameter buffers, 1 fused Adam launch"}
 
 
 def run_ours(args):
