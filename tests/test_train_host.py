@@ -154,7 +154,7 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
     invalidation -- against the reference loop's sequence (img2mse x2 -> backward -> optimizer.step x2 -> lr loop,
     run_plnerf.py:1286-1315) with two stock Adam optimisers.  The renderer and the ray kernel are replaced by small
     differentiable torch stand-ins (this test has no GPU; the real kernels are held to the same sequence in
-    tests/test_ztrain_step.py), so the two runs must agree bit for bit."""
+    tests/test_gpu_train_step.py), so the two runs must agree bit for bit."""
     from plnerf_b200 import ops, run_plnerf as RP
     from plnerf_b200.run_nerf_helpers import NeRF
     H = W = 16
