@@ -8,6 +8,9 @@ What is differentiated follows the reference: gradients flow fro
 acc_map / disp_map (fine and coarse) to both networks' parameters; the importance samples are
 detached (run_plnerf.py:728) and ray inputs carry no gradient.  bf16 tensor-core operands with fp32
 accumulation; use_viewdirs networks only (anything else raises).
+
+``forward_stashed`` / ``backward_stashed`` are the two plain functions behind the autograd.Function; the training
+step (train.TrainStep) calls them back to back without building an autograd graph.
 """
 import torch
 
