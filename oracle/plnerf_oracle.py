@@ -1,6 +1,8 @@
 """CPU oracle for the PL-NeRF ray-rendering hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-A numpy (float32) restatement of the reference's algorithm for the path named by BASELINE.json
+A numpy (float32) restatement -- large MLP / encoding batches run through torch's CPU kernels (the BLAS and vector
+math the reference itself uses, so the timed CPU baseline is not handicapped) -- of the reference's algorithm for the
+path named by BASELINE.json
 (render -> render_rays -> PE + coarse/fine MLP -> piecewise-linear quadrature -> inverse-CDF
 sampler).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module; the product package never does.
@@ -32,6 +34,13 @@ def _cumprod32(x):
     return np.cumprod(x.astype(np.float64), axis=-1).astype(F32)
 
 
+try:  # the reference runs its Linear layers through torch's CPU BLAS (MKL sgemm); use the same
+    import torch as _torch  # library for the big GEMMs so that the timed CPU baseline is not handicapped
+except Exception:  # pragma: no cover
+    _torch = None
+USE_TORCH_BLAS = _torch is not None
+
+
 # --------------------------------------------------------------------------------------------
 # Positional encoding -- run_nerf_helpers.py:24-72 (Embedder.embed / get_embedder)
 # --------------------------------------------------------------------------------------------
@@ -41,6 +50,16 @@ def embed(x, multires):
     x = _f(x)
     if multires < 0:
         return x
+    if USE_TORCH_BLAS and x.size >= 3 * 4096:
+        # large batches: the same elementwise kernels the reference runs (torch CPU sin/cos, all host threads), so
+        # that the timed CPU baseline is not handicapped by single-threaded numpy
+        xt = _torch.from_numpy(np.ascontiguousarray(x))
+        outs = [xt]
+        for k in range(multires):
+            xf = xt * float(2.0 ** k)
+            outs.append(_torch.sin(xf))
+            outs.append(_torch.cos(xf))
+        return _torch.cat(outs, -1).numpy()
     outs = [x]
     for k in range(multires):
         freq = F32(2.0 ** k)
@@ -57,11 +76,6 @@ def embed_dim(multires):
 # --------------------------------------------------------------------------------------------
 # MLP -- run_nerf_helpers.py:105-128 (NeRF.forward)
 # --------------------------------------------------------------------------------------------
-try:  # the reference runs its Linear layers through torch's CPU BLAS (MKL sgemm); use the same
-    import torch as _torch  # library for the big GEMMs so that the timed CPU baseline is not handicapped
-except Exception:  # pragma: no cover
-    _torch = None
-USE_TORCH_BLAS = _torch is not None
 
 
 def _affine(h, w, b, relu=False):
@@ -106,6 +120,8 @@ def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use
     accumulation; biases, the alpha / rgb / output_linear heads and the viewdir columns of
     views_linears stay fp32 and read the un-rounded fp32 activations."""
     x = _f(x)
+    if USE_TORCH_BLAS and not emulate_bf16 and x.shape[0] >= 256:
+        return _nerf_forward_large(params, x, D, skips, input_ch, input_ch_views, use_viewdirs)
     rnd = bf16_round if emulate_bf16 else (lambda a: a)
     input_pts, input_views = x[:, :input_ch], x[:, input_ch:input_ch + input_ch_views]
     pts_q = rnd(input_pts)
@@ -126,6 +142,28 @@ def nerf_forward(params, x, D=8, skips=(4,), input_ch=63, input_ch_views=27, use
         rgb = _linear(hv, params, "rgb_linear")
         return np.concatenate([rgb, alpha], -1).astype(F32)
     return _linear(h32, params, "output_linear").astype(F32)
+
+
+def _nerf_forward_large(params, x, D, skips, input_ch, input_ch_views, use_viewdirs):
+    """nerf_forward for large batches with every intermediate kept in torch CPU tensors (F.linear = MKL sgemm with
+    fused bias, multi-threaded relu / cat): the operations and their order are those of the numpy branch above --
+    and of the reference's forward (run_nerf_helpers.py:105-128) -- without the single-threaded numpy copies."""
+    F_ = _torch.nn.functional
+    t = lambda name: _torch.from_numpy(np.ascontiguousarray(params[name]))
+    xt = _torch.from_numpy(np.ascontiguousarray(x))
+    pts, views = xt[:, :input_ch], xt[:, input_ch:input_ch + input_ch_views]
+    h = pts
+    for i in range(D):
+        h = _torch.relu_(F_.linear(h, t(f"pts_linears.{i}.weight"), t(f"pts_linears.{i}.bias")))
+        if i in skips:
+            h = _torch.cat([pts, h], -1)
+    if not use_viewdirs:
+        return F_.linear(h, t("output_linear.weight"), t("output_linear.bias")).numpy()
+    alpha = F_.linear(h, t("alpha_linear.weight"), t("alpha_linear.bias"))
+    feature = F_.linear(h, t("feature_linear.weight"), t("feature_linear.bias"))
+    hv = _torch.relu_(F_.linear(_torch.cat([feature, views], -1), t("views_linears.0.weight"), t("views_linears.0.bias")))
+    rgb = F_.linear(hv, t("rgb_linear.weight"), t("rgb_linear.bias"))
+    return _torch.cat([rgb, alpha], -1).numpy()
 
 
 def run_network(pts, viewdirs, params, multires=10, multires_views=4, netchunk=1024 * 64, **net_kw):

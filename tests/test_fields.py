@@ -30,9 +30,10 @@ def test_oracle_extract_fields_vs_reference(name):
     u = O.extract_fields((g["X"], g["Y"], g["Z"]), params, **oracle_kw(kw))
     assert u.shape == g["u"].shape and u.dtype == np.float32
     assert np.abs(u - g["u"]).max() <= 1e-5 * float(g["sigma_abs_max"])
-    # block walk: a 7-wide split of the same grid gives the same values (sub-cubes are independent)
+    # block walk: a 7-wide split of the same grid gives the same values (sub-cubes are independent; the small blocks
+    # take the oracle's numpy branches, the full grid its torch branches: libm vs Sleef sin/cos, sgemm blocking)
     u7 = O.extract_fields((g["X"], g["Y"], g["Z"]), params, block=7, **oracle_kw(kw))
-    assert np.abs(u7 - u).max() <= 1e-6 * max(np.abs(u).max(), 1e-6)
+    assert np.abs(u7 - u).max() <= 2e-6 * float(g["sigma_abs_max"])
 
 
 def test_axes_match_reference_linspace():
