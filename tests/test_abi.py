@@ -59,6 +59,30 @@ def test_bad_arguments_return_codes(lib):
     assert rc == -1 and b"null" in lib.plnerf_last_error()
     rc = lib.plnerf_stratified_z(None, 0, 4, 64, 0, 1, None, 0, 0, None, None)
     assert rc == -1  # stride < 8
+    # pixel-subset ray packing: null pixel list / pose with n > 0, bad image size, row stride too small for a viewdir
+    import ctypes
+    buf = (ctypes.c_float * 64)()
+    pixel_rays = lambda H, W, c2w, ld, pix, n, use_viewdirs, out, stride: lib.plnerf_pack_pixel_rays(
+        H, W, 50.0, 50.0, 4.0, 4.0, c2w, ld, pix, n, 0, -1.0, -1.0, 1.0, 2.0, 6.0, use_viewdirs, out, stride, None)
+    assert pixel_rays(8, 8, None, 4, None, 4, 1, buf, 11) == -1 and b"null" in lib.plnerf_last_error()
+    assert pixel_rays(0, 8, buf, 4, buf, 4, 1, buf, 11) == -1
+    assert pixel_rays(8, 8, buf, 3, buf, 4, 1, buf, 11) == -1          # c2w_ld < 4
+    assert pixel_rays(8, 8, buf, 4, buf, 4, 1, buf, 8) == -1 and b"stride" in lib.plnerf_last_error()
+    assert pixel_rays(8, 8, None, 4, None, 0, 1, None, 11) == 0        # empty batch: nothing to do, nothing launched
+
+
+def test_reference_module_surface_mesh_and_train():
+    """The f-2 / f-3 mirrors keep the reference's names and argument order."""
+    import inspect
+    import plnerf_b200.nerf_extract_mesh as M
+    import plnerf_b200.train as T
+    assert list(inspect.signature(M.extract_fields).parameters)[:5] == ["bound_min", "bound_max", "resolution",
+                                                                        "query_func", "model"]
+    assert list(inspect.signature(M.extract_iso_level).parameters) == ["density", "threshold"]
+    assert inspect.signature(M.extract_iso_level).parameters["threshold"].default == 25
+    # TrainStep takes the reference's argparse names (run_plnerf.py:config_parser) for everything it consumes
+    for nme in ("N_rand", "chunk", "lrate", "coarse_lrate", "lrate_decay", "precrop_iters", "precrop_frac", "constant_init"):
+        assert nme in inspect.signature(T.TrainStep.__init__).parameters, nme
 
 
 def test_reference_module_surface():
