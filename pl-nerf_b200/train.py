@@ -259,7 +259,24 @@ class TrainStep:
         local = pix[lo:hi]
         rays = ops.pack_pixel_rays(self.H, self.W, self.K, pose, local, ndc=self.ndc, near=self.near, far=self.far,
                                    use_viewdirs=self.use_viewdirs)
-        target_s = target.reshape(-1, 3)[local]
+        out = self._optimise(rays, target.reshape(-1, 3)[local], B, lo, i, global_step)
+        out["pix"] = pix
+        return out
+
+    def step_rays(self, batch_rays, target_s, i, global_step=None):
+        """The ``use_batching`` branch of the reference loop (run_plnerf.py:1238-1250, the LLFF configs): the caller
+        slices ``batch_rays`` [2, B, 3] (origins, directions) and ``target_s`` [B, 3] out of its pre-shuffled ray bank;
+        everything after that is the same step.  Several ranks: every rank passes the same GLOBAL batch and renders its
+        shard of it."""
+        global_step = i if global_step is None else global_step
+        B = batch_rays.shape[1]
+        lo, hi = pdist.shard_bounds(B)
+        rays, _ = ops.pack_rays(self.H, self.W, self.K, rays=(batch_rays[0][lo:hi], batch_rays[1][lo:hi]), ndc=self.ndc,
+                                near=self.near, far=self.far, use_viewdirs=self.use_viewdirs)
+        return self._optimise(rays, target_s[lo:hi], B, lo, i, global_step)
+
+    def _optimise(self, rays, target_s, B, lo, i, global_step):
+        """rays: this rank's packed shard [n, 8|11] of a global batch of B rays starting at global ray ``lo``."""
         self.bucket.zero_()
         scale = 2.0 / (3.0 * B)                                  # d mean((x - t)^2) / dx over the GLOBAL batch
         if self._direct:
@@ -276,4 +293,4 @@ class TrainStep:
         for g in self.optimizer.param_groups:                    # both groups get the fine rate (Appendix B.1)
             g["lr"] = new_lrate
         loss = img_loss if img_loss0 is None else img_loss + img_loss0
-        return {"loss": loss, "img_loss": img_loss, "img_loss0": img_loss0, "pix": pix}
+        return {"loss": loss, "img_loss": img_loss, "img_loss0": img_loss0}

@@ -136,3 +136,28 @@ def test_train_step_optimises_with_precrop_and_constant_init():
     losses = torch.stack(losses).cpu().numpy()
     assert np.isfinite(losses).all()
     assert losses[-5:].mean() < 0.8 * losses[:5].mean(), losses
+
+
+def test_step_rays_equals_pixel_step():
+    """The use_batching entry (caller-supplied [2, B, 3] rays + targets, run_plnerf.py:1238-1250) against the pixel entry on
+    the same rays: identical packed rays -> identical forward; gradients agree to the weight-gradient atomics' noise."""
+    from plnerf_b200 import ops, train as T
+    H, W, focal, B = 40, 48, 55.0, 256
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = pose(100.0)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(8)
+    target = torch.rand(H, W, 3, device="cuda", generator=gen)
+    pix = T.sample_pixels(H, W, B, "cuda", gen)
+    full, _ = ops.pack_rays(H, W, K, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=True)
+    batch_rays = torch.stack([full[pix, 0:3], full[pix, 3:6]], 0)
+    target_s = target.reshape(-1, 3)[pix]
+    res = []
+    for entry in ("pixels", "rays"):
+        net_c, net_f = make_net(91), make_net(92)
+        step = T.TrainStep(H, W, K, _render_kwargs(net_c, net_f, seed=77), N_rand=B, lrate=5e-4, coarse_lrate=5e-4)
+        out = step(target, c2w, 0, pix=pix) if entry == "pixels" else step.step_rays(batch_rays, target_s, 0)
+        res.append((out["loss"].item(), step.bucket.flat.clone()))
+    (loss_a, g_a), (loss_b, g_b) = res
+    assert abs(loss_a - loss_b) <= 1e-6 * abs(loss_a)
+    assert (g_a - g_b).norm().item() <= 1e-4 * g_a.norm().item()

@@ -189,7 +189,12 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
                     grads[k].add_(gk)
     from plnerf_b200 import autograd as AG
     invalidated = []
+    def fake_pack_rays(H, W, K, rays=None, ndc=True, near=0., far=1., use_viewdirs=False, **kw):
+        r = torch.zeros(rays[0].shape[0], 11)
+        r[:, 0:3], r[:, 3:6] = rays[0], rays[1]
+        return r, tuple(rays[1].shape)
     monkeypatch.setattr(ops, "pack_pixel_rays", fake_pack)
+    monkeypatch.setattr(ops, "pack_rays", fake_pack_rays)
     monkeypatch.setattr(RP, "batchify_rays", fake_batchify)
     monkeypatch.setattr(AG, "forward_stashed", fake_forward)
     monkeypatch.setattr(AG, "backward_stashed", fake_backward)
@@ -216,11 +221,18 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
         opt_c = torch.optim.Adam(ref_c.parameters(), lr=coarse_lrate, betas=(0.9, 0.999))
         target = torch.rand(H, W, 3)
         for i in range(4):
-            out = step(target, torch.eye(4)[:3], i)
-            pix = out["pix"]
-            tgt = target.reshape(-1, 3)[pix]
-            r = fake_batchify(fake_pack(H, W, None, None, pix, False, 2., 6., True), 1, network_query_fn=None,
-                              network_fn=ref_c, network_fine=ref_f)
+            if i < 3:
+                out = step(target, torch.eye(4)[:3], i)
+                pix = out["pix"]
+                tgt = target.reshape(-1, 3)[pix]
+                packed = fake_pack(H, W, None, None, pix, False, 2., 6., True)
+            else:       # the use_batching branch: the caller hands over [2, B, 3] rays + their targets
+                gen = torch.Generator().manual_seed(40 + n_groups)
+                batch_rays, tgt = torch.rand(2, 48, 3, generator=gen), torch.rand(48, 3, generator=gen)
+                out = step.step_rays(batch_rays, tgt, i)
+                assert "pix" not in out
+                packed = fake_pack_rays(H, W, None, rays=(batch_rays[0], batch_rays[1]))[0]
+            r = fake_batchify(packed, 1, network_query_fn=None, network_fn=ref_c, network_fine=ref_f)
             opt.zero_grad(); opt_c.zero_grad()
             loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2)
             loss.backward()
