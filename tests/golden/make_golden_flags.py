@@ -8,7 +8,9 @@
   the CLI never forwards these flags -- SURVEY.md Appendix B.5 -- but the functions accept them).
 
 Inputs are the coarse-pass tensors already stored in lego_linear_mid.npz (raw0, z_vals0, ray_batch, weights0, tau0, T0,
-u, up_*), so this file only adds outputs.
+u, up_*), so flags_lego.npz only adds outputs.
+
+* ``render(..., perturb=0, mode="constant")``: the deterministic path (no jitter, linspace u) end to end -> det_constant.npz.
 """
 import os
 import sys
@@ -66,5 +68,44 @@ def main():
     print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), keys={sorted(out)}")
 
 
+DET = dict(n=16, Ns=64, Ni=64, seeds=(61, 62))
+
+
+def det_net_kwargs():
+    return dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=(4,), use_viewdirs=True)
+
+
+def main_det():
+    """perturb = 0 (no stratified jitter, det=True in the sampler: u = linspace(0, 1, N_importance),
+    run_nerf_helpers.py:248-250) in constant mode -- in linear mode the reference itself raises on u == 1
+    (SURVEY.md 8c caveat 3).  Fully deterministic: no pytest hook needed."""
+    import importlib
+    synth = importlib.import_module("pl-nerf_b200.synth")
+    H, R = refimport.load()
+    kw = det_net_kwargs()
+    pc, pf = synth.nerf_params(DET["seeds"][0], **kw), synth.nerf_params(DET["seeds"][1], **kw)
+
+    def mk(p):
+        net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+        return net
+    ro, rd, K, (Hh, Ww, focal) = synth.lego_rays(DET["n"], seed=9)
+    embed_fn, _ = H.get_embedder(10, 0)
+    embeddirs_fn, _ = H.get_embedder(4, 0)
+    q = lambda p, v, fn: R.run_network(p, v, fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn, netchunk=1024 * 64)
+    with torch.no_grad():
+        rgb, disp, acc, extras = R.render(Hh, Ww, K, chunk=32768, rays=torch.stack([torch.from_numpy(ro), torch.from_numpy(rd)]),
+                                          ndc=False, near=2., far=6., use_viewdirs=True, network_query_fn=q, network_fn=mk(pc),
+                                          network_fine=mk(pf), N_samples=DET["Ns"], N_importance=DET["Ni"], perturb=0.,
+                                          raw_noise_std=0., white_bkgd=True, mode="constant", color_mode="midpoint")
+    out = {"rays_o": ro, "rays_d": rd, "K": K.astype(np.float32), "hwf": np.array([Hh, Ww, focal], np.float64),
+           "rgb_map": rgb.numpy(), "disp_map": disp.numpy(), "acc_map": acc.numpy()}
+    out.update({k: v.numpy() for k, v in extras.items()})
+    path = os.path.join(HERE, "det_constant.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), keys={sorted(out)}")
+
+
 if __name__ == "__main__":
     main()
+    main_det()

@@ -77,3 +77,49 @@ def test_sampler_thresholds_vs_reference():
                                return_inds=True)
     np.testing.assert_array_equal(host(inds), g["inds"])
     assert max_rel(host(zs), f["flags_z_samples"], 1e-2) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# perturb = 0: no stratified jitter, det=True sampler (u = linspace), constant mode (the reference raises in linear mode)
+# ------------------------------------------------------------------------------------------------
+def _det_case():
+    from make_golden_flags import DET, det_net_kwargs
+    from util import synth
+    kw = det_net_kwargs()
+    return DET, kw, synth.nerf_params(DET["seeds"][0], **kw), synth.nerf_params(DET["seeds"][1], **kw), load_golden("det_constant")
+
+
+def test_oracle_deterministic_render_vs_reference():
+    DET, kw, pc, pf, g = _det_case()
+    Hh, Ww, focal = g["hwf"]
+    n, Ni = DET["n"], DET["Ni"]
+    u = np.broadcast_to(torch.linspace(0., 1., steps=Ni).numpy(), (n, Ni)).copy()      # run_nerf_helpers.py:248-250
+    ref = O.render(int(Hh), int(Ww), g["K"], g["rays_o"], g["rays_d"], ndc=False, near=2., far=6., use_viewdirs=True,
+                   t_rand=None, u=u, params_coarse=pc, params_fine=pf, N_samples=DET["Ns"], mode="constant",
+                   color_mode="midpoint", N_importance=Ni, white_bkgd=True,
+                   net_kw=dict(D=8, skips=(4,), input_ch=63, input_ch_views=27, use_viewdirs=True))
+    for k in ("rgb_map", "rgb0", "acc_map", "acc0", "depth_map", "depth0", "disp_map", "disp0", "z_std"):
+        assert max_rel(ref[k], g[k]) < 2e-5, k
+
+
+@pytest.mark.gpu
+def test_deterministic_render_vs_reference():
+    """render(perturb=0) through the public API (bf16x3): the device makes its own linspace u; maps within 1e-4."""
+    from plnerf_b200 import run_plnerf as RP
+    from plnerf_b200.run_nerf_helpers import NeRF
+    DET, kw, pc, pf, g = _det_case()
+
+    def mk(p):
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in p.items()})
+        return net.cuda()
+    Hh, Ww, focal = g["hwf"]
+    rays = torch.stack([dev(g["rays_o"]), dev(g["rays_d"])])
+    with torch.no_grad():
+        rgb, disp, acc, extras = RP.render(int(Hh), int(Ww), g["K"], chunk=1024 * 32, rays=rays, ndc=False, near=2., far=6.,
+                                           use_viewdirs=True, network_query_fn=None, network_fn=mk(pc), network_fine=mk(pf),
+                                           N_samples=DET["Ns"], N_importance=DET["Ni"], perturb=0., raw_noise_std=0.,
+                                           white_bkgd=True, mode="constant", color_mode="midpoint", precision="bf16x3")
+    assert max_rel(host(rgb), g["rgb_map"]) < 1e-4 and max_rel(host(extras["rgb0"]), g["rgb0"]) < 1e-4
+    assert max_rel(host(acc), g["acc_map"]) < 1e-4 and max_rel(host(extras["depth0"]), g["depth0"]) < 1e-4
+    assert max_rel(host(extras["depth_map"]), g["depth_map"]) < 1e-3      # sampler conditioning, see smoke()
