@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PLNERF_ABI_VERSION 1
+#define PLNERF_ABI_VERSION 2
 
 enum {
   PLNERF_OK = 0,
@@ -261,10 +261,6 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
  * synchronises the recorded events and returns the summed device time, launch count and rows. */
 int plnerf_profile_enable(int on);
 int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_rows);
-
-/* ---- debug: single-tile tcgen05 GEMM used by the test-suite to pin descriptor encodings --------
- * D[128,N] = A[128,K] * B[N,K]^T, bf16-rounded operands, fp32 accumulate (K%16==0, N%16==0<=256).*/
-int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream);
 
 #ifdef __cplusplus
 }

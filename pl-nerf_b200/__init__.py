@@ -16,9 +16,9 @@ from . import _lib  # noqa: F401
 from . import synth  # noqa: F401
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA library in-tree (nvcc, sm_100a)."""
-    return _lib.build(force=force, verbose=verbose)
+def build(force=False, verbose=False, debug=False):
+    """Compile the CUDA library in-tree (nvcc, sm_100a); debug=True: the developer library (see _lib.py)."""
+    return _lib.build(force=force, verbose=verbose, debug=debug)
 
 
 def __getattr__(name):

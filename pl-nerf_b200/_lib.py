@@ -9,14 +9,20 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# PLNERF_LIB: developer override (e.g. a -DPLNERF_ENABLE_TRACE build of the same sources); never a fallback
-LIB_PATH = os.environ.get("PLNERF_LIB") or os.path.join(HERE, "libplnerf_b200.so")
+LIB_PATH = os.path.join(HERE, "libplnerf_b200.so")
+# Developer library: the same sources with -DPLNERF_DEBUG (bring-up GEMMs, MMA-rate microbenchmarks, timeline tracing,
+# environment knobs).  PLNERF_DEBUG_LIB=1 makes lib() load it instead of the product library -- a developer switch for
+# the scripts under tests/gpu_*.py, never a fallback: the product library has no debug entry points and reads no
+# environment variables.
+DEBUG_LIB_PATH = os.path.join(HERE, "libplnerf_b200_debug.so")
+USE_DEBUG_LIB = os.environ.get("PLNERF_DEBUG_LIB", "") not in ("", "0")
 SOURCES = ["ops.cu", "mlp_fwd.cu", "api.cu"]
-HEADERS = ["common.cuh", "ops.cuh", "umma.cuh", os.path.join("..", "..", "include", "plnerf_b200.h")]
+HEADERS = ["common.cuh", "ops.cuh", "umma.cuh", "mlp_fwd3.cuh", "debug_kernels.cuh", os.path.join("..", "..", "include", "plnerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 MAX_DEPTH = 16
+ABI_VERSION = 2
 MODE_CONSTANT, MODE_LINEAR = 0, 1
 COLOR_MIDPOINT, COLOR_LEFT = 0, 1
 PREC_BF16, PREC_BF16X3 = 0, 1
@@ -55,19 +61,22 @@ class RenderOut(C.Structure):
                                           "acc0", "depth0", "z_std", "z_vals", "inds")]
 
 
-def needs_build():
-    if not os.path.isfile(LIB_PATH):
+def needs_build(path=None):
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libplnerf_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+def build(force=False, verbose=False, debug=False):
+    """Compile csrc/*.cu into libplnerf_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+    debug=True builds the developer library libplnerf_b200_debug.so (-DPLNERF_DEBUG -DPLNERF_ENABLE_TRACE) instead."""
+    path = DEBUG_LIB_PATH if debug else LIB_PATH
+    if not force and not needs_build(path):
+        return path
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-DPLNERF_DEBUG", "-DPLNERF_ENABLE_TRACE"] if debug else []) + ["-o", path] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
@@ -75,7 +84,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB_PATH
+    return path
 
 
 _lib = None
@@ -129,36 +138,61 @@ _SIGS = {
                                          C.c_void_p]),
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+}
+
+# developer library only (libplnerf_b200_debug.so); not part of the ABI
+_DEBUG_SIGS = {
     "plnerf_debug_umma_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
                                             C.c_void_p]),
     "plnerf_debug_set_trace": (C.c_int, [C.c_void_p]),
-    "plnerf_debug_set_mlp_kernel": (C.c_int, [C.c_int, C.c_int]),
     "plnerf_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "plnerf_debug_umma_gemm_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                             C.c_uint32, C.c_void_p, C.c_void_p]),
 }
 
 # symbols that include/plnerf_b200.h declares (checked by tests/test_abi.py)
-PUBLIC_SYMBOLS = [k for k in _SIGS if k not in ("plnerf_debug_umma_gemm_ex", "plnerf_debug_mma_rate", "plnerf_debug_set_trace", "plnerf_debug_umma_gemm_mn", "plnerf_debug_set_mlp_kernel")]
+PUBLIC_SYMBOLS = list(_SIGS)
 
 
 def lib():
     """The loaded library (loads on first use).  Raises if it is not built / not loadable."""
     global _lib
     if _lib is None:
-        if not os.path.isfile(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        path = DEBUG_LIB_PATH if USE_DEBUG_LIB else LIB_PATH
+        if not os.path.isfile(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(plnerf_b200 has no fallback path)")
-        L = C.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
-            fn = getattr(L, name)
-            fn.restype = res
-            fn.argtypes = args
-        if L.plnerf_abi_version() != 1:
-            raise RuntimeError("libplnerf_b200.so ABI version mismatch")
-        _lib = L
+        _lib = _load(path, dict(_SIGS, **_DEBUG_SIGS) if USE_DEBUG_LIB else _SIGS)
     return _lib
+
+
+def _load(path, sigs):
+    L = C.CDLL(path)
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.plnerf_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{os.path.basename(path)}: ABI version mismatch")
+    return L
+
+
+_dlib = None
+
+
+def debug_lib():
+    """The developer library (bring-up GEMMs, microbenchmarks, tracing) -- for tests/gpu_*.py and the descriptor-pinning
+    test only.  Separate handle from lib(): the product path never touches it."""
+    global _dlib
+    if _dlib is None:
+        if USE_DEBUG_LIB:
+            _dlib = lib()
+        else:
+            if not os.path.isfile(DEBUG_LIB_PATH):
+                raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: build it with plnerf_b200._lib.build(debug=True)")
+            _dlib = _load(DEBUG_LIB_PATH, dict(_SIGS, **_DEBUG_SIGS))
+    return _dlib
 
 
 def check(rc):

@@ -24,11 +24,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+#ifdef PLNERF_DEBUG
+int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);
 int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
 int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st);
 int debug_set_trace(long long* buf);
-int debug_set_mlp_kernel(int variant, int cta);
 int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st);
+#endif
 
 // workspace carving for render_rays
 struct RenderWs {
@@ -247,14 +249,6 @@ int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_
   return profile_read(mlp_ms_sum, mlp_launches, mlp_rows);
 }
 
-int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
-  return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
-}
-
-int plnerf_debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, void* stream) {
-  return plnerf::debug_umma_gemm_mn(X, Y, N, K, lbo, sbo, D, (cudaStream_t)stream);
-}
-
 int plnerf_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
                      const float* c2w_staticcam, int c2w_staticcam_ld, const float* rays_o, const float* rays_d,
                      int64_t n, int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far,
@@ -278,11 +272,19 @@ int plnerf_pack_pixel_rays(int H, int W, float fx, float fy, float cx, float cy,
                           ndc_near, near, far, use_viewdirs, out, stride, (cudaStream_t)stream);
 }
 
+// ---- developer library only (-DPLNERF_DEBUG, libplnerf_b200_debug.so): bring-up / measurement entry points.  They are NOT
+// part of the ABI in include/plnerf_b200.h and the product library does not export them.
+#ifdef PLNERF_DEBUG
+int plnerf_debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, void* stream) {
+  return debug_umma_gemm(A, B, N, K, D, (cudaStream_t)stream);
+}
+
+int plnerf_debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, void* stream) {
+  return plnerf::debug_umma_gemm_mn(X, Y, N, K, lbo, sbo, D, (cudaStream_t)stream);
+}
+
 // debug timeline buffer: 3 regions x 256 events x (clock, code) int64 (not part of the product ABI)
 int plnerf_debug_set_trace(long long* buf) { return plnerf::debug_set_trace(buf); }
-
-// bf16 inference kernel selector: variant 1 = k_mlp_fwd (default), 2 = k_mlp2 with cta = 1 | 2 (not part of the product ABI)
-int plnerf_debug_set_mlp_kernel(int variant, int cta) { return plnerf::debug_set_mlp_kernel(variant, cta); }
 
 // bring-up microbenchmark (not part of the product ABI)
 int plnerf_debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, void* stream) {
@@ -294,5 +296,7 @@ int plnerf_debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int 
                               float* D, void* stream) {
   return debug_umma_gemm_ex(A, B, N, K, a_mode, lbo, sbo, D, (cudaStream_t)stream);
 }
+
+#endif  // PLNERF_DEBUG
 
 }  // extern "C"

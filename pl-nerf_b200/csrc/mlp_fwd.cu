@@ -104,12 +104,6 @@ struct NetPlan {
   int64_t weight_bytes;  // bf16 stream
   int32_t is_dgrad;      // plan describes the backward (input-gradient) chain
   int32_t D;
-  // k_mlp2 only (PLNERF_PREC_BF16): after the fp32 tail, one 4 KB "bias K-step" block per (layer, 128-neuron half)
-  // of every layer whose bias is a per-neuron constant: B-operand image with columns 0,1,2 = bf16 hi/mid/lo parts of
-  // the bias (exact fp32 split); multiplied by a constant ones A operand it adds the bias inside the tensor pipe.
-  int64_t bias_blocks_off;     // byte offset from the start of the packed buffer (16-byte aligned), 0 = none
-  int32_t bias_block_idx[MAX_LAYERS];   // first block of layer l, or -1
-  int32_t n_bias_blocks;
 };
 
 // A (layer, half) streams its K-steps in stages of <= KS_PER_STAGE; the PE K-steps (shared-memory A
@@ -197,12 +191,6 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
   const int nsplit = (precision == PLNERF_PREC_BF16X3) ? 2 : 1;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * (P.L[l].n_pe_ks + P.L[l].n_h_ks) * KS_BYTES * nsplit;
   P.weight_bytes = wb;
-  P.n_bias_blocks = 0;
-  for (int l = 0; l < nl; ++l) {
-    if (precision == PLNERF_PREC_BF16 && P.L[l].epi != EPI_VIEWS) { P.bias_block_idx[l] = P.n_bias_blocks; P.n_bias_blocks += P.L[l].n_halves; }
-    else P.bias_block_idx[l] = -1;
-  }
-  P.bias_blocks_off = (precision == PLNERF_PREC_BF16) ? ((wb + (int64_t)P.tail_floats * 4 + 15) & ~(int64_t)15) : 0;
   return PLNERF_OK;
 }
 
@@ -274,7 +262,6 @@ int build_dgrad_plan(const plnerf_net_desc* d, const plnerf_net_params* p, NetPl
   // const block: rgb_w [3][128] and alpha_w [256] (same offsets as the forward plan so the tail is shared)
   P.alpha_w_off = fwd.alpha_w_off; P.alpha_b_off = fwd.alpha_b_off; P.rgb_w_off = fwd.rgb_w_off; P.rgb_b_off = fwd.rgb_b_off;
   P.const_floats = fwd.const_floats; P.tail_floats = fwd.tail_floats;
-  for (int l = 0; l < MAX_LAYERS; ++l) P.bias_block_idx[l] = -1;
   int64_t wb = 0;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * P.L[l].n_h_ks * KS_BYTES;
   P.weight_bytes = wb;
@@ -375,27 +362,6 @@ __global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
   a.tail[i] = v;
 }
 
-// one block (256 threads) per bias block: thread u -> 16-byte unit (panel = u/128, row = u%128)
-__global__ void __launch_bounds__(256) k_pack_bias(const __grid_constant__ PackArgs a) {
-  const NetPlan& P = a.plan;
-  int l = 0;
-  for (; l < P.n_layers; ++l)
-    if (P.bias_block_idx[l] >= 0 && (int)blockIdx.x >= P.bias_block_idx[l] && (int)blockIdx.x < P.bias_block_idx[l] + P.L[l].n_halves) break;
-  if (l >= P.n_layers) return;
-  const int h = blockIdx.x - P.bias_block_idx[l];
-  const int u = threadIdx.x, panel = u >> 7, row = u & 127;
-  const int trunk_layers = P.use_viewdirs ? P.n_layers - 2 : P.n_layers;
-  const float* b = (l < trunk_layers) ? a.prm.pts_b[l] : a.prm.feature_b;
-  uint4 q = make_uint4(0u, 0u, 0u, 0u);
-  if (panel == 0) {
-    const float v = b[h * 128 + row];
-    const float hi = ptx::bf16_round(v), mid = ptx::bf16_round(v - hi);
-    q.x = ptx::pack_bf16(hi, mid);                      // columns 0,1,2 = hi, mid, lo: the three bf16 terms sum to the
-    q.y = ptx::pack_bf16((v - hi) - mid, 0.f);          // fp32 bias exactly (3 x 8 mantissa bits)
-  }
-  *reinterpret_cast<uint4*>(a.dst + P.bias_blocks_off + (int64_t)blockIdx.x * KS_BYTES + (size_t)u * 16) = q;
-}
-
 // =============================================================================================
 // per-ray view bias:  vb[r][n] = views_b[n] + sum_j Wv[n][256+j] * gamma_dir(viewdir_r)_j   (fp32)
 // (the viewdir columns of views_linears[0], run_nerf_helpers.py:117-121, are constant per ray)
@@ -473,33 +439,33 @@ struct MlpArgs {
   const float* dirpe;      // [rays][32] fp32 dir encoding (padded), MODE 2
   const float* g_raw; int g_stride;   // MODE 3: upstream gradient of the network output [rows, >=4]
   int n_stages;
-  int slot_bytes;          // ring slot size (STAGE_BYTES, or SLOT_BYTES_BIAS when the layer biases are added by the tensor pipe)
-  int bias_mma;            // 1: every biased layer's (layer, half) ends with a bias K-step (ones operand x packed bias block)
   long long* trace;  // debug timeline buffer (null in production)
-  int debug_flags;   // bring-up experiments only (PLNERF_DEBUG_FLAGS): 1 = skip weight re-streaming after tile 0
+  int debug_flags;   // developer library only (PLNERF_DBG): bring-up experiments selected by PLNERF_DEBUG_FLAGS
 };
 
+// Bring-up switches exist only in the developer library (-DPLNERF_DEBUG): in the product build they fold to `false`.
+#ifdef PLNERF_DEBUG
+#define PLNERF_DBG(bit) ((A.debug_flags & (bit)) != 0)
+#else
+#define PLNERF_DBG(bit) false
+#endif
+
 struct SmemLayout {
-  uint32_t pe_hi, pe_lo, ring, consts, xch, prog, prog2, ones, vb, bars;  // byte offsets
+  uint32_t pe_hi, pe_lo, ring, consts, xch, prog, prog2, vb, bars;  // byte offsets
   uint32_t total;
 };
-// A ring slot holds one 32 KB weight stage; with the bias K-step enabled (bf16 forward) it is 36 KB: the 4 KB bias block
-// of the (layer, half) the stage completes rides behind its 8 K-steps.
-constexpr int SLOT_BYTES_BIAS = STAGE_BYTES + KS_BYTES;
 constexpr int VB_SMEM_RAYS = 3;
-__host__ __device__ inline SmemLayout smem_layout(int n_stages, int slot_bytes) {
+__host__ __device__ inline SmemLayout smem_layout(int n_stages) {
   SmemLayout s;
   s.pe_hi = 0;
   s.pe_lo = PE_TILE_BYTES;
   s.ring = 2 * PE_TILE_BYTES;
-  s.consts = s.ring + (uint32_t)n_stages * (uint32_t)slot_bytes;
+  s.consts = s.ring + (uint32_t)n_stages * (uint32_t)STAGE_BYTES;
   s.xch = s.consts + MAX_CONST_FLOATS * 4;
   s.prog = s.xch + (NGRP - 1) * TILE_M * (MAX_OUT_CH + 1) * 4;
   s.prog2 = s.prog + 8 * 128;  // flattened MMA stage program (<= 128 entries)
-  s.ones = s.prog2 + 16 * 128; // the same program, pre-decoded for the asm issue loop (16 bytes per stage)
-  const bool extra = (slot_bytes != STAGE_BYTES);
-  s.vb = s.ones + (extra ? KS_BYTES : 0);   // constant A operand of the bias K-step: panel 0 = [1,1,1,0,0,0,0,0] per row, panel 1 = 0
-  s.bars = s.vb + (extra ? VB_SMEM_RAYS * 128 * 4 : 0);   // the tile's per-ray view-bias rows (<= 3 rays per 128 samples)
+  s.vb = s.prog2 + 16 * 128;   // (prog2: the same program, pre-decoded for the asm issue loop, 16 bytes per stage)
+  s.bars = s.vb + VB_SMEM_RAYS * 128 * 4;   // vb: the tile's per-ray view-bias rows (<= 3 rays per 128 samples)
   s.total = s.bars + 512;
   return s;
 }
@@ -565,11 +531,9 @@ __device__ __forceinline__ void issue_ts8(uint32_t d, uint32_t a, uint32_t a_lo,
 // Ring / dependency state of the issuing thread, carried across tiles.
 struct IssueState { uint32_t slot, batch, uses0, uses1, waited0, waited1, pend0, pend1; };
 // Flags of a program entry: 1 first-of-accumulator, 2 shared-memory A, 4 commit accumulator-full, 8 / 16 batch waits for
-// a_ready[a] / a_ready[b], 32 first entry of a batch, 64 / 128 the batch completes accumulator half a / b, bits 8-15 K-steps,
-// 65536 a bias K-step follows (shared-memory ones operand x the bias block at byte 32768 of the ring slot).
+// a_ready[a] / a_ready[b], 32 first entry of a batch, 64 / 128 the batch completes accumulator half a / b, bits 8-15 K-steps.
 __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, uint32_t n_entries, uint32_t idesc, uint64_t ring_desc,
-                                           uint32_t desc_hi, uint32_t wempty0, uint32_t n_stages, uint32_t bfull0, uint32_t aready0,
-                                           uint32_t slot16, uint32_t ones_lo) {
+                                           uint32_t desc_hi, uint32_t wempty0, uint32_t n_stages, uint32_t bfull0, uint32_t aready0) {
   asm volatile(
       "{\n\t.reg .pred p, p2, pacc, pt, ppe, pl;\n\t"
       ".reg .b32 sl, n, pa, ed, ea, ef, eb, t, k, wb, bt, u0, u1, w0, w1, q0, q1;\n\t.reg .b64 bd, so, ad;\n\t"
@@ -596,7 +560,7 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "NA1:\n\t"
       "tcgen05.fence::after_thread_sync;\n\t"
       "NOBATCH:\n\t"
-      "mul.wide.u32 so, sl, %17;\n\tadd.u64 bd, so, %10;\n\t"
+      "mul.wide.u32 so, sl, 2048;\n\tadd.u64 bd, so, %10;\n\t"
       "and.b32 t, ef, 1;\n\tsetp.eq.b32 pacc, t, 0;\n\t"
       "and.b32 t, ef, 2;\n\tsetp.ne.b32 ppe, t, 0;\n\t"
       "@ppe bra PE;\n\t"
@@ -610,10 +574,6 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "setp.eq.b32 pacc, sl, sl;\n\tadd.u64 ad, ad, 256;\n\tadd.u64 bd, bd, 256;\n\t"
       "sub.u32 k, k, 1;\n\tsetp.ne.b32 p, k, 0;\n\t@p bra PEL;\n\t"
       "COMMIT:\n\t"
-      "and.b32 t, ef, 65536;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOBIAS;\n\t"
-      "add.u64 bd, so, %10;\n\tadd.u64 bd, bd, 2048;\n\tmov.b64 ad, {%18, %12};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [ed], ad, bd, %11, pt;\n\t"
-      "NOBIAS:\n\t"
       "shl.b32 wb, sl, 3;\n\tadd.u32 wb, wb, %13;\n\t"
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [wb];\n\t"
       "and.b32 t, ef, 4;\n\tsetp.ne.b32 pl, t, 0;\n\t"
@@ -623,8 +583,7 @@ __device__ __forceinline__ void issue_tile(IssueState& st, uint32_t prog_addr, u
       "mov.b32 %0, sl;\n\tmov.b32 %1, bt;\n\tmov.b32 %2, u0;\n\tmov.b32 %3, u1;\n\tmov.b32 %4, w0;\n\tmov.b32 %5, w1;\n\t"
       "mov.b32 %6, q0;\n\tmov.b32 %7, q1;\n\t}"
       : "+r"(st.slot), "+r"(st.batch), "+r"(st.uses0), "+r"(st.uses1), "+r"(st.waited0), "+r"(st.waited1), "+r"(st.pend0), "+r"(st.pend1)
-      : "r"(prog_addr), "r"(n_entries), "l"(ring_desc), "r"(idesc), "r"(desc_hi), "r"(wempty0), "r"(n_stages), "r"(bfull0), "r"(aready0),
-        "r"(slot16), "r"(ones_lo)
+      : "r"(prog_addr), "r"(n_entries), "l"(ring_desc), "r"(idesc), "r"(desc_hi), "r"(wempty0), "r"(n_stages), "r"(bfull0), "r"(aready0)
       : "memory");
 }
 
@@ -725,7 +684,7 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
                                             int grp, const float* p_pre = nullptr) {
   constexpr bool X3 = (MODE == 1);
   constexpr bool STASH = (MODE == 2);
-  if (A.debug_flags & 8) return;   // bring-up experiment: no encoding at all (garbage inputs)
+  if (PLNERF_DBG(8)) return;   // bring-up experiment: no encoding at all (garbage inputs)
   const NetPlan& P = A.plan;
   const int64_t g = tile * TILE_M + row;
   const int64_t gc = (g < A.M) ? g : (A.M - 1);
@@ -833,7 +792,7 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
 }
 
 // debug timeline: (clock, code) pairs for block 0, third tile; region r holds up to 256 events
-#ifdef PLNERF_ENABLE_TRACE
+#if defined(PLNERF_DEBUG) && defined(PLNERF_ENABLE_TRACE)
 #define PLNERF_TRACE(region, cnt, code)                                                        \
   do {                                                                                          \
     if (A.trace && blockIdx.x == 0 && trace_on && (cnt) < 256) {                               \
@@ -854,7 +813,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   constexpr bool DGRAD = (MODE == 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   const NetPlan& P = A.plan;
-  const SmemLayout SL = smem_layout(A.n_stages, A.slot_bytes);
+  const SmemLayout SL = smem_layout(A.n_stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nsplit = X3 ? 2 : 1;
 
@@ -902,7 +861,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           const StageInfo si = stage_info(n_pe, n_h, st);
           uint32_t w0 = (uint32_t)si.nks | (si.is_pe ? F_PE : 0u) | (h ? F_H : 0u) | (st == 0 ? F_FIRST : 0u) |
                         (st == nst - 1 ? F_LAST : 0u);
-          if (A.bias_mma && st == nst - 1 && P.bias_block_idx[l] >= 0) w0 |= (uint32_t)(P.bias_block_idx[l] + h + 1) << 20;   // bias K-step
           const uint32_t w1 = si.is_pe ? (uint32_t)si.k0 : (a_col + 8u * si.k0);
           const int bsel = (h == 1 || (!si.is_pe && si.k0 + si.nks > 8)) ? 1 : 0;
           if (batch_first[bsel] < 0) { batch_first[bsel] = n_entries; w0 |= bsel ? F_WAIT_A1 : F_WAIT_A0; }
@@ -918,9 +876,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   }
   if (warp == WARP_TMA) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += NUM_THREADS) consts[i] = A.tail[i];
-  if (A.bias_mma)
-  for (int i = threadIdx.x; i < KS_BYTES / 16; i += NUM_THREADS)     // bf16 1.0 = 0x3F80
-    reinterpret_cast<uint4*>(smem + SL.ones)[i] = (i < 128) ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
@@ -938,7 +893,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       uint32_t slot = 0, phase = 0, batch = 0;
       for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         const uint8_t* src = A.w;
-        const bool copy = !((A.debug_flags & 1) && tile != (int64_t)blockIdx.x);
+        const bool copy = !(PLNERF_DBG(1) && tile != (int64_t)blockIdx.x);
         int i = 0;
         while (i < n_entries) {
           const int blen = (prog[i].x >> 12) & 15;
@@ -946,17 +901,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             // one full-barrier per batch: armed with the batch's total bytes, every stage copy signals it.
             // 8 batch barriers > ring slots, so a barrier is never re-armed before its previous phase was consumed.
             uint32_t total = 0;
-            for (int j = 0; j < blen; ++j) total += (prog[i + j].x & 255u) * KS_BYTES + (((prog[i + j].x >> 20) & 255u) ? KS_BYTES : 0u);
+            for (int j = 0; j < blen; ++j) total += (prog[i + j].x & 255u) * KS_BYTES;
             const uint32_t bar = b_full(batch);
             if (copy) ptx::mbar_arrive_expect_tx(bar, total); else ptx::mbar_arrive(bar);
             for (int j = 0; j < blen; ++j) {
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               ptx::mbar_wait(w_empty(slot), phase ^ 1);
-              if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes, src, bytes, bar);
-              const uint32_t bidx = (prog[i + j].x >> 20) & 255u;     // bias block behind the stage's 8 K-steps
-              if (bidx) {
-                if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes + STAGE_BYTES, A.w + P.bias_blocks_off + (size_t)(bidx - 1) * KS_BYTES, KS_BYTES, bar);
-              }
+              if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, bar);
               src += bytes;
               if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
             }
@@ -966,7 +917,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               for (int rep = 0; rep < 2; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
-                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * (uint32_t)A.slot_bytes, src, bytes, w_full(slot)); }
+                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, w_full(slot)); }
                 else ptx::mbar_arrive(w_full(slot));
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
@@ -1005,7 +956,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       const uint2 e = prog[n];
       const uint32_t fl = ((e.x & F_FIRST) ? 1u : 0u) | ((e.x & F_PE) ? 2u : 0u) | ((e.x & F_LAST) ? 4u : 0u) | ((e.x & 255u) << 8) |
                           ((e.x & F_WAIT_A0) ? 8u : 0u) | ((e.x & F_WAIT_A1) ? 16u : 0u) | (((e.x >> 12) & 15u) ? 32u : 0u) |
-                          ((e.x & F_INC0) ? 64u : 0u) | ((e.x & F_INC1) ? 128u : 0u) | (((e.x >> 20) & 255u) ? 65536u : 0u);
+                          ((e.x & F_INC0) ? 64u : 0u) | ((e.x & F_INC1) ? 128u : 0u);
       prog2[n] = make_uint4(tmem + COL_DA + ((e.x & F_H) ? 128u : 0u), (e.x & F_PE) ? lo_of(s_pe_hi + e.y * KS_BYTES) : tmem + e.y, fl,
                             d_full0 + ((e.x & F_H) ? 8u : 0u));
     }
@@ -1019,12 +970,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
         ptx::mbar_wait(pe_ready, tile_iter & 1);
         ptx::tc_fence_after();
         if (ptx::elect_one())
-          issue_tile(st, sbase + SL.prog2, (uint32_t)n_entries, idesc, ring_desc, desc_hi, w_empty(0), (uint32_t)A.n_stages, b_full(0), a_ready0,
-                     (uint32_t)A.slot_bytes >> 4, lo_of(sbase + SL.ones));
+          issue_tile(st, sbase + SL.prog2, (uint32_t)n_entries, idesc, ring_desc, desc_hi, w_empty(0), (uint32_t)A.n_stages, b_full(0), a_ready0);
         __syncwarp();
         // the state lives in the elected lane; elect.sync of a converged warp picks the same lane every time
       }
-    } else if (!(A.debug_flags & 16)) {
+    } else if (!PLNERF_DBG(16)) {
       // hi+lo split mode: same one-call-per-tile structure (issue_tile_x3); debug flag 16 selects the C++ loop below
       IssueStateX3 st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
       for (int64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_iter) {
@@ -1056,7 +1006,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
             for (int rep = 0; rep < nsplit; ++rep) {
               if (X3) { ptx::mbar_wait(w_full(sl), ph); ptx::tc_fence_after(); }
-              const uint32_t b_lo = lo_of(s_ring + sl * (uint32_t)A.slot_bytes);
+              const uint32_t b_lo = lo_of(s_ring + sl * (uint32_t)STAGE_BYTES);
               if (e.x & F_PE) {
                 const uint32_t a_lo_hi = lo_of(s_pe_hi + e.y * KS_BYTES), a_lo_lo = lo_of(s_pe_lo + e.y * KS_BYTES);
                 for (int k = 0; k < nks; ++k) {
@@ -1142,7 +1092,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       const float* vbrow = A.viewbias ? (A.viewbias + (gc / A.vb_div) * 128) : nullptr;
       // The views layer's epilogue is the tile's last link; with ~3 KB of L1 left its per-ray bias rows would come from L2
       // (~600 cycles on the critical path).  They are copied to shared memory asynchronously at the start of the tile.
-      const bool vb_smem = !DGRAD && A.bias_mma && A.viewbias && A.vb_div >= 64;
+      const bool vb_smem = !DGRAD && A.viewbias && A.vb_div >= 64;
       const int64_t vb_ray0 = (tile * TILE_M) / A.vb_div;
       if (vb_smem && threadIdx.x < VB_SMEM_RAYS * 128) {
         const int64_t last_row = (tile * TILE_M + TILE_M - 1 < A.M) ? tile * TILE_M + TILE_M - 1 : A.M - 1;
@@ -1191,7 +1141,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           PLNERF_TRACE(1 + grp, tcnt, 3000 + l * 10 + h);     // accumulator half observed full
           // all 32-column chunks of this warp are requested before the single wait::ld
           uint32_t r2[CHUNKS_PER_GRP][32];
-          if (!(A.debug_flags & 2)) {
+          if (!PLNERF_DBG(2)) {
 #pragma unroll
             for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc)
               ptx::tmem_ld32(tmem + lane_addr + COL_DA + 128u * h + 32u * (CHUNKS_PER_GRP * grp + cc), r2[cc]);
@@ -1207,7 +1157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           }
 #pragma unroll
           for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc) {
-            if (A.debug_flags & 2) break;
+            if (PLNERF_DBG(2)) break;
             const int c = CHUNKS_PER_GRP * grp + cc;
             const int n0 = h * 128 + c * 32;
             float* val = reinterpret_cast<float*>(r2[cc]);
@@ -1264,7 +1214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 head[2] = fmaf(val[i + 2], w2.z, head[2]); head[2] = fmaf(val[i + 3], w2.w, head[2]);
               }
             } else {
-              if (!(A.bias_mma && P.bias_block_idx[l] >= 0)) {      // else: added by the tensor pipe (bias K-step)
+              {
                 const float* bias = consts + bias_off + n0;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -1327,7 +1277,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           PLNERF_TRACE(1 + grp, tcnt, 4000 + l * 10 + h);     // activations written, arrived
           // heads with tiny N, off the layer-to-layer critical chain: the fp32 values are still in registers (both heads
           // sit behind a ReLU layer; the hot path above did not apply it in place, so it is (re-)applied here)
-          if (!DGRAD && !(A.debug_flags & 2) && epi != EPI_VIEWS && (flags & (FLAG_ALPHA | FLAG_OUTHEAD))) {
+          if (!DGRAD && !PLNERF_DBG(2) && epi != EPI_VIEWS && (flags & (FLAG_ALPHA | FLAG_OUTHEAD))) {
             static_assert(CHUNKS_PER_GRP == 1, "deferred heads assume one chunk per warp and half");
             const float* val = reinterpret_cast<const float*>(r2[0]);
             const int n0 = h * 128 + grp * 32;
@@ -1425,275 +1375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
   if (warp == WARP_TMA) ptx::tmem_dealloc(tmem, 512);
 }
 
-#include "mlp_fwd2.cuh"
-
-// =============================================================================================
-// debug: single tile GEMM  D[128,N] = A[128,K] * B[N,K]^T  through the same primitives
-// (N in {128,256}, K % 16 == 0, K <= 256).  a_mode 0 = A from shared memory panels (SS),
-// 1 = A from tensor memory (TS).  lbo/sbo are passed explicitly so tests can pin the encoding.
-// =============================================================================================
-__global__ void __launch_bounds__(128, 1) k_debug_gemm(const float* __restrict__ Ag, const float* __restrict__ Bg, int N, int K,
-                                                       int a_mode, uint32_t lbo, uint32_t sbo, float* __restrict__ Dg) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  // layout: A panels [K/8][128 rows][16B] | B panels per 128-row half: [half][K/8][128][16B] | barrier | tmem slot
-  const int kp = K / 8;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)kp * 2048;
-  const int nh = N / 128;
-  uint8_t* sBar = sB + (size_t)nh * kp * 2048;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 16);
-  const uint32_t bar = ptx::smem_u32(sBar);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
-  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-  // B -> smem panels (generic-proxy stores + proxy fence)
-  for (int idx = threadIdx.x; idx < N * kp; idx += 128) {
-    const int n = idx % N, p = idx / N;
-    uint32_t w[4];
-    for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16(Bg[(size_t)n * K + p * 8 + 2 * e], Bg[(size_t)n * K + p * 8 + 2 * e + 1]);
-    *reinterpret_cast<uint4*>(sB + ((size_t)(n / 128) * kp + p) * 2048 + (n % 128) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
-  // A -> smem panels or TMEM columns [256, 256+K/2)
-  if (a_mode == 0) {
-    for (int p = 0; p < kp; ++p) {
-      uint32_t w[4];
-      for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16(Ag[(size_t)row * K + p * 8 + 2 * e], Ag[(size_t)row * K + p * 8 + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(sA + (size_t)p * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  } else {
-    for (int c0 = 0; c0 < K / 2; c0 += 16) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k = 2 * (c0 + i);
-        pk[i] = (k < K) ? ptx::pack_bf16(Ag[(size_t)row * K + k], Ag[(size_t)row * K + k + 1]) : 0u;
-      }
-      ptx::tmem_st16(tmem + lane_addr + 256u + (uint32_t)c0, pk);
-    }
-    ptx::tmem_st_wait();
-  }
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
-    for (int h = 0; h < nh; ++h) {
-      for (int ks = 0; ks < K / 16; ++ks) {
-        const uint64_t bd = ptx::smem_desc(ptx::smem_u32(sB + ((size_t)h * kp + 2 * ks) * 2048), lbo, sbo);
-        if (a_mode == 0) ptx::mma_ss(tmem + 128u * h, ptx::smem_desc(ptx::smem_u32(sA + (size_t)(2 * ks) * 2048), lbo, sbo), bd, idesc, ks > 0);
-        else ptx::mma_ts(tmem + 128u * h, tmem + 256u + 8u * ks, bd, idesc, ks > 0);
-      }
-    }
-    ptx::mma_commit(bar);
-  }
-  ptx::mbar_wait(bar, 0);
-  ptx::tc_fence_after();
-  for (int c = 0; c < N / 32; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld32(tmem + lane_addr + 32u * c, r);
-    ptx::tmem_ld_wait();
-    for (int i = 0; i < 32; ++i) Dg[(size_t)row * N + c * 32 + i] = __uint_as_float(r[i]);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
-}
-
-// =============================================================================================
-// debug: MN-major operands (what the weight-gradient GEMM uses).  D[128, N] = sum_k X[k, m] Y[k, n],
-// X [K,128] and Y [K,N] row-major fp32 (so the contraction index k is the strided one).  Operands are
-// staged as no-swizzle MN-major core matrices: block (mn8, k8) = 8 k-rows x 8 mn-values (mn fastest,
-// 128 contiguous bytes) at ((mn8 * K/8) + k8) * 128; descriptor SBO = (K/8)*128 (MN direction),
-// LBO = 128 (K direction).
-// =============================================================================================
-__global__ void __launch_bounds__(128, 1) k_debug_gemm_mn(const float* __restrict__ Xg, const float* __restrict__ Yg, int N, int K,
-                                                          uint32_t lbo, uint32_t sbo, float* __restrict__ Dg) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int k8n = K / 8;
-  uint8_t* sA = smem;                                  // 16 mn8 blocks x k8n x 128 B
-  uint8_t* sB = smem + (size_t)16 * k8n * 128;         // N/8 blocks x k8n x 128 B
-  uint8_t* sBar = sB + (size_t)(N / 8) * k8n * 128;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sBar + 16);
-  const uint32_t bar = ptx::smem_u32(sBar);
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
-  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-  for (int idx = threadIdx.x; idx < K * 128; idx += 128) {
-    const int k = idx / 128, m = idx % 128;
-    reinterpret_cast<__nv_bfloat16*>(sA + ((size_t)(m / 8) * k8n + k / 8) * 128)[(k % 8) * 8 + (m % 8)] = __float2bfloat16_rn(Xg[idx]);
-  }
-  for (int idx = threadIdx.x; idx < K * N; idx += 128) {
-    const int k = idx / N, n = idx % N;
-    reinterpret_cast<__nv_bfloat16*>(sB + ((size_t)(n / 8) * k8n + k / 8) * 128)[(k % 8) * 8 + (n % 8)] = __float2bfloat16_rn(Yg[idx]);
-  }
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = ptx::idesc_bf16_f32_mn(128, N);
-    for (int ks = 0; ks < K / 16; ++ks) {
-      const uint64_t ad = ptx::smem_desc(ptx::smem_u32(sA) + ks * 256, lbo, sbo);
-      const uint64_t bd = ptx::smem_desc(ptx::smem_u32(sB) + ks * 256, lbo, sbo);
-      ptx::mma_ss(tmem, ad, bd, idesc, ks > 0);
-    }
-    ptx::mma_commit(bar);
-  }
-  ptx::mbar_wait(bar, 0);
-  ptx::tc_fence_after();
-  const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
-  for (int c = 0; c < N / 32; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld32(tmem + lane_addr + 32u * c, r);
-    ptx::tmem_ld_wait();
-    for (int i = 0; i < 32; ++i) Dg[(size_t)threadIdx.x * N + c * 32 + i] = __uint_as_float(r[i]);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
-}
-
-// =============================================================================================
-// debug: raw tcgen05.mma issue/execute rate.  mode 0: TS N=128, 1: TS N=256, 2: SS N=128, 3: SS N=256.
-// One CTA per SM issues `iters` x 16 back-to-back MMAs on garbage operands; reports cycles per MMA.
-// =============================================================================================
-__global__ void __launch_bounds__(640, 1) k_debug_mma_rate(int mode, int iters, long long* cycles_out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 160 * 1024);
-  const uint32_t bar = ptx::smem_u32(smem + 160 * 1024 + 16);
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::mbar_init(bar + 8, 1); ptx::mbar_init(bar + 16, 1); ptx::fence_mbar_init(); }
-  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (warp >= 4) {
-    // mode 13/14: extra warps polling an mbarrier (what the epilogue warps of the fused kernels do while they wait)
-    ptx::mbar_wait(bar + 16, 0);
-  } else if (mode >= 20) {
-    // CUDA-core conversion throughput (all 4 warps): 20 = cvt.rn.relu.bf16x2.f32, 21 = max + integer round-half-up + PRMT,
-    // 22 = packed fp32 add (baseline), 23 = cvt.rn.bf16x2.f32 (no relu).  Reports cycles per warp-level "pair" operation.
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (float)(threadIdx.x * 32 + i) * 1.0001f - 1000.f;
-    uint32_t sink = 0;
-    __syncthreads();
-    const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        uint32_t d;
-        if (mode == 20) {
-          d = pack_bf16_relu(v[2 * i], v[2 * i + 1]);
-        } else if (mode == 23) {
-          d = ptx::pack_bf16(v[2 * i], v[2 * i + 1]);
-        } else if (mode == 21) {
-          const uint32_t a = __float_as_uint(fmaxf(v[2 * i], 0.f)) + 0x8000u, b = __float_as_uint(fmaxf(v[2 * i + 1], 0.f)) + 0x8000u;
-          d = __byte_perm(a, b, 0x7632);
-        } else {
-          float x = v[2 * i], y = v[2 * i + 1];
-          add2(x, y, 1.5f, 2.5f);
-          d = __float_as_uint(x) ^ __float_as_uint(y);
-        }
-        sink ^= d;
-        v[2 * i] = __uint_as_float(__float_as_uint(v[2 * i]) ^ (d & 1u));   // keep the chain data-dependent but cheap
-      }
-    }
-    const long long t1 = clock64();
-    if (sink == 0x12345678u) cycles_out[0] = 0;
-    if (threadIdx.x == 32) cycles_out[blockIdx.x] = t1 - t0;
-  } else if (warp == 1) {
-    const int N = ((mode & 1) && mode < 4) ? 256 : 128;
-    const bool ss = (mode == 2 || mode == 3);
-    const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
-    const uint32_t sb = ptx::smem_u32(smem);
-    const uint32_t lbo = N * 16;
-    const uint32_t bar2 = bar + 8;   // second barrier for the per-batch commit experiments
-    long long t0 = clock64(), t_issue = 0;
-    if (mode < 4) {
-      for (int it = 0; it < iters; ++it) {
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint64_t bd = ptx::smem_desc(sb + 64 * 1024 + (j & 3) * (N * 32), lbo, 128);
-            if (ss) ptx::mma_ss(tmem, ptx::smem_desc(sb + j * 4096, 2048, 128), bd, idesc, j > 0);
-            else ptx::mma_ts(tmem, tmem + 256u + 8u * j, bd, idesc, j > 0);
-          }
-        }
-        __syncwarp();
-      }
-    } else if (mode >= 6 && mode <= 14) {
-      // SS-form operand-layout experiments (rate only, operands are garbage):
-      //  6: N=256 no swizzle   7: N=256 A+B SWIZZLE_128B   8: N=256 A swizzled only   9: N=256 B swizzled only
-      // 10: N=128 A+B SWIZZLE_128B   11: N=256 no swizzle, A fixed (same 4 KB every MMA)   12: N=256 no swizzle, B fixed
-      const int N = (mode == 10) ? 128 : 256;
-      const bool a_sw = (mode == 7 || mode == 8 || mode == 10), b_sw = (mode == 7 || mode == 9 || mode == 10);
-      const uint32_t idesc = ptx::idesc_bf16_f32(128, N);
-      const uint32_t sb = ptx::smem_u32(smem);
-      auto desc = [&](uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) -> uint64_t {
-        return ptx::smem_desc(addr, lbo, sbo) | ((uint64_t)layout << 61);
-      };
-      for (int it = 0; it < iters; ++it) {
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ja = (mode == 11) ? 0 : j, jb = (mode == 12) ? 0 : (j & 3);
-            const uint64_t ad = a_sw ? desc(sb + (ja >> 2) * 16384 + (ja & 3) * 32, 16, 1024, 2) : desc(sb + ja * 4096, 2048, 128, 0);
-            const uint64_t bd = b_sw ? desc(sb + 64 * 1024 + jb * 32, 16, 1024, 2) : desc(sb + 64 * 1024 + jb * (N * 32), N * 16, 128, 0);
-            ptx::mma_ss(tmem, ad, bd, idesc, j > 0);
-          }
-        }
-        __syncwarp();
-      }
-    } else if (mode == 4) {
-      // like the kernel's stage loop: 8 MMAs, commit to a barrier, wait for the PREVIOUS batch's barrier
-      for (int it = 0; it < iters * 2; ++it) {
-        if (ptx::elect_one()) {
-          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
-          ptx::mma_commit(bar2);
-        }
-        __syncwarp();
-        if (it > 0) ptx::mbar_wait(bar2, (it - 1) & 1);
-        ptx::tc_fence_after();
-      }
-      ptx::mbar_wait(bar2, (iters * 2 - 1) & 1);
-    } else {
-      // mode 5: how far ahead of the tensor pipe does the issuing thread run?  (queue depth)
-      for (int it = 0; it < iters; ++it) {
-        long long a0 = clock64();
-        if (ptx::elect_one()) {
-          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
-          issue_ts8<false>(tmem, tmem + 256u, tmem + 384u, ptx::smem_desc(sb + 64 * 1024, 2048, 128), idesc, 1);
-        }
-        __syncwarp();
-        long long a1 = clock64();
-        if (ptx::elect_one()) ptx::mma_commit(bar2);
-        __syncwarp();
-        ptx::mbar_wait(bar2, it & 1);
-        t_issue += a1 - a0;
-      }
-    }
-    if (ptx::elect_one()) ptx::mma_commit(bar);
-    __syncwarp();
-    ptx::mbar_wait(bar, 0);
-    long long t1 = clock64();
-    if (threadIdx.x == 32) cycles_out[blockIdx.x] = (mode == 5) ? t_issue : (t1 - t0);
-    if (threadIdx.x == 32) ptx::mbar_arrive(bar + 16);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
-}
+#include "mlp_fwd3.cuh"
 
 // =============================================================================================
 // weight gradients:  dW[n, k] += sum_m dY[m, n] * In[m, k]   (contraction over the sample rows m)
@@ -1904,19 +1586,29 @@ __global__ void __launch_bounds__(256) k_head_grads(const __grid_constant__ Head
   if (tid == 3) atomicAdd(A.d_alpha_b, acc_b);
 }
 
-int g_num_sms = 0;
-int g_max_smem = 0;
-int g_mlp_variant = -1, g_mlp_cta = 2;   // bf16 inference kernel: 1 = k_mlp_fwd, 2 = k_mlp2 (single CTA or CTA pair)
+// Per-device facts and one-time kernel attributes (cudaFuncSetAttribute is per device): indexed by the current device,
+// so one process may drive several GPUs.
+constexpr int MAX_DEVICES = 64;
+struct DeviceInfo { int sms, max_smem; bool ok, attrs_v1, attrs_v3, attrs_wgrad; };
+DeviceInfo g_dev[MAX_DEVICES] = {};
+std::mutex g_dev_mu;
+int g_num_sms = 0, g_max_smem = 0;   // of the current device; refreshed by query_device() at every entry
+DeviceInfo* g_cur = nullptr;
 int query_device() {
-  if (g_num_sms) return PLNERF_OK;
   int dev = 0;
   PLNERF_CUDA(cudaGetDevice(&dev));
-  int sms = 0, smem = 0, major = 0;
-  PLNERF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  PLNERF_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  PLNERF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  if (major != 10) { set_error("plnerf_b200 needs an sm_100a (B200) device, found compute capability %d.x", major); return PLNERF_E_UNSUPPORTED; }
-  g_num_sms = sms; g_max_smem = smem;
+  if (dev < 0 || dev >= MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return PLNERF_E_UNSUPPORTED; }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceInfo& D = g_dev[dev];
+  if (!D.ok) {
+    int sms = 0, smem = 0, major = 0;
+    PLNERF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PLNERF_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    PLNERF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) { set_error("plnerf_b200 needs an sm_100a (B200) device, found compute capability %d.x", major); return PLNERF_E_UNSUPPORTED; }
+    D.sms = sms; D.max_smem = smem; D.ok = true;
+  }
+  g_num_sms = D.sms; g_max_smem = D.max_smem; g_cur = &D;
   return PLNERF_OK;
 }
 
@@ -1932,87 +1624,80 @@ cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-// k_mlp2 (two tiles in flight per CTA, SS operands, optional CTA pairs): experimental alternative to k_mlp_fwd for bf16
-// inference, selected by PLNERF_MLP_KERNEL=v2 / plnerf_debug_set_mlp_kernel (both are CUDA paths on the same packed weights).
-int launch_mlp2(MlpArgs& a, cudaStream_t st, int kcta) {
-  const v2::Smem2 SL = v2::smem2_layout(kcta, a.plan.const_floats - v2::head_const_off(a.plan), g_max_smem);
-  if (SL.n_stages < 2) { set_error("k_mlp2: not enough shared memory for the weight ring"); return PLNERF_E_UNSUPPORTED; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    PLNERF_CUDA(cudaFuncSetAttribute(v2::k_mlp2<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+// developer library only: integer knob from the environment (0 when unset); the product build has no knobs
+inline int dbg_env(const char* name) {
+#ifdef PLNERF_DEBUG
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
+
+// k_mlp3 (two tiles in flight, TMEM-resident activations, shared weight stages): the bf16 inference kernel.
+// Returns 1 when the plan does not fit it (very deep networks / not enough shared memory) so the caller falls back to
+// k_mlp_fwd -- both are sm_100a tcgen05 kernels on the same packed weights.
+int launch_mlp3(MlpArgs& a, cudaStream_t st) {
+  int n_stage_tile = 0;
+  for (int l = 0; l < a.plan.n_layers; ++l) n_stage_tile += a.plan.L[l].n_halves * stages_of(a.plan.L[l].n_pe_ks, a.plan.L[l].n_h_ks);
+  if (n_stage_tile > 48) return 1;
+  int n_slots = v3::MAX_SLOTS;
+  auto total_of = [&](int ns) -> int {
+    return a.plan.use_viewdirs ? (int)v3::smem3_layout<true>(ns, a.plan.const_floats).total : (int)v3::smem3_layout<false>(ns, a.plan.const_floats).total;
+  };
+  while (n_slots > 3 && total_of(n_slots) > g_max_smem) --n_slots;
+  { const int force = dbg_env("PLNERF_STAGES"); if (force >= 3 && force < n_slots) n_slots = force; }
+  const int smem_total = total_of(n_slots);
+  if (smem_total > g_max_smem) return 1;
+  if (!g_cur->attrs_v3) {
+    PLNERF_CUDA(cudaFuncSetAttribute(v3::k_mlp3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA(cudaFuncSetAttribute(v3::k_mlp3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    g_cur->attrs_v3 = true;
   }
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PLNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; } a.debug_flags = dbg; }
-  a.n_stages = g_max_smem;   // k_mlp2 derives its shared-memory layout from the same inputs as the host
+  a.n_stages = n_slots;
   a.trace = g_trace;
-  a.n_tiles = ceil_div(a.M, (int64_t)TILE_M * kcta);   // units of 128*kcta rows
-  const int64_t groups_max = g_num_sms / kcta;
-  const unsigned groups = (unsigned)((a.n_tiles < groups_max) ? a.n_tiles : groups_max);
+  a.debug_flags = dbg_env("PLNERF_DEBUG_FLAGS");
+  a.n_tiles = ceil_div(a.M, TILE_M);
+  const int64_t n_pairs = (a.n_tiles + 1) / 2;
+  const unsigned grid = (unsigned)((n_pairs < g_num_sms) ? n_pairs : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
-  if (kcta == 1) {
-    v2::k_mlp2<1><<<groups, v2::THREADS, SL.total, st>>>(a);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(groups * 2); cfg.blockDim = dim3(v2::THREADS); cfg.dynamicSmemBytes = SL.total; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, v2::k_mlp2<2>, a);
-    if (e != cudaSuccess) return cuda_fail(e, "k_mlp2<2> launch");
-  }
+  if (a.plan.use_viewdirs) v3::k_mlp3<true><<<grid, v3::THREADS3, smem_total, st>>>(a);
+  else v3::k_mlp3<false><<<grid, v3::THREADS3, smem_total, st>>>(a);
   if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
-  PLNERF_LAUNCH_CHECK("k_mlp2");
+  PLNERF_LAUNCH_CHECK("k_mlp3");
   return PLNERF_OK;
 }
 
+// mode: -1 = inference in the plan's precision (bf16 -> k_mlp3, bf16x3 -> k_mlp_fwd<1>), 2 = forward + training stash,
+// 3 = input-gradient chain
 int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   int rc = query_device();
   if (rc) return rc;
-  {
-    if (g_mlp_variant < 0) {
-      // default: the first-generation kernel (faster today); PLNERF_MLP_KERNEL=v2 [PLNERF_MLP_CTA=1|2]
-      // or plnerf_debug_set_mlp_kernel() select k_mlp2
-      const char* e = getenv("PLNERF_MLP_KERNEL");
-      g_mlp_variant = (e && !strcmp(e, "v2")) ? 2 : 1;
-      const char* c = getenv("PLNERF_MLP_CTA");
-      g_mlp_cta = (c && atoi(c) == 1) ? 1 : 2;
-    }
-    const int m = (mode < 0) ? ((a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0) : mode;
-    if (g_mlp_variant == 2 && m == 0) return launch_mlp2(a, st, g_mlp_cta);
-  }
   if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
-  // bf16 forward (inference and stash mode must agree bit for bit): biases added by the tensor pipe, 36 KB ring slots
-  static int no_bias_mma = -1;     // developer A/B switch: keep the layer biases in the epilogue (32 KB ring slots)
-  if (no_bias_mma < 0) no_bias_mma = getenv("PLNERF_NO_BIAS_MMA") ? 1 : 0;
-  a.bias_mma = ((mode == 0 || mode == 2) && a.plan.n_bias_blocks > 0 && !no_bias_mma) ? 1 : 0;
-  a.slot_bytes = a.bias_mma ? SLOT_BYTES_BIAS : STAGE_BYTES;
-  int n_stages = a.bias_mma ? 4 : MAX_STAGES;
-  while (n_stages > 2 && (int)smem_layout(n_stages, a.slot_bytes).total > g_max_smem) --n_stages;
-  { static int force = -1; if (force < 0) { const char* e = getenv("PLNERF_STAGES"); force = e ? atoi(e) : 0; } if (force >= 2 && force < n_stages) n_stages = force; }
+  if (mode == 0 && a.M < ((int64_t)1 << 40) && !dbg_env("PLNERF_MLP_V1")) {
+    rc = launch_mlp3(a, st);
+    if (rc <= 0) return rc;     // > 0: the plan does not fit k_mlp3, fall through to the single-tile kernel
+  }
+  int n_stages = MAX_STAGES;
+  while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
+  { const int force = dbg_env("PLNERF_STAGES"); if (force >= 2 && force < n_stages) n_stages = force; }
   a.n_stages = n_stages;
-  const SmemLayout SL = smem_layout(n_stages, a.slot_bytes);
-  static bool attr_set = false;
-  if (!attr_set) {
+  const SmemLayout SL = smem_layout(n_stages);
+  if (!g_cur->attrs_v1) {
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     PLNERF_CUDA(cudaFuncSetAttribute(k_mlp_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    attr_set = true;
+    g_cur->attrs_v1 = true;
   }
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("PLNERF_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
-  a.debug_flags = dbg;
+  a.debug_flags = dbg_env("PLNERF_DEBUG_FLAGS");
   a.trace = g_trace;
   a.n_tiles = ceil_div(a.M, TILE_M);
   const unsigned grid = (unsigned)((a.n_tiles < g_num_sms) ? a.n_tiles : g_num_sms);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
-  if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
   if (mode == 1) k_mlp_fwd<1><<<grid, NUM_THREADS, SL.total, st>>>(a);
   else if (mode == 2) k_mlp_fwd<2><<<grid, NUM_THREADS, SL.total, st>>>(a);
   else if (mode == 3) k_mlp_fwd<3><<<grid, NUM_THREADS, SL.total, st>>>(a);
@@ -2028,7 +1713,6 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
 size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision) {
   NetPlan P;
   if (build_plan(d, precision, nullptr, &P)) return 0;
-  if (P.n_bias_blocks > 0) return (size_t)P.bias_blocks_off + (size_t)P.n_bias_blocks * KS_BYTES;
   return (size_t)P.weight_bytes + (size_t)P.tail_floats * 4;
 }
 
@@ -2049,10 +1733,6 @@ int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision
   PLNERF_LAUNCH_CHECK("k_pack_weights");
   k_pack_tail<<<(unsigned)ceil_div(a.plan.tail_floats, 256), 256, 0, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_pack_tail");
-  if (a.plan.n_bias_blocks > 0) {
-    k_pack_bias<<<(unsigned)a.plan.n_bias_blocks, 256, 0, st>>>(a);
-    PLNERF_LAUNCH_CHECK("k_pack_bias");
-  }
   return PLNERF_OK;
 }
 
@@ -2119,25 +1799,7 @@ int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int preci
   return run_mlp_common(d, packed, precision, a, m, 0, nullptr, 0, x, a.x_ld, ws, ws_bytes, st);
 }
 
-int debug_umma_gemm_ex(const float* A, const float* B, int N, int K, int a_mode, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st) {
-  PLNERF_CHECK_ARG(A && B && D, "debug_umma_gemm: null argument");
-  PLNERF_CHECK_ARG((N == 128 || N == 256) && K % 16 == 0 && K >= 16 && K <= 256, "debug_umma_gemm: N in {128,256}, K%%16==0, K<=256");
-  int rc = query_device();
-  if (rc) return rc;
-  const size_t smem = (size_t)(K / 8) * 2048 * (1 + N / 128) + 64;
-  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-  k_debug_gemm<<<1, 128, smem, st>>>(A, B, N, K, a_mode, lbo, sbo, D);
-  PLNERF_LAUNCH_CHECK("k_debug_gemm");
-  return PLNERF_OK;
-}
 
-int debug_set_trace(long long* buf) { g_trace = buf; return PLNERF_OK; }
-
-int debug_set_mlp_kernel(int variant, int cta) {
-  PLNERF_CHECK_ARG((variant == 1 || variant == 2) && (cta == 1 || cta == 2), "debug_set_mlp_kernel: variant in {1,2}, cta in {1,2}");
-  g_mlp_variant = variant; g_mlp_cta = cta;
-  return PLNERF_OK;
-}
 
 int profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -2285,9 +1947,8 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   w.n_items = ni;
   w.splits = g_num_sms / ni > 0 ? g_num_sms / ni : 1;
   if ((int64_t)w.splits > w.n_tiles) w.splits = (int)w.n_tiles;
-  static bool wattr = false;
   const size_t wsmem = 2 * WG_STAGE_BYTES + 1024 + 64;
-  if (!wattr) { PLNERF_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); wattr = true; }
+  if (!g_cur->attrs_wgrad) { PLNERF_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); g_cur->attrs_wgrad = true; }
   k_wgrad<<<(unsigned)(ni * w.splits), WG_THREADS, wsmem, st>>>(w);
   PLNERF_LAUNCH_CHECK("k_wgrad");
   // (3) alpha / rgb heads
@@ -2304,30 +1965,11 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   return PLNERF_OK;
 }
 
-int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lbo, uint32_t sbo, float* D, cudaStream_t st) {
-  PLNERF_CHECK_ARG(X && Y && D, "debug_umma_gemm_mn: null argument");
-  PLNERF_CHECK_ARG(N % 32 == 0 && N >= 32 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 128, "debug_umma_gemm_mn: bad N/K");
-  int rc = query_device();
-  if (rc) return rc;
-  const size_t smem = (size_t)(16 + N / 8) * (K / 8) * 128 + 64;
-  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-  k_debug_gemm_mn<<<1, 128, smem, st>>>(X, Y, N, K, lbo, sbo, D);
-  PLNERF_LAUNCH_CHECK("k_debug_gemm_mn");
-  return PLNERF_OK;
-}
 
-int debug_mma_rate(int mode, int iters, int grid, long long* cycles_out, cudaStream_t st) {
-  int rc = query_device();
-  if (rc) return rc;
-  PLNERF_CUDA(cudaFuncSetAttribute(k_debug_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-  const int threads = (mode == 13) ? 640 : (mode == 14 ? 256 : 128);   // 13: 16 polling warps, 14: 4 polling warps
-  k_debug_mma_rate<<<grid, threads, 160 * 1024 + 64, st>>>(mode, iters, cycles_out);
-  PLNERF_LAUNCH_CHECK("k_debug_mma_rate");
-  return PLNERF_OK;
-}
 
-int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st) {
-  return debug_umma_gemm_ex(A, B, N, K, 0, 2048, 128, D, st);
-}
+
+#ifdef PLNERF_DEBUG
+#include "debug_kernels.cuh"
+#endif
 
 }  // namespace plnerf

@@ -1,0 +1,570 @@
+// k_mlp3 -- bf16 inference generation 3 of the fused PE + MLP kernel (included by mlp_fwd.cu).
+//
+// Why: k_mlp_fwd keeps ONE 128-row tile in flight, so the tensor pipe and the epilogue warps wait for each other once
+// per layer (layer period ~2800 cycles against 2080 cycles of MMA).  k_mlp3 keeps TWO tiles ("X" and "Y") in flight at
+// the SAME layer and alternates them on the tensor pipe half by half:
+//
+//      pipe:      X(l,a)  Y(l,a)  X(l,b)  Y(l,b)  X(l+1,a) ...
+//      epilogue:          X(l,a)  Y(l,a)  X(l,b)  Y(l,b)   ...
+//
+// so every half-epilogue (tcgen05.ld, bias, ReLU, bf16 pack, tcgen05.st) hides behind the other tile's 16 MMAs, and both
+// tiles consume every weight stage (L2 -> shared-memory traffic per row halves).
+//
+// Tensor memory (512 columns): tile t owns  D_t = [256t, 256t+128)  one fp32 accumulator HALF (128 neurons)
+//                                           A_t = [256t+128, 256t+256)  the layer input, 128x256 bf16 (TS-form A operand).
+// A_t is single-buffered: the bf16 output of half a cannot overwrite it while half b's MMAs still read it, so the
+// epilogue threads HOLD half a (16 packed registers per thread) and store both halves after half b completed.
+// Layers that do not read A_t (layer 0: the encoding is a shared-memory operand) store directly.
+//
+// Warp roles (20 warps): 0-7 epilogue of tile X, 8-15 epilogue of tile Y (TMEM lane quarter = warp % 4, column half =
+// (warp / 4) % 2: one row x 64 accumulator columns per thread) -- two independent instruction streams, so X's and Y's
+// epilogues overlap each other as well as the MMAs; 16 / 17 = MMA issuer of tile X / Y (16 allocates TMEM, 17 also
+// streams the weights: one bulk-TMA refill per stage it issues); 18-19 =
+// helpers that encode the NEXT pair's rows (one thread per row: the angle reduction is done once per row, not once
+// per column group) and pull the pair after that into L2.
+//
+// Weight ring: N slots of one 32 KB stage (8 K-steps of a 128-neuron half); both issuers walk it, a slot is refilled
+// once both have released it (tcgen05.commit on a count-2 barrier).  Biases are added in the epilogue (a bias
+// K-step would cost 6% of the tensor pipe, which is the bound here).
+namespace v3 {
+
+constexpr int MAX_SLOTS = 6;
+constexpr int EPI_WARPS_PER_TILE = 8;
+constexpr int WARP_MMA3 = 2 * EPI_WARPS_PER_TILE, WARP_HELP3 = WARP_MMA3 + 2, N_HELP_WARPS = 2;   // issuers: WARP_MMA3 + tile
+constexpr int THREADS3 = 32 * (WARP_HELP3 + N_HELP_WARPS);   // 640
+constexpr uint32_t VB_RAYS_SMEM = 3;       // rays whose view-bias rows a 128-sample tile can touch when S >= 64
+
+// Shared-memory map: everything the epilogue warps address sits at COMPILE-TIME offsets (their addresses are instruction
+// immediates, not registers -- the epilogue threads hold two tiles' state in a 96-register budget); the variable-size
+// parts (fp32 constants, weight ring) come last.
+template <bool VD>
+struct Smem3 {
+  static constexpr uint32_t bars = 0;                                    // 256 B of mbarriers + the TMEM base slot
+  static constexpr uint32_t prog = 256;                                  // <= 48 stages per tile: [2][48] entries of 16 B, then the stream table [48] x 8 B
+  static constexpr uint32_t stab = prog + 16u * 2u * 48u;
+  static constexpr uint32_t vb0 = stab + 8u * 48u;                 // [2][3 rays][128] view-bias rows
+  static constexpr uint32_t XCH_CH = VD ? 4 : MAX_OUT_CH;
+  static constexpr uint32_t XCH_BYTES = TILE_M * XCH_CH * 4u;
+  static constexpr uint32_t xch0 = vb0 + 2u * VB_RAYS_SMEM * 128u * 4u;  // [2][128 rows][XCH_CH] head partial sums of the upper column half
+  static constexpr uint32_t pe0 = (xch0 + 2u * XCH_BYTES + 1023u) & ~1023u;   // [2] encoding operand tiles
+  static constexpr uint32_t consts = pe0 + 2u * PE_TILE_BYTES;           // fp32 biases + heads (const_floats)
+  uint32_t ring, total;
+  int n_slots;
+};
+template <bool VD>
+__host__ __device__ inline Smem3<VD> smem3_layout(int n_slots, int const_floats) {
+  Smem3<VD> s;
+  s.n_slots = n_slots;
+  s.ring = (Smem3<VD>::consts + (uint32_t)const_floats * 4u + 1023u) & ~1023u;
+  s.total = s.ring + (uint32_t)n_slots * STAGE_BYTES;
+  return s;
+}
+
+// Program entry flags (see issue_tile3)
+enum : uint32_t { PF_FIRST = 1u, PF_SS = 2u, PF_COMMIT = 4u, PF_WAIT_EP = 8u, PF_WAIT_PE = 16u };
+
+// Per-issuer state carried across tile pairs: consumer ring cursor + phase, parities of the tile's epilogue / encoding
+// barriers; producer duty (tile Y's issuer only): ring cursor + phase, next stage of the weight stream, stages left.
+struct Issue3 { uint32_t sl, ph, c, q, psl, pph, pj, prem; };
+
+#define PLNERF3_MMA_TS(PRED) \
+  "tcgen05.mma.cta_group::1.kind::f16 [ed], [ea], bd, %9, " PRED ";\n\t" \
+  "add.u64 bd, bd, 256;\n\tadd.u32 ea, ea, 8;\n\t"
+#if defined(PLNERF_DEBUG) && defined(PLNERF_ENABLE_TRACE)
+#define PLNERF3_STAMP "@ptr mov.u32 t, %%clock;\n\t@ptr st.global.u32 [tr], t;\n\t@ptr add.u64 tr, tr, 4;\n\t"
+#else
+#define PLNERF3_STAMP ""
+#endif
+
+// One tile's whole stage program of a pair from one PTX loop (an issuing warp retires one dependent instruction per ~6.5
+// cycles: a stage's bookkeeping has to stay at a few dozen instructions, and ONE issuing thread cannot feed the pipe for
+// two tiles -- measured 730 cycles per 8-MMA stage against 520 cycles of tensor work -- hence one issuer warp per tile).
+// Entry (16 bytes): {accumulator tmem address, A operand (tmem address | low word of the shared-memory descriptor),
+// flags, accumulator-full barrier}.  flags: PF_FIRST first MMA overwrites the accumulator, PF_SS shared-memory A operand
+// with bits 8-11 K-steps, PF_COMMIT commit the accumulator-full barrier after the stage, PF_WAIT_EP wait for the tile's
+// epilogue barrier before the stage (+ PF_WAIT_PE: and for its encoding operand).  Every stage waits for its ring slot's
+// weights and releases the slot with a commit (the slot's empty barrier counts both tiles' issuers).
+// Producer duty (prem > 0): after each stage, refill the ring slot released `lag` stages ago with the next stage of the
+// packed stream ({global byte offset, bytes} table at stab_addr, n_stab entries per pair).
+__device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint32_t n_entries, uint64_t ring_desc, uint32_t idesc,
+                                            uint32_t desc_hi, uint32_t wfull0, uint32_t wempty0, uint32_t epdone, uint32_t peready,
+                                            uint32_t n_slots, uint32_t stab_addr, uint32_t n_stab, uint32_t ring_addr,
+                                            unsigned long long wbase, unsigned long long trace_ptr) {
+  asm volatile(
+      "{\n\t.reg .pred p, pacc, pt, ptr;\n\t"
+      ".reg .b32 sl, ph, n, pa, ed, ea, ef, eb, t, k, wb, c, q, psl, pph, pj, prem, so2, sb2;\n\t.reg .b64 bd, so, ad, tr, ga;\n\t"
+      "mov.b64 tr, %19;\n\tsetp.ne.b64 ptr, tr, 0;\n\t"
+      "mov.b32 sl, %0;\n\tmov.b32 ph, %1;\n\tmov.b32 c, %2;\n\tmov.b32 q, %3;\n\t"
+      "mov.b32 psl, %4;\n\tmov.b32 pph, %5;\n\tmov.b32 pj, %6;\n\tmov.b32 prem, %7;\n\t"
+      "mov.b32 n, %11;\n\tmov.b32 pa, %10;\n\tsetp.eq.b32 pt, sl, sl;\n\t"
+      "LOOP3:\n\t"
+      "ld.shared.v4.u32 {ed, ea, ef, eb}, [pa];\n\t"
+      PLNERF3_STAMP
+      // ---- the tile's previous half-epilogue (accumulator drained / layer input written), its encoding operand
+      "and.b32 t, ef, 8;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOEP3;\n\t"
+      "WEP3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%14], c;\n\t@!p bra WEP3;\n\t"
+      "xor.b32 c, c, 1;\n\t"
+      "and.b32 t, ef, 16;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOPE3;\n\t"
+      "WPE3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%15], q;\n\t@!p bra WPE3;\n\t"
+      "xor.b32 q, q, 1;\n\t"
+      "NOPE3:\n\t"
+      "NOEP3:\n\t"
+      // ---- the ring slot's weights
+      "shl.b32 wb, sl, 3;\n\t"
+      "add.u32 t, wb, %12;\n\t"
+      "WAQ3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [t], ph;\n\t@!p bra WAQ3;\n\t"
+      "tcgen05.fence::after_thread_sync;\n\t"
+      PLNERF3_STAMP
+      "mul.wide.u32 so, sl, 2048;\n\tadd.u64 bd, so, %8;\n\t"
+      "and.b32 t, ef, 1;\n\tsetp.eq.b32 pacc, t, 0;\n\t"
+      "and.b32 t, ef, 2;\n\tsetp.ne.b32 p, t, 0;\n\t@p bra SS3;\n\t"
+      PLNERF3_MMA_TS("pacc") PLNERF3_MMA_TS("pt") PLNERF3_MMA_TS("pt") PLNERF3_MMA_TS("pt")
+      PLNERF3_MMA_TS("pt") PLNERF3_MMA_TS("pt") PLNERF3_MMA_TS("pt") PLNERF3_MMA_TS("pt")
+      "bra DONE3;\n\t"
+      "SS3:\n\t"
+      "mov.b64 ad, {ea, %13};\n\tshr.u32 k, ef, 8;\n\tand.b32 k, k, 15;\n\t"
+      "SSL3:\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [ed], ad, bd, %9, pacc;\n\t"
+      "setp.eq.b32 pacc, sl, sl;\n\tadd.u64 ad, ad, 256;\n\tadd.u64 bd, bd, 256;\n\t"
+      "sub.u32 k, k, 1;\n\tsetp.ne.b32 p, k, 0;\n\t@p bra SSL3;\n\t"
+      "DONE3:\n\t"
+      "add.u32 t, wb, %16;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [t];\n\t"
+      "and.b32 t, ef, 4;\n\tsetp.ne.b32 p, t, 0;\n\t"
+      "@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [eb];\n\t"
+      PLNERF3_STAMP
+      "add.u32 sl, sl, 1;\n\tsetp.eq.u32 p, sl, %17;\n\t@p mov.b32 sl, 0;\n\t@p xor.b32 ph, ph, 1;\n\t"
+      // ---- producer duty: refill the slot both tiles released a while ago with the next stage of the stream
+      "setp.eq.u32 p, prem, 0;\n\t@p bra NOPROD3;\n\t"
+      "shl.b32 wb, psl, 3;\n\tadd.u32 t, wb, %16;\n\txor.b32 k, pph, 1;\n\t"
+      "WPR3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [t], k;\n\t@!p bra WPR3;\n\t"
+      "shl.b32 t, pj, 3;\n\tadd.u32 t, t, %18;\n\tld.shared.v2.u32 {so2, sb2}, [t];\n\t"
+      "add.u32 t, wb, %12;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [t], sb2;\n\t"
+      "cvt.u64.u32 ga, so2;\n\tadd.u64 ga, ga, %20;\n\t"
+      "shl.b32 k, psl, 15;\n\tadd.u32 k, k, %21;\n\t"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [k], [ga], sb2, [t];\n\t"
+      "add.u32 psl, psl, 1;\n\tsetp.eq.u32 p, psl, %17;\n\t@p mov.b32 psl, 0;\n\t@p xor.b32 pph, pph, 1;\n\t"
+      "add.u32 pj, pj, 1;\n\tsetp.eq.u32 p, pj, %22;\n\t@p mov.b32 pj, 0;\n\tsub.u32 prem, prem, 1;\n\t"
+      "NOPROD3:\n\t"
+      "add.u32 pa, pa, 16;\n\tsub.u32 n, n, 1;\n\tsetp.ne.b32 p, n, 0;\n\t@p bra LOOP3;\n\t"
+      "mov.b32 %0, sl;\n\tmov.b32 %1, ph;\n\tmov.b32 %2, c;\n\tmov.b32 %3, q;\n\t"
+      "mov.b32 %4, psl;\n\tmov.b32 %5, pph;\n\tmov.b32 %6, pj;\n\tmov.b32 %7, prem;\n\t}"
+      : "+r"(st.sl), "+r"(st.ph), "+r"(st.c), "+r"(st.q), "+r"(st.psl), "+r"(st.pph), "+r"(st.pj), "+r"(st.prem)
+      : "l"(ring_desc), "r"(idesc), "r"(prog_addr), "r"(n_entries), "r"(wfull0), "r"(desc_hi), "r"(epdone), "r"(peready),
+        "r"(wempty0), "r"(n_slots), "r"(stab_addr), "l"(trace_ptr), "l"(wbase), "r"(ring_addr), "r"(n_stab)
+      : "memory");
+}
+
+// Full encoding of one row (all 3 + 6L elements, one thread): p = o + d*z, one 32-bit turn fraction per coordinate, every
+// octave an exact shift of it + SFU sin/cos (common.cuh) -> the row's 16-byte units of the tile's PE operand (bf16,
+// K-major 8x16B core-matrix panels: panel j = columns [8j, 8j+8) at j * 2048 + row * 16).
+__device__ __forceinline__ void pe_write_row(const MlpArgs& A, uint8_t* pe_tile, int64_t tile, int row) {
+  const NetPlan& P = A.plan;
+  const int64_t g = tile * TILE_M + row;
+  const int64_t gc = (g < A.M) ? g : (A.M - 1);
+  const int n_panels = 2 * P.pe_ks;
+  if (A.x_emb) {
+    // pre-embedded rows (NeRF.forward entry)
+    const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
+    for (int j = 0; j < n_panels; ++j) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const int idx = 8 * j + e; v[e] = (idx < P.input_ch) ? xr[idx] : 0.f; }
+      uint4 q4;
+      q4.x = ptx::pack_bf16(v[0], v[1]); q4.y = ptx::pack_bf16(v[2], v[3]); q4.z = ptx::pack_bf16(v[4], v[5]); q4.w = ptx::pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(pe_tile + j * 2048 + row * 16) = q4;
+    }
+    return;
+  }
+  float p[3];
+  const float* rp = A.rays + (gc / A.S) * (int64_t)A.stride;
+  const float zz = A.z[gc];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(rp[c], __fmul_rn(rp[3 + c], zz));   // o + d*z, two roundings like the reference
+  const uint32_t turns[3] = {pe_turns(p[0]), pe_turns(p[1]), pe_turns(p[2])};
+  const int n_ch = P.input_ch;
+#pragma unroll
+  for (int j = 0; j < 2 * MAX_PE_KS; ++j) {
+    if (j < n_panels) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int idx = 8 * j + e;                              // compile-time after unrolling
+        float x;
+        if (idx < 3) x = p[idx];
+        else { const int tt = idx - 3, k = tt / 6, r = tt % 6, c = r % 3; x = (r >= 3) ? pe_cos(turns[c], k) : pe_sin(turns[c], k); }
+        v[e] = (idx < n_ch) ? x : 0.f;
+      }
+      uint4 q4;
+      q4.x = ptx::pack_bf16(v[0], v[1]); q4.y = ptx::pack_bf16(v[2], v[3]); q4.z = ptx::pack_bf16(v[4], v[5]); q4.w = ptx::pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(pe_tile + j * 2048 + row * 16) = q4;
+    }
+  }
+}
+
+// bias + (ReLU) + bf16 pack of 32 accumulator columns -> 16 packed words
+template <bool RELU>
+__device__ __forceinline__ void cvt32(uint32_t (&r)[32], const float* bias, uint32_t* pk) {
+  float* val = reinterpret_cast<float*>(r);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
+    add2(val[i], val[i + 1], b4.x, b4.y);
+    add2(val[i + 2], val[i + 3], b4.z, b4.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = RELU ? pack_bf16_relu(val[2 * i], val[2 * i + 1]) : ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+}
+__device__ __forceinline__ float dot32_relu(const uint32_t (&r)[32], const float* w, float acc) {
+  const float* val = reinterpret_cast<const float*>(r);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+    acc = fmaf(fmaxf(val[i], 0.f), w4.x, acc); acc = fmaf(fmaxf(val[i + 1], 0.f), w4.y, acc);
+    acc = fmaf(fmaxf(val[i + 2], 0.f), w4.z, acc); acc = fmaf(fmaxf(val[i + 3], 0.f), w4.w, acc);
+  }
+  return acc;
+}
+
+// VD: use_viewdirs network (alpha + rgb heads behind a views layer) or not (output_linear behind the last trunk layer)
+#ifdef PLNERF_DEBUG
+#define PLNERF3_DBG(bit) ((A.debug_flags & (bit)) != 0)   // bring-up experiments: 1 = no epilogue TMEM traffic / math, 2 = 16-byte weight copies, 4 = no encoding
+#else
+#define PLNERF3_DBG(bit) false
+#endif
+template <bool VD>
+__global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ MlpArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const NetPlan& P = A.plan;
+  const Smem3<VD> SL = smem3_layout<VD>(A.n_stages, P.const_floats);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = ptx::smem_u32(smem);
+  float* consts = reinterpret_cast<float*>(smem + Smem3<VD>::consts);
+  const uint32_t s_bars = sbase + Smem3<VD>::bars;
+  const uint32_t w_full0 = s_bars, w_empty0 = s_bars + 8u * MAX_SLOTS;
+  const uint32_t d_full0 = s_bars + 8u * (2 * MAX_SLOTS);         // [2] accumulator half of tile t is complete
+  const uint32_t ep_done0 = d_full0 + 16u;                        // [2] tile t's half-epilogue is done (8 warps)
+  const uint32_t pe_ready0 = d_full0 + 32u;                       // [2] tile t's encoding operand is written (helper warps)
+  const uint32_t vb_full0 = d_full0 + 48u;                        // [2] tile t's view-bias rows landed (bulk copy)
+  const uint32_t pe_free0 = d_full0 + 64u;                        // [2] every MMA reading tile t's encoding operand is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem3<VD>::bars + 8u * (2 * MAX_SLOTS) + 96u);
+  const int n_slots = SL.n_slots;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_slots; ++s) { ptx::mbar_init(w_full0 + 8u * s, 1); ptx::mbar_init(w_empty0 + 8u * s, 2); }
+    for (uint32_t t = 0; t < 2; ++t) {
+      ptx::mbar_init(d_full0 + 8u * t, 1);
+      ptx::mbar_init(ep_done0 + 8u * t, EPI_WARPS_PER_TILE);
+      ptx::mbar_init(pe_ready0 + 8u * t, N_HELP_WARPS);
+      ptx::mbar_init(vb_full0 + 8u * t, 1);
+      ptx::mbar_init(pe_free0 + 8u * t, EPI_WARPS_PER_TILE);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == WARP_MMA3) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  for (int i = threadIdx.x; i < P.const_floats; i += THREADS3) consts[i] = A.tail[i];
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_pairs = (int)((A.n_tiles + 1) >> 1);
+  int l_pe_last = 0;
+  for (int l = 0; l < P.n_layers; ++l) if (P.L[l].n_pe_ks > 0) l_pe_last = l;
+
+  if (warp == WARP_MMA3 || warp == WARP_MMA3 + 1) {
+    // ===================== MMA issuers: warp 16 -> tile X, warp 17 -> tile Y (+ weight stream) ============================
+    const uint32_t t = (uint32_t)(warp - WARP_MMA3);
+    const uint32_t idesc = ptx::idesc_bf16_f32(128, 128);
+    const uint64_t desc_base = ptx::smem_desc(0, 2048, 128);
+    const uint32_t desc_hi = (uint32_t)(desc_base >> 32);
+    const uint32_t desc_lo0 = (uint32_t)(desc_base & 0xFFFFFFFFu);
+    auto lo_of = [&](uint32_t saddr) -> uint32_t { return desc_lo0 | ((saddr & 0x3FFFFu) >> 4); };
+    uint4* prog = reinterpret_cast<uint4*>(smem + Smem3<VD>::prog) + 48 * t;
+    uint2* stab = reinterpret_cast<uint2*>(smem + Smem3<VD>::stab);
+    int n_entries = 0;
+    if (lane == 0) {
+      uint32_t off = 0;
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int n_pe = P.L[l].n_pe_ks, n_h = P.L[l].n_h_ks, nst = stages_of(n_pe, n_h);
+        for (int h = 0; h < P.L[l].n_halves; ++h)
+          for (int s2 = 0; s2 < nst; ++s2) {
+            const StageInfo si = stage_info(n_pe, n_h, s2);
+            uint32_t f = (s2 == 0 ? PF_FIRST : 0u);
+            uint32_t a;
+            if (si.is_pe) { f |= PF_SS | ((uint32_t)si.nks << 8); a = lo_of(sbase + Smem3<VD>::pe0 + t * PE_TILE_BYTES + (uint32_t)si.k0 * KS_BYTES); }
+            else a = tmem + 256u * t + 128u + 8u * (uint32_t)si.k0;
+            if (s2 == 0) { f |= PF_WAIT_EP; if (l == 0 && h == 0) f |= PF_WAIT_PE; }
+            if (s2 == nst - 1) f |= PF_COMMIT;
+            if (t == 1) stab[n_entries] = make_uint2(off, PLNERF3_DBG(2) ? 16u : (uint32_t)si.nks * KS_BYTES);
+            off += (uint32_t)si.nks * KS_BYTES;
+            prog[n_entries++] = make_uint4(tmem + 256u * t, a, f, d_full0 + 8u * t);
+          }
+      }
+    }
+    n_entries = __shfl_sync(0xffffffffu, n_entries, 0);
+    __syncwarp();
+    const uint64_t ring_desc = ((uint64_t)desc_hi << 32) | (uint64_t)lo_of(sbase + SL.ring);
+    int my_pairs = 0;
+    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) ++my_pairs;
+    Issue3 st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, (t == 1) ? (uint32_t)(my_pairs * n_entries) : 0u};
+    const uint32_t prog_addr = sbase + Smem3<VD>::prog + 16u * 48u * t, stab_addr = sbase + Smem3<VD>::stab;
+    if (t == 1 && ptx::elect_one()) {
+      // prologue of the weight stream: fill all but REFILL_LAG slots; afterwards every issued stage refills the slot both
+      // tiles released REFILL_LAG stages earlier
+      constexpr uint32_t REFILL_LAG = 2;
+      for (uint32_t s2 = 0; s2 + REFILL_LAG < (uint32_t)n_slots && st.prem > 0; ++s2) {
+        const uint2 e = stab[st.pj];
+        ptx::mbar_arrive_expect_tx(w_full0 + 8u * st.psl, e.y);
+        ptx::bulk_g2s(sbase + SL.ring + st.psl * (uint32_t)STAGE_BYTES, A.w + e.x, e.y, w_full0 + 8u * st.psl);
+        if (++st.psl == (uint32_t)n_slots) { st.psl = 0; st.pph ^= 1u; }
+        if (++st.pj == (uint32_t)n_entries) st.pj = 0;
+        --st.prem;
+      }
+    }
+    __syncwarp();
+    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+      unsigned long long trp = 0ull;
+#if defined(PLNERF_DEBUG) && defined(PLNERF_ENABLE_TRACE)
+      // issue-side stamps of block 0's third pair: 3 x 32-bit clocks per program entry behind the epilogue regions
+      if (A.trace && blockIdx.x == 0 && pr == 2 * (int)gridDim.x) trp = (unsigned long long)(A.trace + 4 * 256 * 2 + 128 * t);
+#endif
+      if (ptx::elect_one())
+        issue_tile3(st, prog_addr, (uint32_t)n_entries, ring_desc, idesc, desc_hi, w_full0, w_empty0, ep_done0 + 8u * t, pe_ready0 + 8u * t,
+                    (uint32_t)n_slots, stab_addr, (uint32_t)n_entries, sbase + SL.ring, (unsigned long long)A.w, trp);
+      __syncwarp();   // the state lives in the elected lane; elect.sync of a converged warp picks the same lane every time
+    }
+  } else if (warp >= WARP_HELP3) {
+    // ===================== helper warps: encode the next pair's rows, prefetch the pair after =============================
+    const int hid = threadIdx.x - 32 * WARP_HELP3;          // 0..63
+    auto encode_pair_tile = [&](int pair, int t) {
+#pragma unroll 1
+      for (int rr = hid; rr < TILE_M; rr += 32 * N_HELP_WARPS)
+        if (!PLNERF3_DBG(4)) pe_write_row(A, smem + Smem3<VD>::pe0 + t * PE_TILE_BYTES, 2 * (int64_t)pair + t, rr);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pe_ready0 + 8u * t);
+    };
+    auto prefetch_pair = [&](int64_t pair) {
+      // depths / ray rows of a later pair -> L2 (a cold DRAM read otherwise): one line per 32 depths, the rows' rays
+      if (A.x_emb || pair >= n_pairs) return;
+#pragma unroll 1
+      for (int rr = 32 * hid; rr < 2 * TILE_M; rr += 32 * 32 * N_HELP_WARPS) {
+        const int64_t gt = 2 * pair * TILE_M + rr, gcn = (gt < A.M) ? gt : (A.M - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.z + gcn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.rays + (gcn / A.S) * (int64_t)A.stride));
+      }
+    };
+    if ((int)blockIdx.x < n_pairs) {
+      encode_pair_tile(blockIdx.x, 0);
+      encode_pair_tile(blockIdx.x, 1);
+      prefetch_pair((int64_t)blockIdx.x + gridDim.x);
+    }
+    uint32_t fph = 0u;                                       // parity of pe_free[0] and pe_free[1] (they advance together)
+    for (int pr = blockIdx.x; pr + (int)gridDim.x < n_pairs; pr += gridDim.x) {
+      // the NEXT pair's tile t, once pair pr's tile t has released its operand (the trunk layers that read it are complete)
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        ptx::mbar_wait(pe_free0 + 8u * t, fph);
+        encode_pair_tile(pr + (int)gridDim.x, t);
+      }
+      fph ^= 1u;
+      prefetch_pair((int64_t)pr + 2 * (int64_t)gridDim.x);
+    }
+  } else {
+    // ===================== epilogue warps: group t = warp / 8 serves tile t ==============================================
+    const int t = warp >> 3;                   // tile of this warp
+    const int q = warp & 3, ch = (warp >> 2) & 1;
+    const int row = q * 32 + lane;
+    const uint32_t tm_row = tmem + (((uint32_t)(q * 32)) << 16) + 256u * (uint32_t)t;
+    const uint32_t tm_d = tm_row + 64u * (uint32_t)ch;             // this thread's 64 accumulator columns of a half
+    const uint32_t tm_a = tm_row + 128u + 32u * (uint32_t)ch;      // its 32 packed columns inside a half of A_t
+    const uint32_t d_full = d_full0 + 8u * t, ep_done = ep_done0 + 8u * t, vb_full = vb_full0 + 8u * t, pe_free = pe_free0 + 8u * t;
+    const bool vb_smem = VD && A.viewbias && A.vb_div >= 64;
+    float* xch = reinterpret_cast<float*>(smem + Smem3<VD>::xch0 + t * Smem3<VD>::XCH_BYTES);
+    const float* vbs = reinterpret_cast<const float*>(smem + Smem3<VD>::vb0 + t * (VB_RAYS_SMEM * 512u));
+    uint32_t dph = 0u, vph = 0u;
+    int vb_idx = 0;
+    if (lane == 0) ptx::mbar_arrive(ep_done);          // the tile starts with a drained accumulator
+    int tcnt = 0;
+
+    auto arrive_ep = [&]() {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ep_done);
+    };
+    auto wait_d = [&]() {
+      ptx::mbar_wait(d_full, dph); dph ^= 1u;
+      ptx::tc_fence_after();
+    };
+
+    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+      const bool trace_on = (pr == (int)blockIdx.x + 2 * (int)gridDim.x) && lane == 0 && q == 0 && ch == 0;
+      const int64_t g = (2 * (int64_t)pr + t) * TILE_M + row;
+      float alpha_acc = 0.f;
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int epi = P.L[l].epi, n_halves = P.L[l].n_halves;
+        const bool reads_a = P.L[l].n_h_ks > 0;
+        const float* bias = consts + P.L[l].bias_off + 64 * ch;
+        if (epi == EPI_RELU_A || epi == EPI_LINEAR_A) {
+          // ---- trunk / feature layer (two 128-neuron halves): bias, (ReLU), bf16 pack -> A_t
+          const bool alpha_here = VD && (P.L[l].flags & FLAG_ALPHA);
+          const float* aw = consts + P.alpha_w_off + 64 * ch;
+          uint32_t held[32];                         // half a (packed), kept until half b's MMAs have read A_t
+          // half a
+          PLNERF_TRACE(t * 2 + ch, tcnt, 2000 + l * 10);
+          wait_d();
+          PLNERF_TRACE(t * 2 + ch, tcnt, 3000 + l * 10);
+          if (PLNERF3_DBG(1)) { arrive_ep(); wait_d(); arrive_ep(); goto layer_tail; }
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tm_d + 32u * c2, r);
+            ptx::tmem_ld_wait();
+            if (c2 == 1 && reads_a) arrive_ep();       // the accumulator is drained: half b may start
+            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2); else cvt32<false>(r, bias + 32 * c2, held + 16 * c2);
+            if (alpha_here) alpha_acc = dot32_relu(r, aw + 32 * c2, alpha_acc);
+          }
+          if (!reads_a) {
+            // layer 0: nothing reads A_t, store right away
+            ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
+            ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
+            ptx::tmem_st_wait();
+            arrive_ep();
+          }
+          PLNERF_TRACE(t * 2 + ch, tcnt, 4000 + l * 10);
+          // half b
+          wait_d();
+          PLNERF_TRACE(t * 2 + ch, tcnt, 3000 + l * 10 + 1);
+          if (reads_a) {
+            ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
+            ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
+          }
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tm_d + 32u * c2, r);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
+            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 128 + 32 * c2, pk); else cvt32<false>(r, bias + 128 + 32 * c2, pk);
+            ptx::tmem_st16(tm_a + 64u + 16u * c2, pk);
+            if (alpha_here) alpha_acc = dot32_relu(r, aw + 128 + 32 * c2, alpha_acc);
+          }
+          ptx::tmem_st_wait();
+          arrive_ep();
+          PLNERF_TRACE(t * 2 + ch, tcnt, 4000 + l * 10 + 1);
+        } else if (VD) {
+          // ---- views layer (one half): per-ray bias (view-direction columns), ReLU, rgb head; then the row's 4 outputs
+          wait_d();
+          const float* vbr;
+          if (vb_smem) {
+            ptx::mbar_wait(vb_full, vph); vph ^= 1u;
+            vbr = vbs + vb_idx * 128 + 64 * ch;
+          } else {
+            const int64_t gc = (g < A.M) ? g : (A.M - 1);
+            vbr = A.viewbias + (gc / A.vb_div) * 128 + 64 * ch;
+          }
+          const float* rw = consts + P.rgb_w_off + 64 * ch;
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tm_d + 32u * c2, r);
+            ptx::tmem_ld_wait();
+            if (c2 == 1) arrive_ep();                  // the accumulator is in registers: hand it back before the head math
+            const float* val = reinterpret_cast<const float*>(r);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(vbr + 32 * c2 + i);
+              const float4 w0 = *reinterpret_cast<const float4*>(rw + 32 * c2 + i);
+              const float4 w1 = *reinterpret_cast<const float4*>(rw + 128 + 32 * c2 + i);
+              const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + 32 * c2 + i);
+              const float v0 = fmaxf(val[i] + b4.x, 0.f), v1 = fmaxf(val[i + 1] + b4.y, 0.f);
+              const float v2 = fmaxf(val[i + 2] + b4.z, 0.f), v3 = fmaxf(val[i + 3] + b4.w, 0.f);
+              h0 = fmaf(v0, w0.x, h0); h0 = fmaf(v1, w0.y, h0); h0 = fmaf(v2, w0.z, h0); h0 = fmaf(v3, w0.w, h0);
+              h1 = fmaf(v0, w1.x, h1); h1 = fmaf(v1, w1.y, h1); h1 = fmaf(v2, w1.z, h1); h1 = fmaf(v3, w1.w, h1);
+              h2 = fmaf(v0, w2.x, h2); h2 = fmaf(v1, w2.y, h2); h2 = fmaf(v2, w2.z, h2); h2 = fmaf(v3, w2.w, h2);
+            }
+          }
+          // combine the two column halves (fixed order: bitwise reproducible) and write the row
+          if (ch == 1) *reinterpret_cast<float4*>(xch + row * 4) = make_float4(h0, h1, h2, alpha_acc);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(32 * EPI_WARPS_PER_TILE) : "memory");
+          if (ch == 0 && g < A.M) {
+            const float4 x = *reinterpret_cast<const float4*>(xch + row * 4);
+            float4 acc;
+            acc.x = h0 + x.x + consts[P.rgb_b_off + 0]; acc.y = h1 + x.y + consts[P.rgb_b_off + 1];
+            acc.z = h2 + x.z + consts[P.rgb_b_off + 2]; acc.w = alpha_acc + x.w + consts[P.alpha_b_off];
+            float* o = A.out + g * (int64_t)A.out_stride;
+            if (A.out_stride == 4) *reinterpret_cast<float4*>(o) = acc;
+            else { o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w; }
+          }
+        } else {
+          // ---- last trunk layer of a network without view directions: ReLU, output_linear on the fp32 values
+          const int nch = P.out_ch;
+          float hp[MAX_OUT_CH];
+#pragma unroll
+          for (int c = 0; c < MAX_OUT_CH; ++c) hp[c] = 0.f;
+          for (int h = 0; h < n_halves; ++h) {
+            wait_d();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              uint32_t r[32];
+              ptx::tmem_ld32(tm_d + 32u * c2, r);
+              ptx::tmem_ld_wait();
+              if (c2 == 1) arrive_ep();
+              float* val = reinterpret_cast<float*>(r);
+              const float* b = bias + 128 * h + 32 * c2;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) val[i] += b[i];
+#pragma unroll
+              for (int c = 0; c < MAX_OUT_CH; ++c)
+                if (c < nch) hp[c] = dot32_relu(r, consts + P.out_w_off + c * 256 + 128 * h + 64 * ch + 32 * c2, hp[c]);
+            }
+          }
+          if (ch == 1) {
+#pragma unroll
+            for (int c = 0; c < MAX_OUT_CH; ++c) if (c < nch) xch[row * MAX_OUT_CH + c] = hp[c];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(32 * EPI_WARPS_PER_TILE) : "memory");
+          if (ch == 0 && g < A.M) {
+            float* o = A.out + g * (int64_t)A.out_stride;
+#pragma unroll
+            for (int c = 0; c < MAX_OUT_CH; ++c) if (c < nch) o[c] = hp[c] + xch[row * MAX_OUT_CH + c] + consts[P.out_b_off + c];
+          }
+        }
+      layer_tail:
+        // ---- bookkeeping hidden behind the MMAs in flight
+        if (l == l_pe_last) {
+          // every MMA that reads this tile's encoding operand has completed: the helper warps may overwrite it
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(pe_free);
+        }
+        if (l == 1 && vb_smem) {
+          // this tile's per-ray view-bias rows -> shared memory, one bulk copy.  All 8 warps of the group are past the
+          // previous pair's views epilogue here (this layer's MMAs needed their arrivals of layer 0's epilogue).
+          const int64_t row0 = (2 * (int64_t)pr + t) * TILE_M;
+          const int64_t gc = (g < A.M) ? g : (A.M - 1);
+          const int64_t ray0 = row0 / A.vb_div;
+          const int d = (int)(gc / A.vb_div - ray0);      // (the 64-bit divisions stay out of the views epilogue)
+          vb_idx = d < 0 ? 0 : (d >= (int)VB_RAYS_SMEM ? (int)VB_RAYS_SMEM - 1 : d);
+          if ((warp & 7) == 0 && lane == 0) {
+            const int64_t n_rays = (A.M + A.vb_div - 1) / A.vb_div;
+            if (ray0 < n_rays) {
+              const int64_t nr = (n_rays - ray0 < (int64_t)VB_RAYS_SMEM) ? n_rays - ray0 : (int64_t)VB_RAYS_SMEM;
+              ptx::mbar_arrive_expect_tx(vb_full, (uint32_t)nr * 512u);
+              ptx::bulk_g2s(sbase + Smem3<VD>::vb0 + t * (VB_RAYS_SMEM * 512u), A.viewbias + ray0 * 128, (uint32_t)nr * 512u, vb_full);
+            } else {
+              ptx::mbar_arrive(vb_full);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA3) ptx::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace v3

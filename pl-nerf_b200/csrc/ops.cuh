@@ -56,6 +56,5 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
                   cudaStream_t st);
 int profile_enable(int on);
 int profile_read(double* ms_sum, int64_t* launches, int64_t* rows);
-int debug_umma_gemm(const float* A, const float* B, int N, int K, float* D, cudaStream_t st);
 
 }  // namespace plnerf

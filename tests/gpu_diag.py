@@ -29,7 +29,7 @@ def gemm():
                 ref = O.bf16_round(A).astype(np.float64) @ O.bf16_round(B).astype(np.float64).T
                 D = torch.zeros((128, N), device="cuda")
                 dA, dB = dev(A), dev(B)
-                rc = L.lib().plnerf_debug_umma_gemm_ex(dA.data_ptr(), dB.data_ptr(), N, K, a_mode, lbo, sbo,
+                rc = L.debug_lib().plnerf_debug_umma_gemm_ex(dA.data_ptr(), dB.data_ptr(), N, K, a_mode, lbo, sbo,
                                                        D.data_ptr(), None)
                 torch.cuda.synchronize()
                 out = D.cpu().numpy()
@@ -68,7 +68,7 @@ def gemm_mn():
             ref = O.bf16_round(X).astype(np.float64).T @ O.bf16_round(Y).astype(np.float64)
             D = torch.zeros((128, N), device="cuda")
             dX, dY = dev(X), dev(Y)
-            rc = L.lib().plnerf_debug_umma_gemm_mn(dX.data_ptr(), dY.data_ptr(), N, K, lbo, sbo, D.data_ptr(), None)
+            rc = L.debug_lib().plnerf_debug_umma_gemm_mn(dX.data_ptr(), dY.data_ptr(), N, K, lbo, sbo, D.data_ptr(), None)
             torch.cuda.synchronize()
             out = D.cpu().numpy()
             err = np.abs(out - ref).max() / np.abs(ref).max()
@@ -83,7 +83,7 @@ def mmarate2():
         out = torch.zeros(148, dtype=torch.int64, device="cuda")
         iters = 200
         for rep in range(2):
-            L.check(L.lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
+            L.check(L.debug_lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
             torch.cuda.synchronize()
         cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
         print(f"{name}: cycles/MMA mean={cyc.mean():.1f} min={cyc.min():.1f} max={cyc.max():.1f}", flush=True)
@@ -94,7 +94,7 @@ def alurate():
         out = torch.zeros(148, dtype=torch.int64, device="cuda")
         iters = 2000
         for rep in range(2):
-            L.check(L.lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
+            L.check(L.debug_lib().plnerf_debug_mma_rate(mode, iters, 148, out.data_ptr(), None))
             torch.cuda.synchronize()
         cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
         print(f"{name}: cycles per pair-op per warp (4 warps/SM, 1 per SMSP) = {cyc.mean():.2f}", flush=True)
@@ -107,7 +107,7 @@ def mmarate():
             out = torch.zeros(grid, dtype=torch.int64, device="cuda")
             iters = 200
             for rep in range(2):
-                L.check(L.lib().plnerf_debug_mma_rate(mode, iters, grid, out.data_ptr(), None))
+                L.check(L.debug_lib().plnerf_debug_mma_rate(mode, iters, grid, out.data_ptr(), None))
                 torch.cuda.synchronize()
             cyc = out.cpu().numpy().astype(np.float64) / (iters * 16)
             print(f"grid={grid} {name}: cycles/MMA mean={cyc.mean():.1f} min={cyc.min():.1f} max={cyc.max():.1f}", flush=True)

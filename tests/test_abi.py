@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_packed_size(lib):
-    assert lib.plnerf_abi_version() == 1
+    assert lib.plnerf_abi_version() == L.ABI_VERSION == 2
     d = L.NetDesc()
     d.D, d.W, d.input_ch, d.input_ch_views, d.output_ch, d.use_viewdirs, d.n_skips = 8, 256, 63, 27, 5, 1, 1
     d.skips[0] = 4
@@ -41,8 +41,7 @@ def test_abi_version_and_packed_size(lib):
     n_fast = lib.plnerf_packed_bytes(C.byref(d), L.PREC_BF16)
     n_x3 = lib.plnerf_packed_bytes(C.byref(d), L.PREC_BF16X3)
     ks = (4 + 7 * 16 + 4) * 2 + 16 * 2 + 16
-    bias_blocks = 9 * 2     # k_mlp2's bias K-step blocks: one 4 KiB block per 128-neuron half of the 9 biased 256-wide layers
-    tail = n_fast - (ks + bias_blocks) * 4096
+    tail = n_fast - ks * 4096
     assert 0 < tail < 64 * 1024
     assert n_x3 == 2 * ks * 4096 + tail
 
