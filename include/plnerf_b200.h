@@ -237,6 +237,20 @@ int plnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb
                       const float* u, uint64_t seed, uint64_t ray_id_offset, float* samples,
                       int64_t* inds, void* stream);
 
+/* ---- f-4 (next row): the depth-experiment sampler variants, forward ------------------------------
+ * sample_pdf_reformulation_return_u (run_nerf_helpers.py:448-533) and sample_pdf_return_u (:286-337): the same
+ * inverse-CDF samplers with `load_u` (explicit u, or NULL = Philox draws) that additionally return what the depth
+ * losses consume: T, tau and the knot at the lower bracket index (`T_below`, `tau_below`, `bin_below`, each [n,Ni])
+ * and the u that was used (`u_out` [n,Ni]).  Any extra output may be NULL. */
+int plnerf_sample_pdf_pl_return_u(const float* z, const float* weights, const float* tau, const float* T,
+                                  const float* rays, int64_t n, int stride, int S, int Ni, const float* load_u,
+                                  uint64_t seed, uint64_t ray_id_offset, float zero_tol, float epsilon,
+                                  float* samples, float* T_below, float* tau_below, float* bin_below, float* u_out,
+                                  int64_t* inds, void* stream);
+int plnerf_sample_pdf_return_u(const float* bins, const float* weights, int64_t n, int nb, int Ni,
+                               const float* load_u, uint64_t seed, uint64_t ray_id_offset, float* samples,
+                               float* u_out, int64_t* inds, void* stream);
+
 /* ---- a13: clamp + sort-merge + z_std (run_plnerf.py:728-734, :752) ----------------------------
  * z [n,S] ascending, samples [n,Ni] -> z_out [n,S+Ni] ascending; z_std [n] or NULL. */
 int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n,

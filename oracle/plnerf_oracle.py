@@ -382,6 +382,21 @@ def sample_pdf_reformulation(bins, weights, tau, T, near, far, u, zero_threshold
     return samples.astype(F32), inds
 
 
+def sample_pdf_return_u(bins, weights, u):
+    """run_nerf_helpers.py:286-337 with the uniforms (`load_u` or the draw) supplied: (samples, u)."""
+    return sample_pdf(bins, weights, u)[0], _f(u)
+
+
+def sample_pdf_reformulation_return_u(bins, weights, tau, T, near, far, u, zero_threshold=1e-4, epsilon_=1e-3):
+    """run_nerf_helpers.py:448-533 with the uniforms supplied: the samples of sample_pdf_reformulation plus T, tau and the
+    knot gathered at the lower bracket index (:523-529) and u -> (samples, T_below, tau_below, bin_below, u)."""
+    samples, inds = sample_pdf_reformulation(bins, weights, tau, T, near, far, u, zero_threshold, epsilon_)
+    knots = np.concatenate([_f(near), _f(bins), _f(far)], -1)
+    below = np.maximum(0, inds - 1)
+    g = lambda a: np.take_along_axis(_f(a), below, -1)
+    return samples, g(T), g(tau), g(knots), _f(u)
+
+
 # --------------------------------------------------------------------------------------------
 # render_rays / render -- run_plnerf.py:95-175, 627-758
 # --------------------------------------------------------------------------------------------

@@ -129,6 +129,12 @@ _SIGS = {
                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_sample_pdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plnerf_sample_pdf_pl_return_u": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_float,
+                                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
+    "plnerf_sample_pdf_return_u": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                             C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_merge_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_render_workspace_bytes": (C.c_size_t, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.c_int64]),

@@ -167,6 +167,24 @@ int plnerf_sample_pdf(const float* bins, const float* weights, int64_t n, int nb
                              (cudaStream_t)stream);
 }
 
+int plnerf_sample_pdf_pl_return_u(const float* z, const float* weights, const float* tau, const float* T, const float* rays,
+                                  int64_t n, int stride, int S, int Ni, const float* load_u, uint64_t seed,
+                                  uint64_t ray_id_offset, float zero_tol, float epsilon, float* samples, float* T_below,
+                                  float* tau_below, float* bin_below, float* u_out, int64_t* inds, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && weights && tau && T && rays && samples)), "sample_pdf_pl_return_u: null argument");
+  PLNERF_CHECK_ARG(stride >= 8 && S >= 1 && Ni >= 0, "sample_pdf_pl_return_u: bad sizes");
+  return launch_sample_pl(z, weights, tau, T, rays, n, stride, S, Ni, load_u, seed, ray_id_offset, zero_tol, epsilon,
+                          samples, inds, (cudaStream_t)stream, T_below, tau_below, bin_below, u_out);
+}
+
+int plnerf_sample_pdf_return_u(const float* bins, const float* weights, int64_t n, int nb, int Ni, const float* load_u,
+                               uint64_t seed, uint64_t ray_id_offset, float* samples, float* u_out, int64_t* inds,
+                               void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (bins && weights && samples)), "sample_pdf_return_u: null argument");
+  return launch_sample_const(bins, nb, 0, weights, nb - 1, n, nb, Ni, load_u, seed, ray_id_offset, samples, inds,
+                             (cudaStream_t)stream, u_out);
+}
+
 int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                          int Ni, float* z_out, float* z_std, void* stream) {
   PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && samples && rays && z_out)), "merge_samples: null argument");

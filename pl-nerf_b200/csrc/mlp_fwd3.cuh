@@ -61,11 +61,11 @@ __host__ __device__ inline Smem3<VD> smem3_layout(int n_slots, int const_floats)
 }
 
 // Program entry flags (see issue_tile3)
-enum : uint32_t { PF_FIRST = 1u, PF_SS = 2u, PF_COMMIT = 4u, PF_WAIT_EP = 8u, PF_WAIT_PE = 16u };
+enum : uint32_t { PF_FIRST = 1u, PF_SS = 2u, PF_COMMIT = 4u, PF_WAIT_EP = 8u, PF_WAIT_PE = 16u, PF_WAIT_EF = 32u };
 
 // Per-issuer state carried across tile pairs: consumer ring cursor + phase, parities of the tile's epilogue / encoding
 // barriers; producer duty (tile Y's issuer only): ring cursor + phase, next stage of the weight stream, stages left.
-struct Issue3 { uint32_t sl, ph, c, q, psl, pph, pj, prem; };
+struct Issue3 { uint32_t sl, ph, c, q, psl, pph, pj, prem; };   // c: bit 0 / 1 = parity of the early / full epilogue barrier
 
 #define PLNERF3_MMA_TS(PRED) \
   "tcgen05.mma.cta_group::1.kind::f16 [ed], [ea], bd, %9, " PRED ";\n\t" \
@@ -82,12 +82,14 @@ struct Issue3 { uint32_t sl, ph, c, q, psl, pph, pj, prem; };
 // Entry (16 bytes): {accumulator tmem address, A operand (tmem address | low word of the shared-memory descriptor),
 // flags, accumulator-full barrier}.  flags: PF_FIRST first MMA overwrites the accumulator, PF_SS shared-memory A operand
 // with bits 8-11 K-steps, PF_COMMIT commit the accumulator-full barrier after the stage, PF_WAIT_EP wait for the tile's
-// epilogue barrier before the stage (+ PF_WAIT_PE: and for its encoding operand).  Every stage waits for its ring slot's
+// "early" epilogue barrier before the stage (accumulator drained, first half of the layer input stored; + PF_WAIT_PE: and
+// for its encoding operand), PF_WAIT_EF wait for the "full" epilogue barrier (whole layer input stored) -- both barriers
+// advance one phase per half-epilogue, so one parity bit per barrier tracks them.  Every stage waits for its ring slot's
 // weights and releases the slot with a commit (the slot's empty barrier counts both tiles' issuers).
 // Producer duty (prem > 0): after each stage, refill the ring slot released `lag` stages ago with the next stage of the
 // packed stream ({global byte offset, bytes} table at stab_addr, n_stab entries per pair).
 __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint32_t n_entries, uint64_t ring_desc, uint32_t idesc,
-                                            uint32_t desc_hi, uint32_t wfull0, uint32_t wempty0, uint32_t epdone, uint32_t peready,
+                                            uint32_t desc_hi, uint32_t wfull0, uint32_t wempty0, uint32_t epearly, uint32_t epfull, uint32_t peready,
                                             uint32_t n_slots, uint32_t stab_addr, uint32_t n_stab, uint32_t ring_addr,
                                             unsigned long long wbase, unsigned long long trace_ptr) {
   asm volatile(
@@ -100,19 +102,25 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
       "LOOP3:\n\t"
       "ld.shared.v4.u32 {ed, ea, ef, eb}, [pa];\n\t"
       PLNERF3_STAMP
-      // ---- the tile's previous half-epilogue (accumulator drained / layer input written), its encoding operand
-      "and.b32 t, ef, 8;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOEP3;\n\t"
-      "WEP3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%14], c;\n\t@!p bra WEP3;\n\t"
-      "xor.b32 c, c, 1;\n\t"
-      "and.b32 t, ef, 16;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOPE3;\n\t"
-      "WPE3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%15], q;\n\t@!p bra WPE3;\n\t"
-      "xor.b32 q, q, 1;\n\t"
-      "NOPE3:\n\t"
-      "NOEP3:\n\t"
-      // ---- the ring slot's weights
+      // ---- the ring slot's weights (they land long before the activations: checked first, off the dependency chain)
       "shl.b32 wb, sl, 3;\n\t"
       "add.u32 t, wb, %12;\n\t"
       "WAQ3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [t], ph;\n\t@!p bra WAQ3;\n\t"
+      // ---- the tile's previous half-epilogue: early barrier (accumulator drained, first input half stored), the
+      // encoding operand, full barrier (whole layer input stored)
+      "and.b32 t, ef, 8;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOEP3;\n\t"
+      "and.b32 k, c, 1;\n\t"
+      "WEP3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%14], k;\n\t@!p bra WEP3;\n\t"
+      "xor.b32 c, c, 1;\n\t"
+      "and.b32 t, ef, 16;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOEP3;\n\t"
+      "WPE3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%15], q;\n\t@!p bra WPE3;\n\t"
+      "xor.b32 q, q, 1;\n\t"
+      "NOEP3:\n\t"
+      "and.b32 t, ef, 32;\n\tsetp.eq.b32 p, t, 0;\n\t@p bra NOEF3;\n\t"
+      "shr.u32 k, c, 1;\n\t"
+      "WEF3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%23], k;\n\t@!p bra WEF3;\n\t"
+      "xor.b32 c, c, 2;\n\t"
+      "NOEF3:\n\t"
       "tcgen05.fence::after_thread_sync;\n\t"
       PLNERF3_STAMP
       "mul.wide.u32 so, sl, 2048;\n\tadd.u64 bd, so, %8;\n\t"
@@ -151,8 +159,8 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
       "mov.b32 %0, sl;\n\tmov.b32 %1, ph;\n\tmov.b32 %2, c;\n\tmov.b32 %3, q;\n\t"
       "mov.b32 %4, psl;\n\tmov.b32 %5, pph;\n\tmov.b32 %6, pj;\n\tmov.b32 %7, prem;\n\t}"
       : "+r"(st.sl), "+r"(st.ph), "+r"(st.c), "+r"(st.q), "+r"(st.psl), "+r"(st.pph), "+r"(st.pj), "+r"(st.prem)
-      : "l"(ring_desc), "r"(idesc), "r"(prog_addr), "r"(n_entries), "r"(wfull0), "r"(desc_hi), "r"(epdone), "r"(peready),
-        "r"(wempty0), "r"(n_slots), "r"(stab_addr), "l"(trace_ptr), "l"(wbase), "r"(ring_addr), "r"(n_stab)
+      : "l"(ring_desc), "r"(idesc), "r"(prog_addr), "r"(n_entries), "r"(wfull0), "r"(desc_hi), "r"(epearly), "r"(peready),
+        "r"(wempty0), "r"(n_slots), "r"(stab_addr), "l"(trace_ptr), "l"(wbase), "r"(ring_addr), "r"(n_stab), "r"(epfull)
       : "memory");
 }
 
@@ -229,7 +237,7 @@ __device__ __forceinline__ float dot32_relu(const uint32_t (&r)[32], const float
 
 // VD: use_viewdirs network (alpha + rgb heads behind a views layer) or not (output_linear behind the last trunk layer)
 #ifdef PLNERF_DEBUG
-#define PLNERF3_DBG(bit) ((A.debug_flags & (bit)) != 0)   // bring-up experiments: 1 = no epilogue TMEM traffic / math, 2 = 16-byte weight copies, 4 = no encoding
+#define PLNERF3_DBG(bit) ((A.debug_flags & (bit)) != 0)   // bring-up experiments: 1 = no epilogue TMEM traffic / math, 2 = 16-byte weight copies, 4 = no encoding, 8 = epilogue signals before it works (no dependency chain, results invalid)
 #else
 #define PLNERF3_DBG(bit) false
 #endif
@@ -248,7 +256,8 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
   const uint32_t pe_ready0 = d_full0 + 32u;                       // [2] tile t's encoding operand is written (helper warps)
   const uint32_t vb_full0 = d_full0 + 48u;                        // [2] tile t's view-bias rows landed (bulk copy)
   const uint32_t pe_free0 = d_full0 + 64u;                        // [2] every MMA reading tile t's encoding operand is complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem3<VD>::bars + 8u * (2 * MAX_SLOTS) + 96u);
+  const uint32_t ep_early0 = d_full0 + 80u;                       // [2] tile t's accumulator is drained and the first half of its layer input stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem3<VD>::bars + 8u * (2 * MAX_SLOTS) + 112u);
   const int n_slots = SL.n_slots;
 
   if (threadIdx.x == 0) {
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       ptx::mbar_init(pe_ready0 + 8u * t, N_HELP_WARPS);
       ptx::mbar_init(vb_full0 + 8u * t, 1);
       ptx::mbar_init(pe_free0 + 8u * t, EPI_WARPS_PER_TILE);
+      ptx::mbar_init(ep_early0 + 8u * t, EPI_WARPS_PER_TILE);
     }
     ptx::fence_mbar_init();
   }
@@ -296,6 +306,8 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             if (si.is_pe) { f |= PF_SS | ((uint32_t)si.nks << 8); a = lo_of(sbase + Smem3<VD>::pe0 + t * PE_TILE_BYTES + (uint32_t)si.k0 * KS_BYTES); }
             else a = tmem + 256u * t + 128u + 8u * (uint32_t)si.k0;
             if (s2 == 0) { f |= PF_WAIT_EP; if (l == 0 && h == 0) f |= PF_WAIT_PE; }
+            // the whole layer input is needed from hidden K-step 8 on (or by the half's only stage group when it has none)
+            if ((!si.is_pe && si.k0 == KS_PER_STAGE) || (s2 == 0 && n_h <= KS_PER_STAGE)) f |= PF_WAIT_EF;
             if (s2 == nst - 1) f |= PF_COMMIT;
             if (t == 1) stab[n_entries] = make_uint2(off, PLNERF3_DBG(2) ? 16u : (uint32_t)si.nks * KS_BYTES);
             off += (uint32_t)si.nks * KS_BYTES;
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       if (A.trace && blockIdx.x == 0 && pr == 2 * (int)gridDim.x) trp = (unsigned long long)(A.trace + 4 * 256 * 2 + 128 * t);
 #endif
       if (ptx::elect_one())
-        issue_tile3(st, prog_addr, (uint32_t)n_entries, ring_desc, idesc, desc_hi, w_full0, w_empty0, ep_done0 + 8u * t, pe_ready0 + 8u * t,
+        issue_tile3(st, prog_addr, (uint32_t)n_entries, ring_desc, idesc, desc_hi, w_full0, w_empty0, ep_early0 + 8u * t, ep_done0 + 8u * t, pe_ready0 + 8u * t,
                     (uint32_t)n_slots, stab_addr, (uint32_t)n_entries, sbase + SL.ring, (unsigned long long)A.w, trp);
       __syncwarp();   // the state lives in the elected lane; elect.sync of a converged warp picks the same lane every time
     }
@@ -380,23 +392,31 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
     const uint32_t tm_row = tmem + (((uint32_t)(q * 32)) << 16) + 256u * (uint32_t)t;
     const uint32_t tm_d = tm_row + 64u * (uint32_t)ch;             // this thread's 64 accumulator columns of a half
     const uint32_t tm_a = tm_row + 128u + 32u * (uint32_t)ch;      // its 32 packed columns inside a half of A_t
-    const uint32_t d_full = d_full0 + 8u * t, ep_done = ep_done0 + 8u * t, vb_full = vb_full0 + 8u * t, pe_free = pe_free0 + 8u * t;
+    const uint32_t d_full = d_full0 + 8u * t, ep_done = ep_done0 + 8u * t, ep_early = ep_early0 + 8u * t, vb_full = vb_full0 + 8u * t, pe_free = pe_free0 + 8u * t;
     const bool vb_smem = VD && A.viewbias && A.vb_div >= 64;
     float* xch = reinterpret_cast<float*>(smem + Smem3<VD>::xch0 + t * Smem3<VD>::XCH_BYTES);
     const float* vbs = reinterpret_cast<const float*>(smem + Smem3<VD>::vb0 + t * (VB_RAYS_SMEM * 512u));
     uint32_t dph = 0u, vph = 0u;
     int vb_idx = 0;
-    if (lane == 0) ptx::mbar_arrive(ep_done);          // the tile starts with a drained accumulator
+    if (lane == 0) { ptx::mbar_arrive(ep_early); ptx::mbar_arrive(ep_done); }   // the tile starts with a drained accumulator
     int tcnt = 0;
 
-    auto arrive_ep = [&]() {
+    // Every half-epilogue arrives exactly once on each of the two barriers the tile's issuer waits on: `early` = the
+    // accumulator is in registers (and, in a second half, the held first half of the layer input is stored), `full` = the
+    // whole layer input is stored.  what: 1 = early, 2 = full, 3 = both.
+    auto arrive_now = [&](int what) {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ep_done);
+      if (lane == 0) {
+        if (what & 1) ptx::mbar_arrive(ep_early);
+        if (what & 2) ptx::mbar_arrive(ep_done);
+      }
     };
+    auto arrive_ep = [&](int what) { if (!PLNERF3_DBG(8)) arrive_now(what); };
     auto wait_d = [&]() {
       ptx::mbar_wait(d_full, dph); dph ^= 1u;
       ptx::tc_fence_after();
+      if (PLNERF3_DBG(8)) arrive_now(3);
     };
 
     for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
@@ -416,13 +436,13 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           PLNERF_TRACE(t * 2 + ch, tcnt, 2000 + l * 10);
           wait_d();
           PLNERF_TRACE(t * 2 + ch, tcnt, 3000 + l * 10);
-          if (PLNERF3_DBG(1)) { arrive_ep(); wait_d(); arrive_ep(); goto layer_tail; }
+          if (PLNERF3_DBG(1)) { arrive_now(3); wait_d(); arrive_now(3); goto layer_tail; }
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
             uint32_t r[32];
             ptx::tmem_ld32(tm_d + 32u * c2, r);
             ptx::tmem_ld_wait();
-            if (c2 == 1 && reads_a) arrive_ep();       // the accumulator is drained: half b may start
+            if (c2 == 1) arrive_ep(reads_a ? 3 : 1);   // the accumulator is drained: half b may start (layer 0: `full` follows the store)
             if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2); else cvt32<false>(r, bias + 32 * c2, held + 16 * c2);
             if (alpha_here) alpha_acc = dot32_relu(r, aw + 32 * c2, alpha_acc);
           }
@@ -431,28 +451,35 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
             ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
             ptx::tmem_st_wait();
-            arrive_ep();
+            arrive_ep(2);
           }
           PLNERF_TRACE(t * 2 + ch, tcnt, 4000 + l * 10);
           // half b
           wait_d();
           PLNERF_TRACE(t * 2 + ch, tcnt, 3000 + l * 10 + 1);
-          if (reads_a) {
-            ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
-            ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
-          }
-#pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            uint32_t r[32];
-            ptx::tmem_ld32(tm_d + 32u * c2, r);
+          {
+            if (reads_a) {
+              ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
+              ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
+            }
+            // both 32-column chunks in flight (the held half's registers are free again), then the early signal: the next
+            // layer's first eight K-steps need only the accumulator drained and the first input half in place
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld32(tm_d, r0);
+            ptx::tmem_ld32(tm_d + 32u, r1);
             ptx::tmem_ld_wait();
+            ptx::tmem_st_wait();
+            arrive_ep(1);
+            PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
             uint32_t pk[16];
-            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 128 + 32 * c2, pk); else cvt32<false>(r, bias + 128 + 32 * c2, pk);
-            ptx::tmem_st16(tm_a + 64u + 16u * c2, pk);
-            if (alpha_here) alpha_acc = dot32_relu(r, aw + 128 + 32 * c2, alpha_acc);
+            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk); else cvt32<false>(r0, bias + 128, pk);
+            ptx::tmem_st16(tm_a + 64u, pk);
+            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk); else cvt32<false>(r1, bias + 160, pk);
+            ptx::tmem_st16(tm_a + 80u, pk);
+            if (alpha_here) { alpha_acc = dot32_relu(r0, aw + 128, alpha_acc); alpha_acc = dot32_relu(r1, aw + 160, alpha_acc); }
           }
           ptx::tmem_st_wait();
-          arrive_ep();
+          arrive_ep(2);
           PLNERF_TRACE(t * 2 + ch, tcnt, 4000 + l * 10 + 1);
         } else if (VD) {
           // ---- views layer (one half): per-ray bias (view-direction columns), ReLU, rgb head; then the row's 4 outputs
@@ -472,7 +499,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             uint32_t r[32];
             ptx::tmem_ld32(tm_d + 32u * c2, r);
             ptx::tmem_ld_wait();
-            if (c2 == 1) arrive_ep();                  // the accumulator is in registers: hand it back before the head math
+            if (c2 == 1) arrive_ep(3);                 // the accumulator is in registers: hand it back before the head math
             const float* val = reinterpret_cast<const float*>(r);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
               uint32_t r[32];
               ptx::tmem_ld32(tm_d + 32u * c2, r);
               ptx::tmem_ld_wait();
-              if (c2 == 1) arrive_ep();
+              if (c2 == 1) arrive_ep(3);
               float* val = reinterpret_cast<float*>(r);
               const float* b = bias + 128 * h + 32 * c2;
 #pragma unroll

@@ -438,6 +438,8 @@ struct SamplePLArgs {
   const float* u; uint64_t seed, ray0;
   float zero_tol, eps;
   float* samples; int64_t* inds;
+  // f-4 (sample_pdf_reformulation_return_u, run_nerf_helpers.py:448-533): optional extra returns, each [n,Ni]
+  float *T_below, *tau_below, *bin_below, *u_out;
 };
 
 __global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
@@ -504,14 +506,19 @@ __global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
     }
     a.samples[r * (int64_t)a.Ni + k] = x;
     if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+    if (a.T_below) a.T_below[r * (int64_t)a.Ni + k] = T_l;
+    if (a.tau_below) a.tau_below[r * (int64_t)a.Ni + k] = tau_l;
+    if (a.bin_below) a.bin_below[r * (int64_t)a.Ni + k] = s_l;
+    if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
   }
 }
 
 int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
                      int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0,
-                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st) {
+                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st, float* T_below,
+                     float* tau_below, float* bin_below, float* u_out) {
   if (n == 0 || Ni == 0) return PLNERF_OK;
-  SamplePLArgs a{z, w, tau, T, rays, n, stride, S, Ni, u, seed, ray0, zero_tol, eps, samples, inds};
+  SamplePLArgs a{z, w, tau, T, rays, n, stride, S, Ni, u, seed, ray0, zero_tol, eps, samples, inds, T_below, tau_below, bin_below, u_out};
   const int wpb = 4;
   const size_t smem = (size_t)wpb * 4 * (S + 2) * sizeof(float);
   if (smem > 48 * 1024) { set_error("sample_pdf_pl: N_samples=%d too large", S); return PLNERF_E_UNSUPPORTED; }
@@ -527,6 +534,7 @@ struct SampleConstArgs {
   int64_t n; int nb, Ni;
   const float* u; uint64_t seed, ray0;
   float* samples; int64_t* inds;
+  float* u_out;                                      // f-4 (sample_pdf_return_u, run_nerf_helpers.py:286-337): optional [n,Ni]
 };
 
 __global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
@@ -565,15 +573,16 @@ __global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
     const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
     a.samples[r * (int64_t)a.Ni + k] = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
     if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+    if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
   }
 }
 
 int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
                         int64_t n, int nb, int Ni, const float* u, uint64_t seed, uint64_t ray0,
-                        float* samples, int64_t* inds, cudaStream_t st) {
+                        float* samples, int64_t* inds, cudaStream_t st, float* u_out) {
   if (n == 0 || Ni == 0) return PLNERF_OK;
   if (nb < 2) { set_error("sample_pdf: need at least 2 bins"); return PLNERF_E_BADARG; }
-  SampleConstArgs a{bins, bins_stride, bins_mid, w, w_stride, n, nb, Ni, u, seed, ray0, samples, inds};
+  SampleConstArgs a{bins, bins_stride, bins_mid, w, w_stride, n, nb, Ni, u, seed, ray0, samples, inds, u_out};
   const int wpb = 4;
   const size_t smem = (size_t)wpb * 2 * nb * sizeof(float);
   if (smem > 48 * 1024) { set_error("sample_pdf: %d bins too many", nb); return PLNERF_E_UNSUPPORTED; }

@@ -21,10 +21,11 @@ int launch_composite_bwd(const float* raw, int raw_stride, const float* z, const
                          float* g_raw, cudaStream_t st);
 int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
                      int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0,
-                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st);
+                     float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st, float* T_below = nullptr,
+                     float* tau_below = nullptr, float* bin_below = nullptr, float* u_out = nullptr);
 int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
                         int64_t n, int nb, int Ni, const float* u, uint64_t seed, uint64_t ray0,
-                        float* samples, int64_t* inds, cudaStream_t st);
+                        float* samples, int64_t* inds, cudaStream_t st, float* u_out = nullptr);
 int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                  int Ni, float* z_out, float* z_std, cudaStream_t st);
 

@@ -212,6 +212,40 @@ def sample_pdf(bins, weights, N_importance, u=None, seed=0, ray_id_offset=0, ret
     return (out, inds) if return_inds else out
 
 
+def sample_pdf_pl_return_u(z_vals, weights, tau, T, rays, N_importance, load_u=None, seed=0, ray_id_offset=0,
+                           zero_tol=1e-4, epsilon=1e-3):
+    """sample_pdf_reformulation_return_u (run_nerf_helpers.py:448-533), forward: -> (samples, T_below, tau_below,
+    bin_below, u, inds), each [n, N_importance]."""
+    z_vals, weights, tau, T, rays = (_f32(t, k) for t, k in ((z_vals, "z_vals"), (weights, "weights"),
+                                                              (tau, "tau"), (T, "T"), (rays, "rays")))
+    n, S = z_vals.shape
+    dev = z_vals.device
+    outs = [torch.empty((n, N_importance), device=dev) for _ in range(5)]
+    inds = torch.empty((n, N_importance), device=dev, dtype=torch.int64)
+    if load_u is not None:
+        load_u = _f32(load_u, "load_u")
+    L.check(L.lib().plnerf_sample_pdf_pl_return_u(_p(z_vals), _p(weights), _p(tau), _p(T), _p(rays), n, rays.shape[1], S,
+                                                   N_importance, _p(load_u), seed, ray_id_offset, zero_tol, epsilon,
+                                                   _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _p(outs[4]),
+                                                   _p(inds), _stream()))
+    return (*outs, inds)
+
+
+def sample_pdf_return_u(bins, weights, N_importance, load_u=None, seed=0, ray_id_offset=0):
+    """sample_pdf_return_u (run_nerf_helpers.py:286-337), forward: -> (samples, u, inds)."""
+    bins, weights = _f32(bins, "bins"), _f32(weights, "weights")
+    n, nb = bins.shape
+    assert weights.shape == (n, nb - 1)
+    out = torch.empty((n, N_importance), device=bins.device)
+    u_out = torch.empty((n, N_importance), device=bins.device)
+    inds = torch.empty((n, N_importance), device=bins.device, dtype=torch.int64)
+    if load_u is not None:
+        load_u = _f32(load_u, "load_u")
+    L.check(L.lib().plnerf_sample_pdf_return_u(_p(bins), _p(weights), n, nb, N_importance, _p(load_u), seed, ray_id_offset,
+                                                _p(out), _p(u_out), _p(inds), _stream()))
+    return out, u_out, inds
+
+
 def merge_samples(z_vals, z_samples, rays):
     """clamp + sort(cat) + std (run_plnerf.py:728-734, :752) -> (z_merged, z_std)."""
     z_vals, z_samples, rays = _f32(z_vals, "z_vals"), _f32(z_samples, "z_samples"), _f32(rays, "rays")

@@ -194,3 +194,72 @@ def sample_pdf_reformulation(bins, weights, tau, T, near, far, N_samples, det=Fa
     below = torch.clamp(inds - 1, min=0)
     full_bins = torch.cat([near.reshape(n, 1), bins, far.reshape(n, 1)], -1)
     return samples, torch.gather(T, 1, below), torch.gather(tau, 1, below), torch.gather(full_bins, 1, below)
+
+
+# ---- f-4: the depth-experiment sampler variants (run_nerf_helpers.py:286-337, 448-533), forward --------------------------
+_return_u_calls = 0
+
+
+def _load_or_draw(load_u, shape, N_samples, det, pytest, device):
+    if load_u is not None:
+        return load_u.to(device).contiguous(), 0
+    global _return_u_calls
+    _return_u_calls += 1
+    return _draw_u(shape, N_samples, det, pytest, device), (torch.initial_seed() * 0x9E3779B97F4A7C15 + _return_u_calls) & ((1 << 63) - 1)
+
+
+def sample_pdf_return_u(bins, weights, N_samples, det=False, pytest=False, load_u=None):
+    """run_nerf_helpers.py:286-337: sample_pdf that takes a saved u (``load_u``) and returns (samples, u).
+    Forward only (the samples carry no gradient here)."""
+    u, seed = _load_or_draw(load_u, [bins.shape[0], N_samples], N_samples, det, pytest, bins.device)
+    samples, u_used, _ = ops.sample_pdf_return_u(bins, weights, N_samples, load_u=u, seed=seed)
+    return samples, u_used
+
+
+def sample_pdf_reformulation_return_u(bins, weights, tau, T, near, far, N_samples, det=False, pytest=False, load_u=None,
+                                      quad_solution_v2=True, zero_threshold=1e-4, epsilon_=1e-3):
+    """run_nerf_helpers.py:448-533: returns (samples, T_below, tau_below, bin_below, u).  Forward only."""
+    n = bins.shape[0]
+    u, seed = _load_or_draw(load_u, [n, N_samples], N_samples, det, pytest, bins.device)
+    rays = _rays_with_bounds(near.reshape(n, 1), far.reshape(n, 1))
+    samples, T_b, tau_b, bin_b, u_used, _ = ops.sample_pdf_pl_return_u(bins, weights, tau, T, rays, N_samples, load_u=u, seed=seed,
+                                                                        zero_tol=zero_threshold, epsilon=epsilon_)
+    return samples, T_b, tau_b, bin_b, u_used
+
+
+# ---- utilities for evaluation (run_nerf_helpers.py:537-570), star-imported by run_plnerf.py ------------------------------
+def compute_rmse(prediction, target):
+    """Root-mean-square error of two tensors (run_nerf_helpers.py:537-538)."""
+    return ((prediction - target) ** 2).mean().sqrt()
+
+
+class MeanTracker(object):
+    """Running weighted means of the entries of metric dicts (run_nerf_helpers.py:541-570): same methods
+    (add / has / get / as_dict / reset / print) and the same update rule."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.mean_dict = {}
+        self.total_weight = 0
+
+    def add(self, input, weight=1.):
+        new_total = self.total_weight + weight
+        for key, value in input.items():
+            old = self.mean_dict.get(key, 0)
+            self.mean_dict[key] = (old * self.total_weight + value) / new_total
+        self.total_weight = new_total
+
+    def has(self, key):
+        return key in self.mean_dict
+
+    def get(self, key):
+        return self.mean_dict[key]
+
+    def as_dict(self):
+        return self.mean_dict
+
+    def print(self, f=None):
+        for key, value in self.mean_dict.items():
+            print("{}: {}".format(key, value), **({} if f is None else {"file": f}))

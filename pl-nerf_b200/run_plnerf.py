@@ -180,7 +180,8 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
 
 _PATCHED = ("render_rays", "raw2outputs", "run_network", "batchify_rays", "render", "compute_weights",
             "compute_weights_piecewise_linear")
-_PATCHED_HELPERS = ("NeRF", "get_embedder", "Embedder", "sample_pdf", "sample_pdf_reformulation")
+_PATCHED_HELPERS = ("NeRF", "get_embedder", "Embedder", "sample_pdf", "sample_pdf_reformulation", "sample_pdf_return_u",
+                    "sample_pdf_reformulation_return_u")
 
 
 def install(ref_run_plnerf, include_helpers=True):
