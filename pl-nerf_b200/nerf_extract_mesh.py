@@ -105,7 +105,10 @@ def extract_fields(bound_min, bound_max, resolution, query_func, model, precisio
     if next(model.parameters()).device.type != "cuda":
         raise RuntimeError("plnerf_b200: the NeRF module must live on a CUDA device (no CPU fallback)")
     R = int(resolution)
-    host = torch.empty((R, R, R), dtype=torch.float32, pin_memory=True)
+    # device='cpu' explicitly: the reference's launchers call torch.set_default_tensor_type('torch.cuda.FloatTensor')
+    # (run_plnerf.py:1582, nerf_extract_mesh.py:1213), under which a device-less factory call would land on CUDA and
+    # pin_memory would raise
+    host = torch.empty((R, R, R), dtype=torch.float32, device="cpu", pin_memory=True)
     with torch.no_grad():
         query_density_grid(model, X, Y, Z, precision=precision, host_out=host)
     return host.numpy()

@@ -248,10 +248,12 @@ class TrainStep:
 
     def __call__(self, target, pose, i, global_step=None, pix=None):
         """target [H, W, 3] (or [H*W, 3]) device image, pose = c2w [3|4, 4], i = iteration number (drives precrop /
-        constant_init exactly like the reference's loop variable).  Returns {"loss", "img_loss", "img_loss0", "pix"}
+        constant_init exactly like the reference's loop variable).  ``global_step`` defaults to i - 1: the reference's
+        loop variable starts at start + 1 while its global_step starts at start and is incremented at the END of the
+        iteration (run_plnerf.py:1153, 1235, 1400), so the decayed rate of iteration i uses i - 1.  Returns {"loss", "img_loss", "img_loss0", "pix"}
         as device tensors (the loss values are detached scalars; nothing is synchronised).  With several ranks each
         loss value is this rank's share of the global mean (their sum over ranks is the reference's loss)."""
-        global_step = i if global_step is None else global_step
+        global_step = max(i - 1, 0) if global_step is None else global_step
         if pix is None:
             pix = self.pixels(i)
         B = pix.shape[0]
@@ -268,7 +270,7 @@ class TrainStep:
         slices ``batch_rays`` [2, B, 3] (origins, directions) and ``target_s`` [B, 3] out of its pre-shuffled ray bank;
         everything after that is the same step.  Several ranks: every rank passes the same GLOBAL batch and renders its
         shard of it."""
-        global_step = i if global_step is None else global_step
+        global_step = max(i - 1, 0) if global_step is None else global_step
         B = batch_rays.shape[1]
         lo, hi = pdist.shard_bounds(B)
         rays, _ = ops.pack_rays(self.H, self.W, self.K, rays=(batch_rays[0][lo:hi], batch_rays[1][lo:hi]), ndc=self.ndc,

@@ -237,7 +237,7 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
             loss = torch.mean((r["rgb_map"] - tgt) ** 2) + torch.mean((r["rgb0"] - tgt) ** 2)
             loss.backward()
             opt.step(); opt_c.step()
-            new_lrate = 5e-4 * (0.1 ** (i / (500 * 1000)))
+            new_lrate = 5e-4 * (0.1 ** (max(i - 1, 0) / (500 * 1000)))     # global_step = i - 1 (run_plnerf.py:1153, 1235, 1400)
             for g in opt.param_groups + opt_c.param_groups:     # run_plnerf.py:1310-1315 (both get the fine rate)
                 g["lr"] = new_lrate
             assert float(out["loss"]) == pytest.approx(float(loss.detach()), rel=1e-6)
