@@ -150,6 +150,7 @@ class CpuReference:
         self.pc, self.pf = pc, pf
         if self.kind == "reference":
             H, R = refimport.load()
+            R.device = torch.device("cpu")      # the module picks cuda when one is visible; this arm is the reference's CPU path
             self.R = R
 
             def mk(prm):
