@@ -270,6 +270,33 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
                            const float* noise1, const plnerf_render_out* out, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---- a3, training: render_rays forward that keeps what loss.backward() needs, and its backward -----------------
+ * The reference's contract (run_plnerf.py:1283-1300): render(..., retraw=True) -> loss = img2mse(rgb) + img2mse(rgb0)
+ * -> loss.backward() reaches both networks' parameters; the importance samples carry no gradient (:728).
+ * plnerf_render_rays_fwd_train == plnerf_render_rays_fwd with the fused MLP in stash mode; everything the backward
+ * reads (depths, raw of both passes, the two stashes) stays in `ws` (plnerf_render_train_workspace_bytes, 1 KiB
+ * aligned), which the caller keeps untouched until plnerf_render_rays_bwd has been enqueued on the same stream.
+ * plnerf_render_rays_bwd: upstream gradients of the eight maps (any may be NULL) -> parameter gradients ADDED into
+ * grads_coarse / grads_fine (fp32, state_dict layout; fine_* NULL = the coarse network served the fine pass).
+ * `*_packed_bwd` = plnerf_pack_weights_bwd.  noise0 / noise1: the same explicit arrays as in the forward (or NULL: the
+ * forward's Philox draws are regenerated from cfg->seed).  bf16 precision, use_viewdirs networks only. */
+typedef struct plnerf_render_grads {
+  const float *g_rgb_map, *g_disp_map, *g_acc_map, *g_depth_map;   /* [n,3], [n], [n], [n] */
+  const float *g_rgb0, *g_disp0, *g_acc0, *g_depth0;               /* coarse maps, read when N_importance > 0 */
+} plnerf_render_grads;
+size_t plnerf_render_train_workspace_bytes(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc,
+                                           const plnerf_net_desc* fine_desc, int64_t n_rays);
+int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc,
+                                 const void* coarse_packed, const plnerf_net_desc* fine_desc, const void* fine_packed,
+                                 const float* rays, int64_t n, int stride, const float* t_rand, const float* u,
+                                 const float* noise0, const float* noise1, const plnerf_render_out* out, void* ws,
+                                 size_t ws_bytes, void* stream);
+int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc, const void* coarse_packed,
+                           const void* coarse_packed_bwd, const plnerf_net_desc* fine_desc, const void* fine_packed,
+                           const void* fine_packed_bwd, const float* rays, int64_t n, int stride, const float* noise0,
+                           const float* noise1, const plnerf_render_grads* g, const plnerf_net_grads* grads_coarse,
+                           const plnerf_net_grads* grads_fine, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py): time every fused-MLP launch with CUDA events on its own stream --
  * plnerf_profile_enable(1) starts recording (and clears old records); plnerf_profile_read
  * synchronises the recorded events and returns the summed device time, launch count and rows. */

@@ -61,6 +61,11 @@ class RenderOut(C.Structure):
                                           "acc0", "depth0", "z_std", "z_vals", "inds")]
 
 
+class RenderGrads(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("g_rgb_map", "g_disp_map", "g_acc_map", "g_depth_map", "g_rgb0", "g_disp0",
+                                          "g_acc0", "g_depth0")]
+
+
 def needs_build(path=None):
     path = path or LIB_PATH
     if not os.path.isfile(path):
@@ -142,6 +147,15 @@ _SIGS = {
                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.POINTER(RenderOut), C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
+    "plnerf_render_train_workspace_bytes": (C.c_size_t, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.POINTER(NetDesc), C.c_int64]),
+    "plnerf_render_rays_fwd_train": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.c_void_p, C.POINTER(NetDesc),
+                                               C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.POINTER(RenderOut), C.c_void_p, C.c_size_t,
+                                               C.c_void_p]),
+    "plnerf_render_rays_bwd": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.c_void_p, C.c_void_p,
+                                         C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.POINTER(RenderGrads), C.POINTER(NetGrads),
+                                         C.POINTER(NetGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

@@ -22,62 +22,35 @@ def _names(net):
 
 
 def forward_stashed(cfg, rays):
-    """The training forward of render_rays: the same kernels as inference with the fused MLP in stash mode.
-    Returns (outs, saved, stashes): ``outs`` = (rgb, disp, acc, depth, raw) for N_importance == 0, else
-    (rgb, disp, acc, depth, raw1, rgb0, disp0, acc0, depth0, z_std); ``saved`` / ``stashes`` feed ``backward_stashed``."""
-    net_c, net_f = cfg["net_c"], cfg["net_f"]
-    Ns, Ni = cfg["N_samples"], cfg["N_importance"]
-    mode, cmode = cfg["mode"], cfg["color_mode"]
-    z0 = ops.stratified_z(rays, Ns, cfg["lindisp"], cfg["perturb"], cfg["t_rand"], cfg["seed"], cfg["ray_id_offset"])
-    raw0, stash0 = ops.network_query_train(net_c, rays, z0)
-    rgb0, disp0, acc0, w0, depth0, tau0, T0 = ops.raw2outputs(raw0, z0, rays, mode, cmode, noise=cfg["noise0"],
-                                                              white_bkgd=cfg["white_bkgd"],
-                                                              farcolorfix=cfg["farcolorfix"])
-    if Ni == 0:
-        return (rgb0, disp0, acc0, depth0, raw0), (rays, z0, raw0), (stash0, None)
-    if mode == "linear":
-        zs = ops.sample_pdf_pl(z0, w0, tau0, T0, rays, Ni, u=cfg["u"], seed=cfg["seed"],
-                               ray_id_offset=cfg["ray_id_offset"], zero_tol=cfg["zero_tol"], epsilon=cfg["epsilon"])
-    else:
-        zmid = 0.5 * (z0[..., 1:] + z0[..., :-1])
-        zs = ops.sample_pdf(zmid, w0[..., 1:-1].contiguous(), Ni, u=cfg["u"], seed=cfg["seed"],
-                            ray_id_offset=cfg["ray_id_offset"])
-    z1, z_std = ops.merge_samples(z0, zs, rays)
-    fine = net_f if net_f is not None else net_c
-    raw1, stash1 = ops.network_query_train(fine, rays, z1)
-    rgb, disp, acc, w1, depth, _, _ = ops.raw2outputs(raw1, z1, rays, mode, cmode, noise=cfg["noise1"],
-                                                      white_bkgd=cfg["white_bkgd"], farcolorfix=cfg["farcolorfix"],
-                                                      want_weights=False)
-    return ((rgb, disp, acc, depth, raw1, rgb0, disp0, acc0, depth0, z_std), (rays, z0, raw0, z1, raw1),
-            (stash0, stash1))
+    """The training forward of render_rays: ONE C call (plnerf_render_rays_fwd_train: the inference kernels with the
+    fused MLP in stash mode).  Returns (outs, saved, stashes): ``outs`` = (rgb, disp, acc, depth, raw) for
+    N_importance == 0, else (rgb, disp, acc, depth, raw1, rgb0, disp0, acc0, depth0, z_std); ``saved`` feeds
+    ``backward_stashed`` (it owns the workspace holding depths, raw and the two stashes); ``stashes`` is unused."""
+    Ni = cfg["N_importance"]
+    ret, ctx = ops.render_rays_fwd_train(rays, cfg["net_c"], cfg["net_f"], cfg["N_samples"], Ni, cfg["mode"], cfg["color_mode"],
+                                         perturb=cfg["perturb"], white_bkgd=cfg["white_bkgd"], lindisp=cfg["lindisp"],
+                                         raw_noise_std=0.0, zero_tol=cfg["zero_tol"], epsilon=cfg["epsilon"],
+                                         farcolorfix=cfg["farcolorfix"], t_rand=cfg["t_rand"], u=cfg["u"], noise0=cfg["noise0"],
+                                         noise1=cfg["noise1"], seed=cfg["seed"], ray_id_offset=cfg["ray_id_offset"],
+                                         retraw=cfg.get("retraw", False))
+    raw = ret.get("raw")
+    if raw is None:
+        raw = torch.empty(0, device=rays.device)
+    outs = (ret["rgb_map"], ret["disp_map"], ret["acc_map"], ret["depth_map"], raw)
+    if Ni > 0:
+        outs += (ret["rgb0"], ret["disp0"], ret["acc0"], ret["depth0"], ret["z_std"])
+    return outs, ctx, None
 
 
 def backward_stashed(cfg, saved, stashes, g_fine, g_coarse, grads_c, grads_f):
-    """Backward of ``forward_stashed``: ``g_fine`` / ``g_coarse`` = (g_rgb, g_disp, g_acc, g_depth) of the fine / coarse
-    maps (entries may be None; for N_importance == 0 only ``g_coarse`` is used).  Parameter gradients are ACCUMULATED
-    into ``grads_c`` / ``grads_f`` ({state_dict name: fp32 tensor}; ``grads_f`` is ignored when there is no separate
-    fine network)."""
-    net_c, net_f = cfg["net_c"], cfg["net_f"]
-    Ns, Ni = cfg["N_samples"], cfg["N_importance"]
-    mode, cmode = cfg["mode"], cfg["color_mode"]
-    rays, z0, raw0 = saved[0], saved[1], saved[2]
-    n = rays.shape[0]
-    kw = dict(white_bkgd=cfg["white_bkgd"], farcolorfix=cfg["farcolorfix"])
-    c = lambda t: None if t is None else t.contiguous()
-    if Ni > 0:
-        z1, raw1 = saved[3], saved[4]
-        g_rgb, g_disp, g_acc, g_depth = g_fine
-        graw1 = ops.raw2outputs_bwd(raw1, z1, rays, mode, cmode, g_rgb=c(g_rgb), g_depth=c(g_depth), g_acc=c(g_acc),
-                                    g_disp=c(g_disp), noise=cfg["noise1"], **kw)
-        if net_f is not None:
-            ops.network_query_bwd(net_f, graw1, stashes[1], n, Ns + Ni, grads_f)
-        else:
-            ops.network_query_bwd(net_c, graw1, stashes[1], n, Ns + Ni, grads_c)
-    g_rgb0, g_disp0, g_acc0, g_depth0 = g_coarse
-    if Ni == 0 or any(t is not None for t in g_coarse):
-        graw0 = ops.raw2outputs_bwd(raw0, z0, rays, mode, cmode, g_rgb=c(g_rgb0), g_depth=c(g_depth0), g_acc=c(g_acc0),
-                                    g_disp=c(g_disp0), noise=cfg["noise0"], **kw)
-        ops.network_query_bwd(net_c, graw0, stashes[0], n, Ns, grads_c)
+    """Backward of ``forward_stashed``: ONE C call (plnerf_render_rays_bwd).  ``g_fine`` / ``g_coarse`` = (g_rgb, g_disp,
+    g_acc, g_depth) of the fine / coarse maps (entries may be None; for N_importance == 0 only ``g_coarse`` is used).
+    Parameter gradients are ACCUMULATED into ``grads_c`` / ``grads_f`` ({state_dict name: fp32 tensor}; ``grads_f`` is
+    ignored when there is no separate fine network)."""
+    if cfg["N_importance"] == 0:
+        ops.render_rays_bwd(saved, g_coarse, None, grads_c, None)
+    else:
+        ops.render_rays_bwd(saved, g_fine, g_coarse, grads_c, grads_f if cfg["net_f"] is not None else grads_c)
 
 
 class _RenderRaysFn(torch.autograd.Function):
@@ -85,8 +58,7 @@ class _RenderRaysFn(torch.autograd.Function):
     def forward(ctx, cfg, rays, *params):
         outs, saved, stashes = forward_stashed(cfg, rays)
         ctx.cfg = cfg
-        ctx.save_for_backward(*saved)
-        ctx.stashes = stashes
+        ctx.saved = saved
         if cfg["N_importance"] == 0:
             ctx.mark_non_differentiable(outs[4])
         else:
@@ -100,11 +72,11 @@ class _RenderRaysFn(torch.autograd.Function):
         grads_c = ops.zero_grads_like(net_c)      # one flat zeroed buffer per network (one fill kernel, not 24)
         grads_f = ops.zero_grads_like(net_f) if (net_f is not None and cfg["N_importance"] > 0) else None
         if cfg["N_importance"] == 0:
-            backward_stashed(cfg, ctx.saved_tensors, ctx.stashes, None, (g[0], g[1], g[2], g[3]), grads_c, None)
+            backward_stashed(cfg, ctx.saved, None, None, (g[0], g[1], g[2], g[3]), grads_c, None)
         else:
-            backward_stashed(cfg, ctx.saved_tensors, ctx.stashes, (g[0], g[1], g[2], g[3]), (g[5], g[6], g[7], g[8]),
+            backward_stashed(cfg, ctx.saved, None, (g[0], g[1], g[2], g[3]), (g[5], g[6], g[7], g[8]),
                              grads_c, grads_f)
-        ctx.stashes = None
+        ctx.saved = None
         out = [None, None] + [grads_c[k] for k in _names(net_c)]
         if net_f is not None:
             out += [grads_f[k] for k in _names(net_f)] if grads_f is not None else [None] * len(_names(net_f))
@@ -129,7 +101,7 @@ def render_rays_autograd(ray_batch, network_fn, network_fine, N_samples, N_impor
     cfg = dict(net_c=network_fn, net_f=network_fine if N_importance > 0 else None, N_samples=N_samples,
                N_importance=N_importance, mode=mode, color_mode=color_mode, perturb=perturb_on, white_bkgd=white_bkgd,
                lindisp=lindisp, zero_tol=zero_tol, epsilon=epsilon, farcolorfix=farcolorfix, t_rand=t_rand, u=u,
-               noise0=noise0, noise1=noise1, seed=seed, ray_id_offset=ray_id_offset)
+               noise0=noise0, noise1=noise1, seed=seed, ray_id_offset=ray_id_offset, retraw=retraw)
     params = list(network_fn.parameters())
     if cfg["net_f"] is not None:
         params += list(cfg["net_f"].parameters())

@@ -262,6 +262,150 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   return rc;
 }
 
+// ---- training: forward with stash + the whole backward of a ray batch, one ABI call each --------------------------
+namespace plnerf {
+struct TrainWs {
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw;
+  void* mlp_ws; size_t mlp_ws_bytes;
+  uint8_t *stash0, *stash1; size_t stash0_bytes, stash1_bytes;
+  size_t total;
+};
+static TrainWs carve_train(const plnerf_render_cfg* c, const plnerf_net_desc* cd, const plnerf_net_desc* fd, int64_t n, uint8_t* base) {
+  TrainWs w;
+  size_t off = 0;
+  const int Ns = c->N_samples, Ni = c->N_importance, S1 = Ns + Ni;
+  auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  auto take = [&](size_t floats) { float* p = reinterpret_cast<float*>(base + off); off += up(floats * sizeof(float)); return p; };
+  w.z0 = take((size_t)n * Ns);
+  w.raw0 = take((size_t)n * Ns * 4);
+  w.w0 = take((size_t)n * (Ns + 1));
+  w.tau0 = take((size_t)n * (Ns + 2));
+  w.T0 = take((size_t)n * (Ns + 2));
+  w.zs = take((size_t)n * (Ni > 0 ? Ni : 1));
+  w.z1 = take((size_t)n * S1);
+  w.raw1 = take((size_t)n * S1 * 4);
+  w.graw = take((size_t)n * S1 * 4);
+  w.mlp_ws = base + off;
+  w.mlp_ws_bytes = mlp_workspace_bytes(cd, n);
+  off += up(w.mlp_ws_bytes);
+  w.stash0 = base + off; w.stash0_bytes = mlp_train_stash_bytes(cd, n, Ns); off += up(w.stash0_bytes);
+  w.stash1 = base + off; w.stash1_bytes = Ni > 0 ? mlp_train_stash_bytes(fd, n, S1) : 0; off += up(w.stash1_bytes);
+  w.total = off;
+  return w;
+}
+}  // namespace plnerf
+
+size_t plnerf_render_train_workspace_bytes(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc,
+                                           const plnerf_net_desc* fine_desc, int64_t n_rays) {
+  if (!cfg || !coarse_desc || n_rays < 0) return 0;
+  if (!fine_desc) fine_desc = coarse_desc;
+  if (mlp_train_stash_bytes(coarse_desc, 1, 1) == 0) return 0;     // unsupported network (error text is set)
+  return carve_train(cfg, coarse_desc, fine_desc, n_rays, nullptr).total;
+}
+
+static int check_train_args(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const plnerf_net_desc* fdesc, int64_t n,
+                            const float* rays, int stride, const void* ws, size_t ws_bytes, const char* who) {
+  PLNERF_CHECK_ARG(cfg && cdesc && fdesc, "%s: null argument", who);
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || rays), "%s: null rays", who);
+  PLNERF_CHECK_ARG(stride >= 11, "%s: training needs rays with a view direction (stride >= 11)", who);
+  PLNERF_CHECK_ARG(cfg->N_samples >= 2 && cfg->N_importance >= 0, "%s: need N_samples >= 2, N_importance >= 0", who);
+  PLNERF_CHECK_ARG(cfg->mode == PLNERF_MODE_LINEAR || cfg->mode == PLNERF_MODE_CONSTANT, "%s: bad mode", who);
+  if (cfg->precision != PLNERF_PREC_BF16) { set_error("%s: gradients are implemented for PLNERF_PREC_BF16 only", who); return PLNERF_E_UNSUPPORTED; }
+  if (!cdesc->use_viewdirs || !fdesc->use_viewdirs) { set_error("%s: gradients are implemented for use_viewdirs networks only", who); return PLNERF_E_UNSUPPORTED; }
+  const size_t need = carve_train(cfg, cdesc, fdesc, n, nullptr).total;
+  if (!ws || ws_bytes < need) { set_error("%s: workspace too small: need %zu bytes, got %zu", who, need, ws_bytes); return PLNERF_E_WORKSPACE; }
+  PLNERF_CHECK_ARG(((uintptr_t)ws & 1023) == 0, "%s: workspace must be 1024-byte aligned", who);
+  return PLNERF_OK;
+}
+
+int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked,
+                                 const plnerf_net_desc* fdesc, const void* fpacked, const float* rays, int64_t n, int stride,
+                                 const float* t_rand, const float* u, const float* noise0, const float* noise1,
+                                 const plnerf_render_out* out, void* ws, size_t ws_bytes, void* stream) {
+  PLNERF_CHECK_ARG(cpacked && out, "render_rays_fwd_train: null argument");
+  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; }
+  int rc = check_train_args(cfg, cdesc, fdesc, n, rays, stride, ws, ws_bytes, "render_rays_fwd_train");
+  if (rc) return rc;
+  PLNERF_CHECK_ARG(out->rgb_map && out->disp_map && out->acc_map && out->depth_map, "render_rays_fwd_train: rgb/disp/acc/depth outputs are required");
+  if (n == 0) return PLNERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
+  const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  const bool fine = Ni > 0;
+  rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, w.z0, st);
+  if (rc) return rc;
+  rc = mlp_query_train(cdesc, cpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z0, Ns, w.raw0, 4, w.stash0,
+                       w.stash0_bytes, w.mlp_ws, w.mlp_ws_bytes, st);
+  if (rc) return rc;
+  rc = launch_composite(w.raw0, 4, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                        noise0, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0,
+                        fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map, fine ? out->acc0 : out->acc_map,
+                        fine ? out->depth0 : out->depth_map, fine ? w.w0 : nullptr, fine ? w.tau0 : nullptr,
+                        fine ? w.T0 : nullptr, st);
+  if (rc) return rc;
+  if (!fine) {
+    if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw0, (size_t)n * Ns * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->z_vals) PLNERF_CUDA(cudaMemcpyAsync(out->z_vals, w.z0, (size_t)n * Ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return PLNERF_OK;
+  }
+  PLNERF_CHECK_ARG(out->rgb0 && out->disp0 && out->acc0 && out->depth0, "render_rays_fwd_train: coarse outputs are required when N_importance > 0");
+  if (cfg->mode == PLNERF_MODE_LINEAR)
+    rc = launch_sample_pl(w.z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed, cfg->ray_id_offset, cfg->zero_tol,
+                          cfg->epsilon, w.zs, out->inds, st);
+  else
+    rc = launch_sample_const(w.z0, Ns, 1, w.w0 + 1, Ns, n, Ns - 1, Ni, u, cfg->seed, cfg->ray_id_offset, w.zs, out->inds, st);
+  if (rc) return rc;
+  rc = launch_merge(w.z0, w.zs, rays, n, stride, Ns, Ni, w.z1, out->z_std, st);
+  if (rc) return rc;
+  rc = mlp_query_train(fdesc, fpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z1, S1, w.raw1, 4, w.stash1,
+                       w.stash1_bytes, w.mlp_ws, w.mlp_ws_bytes, st);
+  if (rc) return rc;
+  rc = launch_composite(w.raw1, 4, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                        noise1, noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1,
+                        out->rgb_map, out->disp_map, out->acc_map, out->depth_map, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw1, (size_t)n * S1 * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (out->z_vals) PLNERF_CUDA(cudaMemcpyAsync(out->z_vals, w.z1, (size_t)n * S1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PLNERF_OK;
+}
+
+int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked, const void* cpacked_bwd,
+                           const plnerf_net_desc* fdesc, const void* fpacked, const void* fpacked_bwd, const float* rays,
+                           int64_t n, int stride, const float* noise0, const float* noise1, const plnerf_render_grads* g,
+                           const plnerf_net_grads* grads_coarse, const plnerf_net_grads* grads_fine, void* ws, size_t ws_bytes,
+                           void* stream) {
+  PLNERF_CHECK_ARG(cpacked && cpacked_bwd && g && grads_coarse, "render_rays_bwd: null argument");
+  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; fpacked_bwd = cpacked_bwd; grads_fine = grads_coarse; }
+  PLNERF_CHECK_ARG(fpacked_bwd && grads_fine, "render_rays_bwd: the fine network needs its transposed weights and gradient buffers");
+  int rc = check_train_args(cfg, cdesc, fdesc, n, rays, stride, ws, ws_bytes, "render_rays_bwd");
+  if (rc) return rc;
+  if (n == 0) return PLNERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
+  const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  if (Ni > 0) {
+    // fine pass: d(maps)/d(raw1) (run_plnerf.py:741 through autograd), then the fine network's parameter gradients
+    rc = launch_composite_bwd(w.raw1, 4, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                              noise1, g->g_rgb_map, g->g_depth_map, g->g_acc_map, g->g_disp_map, w.graw, st,
+                              noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1);
+    if (rc) return rc;
+    rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, 4, w.stash1, w.stash1_bytes, grads_fine, st);
+    if (rc) return rc;
+  }
+  // coarse pass (the importance samples are detached, run_plnerf.py:728: no gradient reaches it from the fine maps)
+  const float *gr = Ni > 0 ? g->g_rgb0 : g->g_rgb_map, *gd = Ni > 0 ? g->g_depth0 : g->g_depth_map;
+  const float *ga = Ni > 0 ? g->g_acc0 : g->g_acc_map, *gp = Ni > 0 ? g->g_disp0 : g->g_disp_map;
+  if (Ni == 0 || gr || gd || ga || gp) {
+    rc = launch_composite_bwd(w.raw0, 4, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                              noise0, gr, gd, ga, gp, w.graw, st, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed,
+                              cfg->ray_id_offset, RNG_STREAM_NOISE0);
+    if (rc) return rc;
+    rc = mlp_query_bwd(cdesc, cpacked, cpacked_bwd, n, Ns, w.graw, 4, w.stash0, w.stash0_bytes, grads_coarse, st);
+    if (rc) return rc;
+  }
+  return PLNERF_OK;
+}
+
 int plnerf_profile_enable(int on) { return profile_enable(on); }
 int plnerf_profile_read(double* mlp_ms_sum, int64_t* mlp_launches, int64_t* mlp_rows) {
   return profile_read(mlp_ms_sum, mlp_launches, mlp_rows);

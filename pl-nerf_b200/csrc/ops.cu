@@ -250,6 +250,7 @@ struct CompositeBwdArgs {
   const float* noise;
   const float *g_rgb, *g_depth, *g_acc, *g_disp;   // any may be null
   float* g_raw;                                      // [n,S,raw_stride]
+  float noise_std; uint64_t seed, ray0; uint32_t noise_stream;   // noise == null && noise_std > 0: the forward's Philox draws
 };
 
 template <int MODE>
@@ -273,6 +274,8 @@ __global__ void __launch_bounds__(128) k_composite_bwd(CompositeBwdArgs a) {
   auto sigma_at = [&](int k) -> float {
     float s = raw[(int64_t)k * a.raw_stride + 3];
     if (a.noise) s += a.noise[r * (int64_t)S + k];
+    else if (a.noise_std > 0.f)
+      s = __fadd_rn(s, __fmul_rn(philox_normal(a.seed, a.ray0 + (uint64_t)r, a.noise_stream, (uint32_t)k), a.noise_std));
     return s;
   };
   auto color_at = [&](int k, int c) -> float { return sigmoidf_(raw[(int64_t)k * a.raw_stride + c]); };
@@ -403,10 +406,10 @@ __global__ void __launch_bounds__(128) k_composite_bwd(CompositeBwdArgs a) {
 int launch_composite_bwd(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n, int stride,
                          int S, int mode, int color_mode, int white_bkgd, int farcolorfix, const float* noise,
                          const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_disp,
-                         float* g_raw, cudaStream_t st) {
+                         float* g_raw, cudaStream_t st, float noise_std, uint64_t seed, uint64_t ray0, uint32_t noise_stream) {
   if (n == 0) return PLNERF_OK;
   CompositeBwdArgs a{raw, raw_stride, z, rays, n, stride, S, color_mode, white_bkgd, farcolorfix, noise,
-                     g_rgb, g_depth, g_acc, g_disp, g_raw};
+                     g_rgb, g_depth, g_acc, g_disp, g_raw, noise_std, seed, ray0, noise_stream};
   const int wpb = 4;
   const size_t smem = (size_t)wpb * 4 * (S + 2) * sizeof(float);
   if (smem > 48 * 1024) { set_error("raw2outputs_bwd: N_samples=%d too large", S); return PLNERF_E_UNSUPPORTED; }

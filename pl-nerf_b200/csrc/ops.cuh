@@ -18,7 +18,8 @@ int launch_composite(const float* raw, int raw_stride, const float* z, const flo
 int launch_composite_bwd(const float* raw, int raw_stride, const float* z, const float* rays, int64_t n, int stride,
                          int S, int mode, int color_mode, int white_bkgd, int farcolorfix, const float* noise,
                          const float* g_rgb, const float* g_depth, const float* g_acc, const float* g_disp,
-                         float* g_raw, cudaStream_t st);
+                         float* g_raw, cudaStream_t st, float noise_std = 0.f, uint64_t seed = 0, uint64_t ray0 = 0,
+                         uint32_t noise_stream = 0);
 int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
                      int64_t n, int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0,
                      float zero_tol, float eps, float* samples, int64_t* inds, cudaStream_t st, float* T_below = nullptr,

@@ -488,6 +488,102 @@ def mlp_forward(net, x, precision=None):
     return out.reshape(*x.shape[:-1], ch)
 
 
+def _render_cfg(pkc, N_samples, N_importance, mode, color_mode, perturb, white_bkgd, lindisp, raw_noise_std, zero_tol,
+                epsilon, farcolorfix, seed, ray_id_offset, precision):
+    if mode not in ("linear", "constant"):
+        raise ValueError(f"mode must be 'linear' or 'constant', got {mode!r}")
+    if color_mode not in ("midpoint", "left"):
+        raise ValueError(f"color_mode must be 'midpoint' or 'left', got {color_mode!r}")
+    cfg = L.RenderCfg()
+    cfg.N_samples, cfg.N_importance = N_samples, N_importance
+    cfg.mode = L.MODE_LINEAR if mode == "linear" else L.MODE_CONSTANT
+    cfg.color_mode = L.COLOR_MIDPOINT if color_mode == "midpoint" else L.COLOR_LEFT
+    cfg.white_bkgd, cfg.lindisp, cfg.farcolorfix = int(bool(white_bkgd)), int(bool(lindisp)), int(bool(farcolorfix))
+    cfg.perturb = int(bool(perturb))
+    cfg.raw_noise_std, cfg.zero_tol, cfg.epsilon = float(raw_noise_std), float(zero_tol), float(epsilon)
+    cfg.multires = _multires_of(pkc.desc.input_ch)
+    cfg.multires_views = _multires_of(pkc.desc.input_ch_views) if pkc.desc.use_viewdirs else -1
+    cfg.precision = _prec(precision)
+    cfg.seed, cfg.ray_id_offset = int(seed), int(ray_id_offset)
+    return cfg
+
+
+def render_rays_fwd_train(rays, net_coarse, net_fine, N_samples, N_importance, mode, color_mode, perturb=True,
+                          white_bkgd=False, lindisp=False, raw_noise_std=0.0, zero_tol=1e-4, epsilon=1e-3, farcolorfix=False,
+                          t_rand=None, u=None, noise0=None, noise1=None, seed=0, ray_id_offset=0, retraw=False):
+    """render_rays forward that keeps what the backward needs (plnerf_render_rays_fwd_train): one C call.
+    Returns (dict of outputs like render_rays_fwd, ctx) -- ctx goes to render_rays_bwd."""
+    rays = _f32(rays, "rays")
+    n, dev = rays.shape[0], rays.device
+    pkc = packed_of(net_coarse)
+    bufc = pkc.get(net_coarse, "bf16")
+    fine = net_fine if (N_importance > 0 and net_fine is not None) else None
+    pkf = packed_of(fine) if fine is not None else None
+    buff = pkf.get(fine, "bf16") if fine is not None else None
+    cfg = _render_cfg(pkc, N_samples, N_importance, mode, color_mode, perturb, white_bkgd, lindisp, raw_noise_std, zero_tol,
+                      epsilon, farcolorfix, seed, ray_id_offset, "bf16")
+    S_last = N_samples + N_importance
+    o, ret = L.RenderOut(), {}
+
+    def new(key, shape, dtype=torch.float32):
+        t = torch.empty(shape, device=dev, dtype=dtype)
+        setattr(o, key, t.data_ptr())
+        ret[key] = t
+    new("rgb_map", (n, 3)); new("disp_map", (n,)); new("acc_map", (n,)); new("depth_map", (n,))
+    if retraw:
+        new("raw", (n, S_last, 4))
+    if N_importance > 0:
+        new("rgb0", (n, 3)); new("disp0", (n,)); new("depth0", (n,)); new("acc0", (n,)); new("z_std", (n,))
+    opt = lambda t, nm: None if t is None else _f32(t, nm)
+    t_rand, u, noise0, noise1 = opt(t_rand, "t_rand"), opt(u, "u"), opt(noise0, "noise0"), opt(noise1, "noise1")
+    fdesc = C.byref(pkf.desc) if pkf else None
+    wsb = L.lib().plnerf_render_train_workspace_bytes(C.byref(cfg), C.byref(pkc.desc), fdesc, n)
+    if wsb == 0:
+        L.check(-2)
+    if wsb > 64 * 2 ** 30:
+        raise RuntimeError(f"plnerf_b200: the training workspace for {n} rays x {S_last} samples would need {wsb / 2**30:.1f} GiB; "
+                           "use a smaller ray batch / chunk for calls that require gradients")
+    ws = torch.empty(wsb + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    L.check(L.lib().plnerf_render_rays_fwd_train(C.byref(cfg), C.byref(pkc.desc), _p(bufc), fdesc, _p(buff), _p(rays), n,
+                                                  rays.shape[1], _p(t_rand), _p(u), _p(noise0), _p(noise1), C.byref(o),
+                                                  C.c_void_p(ws.data_ptr() + off), wsb, _stream()))
+    ctx = dict(cfg=cfg, rays=rays, n=n, ws=ws, off=off, wsb=wsb, net_c=net_coarse, net_f=fine, noise0=noise0, noise1=noise1)
+    return ret, ctx
+
+
+def render_rays_bwd(ctx, g_fine, g_coarse, grads_c, grads_f):
+    """Backward of render_rays_fwd_train (plnerf_render_rays_bwd): g_fine / g_coarse = (g_rgb, g_disp, g_acc, g_depth) of the
+    fine / coarse maps (entries or the whole tuple may be None; with N_importance == 0 the maps are g_fine's).  Parameter
+    gradients are ADDED into grads_c / grads_f ({state_dict name: fp32 tensor})."""
+    net_c, net_f = ctx["net_c"], ctx["net_f"]
+    pkc = packed_of(net_c)
+    bufc, bwdc = pkc.get(net_c, "bf16"), packed_bwd_of(net_c)
+    keep = []
+    gc = L.NetGrads()
+    _fill_params(gc, pkc.desc, grads_c, keep)
+    fdesc = buff = bwdf = gf_ref = None
+    if net_f is not None:
+        pkf = packed_of(net_f)
+        fdesc, buff, bwdf = C.byref(pkf.desc), pkf.get(net_f, "bf16"), packed_bwd_of(net_f)
+        gf = L.NetGrads()
+        _fill_params(gf, pkf.desc, grads_f, keep)
+        gf_ref = C.byref(gf)
+    g = L.RenderGrads()
+    c = lambda t: None if t is None else _f32(t, "upstream gradient")
+    for names, tup in ((("g_rgb_map", "g_disp_map", "g_acc_map", "g_depth_map"), g_fine),
+                       (("g_rgb0", "g_disp0", "g_acc0", "g_depth0"), g_coarse)):
+        for nm, t in zip(names, tup if tup is not None else (None,) * 4):
+            t = c(t)
+            keep.append(t)
+            setattr(g, nm, None if t is None else t.data_ptr())
+    rays = ctx["rays"]
+    L.check(L.lib().plnerf_render_rays_bwd(C.byref(ctx["cfg"]), C.byref(pkc.desc), _p(bufc), _p(bwdc), fdesc, _p(buff), _p(bwdf),
+                                            _p(rays), ctx["n"], rays.shape[1], _p(ctx["noise0"]), _p(ctx["noise1"]), C.byref(g),
+                                            C.byref(gc), gf_ref, C.c_void_p(ctx["ws"].data_ptr() + ctx["off"]), ctx["wsb"],
+                                            _stream()))
+
+
 def render_rays_fwd(rays, net_coarse, net_fine, N_samples, N_importance, mode, color_mode, perturb=True,
                     white_bkgd=False, lindisp=False, raw_noise_std=0.0, zero_tol=1e-4, epsilon=1e-3, farcolorfix=False,
                     t_rand=None, u=None, noise0=None, noise1=None, seed=0, ray_id_offset=0, retraw=False,

@@ -227,6 +227,23 @@ def sample_pdf_reformulation_return_u(bins, weights, tau, T, near, far, N_sample
     return samples, T_b, tau_b, bin_b, u_used
 
 
+def compute_space_carving_loss_corrected(pred_depth, target_hypothesis, is_joint=False, mask=None, norm_p=2, threshold=0.0):
+    """Space-carving depth loss of the depth-supervised experiments (run_nerf_helpers.py:203-238), plain torch (not on
+    the accelerated path; present because run_plnerf.py star-imports the module).  pred_depth [n_rays, n_points];
+    target_hypothesis [n_hyp, n_rays, 1 | n_points].  Per sample, the distance to the closest hypothesis (``is_joint``:
+    the hypothesis is chosen per image from the ray-averaged distances), averaged."""
+    n_points = pred_depth.shape[1]
+    hyp = target_hypothesis.repeat(1, 1, n_points) if target_hypothesis.shape[-1] == 1 else target_hypothesis
+    dist = torch.norm((pred_depth.unsqueeze(-1) - hyp.unsqueeze(-1)), p=norm_p, dim=-1)        # [n_hyp, n_rays, n_points]
+    if mask is not None:
+        dist = dist * mask.unsqueeze(0).repeat(dist.shape[0], 1).unsqueeze(-1)
+    if threshold > 0:
+        dist = torch.where(dist < threshold, torch.zeros((), device=dist.device, dtype=dist.dtype), dist)
+    if is_joint:
+        return torch.mean(torch.min(torch.mean(dist, dim=1), dim=0)[0], dim=-1)
+    return torch.mean(torch.mean(torch.min(dist, dim=0)[0], dim=-1))
+
+
 # ---- utilities for evaluation (run_nerf_helpers.py:537-570), star-imported by run_plnerf.py ------------------------------
 def compute_rmse(prediction, target):
     """Root-mean-square error of two tensors (run_nerf_helpers.py:537-538)."""
