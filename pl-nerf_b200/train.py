@@ -170,7 +170,9 @@ class TrainStep:
         self.optimizer = torch.optim.Adam(segs, lr=lrate, betas=(0.9, 0.999), fused=True)
         # {state_dict name: view of the flat gradient buffer} per network: what the weight-gradient kernels add into
         self._grads = {net: {k: p.grad for k, p in net.named_parameters()} for net in self.nets}
-        self._direct = not any(kw.get(k) is not None for k in ("t_rand", "u", "noise0", "noise1")) and not kw.get("pytest")
+        # explicit depth / sampler draws (t_rand [B, N_samples], u [B, N_importance] of the GLOBAL batch) are sliced per
+        # shard and chunk; explicit noise or the pytest hook go through render_rays' autograd.Function instead
+        self._direct = not any(kw.get(k) is not None for k in ("noise0", "noise1")) and not kw.get("pytest")
         if self._direct:
             if not all(getattr(n, "use_viewdirs", False) for n in self.nets):
                 raise NotImplementedError("plnerf_b200: gradients are implemented for use_viewdirs networks only")
@@ -208,11 +210,12 @@ class TrainStep:
                            mode="constant" if constant_init else kw["mode"], color_mode=kw["color_mode"],
                            perturb=kw.get("perturb", 0.) > 0., white_bkgd=bool(kw.get("white_bkgd", False)),
                            lindisp=bool(kw.get("lindisp", False)), zero_tol=kw.get("zero_tol", 1e-4),
-                           epsilon=kw.get("epsilon", 1e-3), farcolorfix=bool(kw.get("farcolorfix", False)), t_rand=None,
-                           u=None, noise0=torch.randn((n, Ns), device=r.device) * std if std > 0. else None,
+                           epsilon=kw.get("epsilon", 1e-3), farcolorfix=bool(kw.get("farcolorfix", False)),
+                           t_rand=None if kw.get("t_rand") is None else kw["t_rand"][ray0 + c0:ray0 + c0 + n],
+                           u=None if kw.get("u") is None else kw["u"][ray0 + c0:ray0 + c0 + n], noise0=torch.randn((n, Ns), device=r.device) * std if std > 0. else None,
                            noise1=torch.randn((n, Ns + Ni), device=r.device) * std if (std > 0. and Ni > 0) else None,
                            seed=kw["seed"] if kw.get("seed") is not None else RP._next_seed(), ray_id_offset=ray0 + c0)
-                if Ni > 0 and not cfg["perturb"]:      # det=True: the reference's linspace u (see render_rays)
+                if Ni > 0 and not cfg["perturb"] and cfg["u"] is None:      # det=True: the reference's linspace u (see render_rays)
                     cfg["u"] = torch.linspace(0., 1., steps=Ni, device=r.device).expand(n, Ni).contiguous()
                 outs, saved, stashes = AG.forward_stashed(cfg, r)
                 t = target_s[c0:c0 + n]

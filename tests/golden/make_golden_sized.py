@@ -6,6 +6,9 @@
                    linear / midpoint, perturb=1 with the reference's pytest draws.
   c2_lego_1024     config 2 shape: 1024 lego-shaped rays, N_samples=64 + N_importance=128, PL quadrature, view
                    directions, white background, density-boosted coarse + fine nets (the bench's nets).
+  train_c3_1024    config 3 shape: 1024 rays at 128 + 64 samples; loss = img2mse(rgb, t) + img2mse(rgb0, t) against a seeded
+                   random target, back-propagated through the unmodified reference: the loss, and per parameter of both
+                   networks the gradient's L2 norm and its first 2048 entries.
   selfcheck_orders the same network function evaluated by the unmodified reference in two fp32 summation orders
                    (hidden units of every trunk layer permuted consistently: mathematically the identical network),
                    on 256 density-boosted rays at 64/128.  How far the reference disagrees with ITSELF bounds what any
@@ -37,7 +40,12 @@ SIZED = {
                          density_boost=True),
     "selfcheck_orders": dict(n=256, ray_seed=3, Ns=64, Ni=128, use_viewdirs=True, white_bkgd=True, seeds=(1, 2),
                              density_boost=True),
+    # config 3 shape (configs/blender_linear.txt: N_rand=1024, N_samples=128, N_importance=64): the training loss and every
+    # parameter gradient of the unmodified reference (loss.backward() through its own render)
+    "train_c3_1024": dict(n=1024, ray_seed=13, Ns=128, Ni=64, use_viewdirs=True, white_bkgd=True, seeds=(1, 2),
+                          density_boost=True, train=True),
 }
+GRAD_SLICE = 2048      # leading entries of every parameter gradient stored next to its norm
 
 
 def net_kwargs(cfg):
@@ -91,6 +99,10 @@ def permute_hidden_units(params, D, skips, seed):
     return p
 
 
+def train_target(cfg):
+    return np.random.RandomState(99).rand(cfg["n"], 3).astype(np.float32)
+
+
 def ref_render(H, R, cfg, ro, rd, K, hwf, pc, pf):
     kw = net_kwargs(cfg)
 
@@ -117,12 +129,22 @@ def ref_render(H, R, cfg, ro, rd, K, hwf, pc, pf):
         return r
     torch.searchsorted = recording_searchsorted
     try:
-        with torch.no_grad():
+        with torch.set_grad_enabled(bool(cfg.get("train"))):
             rgb, disp, acc, ex = _render(R, Hh, Ww, K, rays_t, cfg, q, net_c, net_f)
     finally:
         torch.searchsorted = real_searchsorted
-    out = {"rgb_map": rgb.numpy(), "disp_map": disp.numpy(), "acc_map": acc.numpy()}
-    out.update({k: v.numpy() for k, v in ex.items()})
+    out = {"rgb_map": rgb.detach().numpy(), "disp_map": disp.detach().numpy(), "acc_map": acc.detach().numpy()}
+    out.update({k: v.detach().numpy() for k, v in ex.items()})
+    if cfg.get("train"):
+        tgt = torch.from_numpy(train_target(cfg))
+        loss = H.img2mse(rgb, tgt) + H.img2mse(ex["rgb0"], tgt)           # run_plnerf.py:1290-1297
+        loss.backward()
+        out["train_loss"] = np.float64(loss.item())
+        for tag, net in (("c", net_c), ("f", net_f)):
+            for k_, p_ in net.named_parameters():
+                g_ = p_.grad.detach().numpy().ravel()
+                out[f"gnorm_{tag}.{k_}"] = np.float64(np.linalg.norm(g_.astype(np.float64)))
+                out[f"ghead_{tag}.{k_}"] = g_[:GRAD_SLICE].copy()
     if captured:
         assert len(captured) == 1
         out["inds"] = captured[0].numpy().astype(np.int16)

@@ -76,7 +76,7 @@ def test_train_step_matches_reference_loop_sequence():
     grads_a = step.bucket.flat.clone()
     after_a = torch.cat([p.detach().flatten() for p in step.bucket.params])
     assert torch.equal(out["pix"], pix)
-    assert step.optimizer.param_groups[0]["lr"] == T.decayed_lrate(5e-4, 500, 7)
+    assert step.optimizer.param_groups[0]["lr"] == T.decayed_lrate(5e-4, 500, 6)      # global_step = i - 1
 
     # --- the reference loop's sequence
     b_c, b_f = make_net(61), make_net(62)
