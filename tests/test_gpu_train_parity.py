@@ -59,11 +59,13 @@ def test_train_step_gradients_vs_reference_golden():
             nrm = got.norm().item() / ref_norm
             worst[f"{tag}.{k}"] = (round(nrm, 4), round(rel, 4), round(cos, 5))
             trunk = k.startswith("pts_linears")
-            # bf16 operand rounding accumulates along the chained gradient GEMMs (heads -> layer 0): gates at ~2x the
-            # measured deviation from the fp32 reference, EVERY layer
-            assert abs(nrm - 1) < (0.06 if trunk else 0.03), (tag, k, worst[f"{tag}.{k}"])
-            assert cos > (0.99 if trunk else 0.997), (tag, k, worst[f"{tag}.{k}"])
-            assert rel < (0.15 if trunk else 0.08), (tag, k, worst[f"{tag}.{k}"])
+            # bf16 operand rounding accumulates along the chained gradient GEMMs (heads -> layer 0).  Measured on a B200
+            # against the fp32 reference: norms within 0.9% (trunk) / 1.9% (heads: alpha_linear.bias), slices within 9.7%
+            # (fine layer 0; 6% at layer 1, <= 2.6% from layer 3 up, <= 1.9% outside the trunk), cosines >= 0.9953.
+            # Gates at ~1.5x that, EVERY layer:
+            assert abs(nrm - 1) < (0.02 if trunk else 0.03), (tag, k, worst[f"{tag}.{k}"])
+            assert cos > (0.993 if trunk else 0.9998), (tag, k, worst[f"{tag}.{k}"])
+            assert rel < (0.14 if trunk else 0.03), (tag, k, worst[f"{tag}.{k}"])
     print("norm ratio / slice rel err / slice cos per parameter:", worst)
 
 
@@ -163,5 +165,6 @@ def test_training_convergence_vs_reference_fp32_autograd():
     print(f"loss first/last a: {loss_a[0]:.5f}/{loss_a[-win:].mean():.5f}  b: {loss_b[0]:.5f}/{loss_b[-win:].mean():.5f}; "
           f"smoothed curve deviation max {dev_curve.max():.4f} mean {dev_curve.mean():.4f}; PSNR a {psnr_a:.3f} dB, b {psnr_b:.3f} dB")
     assert loss_b[-win:].mean() < 0.5 * loss_b[:win].mean()                   # the job actually optimises
-    assert dev_curve.max() < 0.05 and dev_curve.mean() < 0.02                 # loss curves (25-iteration means) within 2% on average
-    assert abs(psnr_a - psnr_b) < 0.15                                        # final PSNR of the full image
+    # measured on a B200: curve deviation max 0.22% / mean 0.06%, PSNR 49.909 vs 49.921 dB
+    assert dev_curve.max() < 0.02 and dev_curve.mean() < 0.005               # loss curves (25-iteration means) within 2%
+    assert abs(psnr_a - psnr_b) < 0.1                                         # final PSNR of the full image within 0.1 dB
