@@ -224,18 +224,24 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, z0, st);
   if (rc) return rc;
   // (2) coarse network query (:714)
+  // (2)+(3) coarse network query (:714) with the quadrature (:715) fused into the kernel where the configuration allows
   float* raw0 = (!fine && out->raw) ? out->raw : w.raw0;
-  rc = mlp_query(cdesc, cpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z0, Ns, raw0, chc,
-                 w.mlp_ws, w.mlp_ws_bytes, st);
-  if (rc) return rc;
-  // (3) coarse quadrature (:715)
   const float std0 = (!noise0) ? cfg->raw_noise_std : 0.f;
-  rc = launch_composite(raw0, chc, z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
-                        noise0, std0, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0,
-                        fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map,
-                        fine ? out->acc0 : out->acc_map, fine ? out->depth0 : out->depth_map,
-                        fine ? w.w0 : nullptr, fine ? w.tau0 : nullptr, fine ? w.T0 : nullptr, st);
+  const FusedComposite fc0{cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix, noise0, std0, cfg->seed,
+                           cfg->ray_id_offset, RNG_STREAM_NOISE0, fine ? out->rgb0 : out->rgb_map,
+                           fine ? out->disp0 : out->disp_map, fine ? out->acc0 : out->acc_map,
+                           fine ? out->depth0 : out->depth_map, fine ? w.w0 : nullptr, fine ? w.tau0 : nullptr,
+                           fine ? w.T0 : nullptr};
+  bool fused0 = false;
+  rc = mlp_query(cdesc, cpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z0, Ns, raw0, chc,
+                 w.mlp_ws, w.mlp_ws_bytes, st, &fc0, /*need_raw=*/(!fine && out->raw != nullptr), &fused0);
   if (rc) return rc;
+  if (!fused0) {
+    rc = launch_composite(raw0, chc, z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                          noise0, std0, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0, fc0.rgb_map, fc0.disp_map,
+                          fc0.acc_map, fc0.depth_map, fc0.weights, fc0.tau, fc0.T, st);
+    if (rc) return rc;
+  }
   if (!fine) return PLNERF_OK;
   // (4) importance sampling (:721-726)
   if (cfg->mode == PLNERF_MODE_LINEAR) {
@@ -252,13 +258,18 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   if (rc) return rc;
   // (6) fine network query (:737-739) and quadrature (:741)
   float* raw1 = out->raw ? out->raw : w.raw1;
-  rc = mlp_query(fdesc, fpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z1, S1, raw1, chf,
-                 w.mlp_ws, w.mlp_ws_bytes, st);
-  if (rc) return rc;
   const float std1 = (!noise1) ? cfg->raw_noise_std : 0.f;
-  rc = launch_composite(raw1, chf, z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
-                        noise1, std1, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1, out->rgb_map, out->disp_map,
-                        out->acc_map, out->depth_map, nullptr, nullptr, nullptr, st);
+  const FusedComposite fc1{cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix, noise1, std1, cfg->seed,
+                           cfg->ray_id_offset, RNG_STREAM_NOISE1, out->rgb_map, out->disp_map, out->acc_map, out->depth_map,
+                           nullptr, nullptr, nullptr};
+  bool fused1 = false;
+  rc = mlp_query(fdesc, fpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z1, S1, raw1, chf,
+                 w.mlp_ws, w.mlp_ws_bytes, st, &fc1, /*need_raw=*/out->raw != nullptr, &fused1);
+  if (rc) return rc;
+  if (!fused1)
+    rc = launch_composite(raw1, chf, z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                          noise1, std1, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1, out->rgb_map, out->disp_map,
+                          out->acc_map, out->depth_map, nullptr, nullptr, nullptr, st);
   return rc;
 }
 

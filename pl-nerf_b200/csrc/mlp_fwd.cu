@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "composite.cuh"
 #include "ops.cuh"
 #include "umma.cuh"
 
@@ -439,6 +440,11 @@ struct MlpArgs {
   const float* dirpe;      // [rays][32] fp32 dir encoding (padded), MODE 2
   const float* g_raw; int g_stride;   // MODE 3: upstream gradient of the network output [rows, >=4]
   int n_stages;
+  // k_mlp3: whole units (rays) per CTA; fused quadrature (composite.cuh) of every completed ray inside the kernel
+  int64_t cta_units;
+  int fuse_comp, comp_mode;
+  int skip_out;            // k_mlp3 with fuse_comp: the rows' outputs are not written to `out` (no retraw)
+  CompositeArgs comp;
   long long* trace;  // debug timeline buffer (null in production)
   int debug_flags;   // developer library only (PLNERF_DBG): bring-up experiments selected by PLNERF_DEBUG_FLAGS
 };
@@ -1659,8 +1665,13 @@ int launch_mlp3(MlpArgs& a, cudaStream_t st) {
   a.trace = g_trace;
   a.debug_flags = dbg_env("PLNERF_DEBUG_FLAGS");
   a.n_tiles = ceil_div(a.M, TILE_M);
-  const int64_t n_pairs = (a.n_tiles + 1) / 2;
-  const unsigned grid = (unsigned)((n_pairs < g_num_sms) ? n_pairs : g_num_sms);
+  // contiguous ranges of whole units (rays) per CTA; a CTA should have at least one full pair of tiles of work
+  const int64_t n_units = ceil_div(a.M, a.vb_div);
+  int64_t cta_units = ceil_div(n_units, g_num_sms);
+  const int64_t min_units = ceil_div(2 * TILE_M, a.vb_div);
+  if (cta_units < min_units) cta_units = min_units;
+  a.cta_units = cta_units;
+  const unsigned grid = (unsigned)ceil_div(n_units, cta_units);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
   if (a.plan.use_viewdirs) v3::k_mlp3<true><<<grid, v3::THREADS3, smem_total, st>>>(a);
@@ -1680,6 +1691,7 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
     rc = launch_mlp3(a, st);
     if (rc <= 0) return rc;     // > 0: the plan does not fit k_mlp3, fall through to the single-tile kernel
   }
+  a.fuse_comp = 0;              // only k_mlp3 composites in-kernel
   int n_stages = MAX_STAGES;
   while (n_stages > 2 && (int)smem_layout(n_stages).total > g_max_smem) --n_stages;
   { const int force = dbg_env("PLNERF_STAGES"); if (force >= 2 && force < n_stages) n_stages = force; }
@@ -1767,7 +1779,8 @@ static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int prec
 
 int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
               const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
-              void* ws, size_t ws_bytes, cudaStream_t st) {
+              void* ws, size_t ws_bytes, cudaStream_t st, const FusedComposite* fc, bool need_raw, bool* fused) {
+  if (fused) *fused = false;
   PLNERF_CHECK_ARG(d && rays && z && raw, "network_query: null argument");
   PLNERF_CHECK_ARG(n >= 0 && S > 0, "network_query: bad sizes");
   if (n == 0) return PLNERF_OK;
@@ -1783,7 +1796,20 @@ int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int m
   memset(&a, 0, sizeof(a));
   a.rays = rays; a.stride = stride; a.z = z; a.S = S; a.multires = multires;
   a.x_emb = nullptr; a.x_ld = 0; a.vb_div = S; a.M = n * S; a.out = raw; a.out_stride = raw_stride;
-  return run_mlp_common(d, packed, precision, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st);
+  if (fc && precision == PLNERF_PREC_BF16 && d->use_viewdirs && S <= 2 * TILE_M && !dbg_env("PLNERF_NO_FUSE")) {
+    a.fuse_comp = 1;
+    a.comp_mode = fc->mode;
+    CompositeArgs& c = a.comp;
+    c.raw = nullptr; c.raw_stride = 4; c.z = z; c.rays = rays; c.n = n; c.stride = stride; c.S = S;
+    c.color_mode = fc->color_mode; c.white_bkgd = fc->white_bkgd; c.farcolorfix = fc->farcolorfix;
+    c.noise = fc->noise; c.noise_std = fc->noise_std; c.seed = fc->seed; c.ray0 = fc->ray0; c.noise_stream = fc->noise_stream;
+    c.rgb_map = fc->rgb_map; c.disp_map = fc->disp_map; c.acc_map = fc->acc_map; c.depth_map = fc->depth_map;
+    c.weights = fc->weights; c.tau = fc->tau; c.T = fc->T;
+    a.skip_out = need_raw ? 0 : 1;
+  }
+  const int rc = run_mlp_common(d, packed, precision, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st);
+  if (rc == PLNERF_OK && a.fuse_comp && fused) *fused = true;     // (launch_mlp clears fuse_comp when it falls back to k_mlp_fwd)
+  return rc;
 }
 
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,

@@ -23,6 +23,12 @@
 // helpers that encode the NEXT pair's rows (one thread per row: the angle reduction is done once per row, not once
 // per column group) and pull the pair after that into L2.
 //
+// Rows -> CTAs: every CTA owns a CONTIGUOUS range of whole rays (units of vb_div rows), tiled from its own first row
+// (the last tile of a CTA may be partial), so that all samples of a ray pass through one CTA in order.  With
+// A.fuse_comp the quadrature (raw2outputs, composite.cuh) runs inside the kernel: the views epilogue leaves each row's
+// four outputs in a shared-memory ring (3 tile pairs deep) and the helper warps composite every ray whose last sample
+// has arrived -- `raw` goes to HBM only when the caller asks for it (retraw).
+//
 // Weight ring: N slots of one 32 KB stage (8 K-steps of a 128-neuron half); both issuers walk it, a slot is refilled
 // once both have released it (tcgen05.commit on a count-2 barrier).  Biases are added in the epilogue (a bias
 // K-step would cost 6% of the tensor pipe, which is the bound here).
@@ -32,7 +38,8 @@ constexpr int MAX_SLOTS = 6;
 constexpr int EPI_WARPS_PER_TILE = 8;
 constexpr int WARP_MMA3 = 2 * EPI_WARPS_PER_TILE, WARP_HELP3 = WARP_MMA3 + 2, N_HELP_WARPS = 2;   // issuers: WARP_MMA3 + tile
 constexpr int THREADS3 = 32 * (WARP_HELP3 + N_HELP_WARPS);   // 640
-constexpr uint32_t VB_RAYS_SMEM = 3;       // rays whose view-bias rows a 128-sample tile can touch when S >= 64
+constexpr uint32_t VB_RAYS_SMEM = 3;
+constexpr int RING_PAIRS = 3, RING_ROWS = RING_PAIRS * 2 * TILE_M;   // output ring: a ray of <= 256 samples spans <= 2 pairs       // rays whose view-bias rows a 128-sample tile can touch when S >= 64
 
 // Shared-memory map: everything the epilogue warps address sits at COMPILE-TIME offsets (their addresses are instruction
 // immediates, not registers -- the epilogue threads hold two tiles' state in a 96-register budget); the variable-size
@@ -43,10 +50,12 @@ struct Smem3 {
   static constexpr uint32_t prog = 256;                                  // <= 48 stages per tile: [2][48] entries of 16 B, then the stream table [48] x 8 B
   static constexpr uint32_t stab = prog + 16u * 2u * 48u;
   static constexpr uint32_t vb0 = stab + 8u * 48u;                 // [2][3 rays][128] view-bias rows
-  static constexpr uint32_t XCH_CH = VD ? 4 : MAX_OUT_CH;
-  static constexpr uint32_t XCH_BYTES = TILE_M * XCH_CH * 4u;
-  static constexpr uint32_t xch0 = vb0 + 2u * VB_RAYS_SMEM * 128u * 4u;  // [2][128 rows][XCH_CH] head partial sums of the upper column half
-  static constexpr uint32_t pe0 = (xch0 + 2u * XCH_BYTES + 1023u) & ~1023u;   // [2] encoding operand tiles
+  // VD: ring of the rows' four outputs (float4), RING_PAIRS tile pairs deep -- also the exchange buffer of the two column
+  // halves' head partial sums; !VD: [2][128 rows][MAX_OUT_CH] exchange buffer only
+  static constexpr uint32_t XCH_BYTES = VD ? RING_ROWS * 16u : 2u * TILE_M * MAX_OUT_CH * 4u;
+  static constexpr uint32_t xch0 = vb0 + 2u * VB_RAYS_SMEM * 128u * 4u;
+  static constexpr uint32_t ctrs = xch0 + XCH_BYTES;                       // flow-control counters (see the kernel)
+  static constexpr uint32_t pe0 = (ctrs + 64u + 1023u) & ~1023u;           // [2] encoding operand tiles
   static constexpr uint32_t consts = pe0 + 2u * PE_TILE_BYTES;           // fp32 biases + heads (const_floats)
   uint32_t ring, total;
   int n_slots;
@@ -167,10 +176,9 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
 // Full encoding of one row (all 3 + 6L elements, one thread): p = o + d*z, one 32-bit turn fraction per coordinate, every
 // octave an exact shift of it + SFU sin/cos (common.cuh) -> the row's 16-byte units of the tile's PE operand (bf16,
 // K-major 8x16B core-matrix panels: panel j = columns [8j, 8j+8) at j * 2048 + row * 16).
-__device__ __forceinline__ void pe_write_row(const MlpArgs& A, uint8_t* pe_tile, int64_t tile, int row) {
+__device__ __forceinline__ void pe_write_row(const MlpArgs& A, uint8_t* pe_tile, int64_t g, int row, int64_t row_end) {
   const NetPlan& P = A.plan;
-  const int64_t g = tile * TILE_M + row;
-  const int64_t gc = (g < A.M) ? g : (A.M - 1);
+  const int64_t gc = (g < row_end) ? g : (row_end - 1);
   const int n_panels = 2 * P.pe_ks;
   if (A.x_emb) {
     // pre-embedded rows (NeRF.forward entry)
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       ptx::mbar_init(ep_early0 + 8u * t, EPI_WARPS_PER_TILE);
     }
     ptx::fence_mbar_init();
+    for (int i = 0; i < 16; ++i) reinterpret_cast<uint32_t*>(smem + Smem3<VD>::ctrs)[i] = 0u;
   }
   if (warp == WARP_MMA3) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += THREADS3) consts[i] = A.tail[i];
@@ -279,7 +288,16 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int n_pairs = (int)((A.n_tiles + 1) >> 1);
+  // this CTA's contiguous range of whole units (rays of vb_div rows): rows [row0, row_end), tiled from row0
+  const int64_t n_units = (A.M + A.vb_div - 1) / A.vb_div;
+  const int64_t unit0 = (int64_t)blockIdx.x * A.cta_units;
+  const int64_t unit1 = (unit0 + A.cta_units < n_units) ? unit0 + A.cta_units : n_units;
+  const int64_t row0 = unit0 * A.vb_div;
+  const int64_t row_end = (unit1 * A.vb_div < A.M) ? unit1 * A.vb_div : A.M;
+  const int n_pairs = (row_end > row0) ? (int)((row_end - row0 + 2 * TILE_M - 1) / (2 * TILE_M)) : 0;
+  // flow control of the output ring (plain counters: the parties may run several pairs apart, which mbarrier parities
+  // cannot express): tiles_done[t] += 1 per final-row warp and pair (4 per pair), comp_done += 1 per helper warp and pair
+  volatile uint32_t* ctrs = reinterpret_cast<volatile uint32_t*>(smem + Smem3<VD>::ctrs);
   int l_pe_last = 0;
   for (int l = 0; l < P.n_layers; ++l) if (P.L[l].n_pe_ks > 0) l_pe_last = l;
 
@@ -318,9 +336,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
     n_entries = __shfl_sync(0xffffffffu, n_entries, 0);
     __syncwarp();
     const uint64_t ring_desc = ((uint64_t)desc_hi << 32) | (uint64_t)lo_of(sbase + SL.ring);
-    int my_pairs = 0;
-    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) ++my_pairs;
-    Issue3 st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, (t == 1) ? (uint32_t)(my_pairs * n_entries) : 0u};
+    Issue3 st = {0u, 0u, 0u, 0u, 0u, 0u, 0u, (t == 1) ? (uint32_t)(n_pairs * n_entries) : 0u};
     const uint32_t prog_addr = sbase + Smem3<VD>::prog + 16u * 48u * t, stab_addr = sbase + Smem3<VD>::stab;
     if (t == 1 && ptx::elect_one()) {
       // prologue of the weight stream: fill all but REFILL_LAG slots; afterwards every issued stage refills the slot both
@@ -336,11 +352,11 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       }
     }
     __syncwarp();
-    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+    for (int pr = 0; pr < n_pairs; ++pr) {
       unsigned long long trp = 0ull;
 #if defined(PLNERF_DEBUG) && defined(PLNERF_ENABLE_TRACE)
       // issue-side stamps of block 0's third pair: 3 x 32-bit clocks per program entry behind the epilogue regions
-      if (A.trace && blockIdx.x == 0 && pr == 2 * (int)gridDim.x) trp = (unsigned long long)(A.trace + 4 * 256 * 2 + 128 * t);
+      if (A.trace && blockIdx.x == 0 && pr == 2) trp = (unsigned long long)(A.trace + 4 * 256 * 2 + 128 * t);
 #endif
       if (ptx::elect_one())
         issue_tile3(st, prog_addr, (uint32_t)n_entries, ring_desc, idesc, desc_hi, w_full0, w_empty0, ep_early0 + 8u * t, ep_done0 + 8u * t, pe_ready0 + 8u * t,
@@ -350,39 +366,70 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
   } else if (warp >= WARP_HELP3) {
     // ===================== helper warps: encode the next pair's rows, prefetch the pair after =============================
     const int hid = threadIdx.x - 32 * WARP_HELP3;          // 0..63
+    const int hw = warp - WARP_HELP3;
     auto encode_pair_tile = [&](int pair, int t) {
+      const int64_t g0 = row0 + (2 * (int64_t)pair + t) * TILE_M;
 #pragma unroll 1
       for (int rr = hid; rr < TILE_M; rr += 32 * N_HELP_WARPS)
-        if (!PLNERF3_DBG(4)) pe_write_row(A, smem + Smem3<VD>::pe0 + t * PE_TILE_BYTES, 2 * (int64_t)pair + t, rr);
+        if (!PLNERF3_DBG(4)) pe_write_row(A, smem + Smem3<VD>::pe0 + t * PE_TILE_BYTES, g0 + rr, rr, row_end);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pe_ready0 + 8u * t);
     };
-    auto prefetch_pair = [&](int64_t pair) {
+    auto prefetch_pair = [&](int pair) {
       // depths / ray rows of a later pair -> L2 (a cold DRAM read otherwise): one line per 32 depths, the rows' rays
       if (A.x_emb || pair >= n_pairs) return;
 #pragma unroll 1
       for (int rr = 32 * hid; rr < 2 * TILE_M; rr += 32 * 32 * N_HELP_WARPS) {
-        const int64_t gt = 2 * pair * TILE_M + rr, gcn = (gt < A.M) ? gt : (A.M - 1);
+        const int64_t gt = row0 + 2 * (int64_t)pair * TILE_M + rr, gcn = (gt < row_end) ? gt : (row_end - 1);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.z + gcn));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.rays + (gcn / A.S) * (int64_t)A.stride));
       }
     };
-    if ((int)blockIdx.x < n_pairs) {
-      encode_pair_tile(blockIdx.x, 0);
-      encode_pair_tile(blockIdx.x, 1);
-      prefetch_pair((int64_t)blockIdx.x + gridDim.x);
+    if (n_pairs > 0) {
+      encode_pair_tile(0, 0);
+      encode_pair_tile(0, 1);
+      prefetch_pair(1);
     }
     uint32_t fph = 0u;                                       // parity of pe_free[0] and pe_free[1] (they advance together)
-    for (int pr = blockIdx.x; pr + (int)gridDim.x < n_pairs; pr += gridDim.x) {
-      // the NEXT pair's tile t, once pair pr's tile t has released its operand (the trunk layers that read it are complete)
+    int cu = 0;                                              // next ray (local index) to composite; same in both helper warps
+    const int n_cta_units = (int)(unit1 - unit0);
+    const int64_t rows_cta = row_end - row0;
+    const float4* ring = reinterpret_cast<const float4*>(smem + Smem3<VD>::xch0);
+    for (int pr = 0; pr < n_pairs; ++pr) {
+      if (pr + 1 < n_pairs) {
+        // the NEXT pair's tile t, once pair pr's tile t has released its operand (the trunk layers that read it are complete)
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        ptx::mbar_wait(pe_free0 + 8u * t, fph);
-        encode_pair_tile(pr + (int)gridDim.x, t);
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(pe_free0 + 8u * t, fph);
+          encode_pair_tile(pr + 1, t);
+        }
+        fph ^= 1u;
+        prefetch_pair(pr + 2);
       }
-      fph ^= 1u;
-      prefetch_pair((int64_t)pr + 2 * (int64_t)gridDim.x);
+      if (VD && A.fuse_comp) {
+        // ---- quadrature of every ray whose last sample arrived with this pair (one warp per ray, alternating warps)
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t need = 4u * (uint32_t)(pr + 1);
+          while (ctrs[t] < need) __nanosleep(200);      // (a busy spin would steal issue slots from the epilogue warps)
+          __threadfence_block();
+          int64_t have = (2 * (int64_t)pr + t + 1) * TILE_M;          // local rows present in the ring
+          if (have > rows_cta) have = rows_cta;
+          while (cu < n_cta_units && (int64_t)(cu + 1) * A.S <= have) {
+            if ((cu & 1) == hw) {
+              const int64_t r = unit0 + cu;
+              const RawRing raw{ring, (int)(((int64_t)cu * A.S) % RING_ROWS), RING_ROWS};
+              if (A.comp_mode == PLNERF_MODE_LINEAR) composite_ray<PLNERF_MODE_LINEAR>(A.comp, r, lane, raw, A.z + r * (int64_t)A.S);
+              else composite_ray<PLNERF_MODE_CONSTANT>(A.comp, r, lane, raw, A.z + r * (int64_t)A.S);
+            }
+            ++cu;
+          }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<uint32_t*>(ctrs + 2), 1u);
+      }
     }
   } else {
     // ===================== epilogue warps: group t = warp / 8 serves tile t ==============================================
@@ -394,7 +441,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
     const uint32_t tm_a = tm_row + 128u + 32u * (uint32_t)ch;      // its 32 packed columns inside a half of A_t
     const uint32_t d_full = d_full0 + 8u * t, ep_done = ep_done0 + 8u * t, ep_early = ep_early0 + 8u * t, vb_full = vb_full0 + 8u * t, pe_free = pe_free0 + 8u * t;
     const bool vb_smem = VD && A.viewbias && A.vb_div >= 64;
-    float* xch = reinterpret_cast<float*>(smem + Smem3<VD>::xch0 + t * Smem3<VD>::XCH_BYTES);
+    float* xch = reinterpret_cast<float*>(smem + Smem3<VD>::xch0) + (VD ? 0 : t * TILE_M * MAX_OUT_CH);   // VD: the output ring
     const float* vbs = reinterpret_cast<const float*>(smem + Smem3<VD>::vb0 + t * (VB_RAYS_SMEM * 512u));
     uint32_t dph = 0u, vph = 0u;
     int vb_idx = 0;
@@ -419,9 +466,9 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       if (PLNERF3_DBG(8)) arrive_now(3);
     };
 
-    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-      const bool trace_on = (pr == (int)blockIdx.x + 2 * (int)gridDim.x) && lane == 0 && q == 0 && ch == 0;
-      const int64_t g = (2 * (int64_t)pr + t) * TILE_M + row;
+    for (int pr = 0; pr < n_pairs; ++pr) {
+      const bool trace_on = (pr == 2) && lane == 0 && q == 0 && ch == 0;
+      const int64_t g = row0 + (2 * (int64_t)pr + t) * TILE_M + row;
       float alpha_acc = 0.f;
       for (int l = 0; l < P.n_layers; ++l) {
         const int epi = P.L[l].epi, n_halves = P.L[l].n_halves;
@@ -489,7 +536,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             ptx::mbar_wait(vb_full, vph); vph ^= 1u;
             vbr = vbs + vb_idx * 128 + 64 * ch;
           } else {
-            const int64_t gc = (g < A.M) ? g : (A.M - 1);
+            const int64_t gc = (g < row_end) ? g : (row_end - 1);
             vbr = A.viewbias + (gc / A.vb_div) * 128 + 64 * ch;
           }
           const float* rw = consts + P.rgb_w_off + 64 * ch;
@@ -514,17 +561,33 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
               h2 = fmaf(v0, w2.x, h2); h2 = fmaf(v1, w2.y, h2); h2 = fmaf(v2, w2.z, h2); h2 = fmaf(v3, w2.w, h2);
             }
           }
-          // combine the two column halves (fixed order: bitwise reproducible) and write the row
-          if (ch == 1) *reinterpret_cast<float4*>(xch + row * 4) = make_float4(h0, h1, h2, alpha_acc);
+          // combine the two column halves (fixed order: bitwise reproducible); the row's four outputs go to the output
+          // ring (slot of pair pr % RING_PAIRS; read by the compositor warps when A.fuse_comp) and, if asked for, to HBM
+          float4* slot = reinterpret_cast<float4*>(xch) + ((2 * pr + t) % (2 * RING_PAIRS)) * TILE_M + row;
+          if (A.fuse_comp && pr >= RING_PAIRS) {
+            // the slot's previous rows (pair pr - 3) are released once every ray ending in pair pr - 2 is composited
+            const uint32_t need = 2u * (uint32_t)(pr - 1);
+            while (ctrs[2] < need) __nanosleep(100);
+            __threadfence_block();
+          }
+          if (ch == 1) *slot = make_float4(h0, h1, h2, alpha_acc);
           asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(32 * EPI_WARPS_PER_TILE) : "memory");
-          if (ch == 0 && g < A.M) {
-            const float4 x = *reinterpret_cast<const float4*>(xch + row * 4);
+          if (ch == 0) {
+            const float4 x = *slot;
             float4 acc;
             acc.x = h0 + x.x + consts[P.rgb_b_off + 0]; acc.y = h1 + x.y + consts[P.rgb_b_off + 1];
             acc.z = h2 + x.z + consts[P.rgb_b_off + 2]; acc.w = alpha_acc + x.w + consts[P.alpha_b_off];
-            float* o = A.out + g * (int64_t)A.out_stride;
-            if (A.out_stride == 4) *reinterpret_cast<float4*>(o) = acc;
-            else { o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w; }
+            *slot = acc;
+            if (!(A.fuse_comp && A.skip_out) && g < row_end) {
+              float* o = A.out + g * (int64_t)A.out_stride;
+              if (A.out_stride == 4) *reinterpret_cast<float4*>(o) = acc;
+              else { o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w; }
+            }
+            if (A.fuse_comp) {
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) atomicAdd(const_cast<uint32_t*>(ctrs + t), 1u);
+            }
           }
         } else {
           // ---- last trunk layer of a network without view directions: ReLU, output_linear on the fp32 values
@@ -554,7 +617,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             for (int c = 0; c < MAX_OUT_CH; ++c) if (c < nch) xch[row * MAX_OUT_CH + c] = hp[c];
           }
           asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "n"(32 * EPI_WARPS_PER_TILE) : "memory");
-          if (ch == 0 && g < A.M) {
+          if (ch == 0 && g < row_end) {
             float* o = A.out + g * (int64_t)A.out_stride;
 #pragma unroll
             for (int c = 0; c < MAX_OUT_CH; ++c) if (c < nch) o[c] = hp[c] + xch[row * MAX_OUT_CH + c] + consts[P.out_b_off + c];
@@ -570,13 +633,13 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
         if (l == 1 && vb_smem) {
           // this tile's per-ray view-bias rows -> shared memory, one bulk copy.  All 8 warps of the group are past the
           // previous pair's views epilogue here (this layer's MMAs needed their arrivals of layer 0's epilogue).
-          const int64_t row0 = (2 * (int64_t)pr + t) * TILE_M;
-          const int64_t gc = (g < A.M) ? g : (A.M - 1);
-          const int64_t ray0 = row0 / A.vb_div;
+          const int64_t trow0 = row0 + (2 * (int64_t)pr + t) * TILE_M;
+          const int64_t gc = (g < row_end) ? g : (row_end - 1);
+          const int64_t ray0 = trow0 / A.vb_div;
           const int d = (int)(gc / A.vb_div - ray0);      // (the 64-bit divisions stay out of the views epilogue)
           vb_idx = d < 0 ? 0 : (d >= (int)VB_RAYS_SMEM ? (int)VB_RAYS_SMEM - 1 : d);
           if ((warp & 7) == 0 && lane == 0) {
-            const int64_t n_rays = (A.M + A.vb_div - 1) / A.vb_div;
+            const int64_t n_rays = n_units;
             if (ray0 < n_rays) {
               const int64_t nr = (n_rays - ray0 < (int64_t)VB_RAYS_SMEM) ? n_rays - ray0 : (int64_t)VB_RAYS_SMEM;
               ptx::mbar_arrive_expect_tx(vb_full, (uint32_t)nr * 512u);

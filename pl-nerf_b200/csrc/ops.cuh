@@ -40,10 +40,19 @@ int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const
 size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision);
 int mlp_pack(const plnerf_net_desc* d, const plnerf_net_params* p, int precision, void* packed, cudaStream_t st);
 size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays);
-// Fused query: rows = n*S samples of rays (PE computed in-kernel).
+// Quadrature to run INSIDE the fused query (k_mlp3's compositor warps): the arguments of launch_composite.
+struct FusedComposite {
+  int mode, color_mode, white_bkgd, farcolorfix;
+  const float* noise; float noise_std; uint64_t seed, ray0; uint32_t noise_stream;
+  float *rgb_map, *disp_map, *acc_map, *depth_map, *weights, *tau, *T;
+};
+// Fused query: rows = n*S samples of rays (PE computed in-kernel).  With `fc`, the quadrature of the rays runs inside the
+// kernel when the configuration allows it (bf16, use_viewdirs network, S <= 256, k_mlp3): *fused tells whether it did
+// (otherwise the caller composites `raw` itself); `raw` is then written only if need_raw.
 int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
               const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
-              void* ws, size_t ws_bytes, cudaStream_t st);
+              void* ws, size_t ws_bytes, cudaStream_t st, const FusedComposite* fc = nullptr, bool need_raw = true,
+              bool* fused = nullptr);
 // NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
                          float* out, void* ws, size_t ws_bytes, cudaStream_t st);
