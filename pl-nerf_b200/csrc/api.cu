@@ -34,7 +34,7 @@ int debug_umma_gemm_mn(const float* X, const float* Y, int N, int K, uint32_t lb
 
 // workspace carving for render_rays
 struct RenderWs {
-  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1;
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *vb_f;
   void* mlp_ws; size_t mlp_ws_bytes;
   size_t total;
 };
@@ -53,6 +53,7 @@ static RenderWs carve(const plnerf_render_cfg* c, const plnerf_net_desc* d, int6
   w.zs = take((size_t)n * (Ni > 0 ? Ni : 1));
   w.z1 = take((size_t)n * S1);
   w.raw1 = take((size_t)n * S1 * ch0);
+  w.vb_f = take(d->use_viewdirs ? (size_t)n * 128 : 0);      // the fine network's per-ray view bias (launch_ray_setup)
   w.mlp_ws = base + off;
   w.mlp_ws_bytes = mlp_workspace_bytes(d, n);
   off += align_up(w.mlp_ws_bytes);
@@ -219,10 +220,18 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
   const bool fine = Ni > 0;
   int rc;
-  // (1) stratified depths (run_plnerf.py:683-705)
+  // (1) stratified depths (run_plnerf.py:683-705) + the per-ray view bias of both networks: one launch where covered
   float* z0 = (!fine && out->z_vals) ? out->z_vals : w.z0;
-  rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, z0, st);
-  if (rc) return rc;
+  const bool two_nets = fine && fpacked != cpacked;
+  float* vb_c = static_cast<float*>(w.mlp_ws);
+  rc = launch_ray_setup(cdesc, cpacked, two_nets ? fdesc : nullptr, fpacked, cfg->precision, cfg->multires_views, rays, n, stride, Ns,
+                        cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, z0, vb_c, w.vb_f, st);
+  if (rc < 0) return rc;
+  const bool have_vb = (rc == 0);
+  if (!have_vb) {
+    rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, z0, st);
+    if (rc) return rc;
+  }
   // (2) coarse network query (:714)
   // (2)+(3) coarse network query (:714) with the quadrature (:715) fused into the kernel where the configuration allows
   float* raw0 = (!fine && out->raw) ? out->raw : w.raw0;
@@ -234,7 +243,7 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
                            fine ? w.T0 : nullptr};
   bool fused0 = false;
   rc = mlp_query(cdesc, cpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z0, Ns, raw0, chc,
-                 w.mlp_ws, w.mlp_ws_bytes, st, &fc0, /*need_raw=*/(!fine && out->raw != nullptr), &fused0);
+                 w.mlp_ws, w.mlp_ws_bytes, st, &fc0, /*need_raw=*/(!fine && out->raw != nullptr), &fused0, have_vb ? vb_c : nullptr);
   if (rc) return rc;
   if (!fused0) {
     rc = launch_composite(raw0, chc, z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
@@ -243,18 +252,10 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
     if (rc) return rc;
   }
   if (!fine) return PLNERF_OK;
-  // (4) importance sampling (:721-726)
-  if (cfg->mode == PLNERF_MODE_LINEAR) {
-    rc = launch_sample_pl(z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed, cfg->ray_id_offset,
-                          cfg->zero_tol, cfg->epsilon, w.zs, out->inds, st);
-  } else {
-    // bins = z_mid [Ns-1], weights[..., 1:-1] [Ns-2]
-    rc = launch_sample_const(z0, Ns, 1, w.w0 + 1, Ns, n, Ns - 1, Ni, u, cfg->seed, cfg->ray_id_offset, w.zs, out->inds, st);
-  }
-  if (rc) return rc;
-  // (5) detach / clamp / sort-merge / z_std (:728-734, :752)
+  // (4)+(5) importance sampling (:721-726), detach / clamp / sort-merge / z_std (:728-734, :752): one kernel
   float* z1 = out->z_vals ? out->z_vals : w.z1;
-  rc = launch_merge(z0, w.zs, rays, n, stride, Ns, Ni, z1, out->z_std, st);
+  rc = launch_sample_merge(cfg->mode == PLNERF_MODE_LINEAR, z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed,
+                           cfg->ray_id_offset, cfg->zero_tol, cfg->epsilon, z1, out->z_std, out->inds, st);
   if (rc) return rc;
   // (6) fine network query (:737-739) and quadrature (:741)
   float* raw1 = out->raw ? out->raw : w.raw1;
@@ -264,7 +265,8 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
                            nullptr, nullptr, nullptr};
   bool fused1 = false;
   rc = mlp_query(fdesc, fpacked, cfg->precision, cfg->multires, cfg->multires_views, rays, n, stride, z1, S1, raw1, chf,
-                 w.mlp_ws, w.mlp_ws_bytes, st, &fc1, /*need_raw=*/out->raw != nullptr, &fused1);
+                 w.mlp_ws, w.mlp_ws_bytes, st, &fc1, /*need_raw=*/out->raw != nullptr, &fused1,
+                 have_vb ? (two_nets ? w.vb_f : vb_c) : nullptr);
   if (rc) return rc;
   if (!fused1)
     rc = launch_composite(raw1, chf, z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,

@@ -416,6 +416,87 @@ __global__ void __launch_bounds__(128) k_viewbias(const float* __restrict__ tail
   }
 }
 
+// Ray setup of render_rays in ONE launch: the stratified depths (run_plnerf.py:683-705, same arithmetic as k_stratified_z)
+// and the per-ray view bias of BOTH networks (coarse and fine differ only in their weights).  Block = 128 threads = the 128
+// neurons of views_linears[0]; each neuron's view-direction weights of both networks stay in registers over a grid-strided
+// loop of VB_RAYS rays.
+struct RaySetupArgs {
+  const float *tail_c, *tail_f;          // fp32 tails of the two packed networks (tail_f may equal tail_c)
+  int views_b_off, dirw_off, icv, multires_views;
+  const float* rays; int stride; int64_t n;
+  float *vb_c, *vb_f;                    // [n,128] each (vb_f null: one network serves both passes)
+  // depths
+  int Ns, lindisp, perturb; const float* t_rand; uint64_t seed, ray0; float* z;
+};
+__device__ __forceinline__ float setup_linspace01(int i, int n, float step) {
+  return (i < n / 2) ? step * (float)i : fmaf(-step, (float)(n - 1 - i), 1.0f);   // torch.linspace(0,1,n)
+}
+__device__ __forceinline__ float setup_base_z(float near, float far, float t, int lindisp) {
+  const float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near), omt), __fmul_rn(__fdiv_rn(1.0f, far), t)));
+}
+__global__ void __launch_bounds__(128) k_ray_setup(const __grid_constant__ RaySetupArgs a) {
+  __shared__ float emb[VB_RAYS][32];
+  const int t = threadIdx.x;
+  const int icv = a.icv;                   // <= 27 on this path (multires_views <= 4)
+  float wc[27], wf[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) {
+    wc[j] = (j < icv) ? a.tail_c[a.dirw_off + t * icv + j] : 0.f;
+    wf[j] = (a.vb_f && j < icv) ? a.tail_f[a.dirw_off + t * icv + j] : 0.f;
+  }
+  const float bc = a.tail_c[a.views_b_off + t], bf = a.vb_f ? a.tail_f[a.views_b_off + t] : 0.f;
+  const float step = (a.Ns > 1) ? __fdiv_rn(1.0f, (float)(a.Ns - 1)) : 0.0f;
+  for (int64_t r0 = (int64_t)blockIdx.x * VB_RAYS; r0 < a.n; r0 += (int64_t)gridDim.x * VB_RAYS) {
+    {
+      const int rr = t >> 5, j = t & 31;
+      const int64_t r = r0 + rr;
+      float v = 0.f;
+      if (r < a.n && j < icv) {
+        const float* vd = a.rays + r * (int64_t)a.stride + (a.stride - 3);
+        if (a.multires_views < 0 || j < 3) v = vd[j % 3];
+        else {
+          const int k = (j - 3) / 6, rem = (j - 3) % 6;
+          const float ang = vd[rem % 3] * exp2f((float)k);
+          v = (rem < 3) ? sinf(ang) : cosf(ang);
+        }
+      }
+      emb[rr][j] = v;
+    }
+    // this block's depths: VB_RAYS rays x Ns samples (k_stratified_z's arithmetic, one rounding per reference op)
+    for (int e = t; e < VB_RAYS * a.Ns; e += 128) {
+      const int rr = e / a.Ns, i = e - rr * a.Ns;
+      const int64_t r = r0 + rr;
+      if (r >= a.n) continue;
+      const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
+      const float zi = setup_base_z(near, far, setup_linspace01(i, a.Ns, step), a.lindisp);
+      float z = zi;
+      if (a.perturb) {
+        float lower = zi, upper = zi;
+        if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(zi, setup_base_z(near, far, setup_linspace01(i - 1, a.Ns, step), a.lindisp)));
+        if (i < a.Ns - 1) upper = __fmul_rn(0.5f, __fadd_rn(setup_base_z(near, far, setup_linspace01(i + 1, a.Ns, step), a.lindisp), zi));
+        const float tr = a.t_rand ? a.t_rand[r * (int64_t)a.Ns + i] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_TRAND, (uint32_t)i);
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+      }
+      a.z[r * (int64_t)a.Ns + i] = z;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < VB_RAYS; ++rr) {
+      const int64_t r = r0 + rr;
+      if (r < a.n) {
+        float acc_c = bc, acc_f = bf;
+#pragma unroll
+        for (int j = 0; j < 27; ++j) if (j < icv) { acc_c = fmaf(wc[j], emb[rr][j], acc_c); acc_f = fmaf(wf[j], emb[rr][j], acc_f); }
+        a.vb_c[r * 128 + t] = acc_c;
+        if (a.vb_f) a.vb_f[r * 128 + t] = acc_f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // =============================================================================================
 // the fused MLP kernel
 // =============================================================================================
@@ -1753,9 +1834,37 @@ size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays) {
   return d->use_viewdirs ? (size_t)n_rays * 128 * sizeof(float) + 256 : 256;
 }
 
+// One launch for what render_rays needs per ray before the first network query: stratified depths + the view bias of both
+// networks.  Returns 1 when the configuration is not covered (no view directions / wide direction encodings): the caller then
+// uses launch_stratified_z and lets mlp_query compute its own view bias.
+int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plnerf_net_desc* fd, const void* fpacked, int precision,
+                     int multires_views, const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
+                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st) {
+  if (!cd->use_viewdirs || cd->input_ch_views > 27 || stride < 11) return 1;
+  if (fd && (fd->input_ch_views != cd->input_ch_views || !fd->use_viewdirs)) return 1;
+  int rc = query_device();
+  if (rc) return rc;
+  NetPlan pc, pf;
+  rc = build_plan(cd, precision, nullptr, &pc);
+  if (rc) return rc;
+  if (fd) { rc = build_plan(fd, precision, nullptr, &pf); if (rc) return rc; }
+  if (fd && (pf.dirw_off != pc.dirw_off || pf.views_b_off != pc.views_b_off)) return 1;
+  RaySetupArgs a;
+  a.tail_c = reinterpret_cast<const float*>(static_cast<const uint8_t*>(cpacked) + pc.weight_bytes);
+  a.tail_f = fd ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(fpacked) + pf.weight_bytes) : a.tail_c;
+  a.views_b_off = pc.views_b_off; a.dirw_off = pc.dirw_off; a.icv = cd->input_ch_views; a.multires_views = multires_views;
+  a.rays = rays; a.stride = stride; a.n = n; a.vb_c = vb_c; a.vb_f = fd ? vb_f : nullptr;
+  a.Ns = Ns; a.lindisp = lindisp; a.perturb = perturb; a.t_rand = t_rand; a.seed = seed; a.ray0 = ray0; a.z = z;
+  const int64_t blocks = ceil_div(n, VB_RAYS);
+  k_ray_setup<<<(unsigned)(blocks < 8 * g_num_sms ? blocks : 8 * g_num_sms), 128, 0, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_ray_setup");
+  return PLNERF_OK;
+}
+
 static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int precision, MlpArgs& a, int64_t vb_rows,
                           int multires_views, const float* rays, int stride, const float* x_emb, int x_ld, void* ws,
-                          size_t ws_bytes, cudaStream_t st, int mode = -1, float* dirpe_out = nullptr) {
+                          size_t ws_bytes, cudaStream_t st, int mode = -1, float* dirpe_out = nullptr,
+                          const float* viewbias_pre = nullptr) {
   int rc = query_device();
   if (rc) return rc;
   rc = build_plan(d, precision, nullptr, &a.plan);
@@ -1764,7 +1873,9 @@ static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int prec
   a.w = static_cast<const uint8_t*>(packed);
   a.tail = reinterpret_cast<const float*>(a.w + a.plan.weight_bytes);
   a.viewbias = nullptr;
-  if (d->use_viewdirs) {
+  if (d->use_viewdirs && viewbias_pre) {
+    a.viewbias = viewbias_pre;          // computed by launch_ray_setup
+  } else if (d->use_viewdirs) {
     const size_t need = (size_t)vb_rows * 128 * sizeof(float);
     if (!ws || ws_bytes < need) { set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes); return PLNERF_E_WORKSPACE; }
     float* vb = static_cast<float*>(ws);
@@ -1779,7 +1890,8 @@ static int run_mlp_common(const plnerf_net_desc* d, const void* packed, int prec
 
 int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
               const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
-              void* ws, size_t ws_bytes, cudaStream_t st, const FusedComposite* fc, bool need_raw, bool* fused) {
+              void* ws, size_t ws_bytes, cudaStream_t st, const FusedComposite* fc, bool need_raw, bool* fused,
+              const float* viewbias_pre) {
   if (fused) *fused = false;
   PLNERF_CHECK_ARG(d && rays && z && raw, "network_query: null argument");
   PLNERF_CHECK_ARG(n >= 0 && S > 0, "network_query: bad sizes");
@@ -1807,7 +1919,8 @@ int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int m
     c.weights = fc->weights; c.tau = fc->tau; c.T = fc->T;
     a.skip_out = need_raw ? 0 : 1;
   }
-  const int rc = run_mlp_common(d, packed, precision, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st);
+  const int rc = run_mlp_common(d, packed, precision, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st, -1, nullptr,
+                                viewbias_pre);
   if (rc == PLNERF_OK && a.fuse_comp && fused) *fused = true;     // (launch_mlp clears fuse_comp when it falls back to k_mlp_fwd)
   return rc;
 }

@@ -294,7 +294,8 @@ int launch_composite_bwd(const float* raw, int raw_stride, const float* z, const
 }
 
 // =============================================================================================
-// samplers
+// samplers + sort-merge.  One warp per ray; the per-ray steps are device functions shared by the op-level kernels
+// (k_sample_pl, k_sample_const, k_merge) and by the fused k_sample_merge that render_rays uses (samples never leave the SM).
 // =============================================================================================
 // torch.searchsorted(cdf, u, right=True): ATen's upper-bound loop, reproduced step for step so the
 // result is identical even where rounding makes cdf non-monotone at its forced last element.
@@ -307,7 +308,7 @@ __device__ __forceinline__ int upper_bound_torch(const float* cdf, int n, float 
   return start;
 }
 
-// a11  sample_pdf_reformulation + pw_linear_sample_{in,de}creasing  (run_nerf_helpers.py:340-445)
+// ---- a11  sample_pdf_reformulation + pw_linear_sample_{in,de}creasing  (run_nerf_helpers.py:340-445)
 struct SamplePLArgs {
   const float *z, *w, *tau, *T, *rays;
   int64_t n; int stride, S, Ni;
@@ -318,18 +319,10 @@ struct SamplePLArgs {
   float *T_below, *tau_below, *bin_below, *u_out;
 };
 
-__global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  if (r >= a.n) return;
+// knots s = [near, z.., far], T, tau -> shared memory; cdf = [0, cumsum(w)] with fp64 accumulation, last forced to 1
+__device__ __forceinline__ void pl_build(const SamplePLArgs& a, int64_t r, int lane, float* cdf, float* s, float* T, float* tau) {
   const int S = a.S, nk = S + 2;
-  float* cdf = smem + (size_t)wib * 4 * nk;
-  float* s = cdf + nk;
-  float* T = s + nk;
-  float* tau = T + nk;
   const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
-  // knots, T, tau -> smem; cdf = [0, cumsum(w)] with fp64 accumulation, last forced to 1
   for (int k = lane; k < nk; k += 32) {
     s[k] = (k == 0) ? near : (k == S + 1 ? far : a.z[r * (int64_t)S + k - 1]);
     T[k] = a.T[r * (int64_t)nk + k];
@@ -345,48 +338,63 @@ __global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
     if (i < S + 1) cdf[i + 1] = (i == S) ? 1.0f : (float)incl;
   }
   __syncwarp();
+}
+
+// sample k of ray r: the draw, the bracket, the closed-form inverse; writes the optional per-sample outputs
+__device__ __forceinline__ float pl_sample(const SamplePLArgs& a, int64_t r, int k, const float* cdf, const float* s,
+                                           const float* T, const float* tau) {
+  const int S = a.S, nk = S + 2;
   const float eps = a.eps, tol = a.zero_tol;
-  for (int k = lane; k < a.Ni; k += 32) {
-    const float u = a.u ? a.u[r * (int64_t)a.Ni + k]
-                        : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
-    const int ind = upper_bound_torch(cdf, nk, u);
-    const int below = max(0, ind - 1);
-    const int above = min(nk - 1, ind);
-    const float s_l = s[below], s_r = s[above];
-    const float T_l = T[below];
-    const float tau_l = tau[below], tau_r = tau[above];
-    // tau_diff gathered at `below` from tau[1:]-tau[:-1] (size S+1); the reference raises for
-    // below == S+1 (only reachable with u >= 1): we clamp instead of faulting.
-    const int bd = min(below, S);
-    const float dtau = __fsub_rn(tau[bd + 1], tau[bd]);
-    float x;
-    if (dtau < tol && dtau > -tol) {
-      x = s_l;
+  const float u = a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+  const int ind = upper_bound_torch(cdf, nk, u);
+  const int below = max(0, ind - 1);
+  const int above = min(nk - 1, ind);
+  const float s_l = s[below], s_r = s[above];
+  const float T_l = T[below];
+  const float tau_l = tau[below], tau_r = tau[above];
+  // tau_diff gathered at `below` from tau[1:]-tau[:-1] (size S+1); the reference raises for
+  // below == S+1 (only reachable with u >= 1): we clamp instead of faulting.
+  const int bd = min(below, S);
+  const float dtau = __fsub_rn(tau[bd + 1], tau[bd]);
+  float x;
+  if (dtau < tol && dtau > -tol) {
+    x = s_l;
+  } else {
+    const float ln_term = -logf(fmaxf(eps, __fdiv_rn(__fsub_rn(1.0f, u), fmaxf(eps, T_l))));
+    const float ds = __fsub_rn(s_r, s_l);
+    float t;
+    if (dtau >= tol) {
+      const float disc = __fadd_rn(__fmul_rn(tau_l, tau_l),
+                                   __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_r, tau_l)), ln_term), fmaxf(eps, ds)));
+      t = __fdiv_rn(__fmul_rn(ds, __fadd_rn(-tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_r, tau_l)));
     } else {
-      const float ln_term = -logf(fmaxf(eps, __fdiv_rn(__fsub_rn(1.0f, u), fmaxf(eps, T_l))));
-      const float ds = __fsub_rn(s_r, s_l);
-      float t;
-      if (dtau >= tol) {
-        const float disc = __fadd_rn(__fmul_rn(tau_l, tau_l),
-                                     __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_r, tau_l)), ln_term), fmaxf(eps, ds)));
-        t = __fdiv_rn(__fmul_rn(ds, __fadd_rn(-tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_r, tau_l)));
-      } else {
-        const float disc = __fsub_rn(__fmul_rn(tau_l, tau_l),
-                                     __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_l, tau_r)), ln_term), fmaxf(eps, ds)));
-        t = __fdiv_rn(__fmul_rn(ds, __fsub_rn(tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_l, tau_r)));
-      }
-      // torch.clamp(t, min=eps, max=ds): min(max(t, eps), ds) -- max wins, NaN propagates
-      if (t == t) t = fminf(fmaxf(t, eps), ds);
-      x = __fadd_rn(s_l, t);
-      if (x != x) x = s_l;
+      const float disc = __fsub_rn(__fmul_rn(tau_l, tau_l),
+                                   __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, __fsub_rn(tau_l, tau_r)), ln_term), fmaxf(eps, ds)));
+      t = __fdiv_rn(__fmul_rn(ds, __fsub_rn(tau_l, sqrtf(fmaxf(eps, disc)))), fmaxf(eps, __fsub_rn(tau_l, tau_r)));
     }
-    a.samples[r * (int64_t)a.Ni + k] = x;
-    if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
-    if (a.T_below) a.T_below[r * (int64_t)a.Ni + k] = T_l;
-    if (a.tau_below) a.tau_below[r * (int64_t)a.Ni + k] = tau_l;
-    if (a.bin_below) a.bin_below[r * (int64_t)a.Ni + k] = s_l;
-    if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
+    // torch.clamp(t, min=eps, max=ds): min(max(t, eps), ds) -- max wins, NaN propagates
+    if (t == t) t = fminf(fmaxf(t, eps), ds);
+    x = __fadd_rn(s_l, t);
+    if (x != x) x = s_l;
   }
+  if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+  if (a.T_below) a.T_below[r * (int64_t)a.Ni + k] = T_l;
+  if (a.tau_below) a.tau_below[r * (int64_t)a.Ni + k] = tau_l;
+  if (a.bin_below) a.bin_below[r * (int64_t)a.Ni + k] = s_l;
+  if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
+  return x;
+}
+
+__global__ void __launch_bounds__(128) k_sample_pl(SamplePLArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int nk = a.S + 2;
+  float* cdf = smem + (size_t)wib * 4 * nk;
+  float *s = cdf + nk, *T = s + nk, *tau = T + nk;
+  pl_build(a, r, lane, cdf, s, T, tau);
+  for (int k = lane; k < a.Ni; k += 32) a.samples[r * (int64_t)a.Ni + k] = pl_sample(a, r, k, cdf, s, T, tau);
 }
 
 int launch_sample_pl(const float* z, const float* w, const float* tau, const float* T, const float* rays,
@@ -403,7 +411,7 @@ int launch_sample_pl(const float* z, const float* w, const float* tau, const flo
   return PLNERF_OK;
 }
 
-// a12  sample_pdf  (run_nerf_helpers.py:241-284)
+// ---- a12  sample_pdf  (run_nerf_helpers.py:241-284)
 struct SampleConstArgs {
   const float* bins; int bins_stride; int bins_mid;   // bins_mid: bins_k = .5*(z[k+1]+z[k]) from z rows
   const float* w; int w_stride;                      // weights row stride (slice [1:-1] of a wider row)
@@ -413,14 +421,8 @@ struct SampleConstArgs {
   float* u_out;                                      // f-4 (sample_pdf_return_u, run_nerf_helpers.py:286-337): optional [n,Ni]
 };
 
-__global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  if (r >= a.n) return;
+__device__ __forceinline__ void const_build(const SampleConstArgs& a, int64_t r, int lane, float* cdf, float* bins) {
   const int nb = a.nb, nw = nb - 1;
-  float* cdf = smem + (size_t)wib * 2 * nb;
-  float* bins = cdf + nb;
   const float* brow = a.bins + r * (int64_t)a.bins_stride;
   for (int k = lane; k < nb; k += 32)
     bins[k] = a.bins_mid ? __fmul_rn(0.5f, __fadd_rn(brow[k + 1], brow[k])) : brow[k];
@@ -438,19 +440,31 @@ __global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
     if (i < nw) cdf[i + 1] = (float)incl;
   }
   __syncwarp();
-  for (int k = lane; k < a.Ni; k += 32) {
-    const float u = a.u ? a.u[r * (int64_t)a.Ni + k]
-                        : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
-    const int ind = upper_bound_torch(cdf, nb, u);
-    const int below = max(0, ind - 1);
-    const int above = min(nb - 1, ind);
-    float denom = __fsub_rn(cdf[above], cdf[below]);
-    if (denom < 1e-5f) denom = 1.0f;
-    const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
-    a.samples[r * (int64_t)a.Ni + k] = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
-    if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
-    if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
-  }
+}
+
+__device__ __forceinline__ float const_sample(const SampleConstArgs& a, int64_t r, int k, const float* cdf, const float* bins) {
+  const int nb = a.nb;
+  const float u = a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+  const int ind = upper_bound_torch(cdf, nb, u);
+  const int below = max(0, ind - 1);
+  const int above = min(nb - 1, ind);
+  float denom = __fsub_rn(cdf[above], cdf[below]);
+  if (denom < 1e-5f) denom = 1.0f;
+  const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
+  if (a.inds) a.inds[r * (int64_t)a.Ni + k] = (int64_t)ind;
+  if (a.u_out) a.u_out[r * (int64_t)a.Ni + k] = u;
+  return __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+}
+
+__global__ void __launch_bounds__(128) k_sample_const(SampleConstArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  float* cdf = smem + (size_t)wib * 2 * a.nb;
+  float* bins = cdf + a.nb;
+  const_build(a, r, lane, cdf, bins);
+  for (int k = lane; k < a.Ni; k += 32) a.samples[r * (int64_t)a.Ni + k] = const_sample(a, r, k, cdf, bins);
 }
 
 int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
@@ -467,44 +481,26 @@ int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const 
   return PLNERF_OK;
 }
 
-// a13  clamp + sort(cat(z_vals, z_samples)) + std   (run_plnerf.py:728-734, :752)
-// Rank-sort the Ni clamped samples inside the warp, then merge the two ascending lists by binary
-// searches (coarse depths first on ties) -- the output is the sorted multiset, like torch.sort.
-struct MergeArgs {
-  const float *z, *samples, *rays; int64_t n; int stride, S, Ni; float *z_out, *z_std;
-};
+// ---- a13  clamp + sort(cat(z_vals, z_samples)) + std   (run_plnerf.py:728-734, :752)
+// Sort the Ni clamped samples inside the warp (bitonic, padded to a power of two), then merge the two ascending lists by
+// binary searches (coarse depths first on ties) -- the output is the sorted multiset, like torch.sort.
+__device__ __forceinline__ float clamp_sample(float x, float near, float far) {
+  if (x == x) x = fminf(fmaxf(x, near), far);  // torch.clamp(x, near, far); NaN propagates
+  return x;
+}
 
-__global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  if (r >= a.n) return;
-  const int S = a.S, Ni = a.Ni;
-  int np2s = 1;
-  while (np2s < Ni) np2s <<= 1;
-  float* zc = smem + (size_t)wib * (S + Ni + np2s);
-  float* xs = zc + S;
-  float* xsorted = xs + Ni;
-  const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
-  for (int k = lane; k < S; k += 32) zc[k] = a.z[r * (int64_t)S + k];
-  float sum = 0.f;
-  for (int k = lane; k < Ni; k += 32) {
-    float x = a.samples[r * (int64_t)Ni + k];
-    if (x == x) x = fminf(fmaxf(x, near), far);  // torch.clamp(x, near, far); NaN propagates
-    xs[k] = x;
-    sum += x;
-  }
-  __syncwarp();
-  if (a.z_std) {  // torch.std(z_samples, unbiased=False)
+// xs[0..Ni) clamped samples (unsorted), xsorted[0..np2) scratch, zc[0..S) ascending coarse depths (all shared memory)
+__device__ __forceinline__ void merge_ray(const float* zc, const float* xs, float* xsorted, int S, int Ni, int np2, int lane,
+                                          float* out, float* z_std_out) {
+  if (z_std_out) {  // torch.std(z_samples, unbiased=False)
+    float sum = 0.f;
+    for (int k = lane; k < Ni; k += 32) sum += xs[k];
     const float mean = __fdiv_rn(warp_sum(sum), (float)Ni);
     float v = 0.f;
     for (int k = lane; k < Ni; k += 32) { const float d = xs[k] - mean; v += d * d; }
     v = warp_sum(v);
-    if (lane == 0) a.z_std[r] = sqrtf(__fdiv_rn(v, (float)Ni));
+    if (lane == 0) *z_std_out = sqrtf(__fdiv_rn(v, (float)Ni));
   }
-  // in-warp bitonic sort of the clamped samples (padded to a power of two with keys that sort last).  The output is the sorted multiset, like torch.sort.
-  int np2 = 1;
-  while (np2 < Ni) np2 <<= 1;
   for (int k = lane; k < np2; k += 32) xsorted[k] = (k < Ni) ? xs[k] : __int_as_float(0x7fffffff);   // pad key: sorts after everything
   __syncwarp();
   auto gt = [](float p, float q) {   // total order: numbers < NaNs (like torch.sort) < pad keys
@@ -524,7 +520,6 @@ __global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
       __syncwarp();
     }
   }
-  float* out = a.z_out + r * (int64_t)(S + Ni);
   for (int i = lane; i < S; i += 32) {  // coarse i lands after every sample strictly smaller
     const float v = zc[i];
     int lo = 0, hi = Ni;
@@ -540,6 +535,28 @@ __global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
   }
 }
 
+struct MergeArgs {
+  const float *z, *samples, *rays; int64_t n; int stride, S, Ni; float *z_out, *z_std;
+};
+
+__global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int S = a.S, Ni = a.Ni;
+  int np2 = 1;
+  while (np2 < Ni) np2 <<= 1;
+  float* zc = smem + (size_t)wib * (S + Ni + np2);
+  float* xs = zc + S;
+  float* xsorted = xs + Ni;
+  const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
+  for (int k = lane; k < S; k += 32) zc[k] = a.z[r * (int64_t)S + k];
+  for (int k = lane; k < Ni; k += 32) xs[k] = clamp_sample(a.samples[r * (int64_t)Ni + k], near, far);
+  __syncwarp();
+  merge_ray(zc, xs, xsorted, S, Ni, np2, lane, a.z_out + r * (int64_t)(S + Ni), a.z_std ? a.z_std + r : nullptr);
+}
+
 int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                  int Ni, float* z_out, float* z_std, cudaStream_t st) {
   if (n == 0) return PLNERF_OK;
@@ -551,6 +568,76 @@ int launch_merge(const float* z, const float* samples, const float* rays, int64_
   if (smem > 48 * 1024) { set_error("merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
   k_merge<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_merge");
+  return PLNERF_OK;
+}
+
+// ---- fused: importance sampling + clamp + sort-merge + z_std of render_rays (run_plnerf.py:721-734, :752) in one kernel.
+// The Ni samples stay in shared memory between the inverse-CDF step and the merge (the unfused pair writes and re-reads
+// [n, Ni] floats and launches twice).  LINEAR: sample_pdf_reformulation on (z, weights, tau, T); otherwise sample_pdf on
+// bins = z_mid, weights[..., 1:-1].
+struct SampleMergeArgs {
+  SamplePLArgs pl; SampleConstArgs cs;
+  const float *z, *rays; int64_t n; int stride, S, Ni;
+  float *z_out, *z_std;
+};
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(128) k_sample_merge(const __grid_constant__ SampleMergeArgs a) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= a.n) return;
+  const int S = a.S, Ni = a.Ni, nk = S + 2;
+  int np2 = 1;
+  while (np2 < Ni) np2 <<= 1;
+  const int per_warp = 4 * nk + S + Ni + np2;
+  float* cdf = smem + (size_t)wib * per_warp;
+  float *s = cdf + nk, *T = s + nk, *tau = T + nk;     // constant mode: s = bins (nb = S - 1), T / tau unused
+  float* zc = tau + nk;
+  float* xs = zc + S;
+  float* xsorted = xs + Ni;
+  const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
+  for (int k = lane; k < S; k += 32) zc[k] = a.z[r * (int64_t)S + k];
+  if (LINEAR) {
+    pl_build(a.pl, r, lane, cdf, s, T, tau);
+    for (int k = lane; k < Ni; k += 32) {
+      const float x = pl_sample(a.pl, r, k, cdf, s, T, tau);
+      if (a.pl.samples) a.pl.samples[r * (int64_t)Ni + k] = x;
+      xs[k] = clamp_sample(x, near, far);
+    }
+  } else {
+    const_build(a.cs, r, lane, cdf, s);
+    for (int k = lane; k < Ni; k += 32) {
+      const float x = const_sample(a.cs, r, k, cdf, s);
+      if (a.cs.samples) a.cs.samples[r * (int64_t)Ni + k] = x;
+      xs[k] = clamp_sample(x, near, far);
+    }
+  }
+  __syncwarp();
+  merge_ray(zc, xs, xsorted, S, Ni, np2, lane, a.z_out + r * (int64_t)(S + Ni), a.z_std ? a.z_std + r : nullptr);
+}
+
+int launch_sample_merge(int linear, const float* z, const float* w, const float* tau, const float* T, const float* rays, int64_t n,
+                        int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0, float zero_tol, float eps,
+                        float* z_out, float* z_std, int64_t* inds, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  SampleMergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.pl = SamplePLArgs{z, w, tau, T, rays, n, stride, S, Ni, u, seed, ray0, zero_tol, eps, nullptr, inds, nullptr, nullptr, nullptr, nullptr};
+  // constant mode (run_plnerf.py:726): bins = z_mid [S-1] from the z rows, weights[..., 1:-1] (row stride S)
+  a.cs = SampleConstArgs{z, S, 1, w ? w + 1 : nullptr, S, n, S - 1, Ni, u, seed, ray0, nullptr, inds, nullptr};
+  a.z = z; a.rays = rays; a.n = n; a.stride = stride; a.S = S; a.Ni = Ni; a.z_out = z_out; a.z_std = z_std;
+  const int wpb = 4;
+  int np2 = 1;
+  while (np2 < Ni) np2 <<= 1;
+  const size_t smem = (size_t)wpb * (4 * (S + 2) + S + Ni + np2) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("sample+merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
+  if (linear) k_sample_merge<true><<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  else {
+    if (S < 3) { set_error("sample_pdf: need at least 2 bins"); return PLNERF_E_BADARG; }
+    k_sample_merge<false><<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  }
+  PLNERF_LAUNCH_CHECK("k_sample_merge");
   return PLNERF_OK;
 }
 

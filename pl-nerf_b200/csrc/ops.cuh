@@ -29,6 +29,11 @@ int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const 
                         float* samples, int64_t* inds, cudaStream_t st, float* u_out = nullptr);
 int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                  int Ni, float* z_out, float* z_std, cudaStream_t st);
+// importance sampling (linear: sample_pdf_reformulation; else sample_pdf on z_mid / weights[1:-1] of a constant-mode weight
+// row [n,S]) + clamp + sort-merge + z_std in one kernel
+int launch_sample_merge(int linear, const float* z, const float* w, const float* tau, const float* T, const float* rays, int64_t n,
+                        int stride, int S, int Ni, const float* u, uint64_t seed, uint64_t ray0, float zero_tol, float eps,
+                        float* z_out, float* z_std, int64_t* inds, cudaStream_t st);
 
 int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int c2w_ld,
                      const float* c2w_static, int c2w_static_ld, const float* rays_o, const float* rays_d,
@@ -52,7 +57,11 @@ struct FusedComposite {
 int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int multires, int multires_views,
               const float* rays, int64_t n, int stride, const float* z, int S, float* raw, int raw_stride,
               void* ws, size_t ws_bytes, cudaStream_t st, const FusedComposite* fc = nullptr, bool need_raw = true,
-              bool* fused = nullptr);
+              bool* fused = nullptr, const float* viewbias_pre = nullptr);
+// stratified depths + the per-ray view bias of both networks in one launch (returns 1 when the configuration is not covered)
+int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plnerf_net_desc* fd, const void* fpacked, int precision,
+                     int multires_views, const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
+                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st);
 // NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
                          float* out, void* ws, size_t ws_bytes, cudaStream_t st);
