@@ -475,3 +475,29 @@ def test_full_size_properties(P):
         assert torch.equal(c[k][perm], d[k]), k
     assert torch.equal(rgb2, a["rgb_map"]) and torch.equal(acc2, a["acc_map"]) and torch.equal(depth2, a["depth_map"])
     assert float((w2.sum(-1) - a["acc_map"]).abs().max()) < 1e-5      # checksum: the weights add up to the opacity
+
+
+@pytest.mark.parametrize("Ns,Ni,mode,two_nets", [(64, 128, "linear", True), (64, 128, "constant", True), (32, 64, "linear", False),
+                                                 (64, 256, "linear", True), (96, 300, "constant", True)])
+def test_fused_quadrature_paths_agree(P, Ns, Ni, mode, two_nets):
+    """render_rays runs the quadrature inside k_mlp3 when a ray's samples fit the output ring (S <= 256) and as the separate
+    kernel otherwise; `raw` reaches HBM only with retraw.  With and without retraw the maps are bit-identical, and the
+    op-level quadrature on the returned raw reproduces them bit for bit -- for both routes, both modes, one or two networks,
+    ray counts that leave partial tiles and partial CTA ranges."""
+    n = 1000
+    kw = dict(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=(4,), use_viewdirs=True)
+    net_c = make_net(kw, synth.nerf_params(1, **kw))
+    net_f = make_net(kw, synth.nerf_params(2, **kw)) if two_nets else None
+    ro, rd, K, _ = synth.lego_rays(n, seed=11)
+    vd = rd / np.linalg.norm(rd, axis=-1, keepdims=True)
+    rays = dev(np.concatenate([ro, rd, np.full((n, 1), 2, np.float32), np.full((n, 1), 6, np.float32), vd], -1).astype(np.float32))
+    common = dict(N_samples=Ns, N_importance=Ni, mode=mode, color_mode="midpoint", perturb=True, white_bkgd=True, seed=5,
+                  raw_noise_std=0.5, precision="bf16")
+    with torch.no_grad():
+        a = P.render_rays_fwd(rays, net_c, net_f, retraw=True, want_z=True, **common)
+        b = P.render_rays_fwd(rays, net_c, net_f, retraw=False, **common)
+    for k in b:
+        assert torch.equal(a[k], b[k]), k
+    assert bool(torch.isfinite(a["rgb_map"]).all()) and bool(torch.isfinite(a["depth_map"]).all())
+    z = a["z_vals"]
+    assert z.shape == (n, Ns + Ni) and bool((z[:, 1:] >= z[:, :-1]).all())
