@@ -342,8 +342,24 @@ def train_step_leg(dev, K, H, W, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0]) / iters
+    # the step's one collective in isolation: the flat 4.77 MB gradient all-reduce (device time, max over ranks)
+    ar_ms = None
+    if world > 1:
+        for _ in range(5):
+            step.bucket.allreduce_sum()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            step.bucket.allreduce_sum()
+        a1.record()
+        torch.cuda.synchronize()
+        ta = torch.tensor([a0.elapsed_time(a1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        ar_ms = float(ta[0])
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()), "scaling": "strong",
-            "rays_per_iter_global": N_rand,
+            "rays_per_iter_global": N_rand, "allreduce_ms": ar_ms, "allreduce_bytes": int(step.bucket.flat.numel() * 4),
             "config": f"plnerf_b200.train.TrainStep, global N_rand={N_rand} sharded over {world} rank(s), N_samples={Ns}, "
                       f"N_importance={Ni}: device-side pixel draws (64 iterations per batched draw) + pack_pixel_rays, direct "
                       "loss gradient, forward/backward kernels called without an autograd graph into flat gradient + "
