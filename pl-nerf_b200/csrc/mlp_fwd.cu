@@ -523,6 +523,7 @@ struct MlpArgs {
   int n_stages;
   // k_mlp3: whole units (rays) per CTA; fused quadrature (composite.cuh) of every completed ray inside the kernel
   int64_t cta_units;
+  int64_t unit_rows;       // rows per unit: S (a ray) with the fused quadrature, else one tile pair
   int fuse_comp, comp_mode;
   int skip_out;            // k_mlp3 with fuse_comp: the rows' outputs are not written to `out` (no retraw)
   CompositeArgs comp;
@@ -1725,7 +1726,8 @@ inline int dbg_env(const char* name) {
 // k_mlp3 (two tiles in flight, TMEM-resident activations, shared weight stages): the bf16 inference kernel.
 // Returns 1 when the plan does not fit it (very deep networks / not enough shared memory) so the caller falls back to
 // k_mlp_fwd -- both are sm_100a tcgen05 kernels on the same packed weights.
-int launch_mlp3(MlpArgs& a, cudaStream_t st) {
+int launch_mlp3(MlpArgs& a, cudaStream_t st, bool stash = false) {
+  if (stash && !a.plan.use_viewdirs) return 1;
   int n_stage_tile = 0;
   for (int l = 0; l < a.plan.n_layers; ++l) n_stage_tile += a.plan.L[l].n_halves * stages_of(a.plan.L[l].n_pe_ks, a.plan.L[l].n_h_ks);
   if (n_stage_tile > 48) return 1;
@@ -1740,6 +1742,7 @@ int launch_mlp3(MlpArgs& a, cudaStream_t st) {
   if (!g_cur->attrs_v3) {
     PLNERF_CUDA(cudaFuncSetAttribute(v3::k_mlp3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
     PLNERF_CUDA(cudaFuncSetAttribute(v3::k_mlp3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    PLNERF_CUDA((cudaFuncSetAttribute(v3::k_mlp3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem)));
     g_cur->attrs_v3 = true;
   }
   a.n_stages = n_slots;
@@ -1747,15 +1750,17 @@ int launch_mlp3(MlpArgs& a, cudaStream_t st) {
   a.debug_flags = dbg_env("PLNERF_DEBUG_FLAGS");
   a.n_tiles = ceil_div(a.M, TILE_M);
   // contiguous ranges of whole units (rays) per CTA; a CTA should have at least one full pair of tiles of work
-  const int64_t n_units = ceil_div(a.M, a.vb_div);
+  a.unit_rows = a.fuse_comp ? a.vb_div : 2 * TILE_M;
+  const int64_t n_units = ceil_div(a.M, a.unit_rows);
   int64_t cta_units = ceil_div(n_units, g_num_sms);
-  const int64_t min_units = ceil_div(2 * TILE_M, a.vb_div);
+  const int64_t min_units = ceil_div(2 * TILE_M, a.unit_rows);
   if (cta_units < min_units) cta_units = min_units;
   a.cta_units = cta_units;
   const unsigned grid = (unsigned)ceil_div(n_units, cta_units);
   ProfRec rec{nullptr, nullptr, a.M};
   if (g_prof_on) { rec.e0 = get_event(); rec.e1 = get_event(); cudaEventRecord(rec.e0, st); }
-  if (a.plan.use_viewdirs) v3::k_mlp3<true><<<grid, v3::THREADS3, smem_total, st>>>(a);
+  if (stash) v3::k_mlp3<true, true><<<grid, v3::THREADS3, smem_total, st>>>(a);
+  else if (a.plan.use_viewdirs) v3::k_mlp3<true><<<grid, v3::THREADS3, smem_total, st>>>(a);
   else v3::k_mlp3<false><<<grid, v3::THREADS3, smem_total, st>>>(a);
   if (g_prof_on) { cudaEventRecord(rec.e1, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
   PLNERF_LAUNCH_CHECK("k_mlp3");
@@ -1768,8 +1773,8 @@ int launch_mlp(MlpArgs& a, cudaStream_t st, int mode = -1) {
   int rc = query_device();
   if (rc) return rc;
   if (mode < 0) mode = (a.plan.precision == PLNERF_PREC_BF16X3) ? 1 : 0;
-  if (mode == 0 && a.M < ((int64_t)1 << 40) && !dbg_env("PLNERF_MLP_V1")) {
-    rc = launch_mlp3(a, st);
+  if ((mode == 0 || mode == 2) && a.M < ((int64_t)1 << 40) && !dbg_env("PLNERF_MLP_V1")) {
+    rc = launch_mlp3(a, st, mode == 2);
     if (rc <= 0) return rc;     // > 0: the plan does not fit k_mlp3, fall through to the single-tile kernel
   }
   a.fuse_comp = 0;              // only k_mlp3 composites in-kernel

@@ -176,10 +176,25 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
 // Full encoding of one row (all 3 + 6L elements, one thread): p = o + d*z, one 32-bit turn fraction per coordinate, every
 // octave an exact shift of it + SFU sin/cos (common.cuh) -> the row's 16-byte units of the tile's PE operand (bf16,
 // K-major 8x16B core-matrix panels: panel j = columns [8j, 8j+8) at j * 2048 + row * 16).
+template <bool STASH>
 __device__ __forceinline__ void pe_write_row(const MlpArgs& A, uint8_t* pe_tile, int64_t g, int row, int64_t row_end) {
   const NetPlan& P = A.plan;
   const int64_t gc = (g < row_end) ? g : (row_end - 1);
   const int n_panels = 2 * P.pe_ks;
+  // training: the encoding (and the ray's padded direction encoding) also go to the stash as weight-gradient operand
+  // tiles; tiles are globally aligned in this mode (row0 is a multiple of 256)
+  uint8_t* st_in = STASH ? A.in_stash + (g / TILE_M) * (int64_t)A.tl.in_tile_bytes : nullptr;
+  if (STASH) {
+    const float* dp = A.dirpe + (gc / A.vb_div) * 32;
+    uint8_t* tile_dir = st_in + A.tl.in_off[A.tl.idx_dir];
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      uint4 q4;
+      q4.x = ptx::pack_bf16(dp[8 * c8 + 0], dp[8 * c8 + 1]); q4.y = ptx::pack_bf16(dp[8 * c8 + 2], dp[8 * c8 + 3]);
+      q4.z = ptx::pack_bf16(dp[8 * c8 + 4], dp[8 * c8 + 5]); q4.w = ptx::pack_bf16(dp[8 * c8 + 6], dp[8 * c8 + 7]);
+      stash_store8(tile_dir, 32, row, c8, q4);
+    }
+  }
   if (A.x_emb) {
     // pre-embedded rows (NeRF.forward entry)
     const float* xr = A.x_emb + gc * (int64_t)A.x_ld;
@@ -215,19 +230,26 @@ __device__ __forceinline__ void pe_write_row(const MlpArgs& A, uint8_t* pe_tile,
       uint4 q4;
       q4.x = ptx::pack_bf16(v[0], v[1]); q4.y = ptx::pack_bf16(v[2], v[3]); q4.z = ptx::pack_bf16(v[4], v[5]); q4.w = ptx::pack_bf16(v[6], v[7]);
       *reinterpret_cast<uint4*>(pe_tile + j * 2048 + row * 16) = q4;
+      if (STASH) stash_store8(st_in + A.tl.in_off[A.tl.idx_pe], A.tl.in_width[A.tl.idx_pe], row, j, q4);
     }
   }
 }
 
 // bias + (ReLU) + bf16 pack of 32 accumulator columns -> 16 packed words
 template <bool RELU>
-__device__ __forceinline__ void cvt32(uint32_t (&r)[32], const float* bias, uint32_t* pk) {
+__device__ __forceinline__ void cvt32(uint32_t (&r)[32], const float* bias, uint32_t* pk, uint32_t* mask = nullptr) {
   float* val = reinterpret_cast<float*>(r);
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias + i);
     add2(val[i], val[i + 1], b4.x, b4.y);
     add2(val[i + 2], val[i + 3], b4.z, b4.w);
+  }
+  if (mask) {          // training: the ReLU mask of these 32 columns (bit i = value i is positive)
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+    *mask = m;
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) pk[i] = RELU ? pack_bf16_relu(val[2 * i], val[2 * i + 1]) : ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
@@ -249,7 +271,9 @@ __device__ __forceinline__ float dot32_relu(const uint32_t (&r)[32], const float
 #else
 #define PLNERF3_DBG(bit) false
 #endif
-template <bool VD>
+// STASH (training forward, VD only): every layer's bf16 activations + ReLU masks also go to the training stash (the
+// weight-gradient operand tiles k_mlp_fwd<2> writes; same values, same layout)
+template <bool VD, bool STASH = false>
 __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ MlpArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const NetPlan& P = A.plan;
@@ -289,11 +313,11 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // this CTA's contiguous range of whole units (rays of vb_div rows): rows [row0, row_end), tiled from row0
-  const int64_t n_units = (A.M + A.vb_div - 1) / A.vb_div;
+  const int64_t n_units = (A.M + A.unit_rows - 1) / A.unit_rows;     // unit = a ray (fused quadrature) or a tile pair
   const int64_t unit0 = (int64_t)blockIdx.x * A.cta_units;
   const int64_t unit1 = (unit0 + A.cta_units < n_units) ? unit0 + A.cta_units : n_units;
-  const int64_t row0 = unit0 * A.vb_div;
-  const int64_t row_end = (unit1 * A.vb_div < A.M) ? unit1 * A.vb_div : A.M;
+  const int64_t row0 = unit0 * A.unit_rows;
+  const int64_t row_end = (unit1 * A.unit_rows < A.M) ? unit1 * A.unit_rows : A.M;
   const int n_pairs = (row_end > row0) ? (int)((row_end - row0 + 2 * TILE_M - 1) / (2 * TILE_M)) : 0;
   // flow control of the output ring (plain counters: the parties may run several pairs apart, which mbarrier parities
   // cannot express): tiles_done[t] += 1 per final-row warp and pair (4 per pair), comp_done += 1 per helper warp and pair
@@ -371,7 +395,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       const int64_t g0 = row0 + (2 * (int64_t)pair + t) * TILE_M;
 #pragma unroll 1
       for (int rr = hid; rr < TILE_M; rr += 32 * N_HELP_WARPS)
-        if (!PLNERF3_DBG(4)) pe_write_row(A, smem + Smem3<VD>::pe0 + t * PE_TILE_BYTES, g0 + rr, rr, row_end);
+        if (!PLNERF3_DBG(4)) pe_write_row<STASH>(A, smem + Smem3<VD>::pe0 + t * PE_TILE_BYTES, g0 + rr, rr, row_end);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pe_ready0 + 8u * t);
@@ -479,6 +503,16 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           const bool alpha_here = VD && (P.L[l].flags & FLAG_ALPHA);
           const float* aw = consts + P.alpha_w_off + 64 * ch;
           uint32_t held[32];                         // half a (packed), kept until half b's MMAs have read A_t
+          // training stash of this layer's output: tile pointers, operand tile of width 256, mask words
+          const int64_t gtile = STASH ? g / TILE_M : 0;
+          uint8_t* st_t = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx] : nullptr;
+          uint32_t* st_m = (STASH && P.L[l].mask_idx >= 0) ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] : nullptr;
+          auto stash32 = [&](const uint32_t* pk16, uint32_t m, int h, int c2) {   // 32 columns [128 h + 64 ch + 32 c2, +32)
+            if (st_m) st_m[(4 * h + 2 * ch + c2) * 128 + row] = m;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              stash_store8(st_t, 256, row, 16 * h + 8 * ch + 4 * c2 + q4, make_uint4(pk16[4 * q4], pk16[4 * q4 + 1], pk16[4 * q4 + 2], pk16[4 * q4 + 3]));
+          };
           // half a
           PLNERF_TRACE(t * 2 + ch, tcnt, 2000 + l * 10);
           wait_d();
@@ -490,7 +524,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             ptx::tmem_ld32(tm_d + 32u * c2, r);
             ptx::tmem_ld_wait();
             if (c2 == 1) arrive_ep(reads_a ? 3 : 1);   // the accumulator is drained: half b may start (layer 0: `full` follows the store)
-            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2); else cvt32<false>(r, bias + 32 * c2, held + 16 * c2);
+            uint32_t m = 0;
+            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2, STASH ? &m : nullptr);
+            else cvt32<false>(r, bias + 32 * c2, held + 16 * c2);
+            if (STASH) stash32(held + 16 * c2, m, 0, c2);
             if (alpha_here) alpha_acc = dot32_relu(r, aw + 32 * c2, alpha_acc);
           }
           if (!reads_a) {
@@ -518,11 +555,13 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             ptx::tmem_st_wait();
             arrive_ep(1);
             PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
-            uint32_t pk[16];
-            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk); else cvt32<false>(r0, bias + 128, pk);
+            uint32_t pk[16], m = 0;
+            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, STASH ? &m : nullptr); else cvt32<false>(r0, bias + 128, pk);
             ptx::tmem_st16(tm_a + 64u, pk);
-            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk); else cvt32<false>(r1, bias + 160, pk);
+            if (STASH) stash32(pk, m, 1, 0);
+            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, STASH ? &m : nullptr); else cvt32<false>(r1, bias + 160, pk);
             ptx::tmem_st16(tm_a + 80u, pk);
+            if (STASH) stash32(pk, m, 1, 1);
             if (alpha_here) { alpha_acc = dot32_relu(r0, aw + 128, alpha_acc); alpha_acc = dot32_relu(r1, aw + 160, alpha_acc); }
           }
           ptx::tmem_st_wait();
@@ -556,9 +595,24 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
               const float4 w2 = *reinterpret_cast<const float4*>(rw + 256 + 32 * c2 + i);
               const float v0 = fmaxf(val[i] + b4.x, 0.f), v1 = fmaxf(val[i + 1] + b4.y, 0.f);
               const float v2 = fmaxf(val[i + 2] + b4.z, 0.f), v3 = fmaxf(val[i + 3] + b4.w, 0.f);
+              if (STASH) { r[i] = __float_as_uint(v0); r[i + 1] = __float_as_uint(v1); r[i + 2] = __float_as_uint(v2); r[i + 3] = __float_as_uint(v3); }
               h0 = fmaf(v0, w0.x, h0); h0 = fmaf(v1, w0.y, h0); h0 = fmaf(v2, w0.z, h0); h0 = fmaf(v3, w0.w, h0);
               h1 = fmaf(v0, w1.x, h1); h1 = fmaf(v1, w1.y, h1); h1 = fmaf(v2, w1.z, h1); h1 = fmaf(v3, w1.w, h1);
               h2 = fmaf(v0, w2.x, h2); h2 = fmaf(v1, w2.y, h2); h2 = fmaf(v2, w2.z, h2); h2 = fmaf(v3, w2.w, h2);
+            }
+            if (STASH) {
+              // the views layer's output (128 wide) and its ReLU mask
+              const int64_t gtile = g / TILE_M;
+              uint8_t* st_t = A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx];
+              uint32_t m = 0, pk[16];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+              A.masks[gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] + (2 * ch + c2) * 128 + row] = m;
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                stash_store8(st_t, 128, row, 8 * ch + 4 * c2 + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
             }
           }
           // combine the two column halves (fixed order: bitwise reproducible); the row's four outputs go to the output
@@ -639,7 +693,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           const int d = (int)(gc / A.vb_div - ray0);      // (the 64-bit divisions stay out of the views epilogue)
           vb_idx = d < 0 ? 0 : (d >= (int)VB_RAYS_SMEM ? (int)VB_RAYS_SMEM - 1 : d);
           if ((warp & 7) == 0 && lane == 0) {
-            const int64_t n_rays = n_units;
+            const int64_t n_rays = (A.M + A.vb_div - 1) / A.vb_div;
             if (ray0 < n_rays) {
               const int64_t nr = (n_rays - ray0 < (int64_t)VB_RAYS_SMEM) ? n_rays - ray0 : (int64_t)VB_RAYS_SMEM;
               ptx::mbar_arrive_expect_tx(vb_full, (uint32_t)nr * 512u);
