@@ -251,6 +251,22 @@ int plnerf_sample_pdf_return_u(const float* bins, const float* weights, int64_t 
                                const float* load_u, uint64_t seed, uint64_t ray_id_offset, float* samples,
                                float* u_out, int64_t* inds, void* stream);
 
+/* ---- f-4, differentiable form: what autograd computes through the two return_u samplers (the depth experiments,
+ * depth_supervised_exps/run_nerf_sample_based_depth.py:881-932, back-propagate through the samples).  The bracket comes from
+ * searchsorted (no gradient); each sample sends gradient to the two knots of its bracket.  u = the forward's draws (u_out or
+ * load_u).  Cotangents g_samples / g_T_below / g_tau_below / g_bin_below [n,Ni] (NULL = zero).  Outputs are WRITTEN, any may
+ * be NULL: g_z [n,S], g_near [n], g_far [n] (the knots s = [near, z, far]), g_tau [n,S+2], g_T [n,S+2]; the weights get no
+ * gradient in the piecewise-linear variant (they only enter the cdf).  Rules at kinks follow torch: max(eps, x) splits
+ * ties, clamp(t, eps, ds) sends the gradient to the bound it returns, a NaN sample's gradient goes to s_left.
+ * plnerf_sample_pdf_return_u_bwd: g_bins [n,nb] and g_weights [n,nb-1] (through pdf = (w + 1e-5) / sum and its cumsum). */
+int plnerf_sample_pdf_pl_return_u_bwd(const float* z, const float* weights, const float* tau, const float* T, const float* rays,
+                                      int64_t n, int stride, int S, int Ni, const float* u, float zero_tol, float epsilon,
+                                      const float* g_samples, const float* g_T_below, const float* g_tau_below,
+                                      const float* g_bin_below, float* g_z, float* g_near, float* g_far, float* g_tau, float* g_T,
+                                      void* stream);
+int plnerf_sample_pdf_return_u_bwd(const float* bins, const float* weights, int64_t n, int nb, int Ni, const float* u,
+                                   const float* g_samples, float* g_bins, float* g_weights, void* stream);
+
 /* ---- a13: clamp + sort-merge + z_std (run_plnerf.py:728-734, :752) ----------------------------
  * z [n,S] ascending, samples [n,Ni] -> z_out [n,S+Ni] ascending; z_std [n] or NULL. */
 int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n,
@@ -296,6 +312,20 @@ int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
                            const void* fine_packed_bwd, const float* rays, int64_t n, int stride, const float* noise0,
                            const float* noise1, const plnerf_render_grads* g, const plnerf_net_grads* grads_coarse,
                            const plnerf_net_grads* grads_fine, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- f-2: the loss and optimiser steps of the training loop (run_plnerf.py:1289-1315) ------------------------------
+ * plnerf_mse_loss_grad: img_loss = img2mse(rgb, target_s), img_loss0 = img2mse(rgb0, target_s) (run_nerf_helpers.py:17,
+ * run_plnerf.py:1289-1297) and the start of loss.backward(): g_rgb = scale (rgb - t), g_rgb0 = scale (rgb0 - t) with
+ * scale = 2 / (3 B) for the mean over a global batch of B rays; the sums of squared errors are ADDED to sqerr[0] (fine) and
+ * sqerr[1] (coarse) in a fixed order (reproducible).  The target row of ray i is target[pix[i]] (the gather :1280) or
+ * target[i] when pix is NULL.  rgb0 / g_rgb0 may be NULL (N_importance == 0).
+ * plnerf_adam_step: torch.optim.Adam(betas=(beta1, beta2), eps, amsgrad=False, weight_decay=0) (:431-447, :1302-1303) on
+ * one flat fp32 segment (parameters, gradients and both moments contiguous, same length); step = the 1-based count of this
+ * update; zero_grads != 0 also clears the gradients (the next iteration's optimizer.zero_grad(), :1286). */
+int plnerf_mse_loss_grad(const float* rgb, const float* rgb0, const float* target, const int64_t* pix, int64_t n,
+                         float scale, float* g_rgb, float* g_rgb0, float* sqerr, void* stream);
+int plnerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                     double beta2, double eps, int64_t step, int zero_grads, void* stream);
 
 /* ---- measurement hooks (bench.py): time every fused-MLP launch with CUDA events on its own stream --
  * plnerf_profile_enable(1) starts recording (and clears old records); plnerf_profile_read

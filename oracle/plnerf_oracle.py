@@ -397,6 +397,111 @@ def sample_pdf_reformulation_return_u(bins, weights, tau, T, near, far, u, zero_
     return samples, g(T), g(tau), g(knots), _f(u)
 
 
+def _max_grad(c, x):
+    """d max(c, x) / dx as torch.max(tensor, tensor) routes it: 1 where x > c, 1/2 at ties, 0 below."""
+    return np.where(x > c, F32(1), np.where(x == c, F32(0.5), F32(0))).astype(F32)
+
+
+def _scatter_rows(n_cols, idx, vals):
+    out = np.zeros((idx.shape[0], n_cols), np.float64)
+    rows = np.broadcast_to(np.arange(idx.shape[0])[:, None], idx.shape)
+    np.add.at(out, (rows, idx), vals.astype(np.float64))
+    return out
+
+
+def sample_pdf_reformulation_return_u_bwd(bins, weights, tau, T, near, far, u, g_samples=None, g_T_below=None,
+                                          g_tau_below=None, g_bin_below=None, zero_threshold=1e-4, epsilon_=1e-3):
+    """What torch autograd computes through run_nerf_helpers.py:448-533 (the depth experiments back-propagate through the
+    samples, depth_supervised_exps/run_nerf_sample_based_depth.py:881-932): cotangents [N,Ni] of (samples, T_below, tau_below,
+    bin_below) -> (g_bins [N,S], g_near [N,1], g_far [N,1], g_tau [N,S+2], g_T [N,S+2]).  searchsorted has no gradient, so
+    the weights get none; per sample the chain rule of pw_linear_sample_increasing / _decreasing (:340-361) with torch's
+    rules at the kinks: max(eps, x) splits ties, clamp(t, eps, ds) sends the gradient to the bound it returns (ds when
+    ds < eps or t > ds, nothing when t < eps), a NaN sample's gradient goes to s_left (:514)."""
+    knots = np.concatenate([_f(near), _f(bins), _f(far)], -1)
+    tau, T, u = _f(tau), _f(T), _f(u)
+    nk = knots.shape[-1]
+    z = lambda g: np.zeros_like(u) if g is None else _f(g)
+    gx, gTb, gtb, gbb = z(g_samples), z(g_T_below), z(g_tau_below), z(g_bin_below)
+    _, inds = sample_pdf_reformulation(bins, weights, tau, T, near, far, u, zero_threshold, epsilon_)
+    below = np.maximum(0, inds - 1)
+    above = np.minimum(nk - 1, inds)
+    g = lambda a, i: np.take_along_axis(a, i, -1)
+    s_l, s_r, T_l, tau_l, tau_r = g(knots, below), g(knots, above), g(T, below), g(tau, below), g(tau, above)
+    dtau = g(tau[..., 1:] - tau[..., :-1], below)
+    eps, zt = F32(epsilon_), F32(zero_threshold)
+    const = (dtau < zt) & (dtau > -zt)
+    inc = dtau >= zt
+    sgn = np.where(inc, F32(1), F32(-1))
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        Tm = np.maximum(eps, T_l); c1 = (F32(1) - u) / Tm; m1 = np.maximum(eps, c1); L = -np.log(m1)
+        dsr = s_r - s_l; dsm = np.maximum(eps, dsr)
+        A = np.where(inc, tau_r - tau_l, tau_l - tau_r)
+        D = tau_l * tau_l + sgn * (F32(2) * A * L) / dsm
+        sq = np.sqrt(np.maximum(eps, D)); dt = np.maximum(eps, A)
+        num = np.where(inc, -tau_l + sq, tau_l - sq)
+        t0 = dsr * num / dt
+        t = np.minimum(np.maximum(t0, eps), dsr)
+        x = s_l + t
+        live = ~const & ~np.isnan(x)
+        to_bound = (dsr < eps) | (t0 > dsr)
+        g_dsr = np.where(to_bound, gx, F32(0))
+        g_t0 = np.where(~to_bound & (t0 >= eps), gx, F32(0))
+        g_dsr = g_dsr + g_t0 * (num / dt)
+        g_num = g_t0 * (dsr / dt)
+        g_dt = -g_t0 * (t0 / dt)
+        g_tl = np.where(inc, -g_num, g_num)
+        g_sq = np.where(inc, g_num, -g_num)
+        g_D = g_sq * (F32(0.5) / sq) * _max_grad(eps, D)
+        g_tl = g_tl + F32(2) * tau_l * g_D
+        g_A = sgn * (F32(2) * L / dsm) * g_D + _max_grad(eps, A) * g_dt
+        g_L = sgn * (F32(2) * A / dsm) * g_D
+        g_dsm = -sgn * (F32(2) * A * L) / (dsm * dsm) * g_D
+        g_tr = np.where(inc, g_A, -g_A)
+        g_tl = g_tl + np.where(inc, -g_A, g_A)
+        g_dsr = g_dsr + _max_grad(eps, dsr) * g_dsm
+        g_c1 = _max_grad(eps, c1) * (-g_L / m1)
+        g_Tl = _max_grad(eps, T_l) * (-g_c1 * (c1 / Tm))
+    zero = F32(0)
+    g_sl = gx + np.where(live, -g_dsr, zero) + gbb
+    g_sr = np.where(live, g_dsr, zero)
+    g_Tl = np.where(live, g_Tl, zero) + gTb
+    g_tl = np.where(live, g_tl, zero) + gtb
+    g_tr = np.where(live, g_tr, zero)
+    g_knots = _scatter_rows(nk, below, g_sl) + _scatter_rows(nk, above, g_sr)
+    g_tau = _scatter_rows(nk, below, g_tl) + _scatter_rows(nk, above, g_tr)
+    g_T = _scatter_rows(nk, below, g_Tl)
+    return (g_knots[:, 1:-1].astype(F32), g_knots[:, :1].astype(F32), g_knots[:, -1:].astype(F32), g_tau.astype(F32),
+            g_T.astype(F32))
+
+
+def sample_pdf_return_u_bwd(bins, weights, u, g_samples):
+    """Autograd through run_nerf_helpers.py:286-337: x = bins_b + t (bins_a - bins_b), t = (u - cdf_b) / denom (denom
+    replaced by 1 below 1e-5, :331: no gradient through it then), cdf = [0, cumsum(pdf)], pdf = (w + 1e-5) / sum(w + 1e-5)
+    -> (g_bins [N,nb], g_weights [N,nb-1])."""
+    bins, u, gx = _f(bins), _f(u), _f(g_samples)
+    wt = _f(weights) + F32(1e-5)
+    W = np.sum(wt, -1, keepdims=True, dtype=F32)
+    pdf = wt / W
+    cdf = _cumsum32(pdf)
+    cdf = np.concatenate([np.zeros_like(cdf[..., :1]), cdf], -1)
+    nb = cdf.shape[-1]
+    inds = _searchsorted_right(cdf, u)
+    below = np.maximum(0, inds - 1)
+    above = np.minimum(nb - 1, inds)
+    g = lambda a, i: np.take_along_axis(a, i, -1)
+    denom0 = g(cdf, above) - g(cdf, below)
+    small = denom0 < F32(1e-5)
+    denom = np.where(small, F32(1), denom0)
+    t = (u - g(cdf, below)) / denom
+    g_t = gx * (g(bins, above) - g(bins, below))
+    g_den = np.where(small, F32(0), -g_t * t / denom)
+    g_bins = _scatter_rows(nb, below, gx * (F32(1) - t)) + _scatter_rows(nb, above, gx * t)
+    g_cdf = _scatter_rows(nb, below, -g_t / denom - g_den) + _scatter_rows(nb, above, g_den)
+    g_pdf = np.cumsum(g_cdf[:, ::-1], -1)[:, ::-1][:, 1:]            # cdf[i] = sum_{j<i} pdf[j]
+    g_w = (g_pdf - np.sum(g_pdf * pdf, -1, keepdims=True)) / W
+    return g_bins.astype(F32), g_w.astype(F32)
+
+
 # --------------------------------------------------------------------------------------------
 # render_rays / render -- run_plnerf.py:95-175, 627-758
 # --------------------------------------------------------------------------------------------

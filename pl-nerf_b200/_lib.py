@@ -140,6 +140,12 @@ _SIGS = {
                                                 C.c_void_p, C.c_void_p]),
     "plnerf_sample_pdf_return_u": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plnerf_sample_pdf_pl_return_u_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plnerf_sample_pdf_return_u_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_merge_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_render_workspace_bytes": (C.c_size_t, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.c_int64]),
@@ -156,6 +162,10 @@ _SIGS = {
                                          C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                          C.c_void_p, C.c_void_p, C.POINTER(RenderGrads), C.POINTER(NetGrads),
                                          C.POINTER(NetGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plnerf_mse_loss_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plnerf_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, C.c_int64, C.c_int, C.c_void_p]),
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

@@ -186,6 +186,23 @@ int plnerf_sample_pdf_return_u(const float* bins, const float* weights, int64_t 
                              (cudaStream_t)stream, u_out);
 }
 
+int plnerf_sample_pdf_pl_return_u_bwd(const float* z, const float* weights, const float* tau, const float* T, const float* rays,
+                                      int64_t n, int stride, int S, int Ni, const float* u, float zero_tol, float epsilon,
+                                      const float* g_samples, const float* g_T_below, const float* g_tau_below,
+                                      const float* g_bin_below, float* g_z, float* g_near, float* g_far, float* g_tau, float* g_T,
+                                      void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && weights && tau && T && rays && u)), "sample_pdf_pl_return_u_bwd: null argument");
+  PLNERF_CHECK_ARG(stride >= 8 && S >= 1 && Ni >= 0, "sample_pdf_pl_return_u_bwd: bad sizes");
+  return launch_sample_pl_bwd(z, weights, tau, T, rays, n, stride, S, Ni, u, zero_tol, epsilon, g_samples, g_T_below, g_tau_below,
+                              g_bin_below, g_z, g_near, g_far, g_tau, g_T, (cudaStream_t)stream);
+}
+
+int plnerf_sample_pdf_return_u_bwd(const float* bins, const float* weights, int64_t n, int nb, int Ni, const float* u,
+                                   const float* g_samples, float* g_bins, float* g_weights, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (bins && weights && u && g_samples)), "sample_pdf_return_u_bwd: null argument");
+  return launch_sample_const_bwd(bins, weights, n, nb, Ni, u, g_samples, g_bins, g_weights, (cudaStream_t)stream);
+}
+
 int plnerf_merge_samples(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                          int Ni, float* z_out, float* z_std, void* stream) {
   PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (z && samples && rays && z_out)), "merge_samples: null argument");
@@ -278,7 +295,7 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
 // ---- training: forward with stash + the whole backward of a ray batch, one ABI call each --------------------------
 namespace plnerf {
 struct TrainWs {
-  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw;
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw, *vb_f, *dirpe;
   void* mlp_ws; size_t mlp_ws_bytes;
   uint8_t *stash0, *stash1; size_t stash0_bytes, stash1_bytes;
   size_t total;
@@ -298,6 +315,8 @@ static TrainWs carve_train(const plnerf_render_cfg* c, const plnerf_net_desc* cd
   w.z1 = take((size_t)n * S1);
   w.raw1 = take((size_t)n * S1 * 4);
   w.graw = take((size_t)n * S1 * 4);
+  w.vb_f = take((size_t)n * 128);
+  w.dirpe = take((size_t)n * 32);
   w.mlp_ws = base + off;
   w.mlp_ws_bytes = mlp_workspace_bytes(cd, n);
   off += up(w.mlp_ws_bytes);
@@ -345,10 +364,19 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
   TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
   const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
   const bool fine = Ni > 0;
-  rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, w.z0, st);
-  if (rc) return rc;
+  // depths + the view bias of both networks + the direction encoding in one launch where covered (as in the inference entry)
+  const bool two_nets = fine && fpacked != cpacked;
+  float* vb_c = static_cast<float*>(w.mlp_ws);
+  rc = launch_ray_setup(cdesc, cpacked, two_nets ? fdesc : nullptr, fpacked, cfg->precision, cfg->multires_views, rays, n, stride, Ns,
+                        cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, w.z0, vb_c, w.vb_f, st, w.dirpe);
+  if (rc < 0) return rc;
+  const bool have_vb = (rc == 0);
+  if (!have_vb) {
+    rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, w.z0, st);
+    if (rc) return rc;
+  }
   rc = mlp_query_train(cdesc, cpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z0, Ns, w.raw0, 4, w.stash0,
-                       w.stash0_bytes, w.mlp_ws, w.mlp_ws_bytes, st);
+                       w.stash0_bytes, w.mlp_ws, w.mlp_ws_bytes, st, have_vb ? vb_c : nullptr, have_vb ? w.dirpe : nullptr);
   if (rc) return rc;
   rc = launch_composite(w.raw0, 4, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                         noise0, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0,
@@ -362,16 +390,12 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
     return PLNERF_OK;
   }
   PLNERF_CHECK_ARG(out->rgb0 && out->disp0 && out->acc0 && out->depth0, "render_rays_fwd_train: coarse outputs are required when N_importance > 0");
-  if (cfg->mode == PLNERF_MODE_LINEAR)
-    rc = launch_sample_pl(w.z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed, cfg->ray_id_offset, cfg->zero_tol,
-                          cfg->epsilon, w.zs, out->inds, st);
-  else
-    rc = launch_sample_const(w.z0, Ns, 1, w.w0 + 1, Ns, n, Ns - 1, Ni, u, cfg->seed, cfg->ray_id_offset, w.zs, out->inds, st);
-  if (rc) return rc;
-  rc = launch_merge(w.z0, w.zs, rays, n, stride, Ns, Ni, w.z1, out->z_std, st);
+  rc = launch_sample_merge(cfg->mode == PLNERF_MODE_LINEAR, w.z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed,
+                           cfg->ray_id_offset, cfg->zero_tol, cfg->epsilon, w.z1, out->z_std, out->inds, st);
   if (rc) return rc;
   rc = mlp_query_train(fdesc, fpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z1, S1, w.raw1, 4, w.stash1,
-                       w.stash1_bytes, w.mlp_ws, w.mlp_ws_bytes, st);
+                       w.stash1_bytes, w.mlp_ws, w.mlp_ws_bytes, st, have_vb ? (two_nets ? w.vb_f : vb_c) : nullptr,
+                       have_vb ? w.dirpe : nullptr);
   if (rc) return rc;
   rc = launch_composite(w.raw1, 4, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                         noise1, noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1,
@@ -417,6 +441,20 @@ int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
     if (rc) return rc;
   }
   return PLNERF_OK;
+}
+
+int plnerf_mse_loss_grad(const float* rgb, const float* rgb0, const float* target, const int64_t* pix, int64_t n,
+                         float scale, float* g_rgb, float* g_rgb0, float* sqerr, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (rgb && target && g_rgb && sqerr)), "mse_loss_grad: null argument");
+  PLNERF_CHECK_ARG((rgb0 == nullptr) == (g_rgb0 == nullptr), "mse_loss_grad: rgb0 and g_rgb0 go together");
+  return launch_mse_loss_grad(rgb, rgb0, target, pix, n, scale, g_rgb, g_rgb0, sqerr, (cudaStream_t)stream);
+}
+
+int plnerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                     double beta2, double eps, int64_t step, int zero_grads, void* stream) {
+  PLNERF_CHECK_ARG(n >= 0 && (n == 0 || (params && grads && exp_avg && exp_avg_sq)), "adam_step: null argument");
+  PLNERF_CHECK_ARG(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "adam_step: need step >= 1 and betas in [0, 1)");
+  return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, zero_grads, (cudaStream_t)stream);
 }
 
 int plnerf_profile_enable(int on) { return profile_enable(on); }

@@ -90,7 +90,7 @@ struct TrainLayout {
   int32_t mask_words[MAX_STASH], mask_off[MAX_STASH]; // relu masks: [word][row] uint32, word offsets
   int32_t in_tile_bytes, dy_tile_bytes, mask_tile_words;
   int32_t idx_pe, idx_h0, idx_feat, idx_hv, idx_dir;  // In tensors
-  int32_t dy_h0, dy_feat, dy_views;                    // dY tensors
+  int32_t dy_h0, dy_feat, dy_views, dy_head;           // dY tensors (dy_head: the network output's gradient, 16 wide)
   int32_t mask_views;                                  // mask index of the views layer (trunk layer l -> l)
 };
 
@@ -217,6 +217,7 @@ int build_train_layout(const plnerf_net_desc* d, TrainLayout* out) {
   for (int l = 0; l < d->D; ++l) add_dy(256);
   T.dy_feat = add_dy(256);
   T.dy_views = add_dy(128);
+  T.dy_head = add_dy(16);        // [g_rgb(3), g_alpha, 0 ...]: N operand of the alpha / rgb head weight gradients
   T.n_dy = n; T.dy_tile_bytes = off;
   n = 0; off = 0;
   for (int l = 0; l < d->D; ++l) { T.mask_words[n] = 8; T.mask_off[n] = off; off += 8 * 128; ++n; }
@@ -425,6 +426,7 @@ struct RaySetupArgs {
   int views_b_off, dirw_off, icv, multires_views;
   const float* rays; int stride; int64_t n;
   float *vb_c, *vb_f;                    // [n,128] each (vb_f null: one network serves both passes)
+  float* dirpe;                          // [n,32] or null: the (zero-padded) direction encoding itself (training stash input)
   // depths
   int Ns, lindisp, perturb; const float* t_rand; uint64_t seed, ray0; float* z;
 };
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(128) k_ray_setup(const __grid_constant__ RaySe
         }
       }
       emb[rr][j] = v;
+      if (a.dirpe && r < a.n) a.dirpe[r * 32 + j] = v;
     }
     // this block's depths: VB_RAYS rays x Ns samples (k_stratified_z's arithmetic, one rounding per reference op)
     for (int e = t; e < VB_RAYS * a.Ns; e += 128) {
@@ -520,6 +523,7 @@ struct MlpArgs {
   uint32_t* masks;         // [tiles][tl.mask_tile_words] relu masks
   const float* dirpe;      // [rays][32] fp32 dir encoding (padded), MODE 2
   const float* g_raw; int g_stride;   // MODE 3: upstream gradient of the network output [rows, >=4]
+  float *d_rgb_b, *d_alpha_b;         // MODE 3: bias gradients of the two heads (column sums of g_raw), accumulated
   int n_stages;
   // k_mlp3: whole units (rays) per CTA; fused quadrature (composite.cuh) of every completed ray inside the kernel
   int64_t cta_units;
@@ -767,6 +771,28 @@ __device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, 
   *reinterpret_cast<uint4*>(tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16) = v;
 }
 
+// ReLU masks of the training stash: one 32-bit word per (row, 32 columns).  The bit order is chosen for the gradient chain,
+// which applies the mask to PACKED bf16 pairs: column 2k sits at bit 7 + k, column 2k + 1 at bit (23 + k) % 32 (k = 0..15), so
+// the AND mask of packed word k is one rotate + one byte permute (sign replication).  A bit is set iff the stored bf16
+// activation is non-zero (= relu'(x) of the reference, which is 0 at x <= 0).
+__device__ __forceinline__ uint32_t relu_mask_from_packed(const uint32_t* pk) {   // pk[16]: post-ReLU (non-negative) bf16 pairs
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t t = pk[k] + 0x7FFF7FFFu;               // bit 15 / bit 31 = (low / high half != 0); halves < 0x8000: no carry
+    const int s = (8 - k) & 31;
+    const uint32_t c = s ? ((0x80008000u >> s) | (0x80008000u << (32 - s))) : 0x80008000u;
+    m |= __funnelshift_r(t, t, s) & c;
+  }
+  return m;
+}
+__device__ __forceinline__ uint32_t relu_mask_word(uint32_t m, int k) {           // 0xFFFF per kept half of packed word k
+  const uint32_t t = __funnelshift_r(m, m, k);
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(0u), "r"(0xAA88u));   // bytes 0,1 <- sign of byte 0; bytes 2,3 <- sign of byte 2
+  return r;
+}
+
 template <int MODE>
 __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, const SmemLayout& SL, int64_t tile, int row,
                                             int grp, const float* p_pre = nullptr) {
@@ -851,11 +877,27 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
 // Input of the gradient chain: d_hv = (g_rgb . W_rgb) * relu'(views) for this thread's columns
 // -> bf16 A operand in TMEM (cols COL_A1 + n/2) and the dY_views stash tile (128 columns over the column groups).
 __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* consts, uint32_t tmem_lane_a1, int64_t tile,
-                                               int row, int grp) {
+                                               int row, int grp, float g_alpha) {
   const NetPlan& P = A.plan;
   const int64_t g = tile * TILE_M + row;
   float gr = 0.f, gg = 0.f, gb = 0.f;
   if (g < A.M) { const float* q = A.g_raw + g * (int64_t)A.g_stride; gr = q[0]; gg = q[1]; gb = q[2]; }
+  if (grp == 0) {
+    // the heads' weight gradients are k_wgrad items against this 16-column tile [g_rgb, g_alpha, 0...] (rows past the end: 0);
+    // their bias gradients are its column sums
+    uint8_t* tile_h = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_head];
+    stash_store8(tile_h, 16, row, 0, make_uint4(ptx::pack_bf16(gr, gg), ptx::pack_bf16(gb, g_alpha), 0u, 0u));
+    stash_store8(tile_h, 16, row, 1, make_uint4(0u, 0u, 0u, 0u));
+    float s0 = gr, s1 = gg, s2 = gb, s3 = g_alpha;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(A.d_rgb_b + 0, s0); atomicAdd(A.d_rgb_b + 1, s1); atomicAdd(A.d_rgb_b + 2, s2); atomicAdd(A.d_alpha_b, s3);
+    }
+  }
   const float* rw = consts + P.rgb_w_off;
   const uint32_t* mk = A.masks + tile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[A.tl.mask_views];
   uint8_t* tile_dy = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_views];
@@ -865,11 +907,9 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      float v0 = gr * rw[n0 + i] + gg * rw[128 + n0 + i] + gb * rw[256 + n0 + i];
-      float v1 = gr * rw[n0 + i + 1] + gg * rw[128 + n0 + i + 1] + gb * rw[256 + n0 + i + 1];
-      v0 = ((m >> i) & 1u) ? v0 : 0.f;
-      v1 = ((m >> (i + 1)) & 1u) ? v1 : 0.f;
-      pk[i >> 1] = ptx::pack_bf16(v0, v1);
+      const float v0 = gr * rw[n0 + i] + gg * rw[128 + n0 + i] + gb * rw[256 + n0 + i];
+      const float v1 = gr * rw[n0 + i + 1] + gg * rw[128 + n0 + i + 1] + gb * rw[256 + n0 + i + 1];
+      pk[i >> 1] = ptx::pack_bf16(v0, v1) & relu_mask_word(m, i >> 1);
     }
     ptx::tmem_st16(tmem_lane_a1 + (uint32_t)(n0 >> 1), pk);
 #pragma unroll
@@ -1197,7 +1237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       if (DGRAD) {
         // the chain's input buffer (A1) is free again: the previous tile's last layer has been drained
         g_alpha = valid ? A.g_raw[g * (int64_t)A.g_stride + 3] : 0.f;
-        dgrad_prologue(A, consts, tmem + lane_addr + COL_A1, tile, row, grp);
+        dgrad_prologue(A, consts, tmem + lane_addr + COL_A1, tile, row, grp, g_alpha);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(pe_ready);
@@ -1256,14 +1296,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) val[i] = fmaf(g_alpha, aw[i], val[i]);
               }
-              if (mask_idx >= 0) {
-                const uint32_t m = mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) val[i] = ((m >> i) & 1u) ? val[i] : 0.f;
-              }
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+              if (mask_idx >= 0) {
+                const uint32_t m = mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] &= relu_mask_word(m, i);
+              }
               ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
               uint8_t* t = dy_tile + A.tl.dy_off[stash_idx];
 #pragma unroll
@@ -1277,12 +1317,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 val[i + 2] = fmaxf(val[i + 2] + b4.z, 0.f); val[i + 3] = fmaxf(val[i + 3] + b4.w, 0.f);
               }
               if (STASH) {
-                uint32_t m = 0, pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+                uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-                mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = m;
+                mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
                 uint8_t* t = in_tile + A.tl.in_off[stash_idx];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
@@ -1334,12 +1372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                   for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
                   ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
                   if (STASH) {
-                    if (mask_idx >= 0) {
-                      uint32_t m = 0;
-#pragma unroll
-                      for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
-                      mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = m;
-                    }
+                    if (mask_idx >= 0) mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
                     uint8_t* t = in_tile + A.tl.in_off[stash_idx];
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
@@ -1474,10 +1507,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 // =============================================================================================
 constexpr int MAX_WG_ITEMS = 40;
 struct WgradItem {
-  int32_t dy_idx, dy_half, in_idx;
-  int32_t ldw, col0, ncols;
-  float* dW;   // dW[(128*dy_half + r) * ldw + col0 + c]
-  float* db;   // db[128*dy_half + r] or null
+  // M side (128 accumulator rows) = columns [128 half, +128) of the dY tensor dy_idx; N side = the In tensor in_idx.
+  // swapped (the alpha / rgb heads): M side = that column half of the In tensor, N side = the dY tensor (dy_head, 16 wide).
+  int32_t dy_idx, half, in_idx, swapped;
+  int32_t row_stride, col_stride, c_first, ncols;
+  float* dW;   // accumulator (r, c), c in [c_first, c_first + ncols) -> dW[(128 half + r) * row_stride + (c - c_first) * col_stride]
+  float* db;   // db[128 half + r] (row sums of the M side against ones) or null
 };
 struct WgradArgs {
   WgradItem items[MAX_WG_ITEMS];
@@ -1495,8 +1530,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
   const WgradItem& it = A.items[blockIdx.x / A.splits];
   const int split = blockIdx.x % A.splits;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Wd = A.tl.in_width[it.in_idx];
-  const int Wdy = A.tl.dy_width[it.dy_idx];
+  const uint8_t* m_base = it.swapped ? A.in_stash + A.tl.in_off[it.in_idx] : A.dy_stash + A.tl.dy_off[it.dy_idx];
+  const uint8_t* n_base = it.swapped ? A.dy_stash + A.tl.dy_off[it.dy_idx] : A.in_stash + A.tl.in_off[it.in_idx];
+  const int64_t m_tile_bytes = it.swapped ? A.tl.in_tile_bytes : A.tl.dy_tile_bytes;
+  const int64_t n_tile_bytes = it.swapped ? A.tl.dy_tile_bytes : A.tl.in_tile_bytes;
+  const int Wd = it.swapped ? A.tl.dy_width[it.dy_idx] : A.tl.in_width[it.in_idx];     // N extent
+  const int Wdy = it.swapped ? A.tl.in_width[it.in_idx] : A.tl.dy_width[it.dy_idx];    // width of the M-side tensor
   uint8_t* s_ones = smem + 2 * WG_STAGE_BYTES;
   const uint32_t sbase = ptx::smem_u32(smem);
   const uint32_t s_bars = sbase + 2 * WG_STAGE_BYTES + 1024;
@@ -1526,11 +1565,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
         ptx::mbar_wait(empty(st), ph ^ 1);
         const uint32_t in_bytes = (uint32_t)Wd * 256u;
         ptx::mbar_arrive_expect_tx(full(st), 32768u + in_bytes);
-        const uint8_t* dy = A.dy_stash + t * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[it.dy_idx];
+        const uint8_t* dy = m_base + t * m_tile_bytes;
         const uint32_t sdst = sbase + st * WG_STAGE_BYTES;
         for (int mh = 0; mh < 2; ++mh)
-          ptx::bulk_g2s(sdst + mh * 16384, dy + ((size_t)(mh * (Wdy >> 3) + 16 * it.dy_half)) * 1024, 16384u, full(st));
-        ptx::bulk_g2s(sdst + 32768, A.in_stash + t * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[it.in_idx], in_bytes, full(st));
+          ptx::bulk_g2s(sdst + mh * 16384, dy + ((size_t)(mh * (Wdy >> 3) + 16 * it.half)) * 1024, 16384u, full(st));
+        ptx::bulk_g2s(sdst + 32768, n_base + t * n_tile_bytes, in_bytes, full(st));
         if (++st == 2) { st = 0; ph ^= 1; }
       }
     }
@@ -1571,107 +1610,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
       const int q = warp & 3;
       const int r = q * 32 + lane;
       const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
-      float* drow = it.dW + (int64_t)(128 * it.dy_half + r) * it.ldw + it.col0;
+      float* drow = it.dW + (int64_t)(128 * it.half + r) * it.row_stride;
       for (int c0 = 0; c0 < Wd; c0 += 32) {
         uint32_t v[32];
-        ptx::tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);
+        ptx::tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);     // (columns past Wd: allocated, never written, filtered below)
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < it.ncols) atomicAdd(drow + c0 + i, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i - it.c_first;
+          if (c >= 0 && c < it.ncols) atomicAdd(drow + (int64_t)c * it.col_stride, __uint_as_float(v[i]));
+        }
       }
       if (it.db) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem + lane_addr + 256u, v);
         ptx::tmem_ld_wait();
-        atomicAdd(it.db + 128 * it.dy_half + r, __uint_as_float(v[0]));
+        atomicAdd(it.db + 128 * it.half + r, __uint_as_float(v[0]));
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem, 512);
-}
-
-// Head gradients on CUDA cores: d alpha_linear = sum_m g_alpha[m] h_{D-1}[m,:], d rgb_linear = sum_m g_rgb[m,:] (x) hv[m,:]
-struct HeadGradArgs {
-  TrainLayout tl; const uint8_t* in_stash; const float* g_raw; int g_stride; int64_t M, n_tiles;
-  int idx_hlast;
-  float *d_alpha_w, *d_alpha_b, *d_rgb_w, *d_rgb_b;
-};
-__global__ void __launch_bounds__(256) k_head_grads(const __grid_constant__ HeadGradArgs A) {
-  // The stash tiles are MN-major 8x8 core matrices: 128 contiguous bytes = 8 rows x 8 columns (16 bytes per row).
-  // Lane = (row-in-group i = lane % 8, column group jj = lane / 8): a warp reads four whole 128-byte blocks per step
-  // (fully coalesced), every thread keeps 8 column partial sums over its rows, the 8 lanes of a column group are
-  // reduced by shuffles at the end.  Warp w owns column groups 4w..4w+3: 8 warps cover h_last's 32 groups (alpha head),
-  // warps 0-3 the 16 groups of the views layer output (rgb head).
-  __shared__ __align__(16) float sg[128][4];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i = lane & 7, j8 = 4 * warp + (lane >> 3);          // row within an 8-row group, column group
-  float acc_a[8], acc_r[3][8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) { acc_a[c] = 0.f; acc_r[0][c] = 0.f; acc_r[1][c] = 0.f; acc_r[2][c] = 0.f; }
-  float acc_b = 0.f;                                             // bias sums: thread tid < 4 -> g column tid
-  auto unpack8 = [](const uint4& q, float (&v)[8]) {
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u); }
-  };
-  for (int64_t t = blockIdx.x; t < A.n_tiles; t += gridDim.x) {
-    __syncthreads();
-    for (int e = tid; e < 512; e += 256) {
-      const int m = e >> 2, c = e & 3;
-      const int64_t g = t * 128 + m;
-      sg[m][c] = (g < A.M) ? A.g_raw[g * (int64_t)A.g_stride + c] : 0.f;
-    }
-    __syncthreads();
-    const uint8_t* tile = A.in_stash + t * (int64_t)A.tl.in_tile_bytes;
-    const uint8_t* th = tile + A.tl.in_off[A.idx_hlast];         // [mh(2)][col8(32)][m8(8)][8 rows x 16 B]
-    const uint8_t* tv = tile + A.tl.in_off[A.tl.idx_hv];         // [mh(2)][col8(16)][m8(8)][8 rows x 16 B]
-#pragma unroll 4
-    for (int s8 = 0; s8 < 16; ++s8) {
-      const int mh = s8 >> 3, m8 = s8 & 7, m = mh * 64 + m8 * 8 + i;
-      const float4 g4 = *reinterpret_cast<const float4*>(&sg[m][0]);
-      float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(th + ((size_t)((mh * 32 + j8) * 8 + m8)) * 128 + i * 16), v);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc_a[c] = fmaf(g4.w, v[c], acc_a[c]);
-      if (warp < 4) {
-        unpack8(*reinterpret_cast<const uint4*>(tv + ((size_t)((mh * 16 + j8) * 8 + m8)) * 128 + i * 16), v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          acc_r[0][c] = fmaf(g4.x, v[c], acc_r[0][c]);
-          acc_r[1][c] = fmaf(g4.y, v[c], acc_r[1][c]);
-          acc_r[2][c] = fmaf(g4.z, v[c], acc_r[2][c]);
-        }
-      }
-    }
-    if (tid < 4) for (int m = 0; m < 128; ++m) acc_b += sg[m][tid];
-  }
-  // reduce over the 8 row lanes of each column group (lanes differing in bits 0-2), then one atomic per column
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      acc_a[c] += __shfl_xor_sync(0xffffffffu, acc_a[c], o);
-      acc_r[0][c] += __shfl_xor_sync(0xffffffffu, acc_r[0][c], o);
-      acc_r[1][c] += __shfl_xor_sync(0xffffffffu, acc_r[1][c], o);
-      acc_r[2][c] += __shfl_xor_sync(0xffffffffu, acc_r[2][c], o);
-    }
-  }
-  if (i == 0) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      atomicAdd(A.d_alpha_w + 8 * j8 + c, acc_a[c]);
-      if (warp < 4) {
-        atomicAdd(A.d_rgb_w + 8 * j8 + c, acc_r[0][c]);
-        atomicAdd(A.d_rgb_w + 128 + 8 * j8 + c, acc_r[1][c]);
-        atomicAdd(A.d_rgb_w + 256 + 8 * j8 + c, acc_r[2][c]);
-      }
-    }
-  }
-  if (tid < 3) atomicAdd(A.d_rgb_b + tid, acc_b);
-  if (tid == 3) atomicAdd(A.d_alpha_b, acc_b);
 }
 
 // Per-device facts and one-time kernel attributes (cudaFuncSetAttribute is per device): indexed by the current device,
@@ -1844,7 +1804,8 @@ size_t mlp_workspace_bytes(const plnerf_net_desc* d, int64_t n_rays) {
 // uses launch_stratified_z and lets mlp_query compute its own view bias.
 int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plnerf_net_desc* fd, const void* fpacked, int precision,
                      int multires_views, const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
-                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st) {
+                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st,
+                     float* dirpe) {
   if (!cd->use_viewdirs || cd->input_ch_views > 27 || stride < 11) return 1;
   if (fd && (fd->input_ch_views != cd->input_ch_views || !fd->use_viewdirs)) return 1;
   int rc = query_device();
@@ -1858,7 +1819,7 @@ int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plner
   a.tail_c = reinterpret_cast<const float*>(static_cast<const uint8_t*>(cpacked) + pc.weight_bytes);
   a.tail_f = fd ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(fpacked) + pf.weight_bytes) : a.tail_c;
   a.views_b_off = pc.views_b_off; a.dirw_off = pc.dirw_off; a.icv = cd->input_ch_views; a.multires_views = multires_views;
-  a.rays = rays; a.stride = stride; a.n = n; a.vb_c = vb_c; a.vb_f = fd ? vb_f : nullptr;
+  a.rays = rays; a.stride = stride; a.n = n; a.vb_c = vb_c; a.vb_f = fd ? vb_f : nullptr; a.dirpe = dirpe;
   a.Ns = Ns; a.lindisp = lindisp; a.perturb = perturb; a.t_rand = t_rand; a.seed = seed; a.ray0 = ray0; a.z = z;
   const int64_t blocks = ceil_div(n, VB_RAYS);
   k_ray_setup<<<(unsigned)(blocks < 8 * g_num_sms ? blocks : 8 * g_num_sms), 128, 0, st>>>(a);
@@ -1993,8 +1954,10 @@ size_t mlp_train_stash_bytes(const plnerf_net_desc* d, int64_t n_rays, int S) {
 
 int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, int multires_views, const float* rays,
                     int64_t n, int stride, const float* z, int S, float* raw, int raw_stride, void* stash,
-                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st, const float* viewbias_pre,
+                    const float* dirpe_pre) {
   PLNERF_CHECK_ARG(d && rays && z && raw && stash, "network_query_train: null argument");
+  PLNERF_CHECK_ARG((viewbias_pre == nullptr) == (dirpe_pre == nullptr), "network_query_train: view bias and direction encoding go together");
   PLNERF_CHECK_ARG(n >= 0 && S > 0 && stride >= 11, "network_query_train: bad sizes (rays need a viewdir)");
   if (n == 0) return PLNERF_OK;
   PLNERF_CHECK_ARG(((uintptr_t)stash & 1023) == 0, "network_query_train: stash must be 1024-byte aligned");
@@ -2010,8 +1973,9 @@ int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, 
                    "network_query_train: multires/multires_views do not match the network");
   a.rays = rays; a.stride = stride; a.z = z; a.S = S; a.multires = multires;
   a.vb_div = S; a.M = n * S; a.out = raw; a.out_stride = raw_stride;
-  a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = sp.dirpe;
-  return run_mlp_common(d, packed, PLNERF_PREC_BF16, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st, 2, sp.dirpe);
+  a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = dirpe_pre ? dirpe_pre : sp.dirpe;
+  return run_mlp_common(d, packed, PLNERF_PREC_BF16, a, n, multires_views, rays, stride, nullptr, 0, ws, ws_bytes, st, 2, sp.dirpe,
+                        viewbias_pre);
 }
 
 size_t mlp_packed_bwd_bytes(const plnerf_net_desc* d) {
@@ -2062,6 +2026,7 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   a.S = S; a.vb_div = S; a.M = n * S;
   a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = sp.dirpe;
   a.g_raw = g_raw; a.g_stride = g_stride;
+  a.d_rgb_b = g->rgb_b; a.d_alpha_b = g->alpha_b;
   rc = launch_mlp(a, st, 3);
   if (rc) return rc;
   // (2) weight gradients
@@ -2072,7 +2037,17 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   auto add = [&](int dy_idx, int halves, int in_idx, float* dW, int ldw, int col0, int ncols, float* db) {
     for (int h = 0; h < halves; ++h) {
       WgradItem& it = w.items[ni++];
-      it.dy_idx = dy_idx; it.dy_half = h; it.in_idx = in_idx; it.dW = dW; it.ldw = ldw; it.col0 = col0; it.ncols = ncols; it.db = db;
+      it.dy_idx = dy_idx; it.half = h; it.in_idx = in_idx; it.swapped = 0; it.dW = dW + col0; it.row_stride = ldw; it.col_stride = 1;
+      it.c_first = 0; it.ncols = ncols; it.db = db;
+    }
+  };
+  // heads (CUDA-core layers in the forward): d alpha_linear.weight[0, k] = sum_m g_alpha[m] h_{D-1}[m, k],
+  // d rgb_linear.weight[c, k] = sum_m g_rgb[m, c] hv[m, k] -- the activation tensor on the M side against the 16-wide g tile
+  auto add_head = [&](int in_idx, int halves, float* dW, int col_stride, int c_first, int ncols) {
+    for (int h = 0; h < halves; ++h) {
+      WgradItem& it = w.items[ni++];
+      it.dy_idx = a.tl.dy_head; it.half = h; it.in_idx = in_idx; it.swapped = 1; it.dW = dW; it.row_stride = 1; it.col_stride = col_stride;
+      it.c_first = c_first; it.ncols = ncols; it.db = nullptr;
     }
   };
   auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
@@ -2088,6 +2063,8 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   add(T.dy_feat, 2, T.idx_h0 + d->D - 1, g->feature_w, 256, 0, 256, g->feature_b);
   add(T.dy_views, 1, T.idx_feat, g->views_w, 256 + d->input_ch_views, 0, 256, g->views_b);
   add(T.dy_views, 1, T.idx_dir, g->views_w, 256 + d->input_ch_views, 256, d->input_ch_views, nullptr);
+  add_head(T.idx_h0 + d->D - 1, 2, g->alpha_w, 0, 3, 1);
+  add_head(T.idx_hv, 1, g->rgb_w, 128, 0, 3);
   w.n_items = ni;
   w.splits = g_num_sms / ni > 0 ? g_num_sms / ni : 1;
   if ((int64_t)w.splits > w.n_tiles) w.splits = (int)w.n_tiles;
@@ -2095,17 +2072,6 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   if (!g_cur->attrs_wgrad) { PLNERF_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); g_cur->attrs_wgrad = true; }
   k_wgrad<<<(unsigned)(ni * w.splits), WG_THREADS, wsmem, st>>>(w);
   PLNERF_LAUNCH_CHECK("k_wgrad");
-  // (3) alpha / rgb heads
-  HeadGradArgs hg;
-  hg.tl = a.tl; hg.in_stash = sp.in; hg.g_raw = g_raw; hg.g_stride = g_stride; hg.M = n * S; hg.n_tiles = w.n_tiles;
-  hg.idx_hlast = T.idx_h0 + d->D - 1;
-  hg.d_alpha_w = g->alpha_w; hg.d_alpha_b = g->alpha_b; hg.d_rgb_w = g->rgb_w; hg.d_rgb_b = g->rgb_b;
-  // blocks: the kernel is latency-shaped per tile (more blocks help) until the final atomics on the 640 shared addresses
-  // start to queue (measured on 1536 tiles: 296 blocks 127 us, 592 blocks 98 us, 1184 blocks 128 us)
-  const int64_t hmax = 4 * (int64_t)g_num_sms;
-  const unsigned hgrid = (unsigned)(hg.n_tiles < hmax ? hg.n_tiles : hmax);
-  k_head_grads<<<hgrid, 256, 0, st>>>(hg);
-  PLNERF_LAUNCH_CHECK("k_head_grads");
   return PLNERF_OK;
 }
 

@@ -245,14 +245,9 @@ __device__ __forceinline__ void cvt32(uint32_t (&r)[32], const float* bias, uint
     add2(val[i], val[i + 1], b4.x, b4.y);
     add2(val[i + 2], val[i + 3], b4.z, b4.w);
   }
-  if (mask) {          // training: the ReLU mask of these 32 columns (bit i = value i is positive)
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
-    *mask = m;
-  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) pk[i] = RELU ? pack_bf16_relu(val[2 * i], val[2 * i + 1]) : ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+  if (RELU && mask) *mask = relu_mask_from_packed(pk);     // training: the ReLU mask of these 32 columns
 }
 __device__ __forceinline__ float dot32_relu(const uint32_t (&r)[32], const float* w, float acc) {
   const float* val = reinterpret_cast<const float*>(r);
@@ -604,12 +599,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
               // the views layer's output (128 wide) and its ReLU mask
               const int64_t gtile = g / TILE_M;
               uint8_t* st_t = A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx];
-              uint32_t m = 0, pk[16];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) m |= (val[i] > 0.f ? 1u : 0u) << i;
+              uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-              A.masks[gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] + (2 * ch + c2) * 128 + row] = m;
+              A.masks[gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] + (2 * ch + c2) * 128 + row] = relu_mask_from_packed(pk);
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
                 stash_store8(st_t, 128, row, 8 * ch + 4 * c2 + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));

@@ -481,6 +481,201 @@ int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const 
   return PLNERF_OK;
 }
 
+// ---- f-4  gradients of the depth-experiment samplers (what autograd computes through
+// sample_pdf_reformulation_return_u, run_nerf_helpers.py:448-533, and sample_pdf_return_u, :286-337): the bracket comes
+// from searchsorted (no gradient); the sample is a closed-form function of the gathered knots, so each sample sends
+// gradient to the two knots of its bracket.  One warp per ray: pass 1 leaves every sample's contributions in shared memory,
+// pass 2 gives each knot to one lane, which adds its samples' contributions in sample order (deterministic, no atomics).
+// max(eps, x) routes like torch.max (ties 1/2), clamp(t, min=eps, max=ds) like torch.clamp with tensor bounds
+// (max < min or t > max: to the bound; min <= t <= max: to t), where(isnan) sends a NaN sample's gradient to s_left.
+struct SamplePLBwdArgs {
+  SamplePLArgs f;                                                    // forward inputs; f.u = the forward's u (u_out / load_u)
+  const float *g_samples, *g_T_below, *g_tau_below, *g_bin_below;   // [n,Ni] cotangents, any may be null
+  float *g_z, *g_near, *g_far, *g_tau, *g_T;                         // [n,S], [n], [n], [n,S+2], [n,S+2]: written; any may be null
+};
+__device__ __forceinline__ float max_grad_first(float c, float x) {   // d max(c, x) / dx with torch's tie rule
+  return x > c ? 1.0f : (x == c ? 0.5f : 0.0f);
+}
+__global__ void __launch_bounds__(128) k_sample_pl_bwd(const __grid_constant__ SamplePLBwdArgs a) {
+  extern __shared__ float smem[];
+  const SamplePLArgs& f = a.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= f.n) return;
+  const int S = f.S, nk = S + 2, Ni = f.Ni;
+  float* cdf = smem + (size_t)wib * (4 * nk + 7 * Ni);
+  float *s = cdf + nk, *T = s + nk, *tau = T + nk;
+  int* rb = reinterpret_cast<int*>(tau + nk);          // per sample: below, above, then 5 gradient values
+  int* ra = rb + Ni;
+  float *r_sl = reinterpret_cast<float*>(ra + Ni), *r_sr = r_sl + Ni, *r_T = r_sr + Ni, *r_tl = r_T + Ni, *r_tr = r_tl + Ni;
+  pl_build(f, r, lane, cdf, s, T, tau);
+  const float eps = f.eps, tol = f.zero_tol;
+  for (int k = lane; k < Ni; k += 32) {
+    const int64_t o = r * (int64_t)Ni + k;
+    const float u = f.u[o];
+    const int ind = upper_bound_torch(cdf, nk, u);
+    const int below = max(0, ind - 1), above = min(nk - 1, ind);
+    const float s_l = s[below], s_r = s[above], T_l = T[below], tau_l = tau[below], tau_r = tau[above];
+    const int bd = min(below, S);
+    const float dtau = __fsub_rn(tau[bd + 1], tau[bd]);
+    const float gx = a.g_samples ? a.g_samples[o] : 0.f;
+    float g_sl = gx, g_sr = 0.f, g_Tl = 0.f, g_tl = 0.f, g_tr = 0.f;
+    if (!(dtau < tol && dtau > -tol)) {
+      const bool inc = dtau >= tol;
+      const float Tm = fmaxf(eps, T_l), c1 = (1.0f - u) / Tm, m1 = fmaxf(eps, c1), L = -logf(m1);
+      const float dsr = s_r - s_l, dsm = fmaxf(eps, dsr);
+      const float A = inc ? tau_r - tau_l : tau_l - tau_r;          // the positive slope term of either branch
+      const float sgn = inc ? 1.0f : -1.0f;
+      const float D = tau_l * tau_l + sgn * (2.0f * A * L) / dsm;
+      const float sq = sqrtf(fmaxf(eps, D)), dt = fmaxf(eps, A);
+      const float num = inc ? (-tau_l + sq) : (tau_l - sq);
+      const float t0 = (dsr * num) / dt;
+      float t = t0;
+      if (t == t) t = fminf(fmaxf(t, eps), dsr);
+      const float x = s_l + t;
+      if (x == x) {
+        float g_dsr = 0.f, g_t0 = 0.f;
+        if (dsr < eps || t0 > dsr) g_dsr = gx;                     // the result is the max bound
+        else if (t0 >= eps) g_t0 = gx;                              // (t0 < eps: the constant min bound)
+        g_dsr += g_t0 * (num / dt);
+        const float g_num = g_t0 * (dsr / dt);
+        const float g_dt = -g_t0 * (t0 / dt);
+        g_tl += inc ? -g_num : g_num;
+        const float g_sq = inc ? g_num : -g_num;
+        const float g_D = g_sq * (0.5f / sq) * max_grad_first(eps, D);
+        g_tl += 2.0f * tau_l * g_D;
+        float g_A = sgn * (2.0f * L / dsm) * g_D;
+        const float g_L = sgn * (2.0f * A / dsm) * g_D;
+        const float g_dsm = -sgn * (2.0f * A * L) / (dsm * dsm) * g_D;
+        g_A += max_grad_first(eps, A) * g_dt;
+        if (inc) { g_tr += g_A; g_tl -= g_A; } else { g_tl += g_A; g_tr -= g_A; }
+        g_dsr += max_grad_first(eps, dsr) * g_dsm;
+        g_sr += g_dsr; g_sl -= g_dsr;
+        const float g_m1 = -g_L / m1;
+        const float g_c1 = max_grad_first(eps, c1) * g_m1;
+        const float g_Tm = -g_c1 * (c1 / Tm);
+        g_Tl += max_grad_first(eps, T_l) * g_Tm;
+      }
+    }
+    if (a.g_bin_below) g_sl += a.g_bin_below[o];
+    if (a.g_T_below) g_Tl += a.g_T_below[o];
+    if (a.g_tau_below) g_tl += a.g_tau_below[o];
+    rb[k] = below; ra[k] = above;
+    r_sl[k] = g_sl; r_sr[k] = g_sr; r_T[k] = g_Tl; r_tl[k] = g_tl; r_tr[k] = g_tr;
+  }
+  __syncwarp();
+  for (int j = lane; j < nk; j += 32) {
+    float gs = 0.f, gT = 0.f, gt = 0.f;
+    for (int k = 0; k < Ni; ++k) {
+      if (rb[k] == j) { gs += r_sl[k]; gT += r_T[k]; gt += r_tl[k]; }
+      if (ra[k] == j) { gs += r_sr[k]; gt += r_tr[k]; }
+    }
+    if (a.g_T) a.g_T[r * (int64_t)nk + j] = gT;
+    if (a.g_tau) a.g_tau[r * (int64_t)nk + j] = gt;
+    if (j == 0) { if (a.g_near) a.g_near[r] = gs; }
+    else if (j == S + 1) { if (a.g_far) a.g_far[r] = gs; }
+    else if (a.g_z) a.g_z[r * (int64_t)S + j - 1] = gs;
+  }
+}
+
+int launch_sample_pl_bwd(const float* z, const float* w, const float* tau, const float* T, const float* rays, int64_t n,
+                         int stride, int S, int Ni, const float* u, float zero_tol, float eps, const float* g_samples,
+                         const float* g_T_below, const float* g_tau_below, const float* g_bin_below, float* g_z, float* g_near,
+                         float* g_far, float* g_tau, float* g_T, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  SamplePLBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.f = SamplePLArgs{z, w, tau, T, rays, n, stride, S, Ni, u, 0, 0, zero_tol, eps, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  a.g_samples = g_samples; a.g_T_below = g_T_below; a.g_tau_below = g_tau_below; a.g_bin_below = g_bin_below;
+  a.g_z = g_z; a.g_near = g_near; a.g_far = g_far; a.g_tau = g_tau; a.g_T = g_T;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (4 * (S + 2) + 7 * Ni) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("sample_pdf_pl backward: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
+  k_sample_pl_bwd<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_sample_pl_bwd");
+  return PLNERF_OK;
+}
+
+// sample_pdf_return_u (:286-337): x = bins_b + t (bins_a - bins_b), t = (u - cdf_b) / denom, cdf = [0, cumsum(pdf)],
+// pdf = (w + 1e-5) / sum(w + 1e-5): gradient reaches the bins directly and the weights through the cdf.
+struct SampleConstBwdArgs {
+  SampleConstArgs f;              // forward inputs (bins_mid must be 0: explicit bins); f.u = the forward's u
+  const float* g_samples;         // [n,Ni]
+  float *g_bins, *g_w;            // [n,nb], [n,nb-1]: written; either may be null
+};
+__global__ void __launch_bounds__(128) k_sample_const_bwd(const __grid_constant__ SampleConstBwdArgs a) {
+  extern __shared__ float smem[];
+  const SampleConstArgs& f = a.f;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= f.n) return;
+  const int nb = f.nb, nw = nb - 1, Ni = f.Ni;
+  float* cdf = smem + (size_t)wib * (3 * nb + 6 * Ni);
+  float* bins = cdf + nb;
+  float* gcdf = bins + nb;                              // d L / d cdf, then (in place) d L / d pdf
+  int* rb = reinterpret_cast<int*>(gcdf + nb);
+  int* ra = rb + Ni;
+  float *r_bb = reinterpret_cast<float*>(ra + Ni), *r_ba = r_bb + Ni, *r_cb = r_ba + Ni, *r_ca = r_cb + Ni;
+  const_build(f, r, lane, cdf, bins);
+  for (int k = lane; k < Ni; k += 32) {
+    const int64_t o = r * (int64_t)Ni + k;
+    const float u = f.u[o], gx = a.g_samples[o];
+    const int ind = upper_bound_torch(cdf, nb, u);
+    const int below = max(0, ind - 1), above = min(nb - 1, ind);
+    const float denom0 = __fsub_rn(cdf[above], cdf[below]);
+    const float denom = denom0 < 1e-5f ? 1.0f : denom0;
+    const float t = (u - cdf[below]) / denom;
+    const float g_t = gx * (bins[above] - bins[below]);
+    float g_cb = -g_t / denom, g_ca = 0.f;
+    if (!(denom0 < 1e-5f)) { const float g_den = -g_t * t / denom; g_ca = g_den; g_cb -= g_den; }
+    rb[k] = below; ra[k] = above;
+    r_bb[k] = gx * (1.0f - t); r_ba[k] = gx * t; r_cb[k] = g_cb; r_ca[k] = g_ca;
+  }
+  __syncwarp();
+  for (int j = lane; j < nb; j += 32) {
+    float gb = 0.f, gc = 0.f;
+    for (int k = 0; k < Ni; ++k) {
+      if (rb[k] == j) { gb += r_bb[k]; gc += r_cb[k]; }
+      if (ra[k] == j) { gb += r_ba[k]; gc += r_ca[k]; }
+    }
+    if (a.g_bins) a.g_bins[r * (int64_t)nb + j] = gb;
+    gcdf[j] = gc;
+  }
+  __syncwarp();
+  if (!a.g_w) return;
+  // cdf[i] = sum_{j < i} pdf[j]  ->  d/d pdf[j] = sum_{i > j} gcdf[i] (suffix sums, sequential per lane chunk: nb is small);
+  // pdf = wt / W  ->  d/d w[j] = (gpdf[j] - sum_k gpdf[k] pdf[k]) / W
+  const float* wrow = f.w + r * (int64_t)f.w_stride;
+  float tot = 0.f;
+  for (int k = lane; k < nw; k += 32) tot += __fadd_rn(wrow[k], 1e-5f);
+  tot = warp_sum(tot);
+  if (lane == 0) {
+    float run = 0.f;
+    for (int j = nw - 1; j >= 0; --j) { run += gcdf[j + 1]; gcdf[j] = run; }     // gcdf[j] := d L / d pdf[j]
+  }
+  __syncwarp();
+  float dot = 0.f;
+  for (int k = lane; k < nw; k += 32) dot += gcdf[k] * (__fadd_rn(wrow[k], 1e-5f) / tot);
+  dot = warp_sum(dot);
+  for (int k = lane; k < nw; k += 32) a.g_w[r * (int64_t)nw + k] = (gcdf[k] - dot) / tot;
+}
+
+int launch_sample_const_bwd(const float* bins, const float* w, int64_t n, int nb, int Ni, const float* u, const float* g_samples,
+                            float* g_bins, float* g_w, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  if (nb < 2) { set_error("sample_pdf backward: need at least 2 bins"); return PLNERF_E_BADARG; }
+  SampleConstBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.f = SampleConstArgs{bins, nb, 0, w, nb - 1, n, nb, Ni, u, 0, 0, nullptr, nullptr, nullptr};
+  a.g_samples = g_samples; a.g_bins = g_bins; a.g_w = g_w;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (3 * nb + 6 * Ni) * sizeof(float);
+  if (smem > 48 * 1024) { set_error("sample_pdf backward: nb=%d Ni=%d too large", nb, Ni); return PLNERF_E_UNSUPPORTED; }
+  k_sample_const_bwd<<<(unsigned)ceil_div(n, wpb), wpb * 32, smem, st>>>(a);
+  PLNERF_LAUNCH_CHECK("k_sample_const_bwd");
+  return PLNERF_OK;
+}
+
 // ---- a13  clamp + sort(cat(z_vals, z_samples)) + std   (run_plnerf.py:728-734, :752)
 // Sort the Ni clamped samples inside the warp (bitonic, padded to a power of two), then merge the two ascending lists by
 // binary searches (coarse depths first on ties) -- the output is the sorted multiset, like torch.sort.
@@ -741,6 +936,107 @@ int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const
   a.near = near; a.far = far; a.out = out; a.stride = stride;
   k_pack_rays<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_pack_rays");
+  return PLNERF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f-2: the training loop's loss and optimiser steps (run_plnerf.py:1289-1315)
+// ---------------------------------------------------------------------------------------------
+// img2mse twice + the start of loss.backward() (run_plnerf.py:1289-1297, run_nerf_helpers.py:17): d = rgb - target,
+// g = scale * d (scale = 2 / (3 B) for the mean over the global batch) for the fine and the coarse map, and the two sums of
+// squares ADDED to sqerr[0:2].  One block: the reduction order is fixed (the loss is reproducible bit for bit); the target
+// row of ray i is target[pix[i]] when pixel ids are given (the gather target_s = target[select_coords], :1280).
+__global__ void __launch_bounds__(1024) k_mse_loss_grad(const float* __restrict__ rgb, const float* __restrict__ rgb0,
+                                                        const float* __restrict__ target, const int64_t* __restrict__ pix,
+                                                        int64_t n, float scale, float* __restrict__ g_rgb,
+                                                        float* __restrict__ g_rgb0, float* __restrict__ sqerr) {
+  __shared__ float red[2][32];
+  float s = 0.f, s0 = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* t = target + 3 * (pix ? pix[i] : i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float tc = t[c];
+      const float d = rgb[3 * i + c] - tc;
+      g_rgb[3 * i + c] = d * scale;
+      s = fmaf(d, d, s);
+      if (rgb0) {
+        const float d0 = rgb0[3 * i + c] - tc;
+        g_rgb0[3 * i + c] = d0 * scale;
+        s0 = fmaf(d0, d0, s0);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o); }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = s0; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? red[0][lane] : 0.f;
+    s0 = lane < nw ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s0 += __shfl_xor_sync(0xffffffffu, s0, o); }
+    if (lane == 0) { sqerr[0] += s; if (rgb0) sqerr[1] += s0; }
+  }
+}
+
+int launch_mse_loss_grad(const float* rgb, const float* rgb0, const float* target, const int64_t* pix, int64_t n, float scale,
+                         float* g_rgb, float* g_rgb0, float* sqerr, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  k_mse_loss_grad<<<1, 1024, 0, st>>>(rgb, rgb0, target, pix, n, scale, g_rgb, g_rgb0, sqerr);
+  PLNERF_LAUNCH_CHECK("k_mse_loss_grad");
+  return PLNERF_OK;
+}
+
+// torch.optim.Adam (amsgrad=False, weight_decay=0; run_plnerf.py:431-447, :1302-1303) over ONE flat fp32 segment instead of
+// 24 tensors per network: exp_avg <- lerp(exp_avg, g, 1 - beta1); exp_avg_sq <- beta2 exp_avg_sq + (1 - beta2) g^2;
+// p <- p - step_size * exp_avg / (sqrt(exp_avg_sq) / sqrt(bias_correction2) + eps).  Optionally clears the gradient (the
+// optimizer.zero_grad() of the next iteration, :1286).
+__global__ void __launch_bounds__(256) k_adam_flat(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                   float4* __restrict__ v, int64_t n4, float* __restrict__ pt,
+                                                   float* __restrict__ gt, float* __restrict__ mt, float* __restrict__ vt,
+                                                   int n_tail, float w1, float beta2, float w2, float step_size,
+                                                   float bc2_sqrt, float eps, int zero_grads) {
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    mm = mm + w1 * (gg - mm);
+    vv = beta2 * vv + w2 * gg * gg;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = g[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (zero_grads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (i - n4 < n_tail) {
+    const int k = (int)(i - n4);
+    float pp = pt[k], mm = mt[k], vv = vt[k];
+    upd(pp, gt[k], mm, vv);
+    pt[k] = pp; mt[k] = mm; vt[k] = vv;
+    if (zero_grads) gt[k] = 0.f;
+  }
+}
+
+int launch_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                     double beta2, double eps, int64_t step, int zero_grads, cudaStream_t st) {
+  if (n == 0) return PLNERF_OK;
+  // scalar terms in double, like torch's fused kernel
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+  // 16-byte vector body when the four arrays are 16-byte aligned (flat buffers are), scalar tail; otherwise all scalar
+  const bool vec = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0, tail = n - 4 * n4;
+  if (tail >= ((int64_t)1 << 31)) { set_error("adam_step: unaligned segments above 2^31 elements are not supported"); return PLNERF_E_UNSUPPORTED; }
+  const int64_t o = 4 * n4;
+  k_adam_flat<<<(unsigned)ceil_div(n4 + tail, 256), 256, 0, st>>>(
+      reinterpret_cast<float4*>(params), reinterpret_cast<float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+      reinterpret_cast<float4*>(exp_avg_sq), n4, params + o, grads + o, exp_avg + o, exp_avg_sq + o, (int)tail,
+      (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps, zero_grads);
+  PLNERF_LAUNCH_CHECK("k_adam_flat");
   return PLNERF_OK;
 }
 

@@ -27,6 +27,13 @@ int launch_sample_pl(const float* z, const float* w, const float* tau, const flo
 int launch_sample_const(const float* bins, int bins_stride, int bins_mid, const float* w, int w_stride,
                         int64_t n, int nb, int Ni, const float* u, uint64_t seed, uint64_t ray0,
                         float* samples, int64_t* inds, cudaStream_t st, float* u_out = nullptr);
+// f-4: gradients of the return_u sampler variants (the depth experiments differentiate through the samples)
+int launch_sample_pl_bwd(const float* z, const float* w, const float* tau, const float* T, const float* rays, int64_t n,
+                         int stride, int S, int Ni, const float* u, float zero_tol, float eps, const float* g_samples,
+                         const float* g_T_below, const float* g_tau_below, const float* g_bin_below, float* g_z, float* g_near,
+                         float* g_far, float* g_tau, float* g_T, cudaStream_t st);
+int launch_sample_const_bwd(const float* bins, const float* w, int64_t n, int nb, int Ni, const float* u, const float* g_samples,
+                            float* g_bins, float* g_w, cudaStream_t st);
 int launch_merge(const float* z, const float* samples, const float* rays, int64_t n, int stride, int S,
                  int Ni, float* z_out, float* z_std, cudaStream_t st);
 // importance sampling (linear: sample_pdf_reformulation; else sample_pdf on z_mid / weights[1:-1] of a constant-mode weight
@@ -40,6 +47,12 @@ int launch_pack_rays(int H, int W, float fx, float fy, float cx, float cy, const
                      const int64_t* pix, int64_t n,
                      int ndc, float ndc_cx, float ndc_cy, float ndc_near, float near, float far, int use_viewdirs,
                      float* out, int stride, cudaStream_t st);
+
+// f-2: loss gradient of the two MSE terms and the flat Adam step of the training loop
+int launch_mse_loss_grad(const float* rgb, const float* rgb0, const float* target, const int64_t* pix, int64_t n, float scale,
+                         float* g_rgb, float* g_rgb0, float* sqerr, cudaStream_t st);
+int launch_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                     double beta2, double eps, int64_t step, int zero_grads, cudaStream_t st);
 
 // ---- fused MLP (mlp_fwd.cu) ----------------------------------------------------------------
 size_t mlp_packed_bytes(const plnerf_net_desc* d, int precision);
@@ -61,14 +74,16 @@ int mlp_query(const plnerf_net_desc* d, const void* packed, int precision, int m
 // stratified depths + the per-ray view bias of both networks in one launch (returns 1 when the configuration is not covered)
 int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plnerf_net_desc* fd, const void* fpacked, int precision,
                      int multires_views, const float* rays, int64_t n, int stride, int Ns, int lindisp, int perturb,
-                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st);
+                     const float* t_rand, uint64_t seed, uint64_t ray0, float* z, float* vb_c, float* vb_f, cudaStream_t st,
+                     float* dirpe = nullptr);
 // NeRF.forward on embedded rows x [m, input_ch + input_ch_views].
 int mlp_forward_embedded(const plnerf_net_desc* d, const void* packed, int precision, const float* x, int64_t m,
                          float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t mlp_train_stash_bytes(const plnerf_net_desc* d, int64_t n_rays, int S);
 int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, int multires_views, const float* rays,
                     int64_t n, int stride, const float* z, int S, float* raw, int raw_stride, void* stash,
-                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
+                    size_t stash_bytes, void* ws, size_t ws_bytes, cudaStream_t st, const float* viewbias_pre = nullptr,
+                    const float* dirpe_pre = nullptr);
 size_t mlp_packed_bwd_bytes(const plnerf_net_desc* d);
 int mlp_pack_bwd(const plnerf_net_desc* d, const plnerf_net_params* p, void* packed, cudaStream_t st);
 int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* packed_bwd, int64_t n, int S,

@@ -67,12 +67,16 @@ class FlatGradBucket:
     """One flat fp32 buffer aliasing the .grad of every parameter of the given modules, so that the
     data-parallel reduction is a single all-reduce (never one per layer or per network)."""
 
-    def __init__(self, modules):
+    def __init__(self, modules, extra=0):
         self.params = [p for m in modules if m is not None for p in m.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        n = sum(p.numel() for p in self.params)
+        # `extra` floats behind the gradients are cleared by the same fill but stay out of the all-reduce
+        # (train.TrainStep keeps its loss accumulators there)
+        self._store = torch.zeros(n + extra, dtype=torch.float32, device=dev)
+        self.flat, self.extra = self._store[:n], self._store[n:]
         off = 0
         for p in self.params:
             n = p.numel()
@@ -80,7 +84,7 @@ class FlatGradBucket:
             off += n
 
     def zero_(self):
-        self.flat.zero_()
+        self._store.zero_()
 
     def allreduce_mean(self):
         """SUM over ranks then divide by world: the loss is a mean over the global ray batch."""

@@ -246,6 +246,36 @@ def sample_pdf_return_u(bins, weights, N_importance, load_u=None, seed=0, ray_id
     return out, u_out, inds
 
 
+def sample_pdf_pl_return_u_bwd(z_vals, weights, tau, T, rays, u, g_samples=None, g_T_below=None, g_tau_below=None,
+                               g_bin_below=None, zero_tol=1e-4, epsilon=1e-3):
+    """Backward of sample_pdf_reformulation_return_u (run_nerf_helpers.py:448-533) as autograd computes it: cotangents
+    [n, Ni] (None = zero) -> (g_z [n,S], g_near [n], g_far [n], g_tau [n,S+2], g_T [n,S+2]).  ``u`` = the forward's draws."""
+    z_vals, weights, tau, T, rays, u = (_f32(t, k) for t, k in ((z_vals, "z_vals"), (weights, "weights"), (tau, "tau"),
+                                                                 (T, "T"), (rays, "rays"), (u, "u")))
+    n, S = z_vals.shape
+    Ni = u.shape[1]
+    dev = z_vals.device
+    gs = [None if g is None else _f32(g, "cotangent") for g in (g_samples, g_T_below, g_tau_below, g_bin_below)]
+    g_z, g_near, g_far = torch.empty((n, S), device=dev), torch.empty((n,), device=dev), torch.empty((n,), device=dev)
+    g_tau, g_T = torch.empty((n, S + 2), device=dev), torch.empty((n, S + 2), device=dev)
+    L.check(L.lib().plnerf_sample_pdf_pl_return_u_bwd(_p(z_vals), _p(weights), _p(tau), _p(T), _p(rays), n, rays.shape[1], S, Ni,
+                                                       _p(u), zero_tol, epsilon, _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]),
+                                                       _p(g_z), _p(g_near), _p(g_far), _p(g_tau), _p(g_T), _stream()))
+    return g_z, g_near, g_far, g_tau, g_T
+
+
+def sample_pdf_return_u_bwd(bins, weights, u, g_samples):
+    """Backward of sample_pdf_return_u (run_nerf_helpers.py:286-337): -> (g_bins [n,nb], g_weights [n,nb-1])."""
+    bins, weights, u, g_samples = (_f32(t, k) for t, k in ((bins, "bins"), (weights, "weights"), (u, "u"),
+                                                           (g_samples, "g_samples")))
+    n, nb = bins.shape
+    assert weights.shape == (n, nb - 1) and g_samples.shape == u.shape
+    g_bins, g_w = torch.empty((n, nb), device=bins.device), torch.empty((n, nb - 1), device=bins.device)
+    L.check(L.lib().plnerf_sample_pdf_return_u_bwd(_p(bins), _p(weights), n, nb, u.shape[1], _p(u), _p(g_samples),
+                                                    _p(g_bins), _p(g_w), _stream()))
+    return g_bins, g_w
+
+
 def merge_samples(z_vals, z_samples, rays):
     """clamp + sort(cat) + std (run_plnerf.py:728-734, :752) -> (z_merged, z_std)."""
     z_vals, z_samples, rays = _f32(z_vals, "z_vals"), _f32(z_samples, "z_samples"), _f32(rays, "rays")
@@ -298,7 +328,7 @@ class PackedNet:
         nbytes = L.lib().plnerf_packed_bytes(C.byref(self.desc), prec)
         if nbytes == 0:
             L.check(-2)
-        if prec not in self.buf or self.buf[prec].numel() != nbytes:
+        if prec not in self.buf or self.buf[prec].numel() != nbytes or self.buf[prec].device != first.device:
             self.buf[prec] = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
         prm = L.NetParams()
         sd = {k: v.detach() for k, v in net.named_parameters()}
@@ -422,6 +452,39 @@ def network_query_bwd(net, g_raw, stash, n, S, grads=None):
     L.check(L.lib().plnerf_network_query_bwd(C.byref(pk.desc), _p(buf), _p(bwd), n, S, _p(g_raw), g_raw.shape[-1],
                                               C.c_void_p(stash_t.data_ptr() + off), sb, C.byref(gs), _stream()))
     return grads
+
+
+def mse_loss_grad(rgb, rgb0, target, scale, sqerr, pix=None):
+    """img2mse of the fine and the coarse map and the gradient loss.backward() starts from (run_plnerf.py:1289-1297):
+    returns (g_rgb, g_rgb0) = scale * (rgb - t), scale * (rgb0 - t) and ADDS the two sums of squared errors to
+    ``sqerr`` [2] (device tensor).  ``target`` [*, 3]: row i is the target of ray i, or row pix[i] when ``pix`` (int64 ids)
+    is given.  rgb0 may be None."""
+    rgb = _f32(rgb, "rgb")
+    target = _f32(target, "target")
+    n = rgb.shape[0]
+    g = torch.empty_like(rgb)
+    g0 = None
+    if rgb0 is not None:
+        rgb0 = _f32(rgb0, "rgb0")
+        g0 = torch.empty_like(rgb0)
+    if pix is not None and (pix.dtype != torch.int64 or not pix.is_contiguous() or not pix.is_cuda):
+        raise RuntimeError("pix: expected a contiguous int64 CUDA tensor")
+    if sqerr.dtype != torch.float32 or sqerr.numel() < 2 or not sqerr.is_cuda:
+        raise RuntimeError("sqerr: expected a float32 CUDA tensor of 2 elements")
+    L.check(L.lib().plnerf_mse_loss_grad(_p(rgb), _p(rgb0) if rgb0 is not None else None, _p(target),
+                                         _p(pix) if pix is not None else None, n, float(scale), _p(g),
+                                         _p(g0) if g0 is not None else None, _p(sqerr), _stream()))
+    return g, g0
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, zero_grads=False):
+    """One torch.optim.Adam update (amsgrad=False, weight_decay=0) of a flat fp32 segment, in place; ``step`` is the
+    1-based count of this update."""
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != params.numel():
+            raise RuntimeError(f"{name}: expected a contiguous float32 CUDA tensor of {params.numel()} elements")
+    L.check(L.lib().plnerf_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr),
+                                     float(betas[0]), float(betas[1]), float(eps), int(step), int(bool(zero_grads)), _stream()))
 
 
 def packed_of(net):

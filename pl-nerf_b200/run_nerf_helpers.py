@@ -208,19 +208,67 @@ def _load_or_draw(load_u, shape, N_samples, det, pytest, device):
     return _draw_u(shape, N_samples, det, pytest, device), (torch.initial_seed() * 0x9E3779B97F4A7C15 + _return_u_calls) & ((1 << 63) - 1)
 
 
+class _SamplePdfReturnU(torch.autograd.Function):
+    """sample_pdf_return_u with the gradient autograd gives the reference (bins directly, weights through the cdf)."""
+
+    @staticmethod
+    def forward(ctx, bins, weights, N_samples, u, seed):
+        samples, u_used, _ = ops.sample_pdf_return_u(bins, weights, N_samples, load_u=u, seed=seed)
+        ctx.save_for_backward(bins, weights, u_used)
+        ctx.mark_non_differentiable(u_used)
+        return samples, u_used
+
+    @staticmethod
+    def backward(ctx, g_samples, _g_u):
+        bins, weights, u = ctx.saved_tensors
+        g_bins, g_w = ops.sample_pdf_return_u_bwd(bins, weights, u, g_samples)
+        return g_bins, g_w, None, None, None
+
+
 def sample_pdf_return_u(bins, weights, N_samples, det=False, pytest=False, load_u=None):
-    """run_nerf_helpers.py:286-337: sample_pdf that takes a saved u (``load_u``) and returns (samples, u).
-    Forward only (the samples carry no gradient here)."""
+    """run_nerf_helpers.py:286-337: sample_pdf that takes a saved u (``load_u``) and returns (samples, u).  Differentiable
+    like the reference's (the depth experiments back-propagate through the samples): gradients reach ``bins`` and
+    ``weights`` (plnerf_sample_pdf_return_u_bwd)."""
     u, seed = _load_or_draw(load_u, [bins.shape[0], N_samples], N_samples, det, pytest, bins.device)
+    if torch.is_grad_enabled() and (bins.requires_grad or weights.requires_grad):
+        return _SamplePdfReturnU.apply(bins, weights, N_samples, u, seed)
     samples, u_used, _ = ops.sample_pdf_return_u(bins, weights, N_samples, load_u=u, seed=seed)
     return samples, u_used
 
 
+class _SamplePdfPLReturnU(torch.autograd.Function):
+    """sample_pdf_reformulation_return_u with the gradient autograd gives the reference: every sample sends gradient to the
+    two knots of its bracket (bins / near / far, tau, T); the weights only choose the bracket (searchsorted) and get none."""
+
+    @staticmethod
+    def forward(ctx, bins, weights, tau, T, near, far, N_samples, u, seed, zero_tol, eps):
+        n = bins.shape[0]
+        rays = _rays_with_bounds(near.reshape(n, 1), far.reshape(n, 1))
+        samples, T_b, tau_b, bin_b, u_used, _ = ops.sample_pdf_pl_return_u(bins, weights, tau, T, rays, N_samples, load_u=u,
+                                                                            seed=seed, zero_tol=zero_tol, epsilon=eps)
+        ctx.save_for_backward(bins, weights, tau, T, rays, u_used)
+        ctx.cfg = (zero_tol, eps, near.shape, far.shape)
+        ctx.mark_non_differentiable(u_used)
+        return samples, T_b, tau_b, bin_b, u_used
+
+    @staticmethod
+    def backward(ctx, g_samples, g_T_b, g_tau_b, g_bin_b, _g_u):
+        bins, weights, tau, T, rays, u = ctx.saved_tensors
+        zero_tol, eps, near_shape, far_shape = ctx.cfg
+        g_z, g_near, g_far, g_tau, g_T = ops.sample_pdf_pl_return_u_bwd(bins, weights, tau, T, rays, u, g_samples, g_T_b, g_tau_b,
+                                                                       g_bin_b, zero_tol=zero_tol, epsilon=eps)
+        return g_z, None, g_tau, g_T, g_near.reshape(near_shape), g_far.reshape(far_shape), None, None, None, None, None
+
+
 def sample_pdf_reformulation_return_u(bins, weights, tau, T, near, far, N_samples, det=False, pytest=False, load_u=None,
                                       quad_solution_v2=True, zero_threshold=1e-4, epsilon_=1e-3):
-    """run_nerf_helpers.py:448-533: returns (samples, T_below, tau_below, bin_below, u).  Forward only."""
+    """run_nerf_helpers.py:448-533: returns (samples, T_below, tau_below, bin_below, u).  Differentiable like the
+    reference's: gradients of all four outputs reach ``bins``, ``near``, ``far``, ``tau`` and ``T``
+    (plnerf_sample_pdf_pl_return_u_bwd)."""
     n = bins.shape[0]
     u, seed = _load_or_draw(load_u, [n, N_samples], N_samples, det, pytest, bins.device)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (bins, tau, T, near, far)):
+        return _SamplePdfPLReturnU.apply(bins, weights, tau, T, near, far, N_samples, u, seed, zero_threshold, epsilon_)
     rays = _rays_with_bounds(near.reshape(n, 1), far.reshape(n, 1))
     samples, T_b, tau_b, bin_b, u_used, _ = ops.sample_pdf_pl_return_u(bins, weights, tau, T, rays, N_samples, load_u=u, seed=seed,
                                                                         zero_tol=zero_threshold, epsilon=epsilon_)

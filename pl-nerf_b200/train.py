@@ -129,6 +129,99 @@ def alias_parameters_flat(params):
     return flat
 
 
+class FlatAdam:
+    """The reference's two ``torch.optim.Adam(params, lr, betas=(0.9, 0.999))`` (run_plnerf.py:431-447) as ONE optimiser over
+    contiguous segments of a flat parameter / gradient buffer: one ``plnerf_adam_step`` launch per parameter group (one
+    group when all segments share the learning rate) instead of a multi-tensor launch over 48 tensors.
+
+    ``segments``: [(name, n_elements, lr)] in buffer order.  ``param_groups`` is a list of {"lr", "segments"} dicts that
+    the learning-rate loop writes like the reference does (:1310-1315).  State (``exp_avg``, ``exp_avg_sq`` flat like the
+    parameters, one ``step`` count) converts to and from the per-tensor ``optimizer.state_dict()`` of the reference's
+    checkpoints with ``export_reference_state`` / ``import_reference_state``."""
+
+    def __init__(self, flat_params, flat_grads, segments, betas=(0.9, 0.999), eps=1e-8):
+        self.flat_params, self.flat_grads = flat_params, flat_grads
+        self.betas, self.eps = betas, eps
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+        self.step_count = 0
+        self.segments, off = {}, 0
+        for name, n, _ in segments:
+            self.segments[name] = (off, off + n)
+            off += n
+        if off != flat_params.numel():
+            raise ValueError("segments do not cover the flat buffer")
+        lrs = [lr for _, _, lr in segments]
+        if all(lr == lrs[0] for lr in lrs):
+            self.param_groups = [{"lr": lrs[0], "segments": [name for name, _, _ in segments]}]
+        else:
+            self.param_groups = [{"lr": lr, "segments": [name]} for name, _, lr in segments]
+
+    def _range(self, group):
+        lo = min(self.segments[k][0] for k in group["segments"])
+        hi = max(self.segments[k][1] for k in group["segments"])
+        return lo, hi
+
+    def step(self):
+        self.step_count += 1
+        for g in self.param_groups:
+            lo, hi = self._range(g)
+            ops.adam_step(self.flat_params[lo:hi], self.flat_grads[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                          g["lr"], self.step_count, self.betas, self.eps)
+
+    def zero_grad(self):
+        self.flat_grads.zero_()
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for g, src in zip(self.param_groups, sd["param_groups"]):
+            g["lr"] = src["lr"]
+
+    def export_reference_state(self, name, params):
+        """``torch.optim.Adam(params).state_dict()`` of segment ``name`` (e.g. "fine": the ``optimizer_state_dict`` entry of
+        the reference's checkpoints, run_plnerf.py:1326-1331), ``params`` = that network's parameters in order."""
+        lo, hi = self.segments[name]
+        lr = next(g["lr"] for g in self.param_groups if name in g["segments"])
+        state, off = {}, lo
+        for i, p in enumerate(params):
+            n = p.numel()
+            if self.step_count > 0:
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        if off != hi:
+            raise ValueError(f"parameters do not match segment {name!r}")
+        group = {"lr": lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def import_reference_state(self, name, params, sd):
+        """Load a reference ``optimizer.state_dict()`` (per-tensor moments) into segment ``name``.  The flat optimiser keeps
+        ONE step count: it is taken from the loaded state."""
+        lo, hi = self.segments[name]
+        off = lo
+        for i, p in enumerate(params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count = int(st["step"])
+            off += n
+        if off != hi:
+            raise ValueError(f"parameters do not match segment {name!r}")
+        for g in self.param_groups:
+            if name in g["segments"]:
+                g["lr"] = sd["param_groups"][0]["lr"]
+
+
 class TrainStep:
     """Callable optimisation step.  ``render_kwargs`` is the reference's ``render_kwargs_train`` dict
     (run_plnerf.py:475-487: network_fn, network_fine, N_samples, N_importance, perturb, white_bkgd, raw_noise_std,
@@ -155,19 +248,13 @@ class TrainStep:
         self.device = next(self.net_c.parameters()).device
         self._check_device()
         self.nets = [n for n in (self.net_f, self.net_c) if n is not None]
-        self.bucket = pdist.FlatGradBucket(self.nets)
+        self.bucket = pdist.FlatGradBucket(self.nets, extra=2)     # + the two squared-error accumulators of the loss
         self.flat_params = alias_parameters_flat(self.bucket.params)
-        # one optimizer "parameter" per network = a segment of the flat buffers (fine first, like the bucket)
-        segs, off = [], 0
-        for net, lr in zip(self.nets, [lrate, coarse_lrate] if self.net_f is not None else [coarse_lrate]):
-            n = sum(p.numel() for p in net.parameters() if p.requires_grad)
-            seg = torch.nn.Parameter(self.flat_params[off:off + n])
-            seg.grad = self.bucket.flat[off:off + n]
-            segs.append({"params": [seg], "lr": lr})
-            off += n
-        if len(segs) == 2 and lrate == coarse_lrate:        # one param group -> one fused launch over both segments
-            segs = [{"params": segs[0]["params"] + segs[1]["params"], "lr": lrate}]
-        self.optimizer = torch.optim.Adam(segs, lr=lrate, betas=(0.9, 0.999), fused=True)
+        # one optimiser segment per network (fine first, like the bucket); equal rates -> one launch over both
+        segs = [(name, sum(p.numel() for p in net.parameters() if p.requires_grad), lr)
+                for name, net, lr in zip(["fine", "coarse"] if self.net_f is not None else ["coarse"], self.nets,
+                                         [lrate, coarse_lrate] if self.net_f is not None else [coarse_lrate])]
+        self.optimizer = FlatAdam(self.flat_params, self.bucket.flat, segs, betas=(0.9, 0.999))
         # {state_dict name: view of the flat gradient buffer} per network: what the weight-gradient kernels add into
         self._grads = {net: {k: p.grad for k, p in net.named_parameters()} for net in self.nets}
         # explicit depth / sampler draws (t_rand [B, N_samples], u [B, N_importance] of the GLOBAL batch) are sliced per
@@ -193,15 +280,17 @@ class TrainStep:
         """The global pixel batch of iteration i (precrop window for the first precrop_iters iterations)."""
         return self.sampler.next(self.precrop_frac if i < self.precrop_iters else None)
 
-    def _forward_backward_direct(self, rays, target_s, scale, ray0, constant_init):
+    def _forward_backward_direct(self, rays, target_s, scale, ray0, constant_init, pix=None):
         """Forward (stash mode) and backward kernels called back to back, the weight-gradient kernels accumulating
         straight into the flat gradient buffer: no autograd graph, no per-parameter AccumulateGrad add (48 launches
         per step through ``loss.backward()``), no zero-filled placeholders for the unused map gradients.
-        Returns (sum of squared errors of rgb_map, of rgb0 | None) of these rays."""
+        ``target_s`` [n, 3] holds the rays' targets, or -- with ``pix`` (their pixel ids) -- the whole image [H*W, 3]
+        (the gather :1280 then happens inside the loss kernel).  The sums of squared errors of rgb_map / rgb0 are added
+        to ``self.bucket.extra``; returns whether a coarse term exists."""
         kw = self.render_kwargs
         Ns, Ni = int(kw["N_samples"]), int(kw.get("N_importance", 0))
         std = float(kw.get("raw_noise_std", 0.))
-        sq = sq0 = None
+        sqerr = self.bucket.extra
         with torch.no_grad():
             for c0 in range(0, rays.shape[0], self.chunk):
                 r = rays[c0:c0 + self.chunk]
@@ -218,18 +307,14 @@ class TrainStep:
                 if Ni > 0 and not cfg["perturb"] and cfg["u"] is None:      # det=True: the reference's linspace u (see render_rays)
                     cfg["u"] = torch.linspace(0., 1., steps=Ni, device=r.device).expand(n, Ni).contiguous()
                 outs, saved, stashes = AG.forward_stashed(cfg, r)
-                t = target_s[c0:c0 + n]
-                d = outs[0] - t
-                sq = (d * d).sum() if sq is None else sq + (d * d).sum()
-                g_main = (d * scale, None, None, None)
+                t, px = (target_s, pix[c0:c0 + n]) if pix is not None else (target_s[c0:c0 + n], None)
+                g, g0 = ops.mse_loss_grad(outs[0], outs[5] if Ni > 0 else None, t, scale, sqerr, pix=px)
                 if Ni > 0:
-                    d0 = outs[5] - t
-                    sq0 = (d0 * d0).sum() if sq0 is None else sq0 + (d0 * d0).sum()
-                    AG.backward_stashed(cfg, saved, stashes, g_main, (d0 * scale, None, None, None),
+                    AG.backward_stashed(cfg, saved, stashes, (g, None, None, None), (g0, None, None, None),
                                         self._grads[self.net_c], self._grads.get(self.net_f))
                 else:
-                    AG.backward_stashed(cfg, saved, stashes, None, g_main, self._grads[self.net_c], None)
-        return sq, sq0
+                    AG.backward_stashed(cfg, saved, stashes, None, (g, None, None, None), self._grads[self.net_c], None)
+        return Ni > 0
 
     def _forward_backward_autograd(self, rays, target_s, scale, ray0, constant_init):
         """The same step through render_rays' autograd.Function (used when explicit draws / the pytest hook are asked
@@ -238,16 +323,9 @@ class TrainStep:
             ret = RP.batchify_rays(rays, self.chunk, ray_id_offset=ray0, retraw=False, constant_init=constant_init,
                                    **self.render_kwargs)
         rgb, rgb0 = ret["rgb_map"], ret.get("rgb0")
-        d = rgb.detach() - target_s
-        outs, grads = [rgb], [d * scale]
-        sq, sq0 = (d * d).sum(), None
-        if rgb0 is not None:
-            d0 = rgb0.detach() - target_s
-            outs.append(rgb0)
-            grads.append(d0 * scale)
-            sq0 = (d0 * d0).sum()
-        torch.autograd.backward(outs, grads)
-        return sq, sq0
+        g, g0 = ops.mse_loss_grad(rgb.detach(), None if rgb0 is None else rgb0.detach(), target_s, scale, self.bucket.extra)
+        torch.autograd.backward([rgb] if rgb0 is None else [rgb, rgb0], [g] if rgb0 is None else [g, g0])
+        return rgb0 is not None
 
     def __call__(self, target, pose, i, global_step=None, pix=None):
         """target [H, W, 3] (or [H*W, 3]) device image, pose = c2w [3|4, 4], i = iteration number (drives precrop /
@@ -264,7 +342,7 @@ class TrainStep:
         local = pix[lo:hi]
         rays = ops.pack_pixel_rays(self.H, self.W, self.K, pose, local, ndc=self.ndc, near=self.near, far=self.far,
                                    use_viewdirs=self.use_viewdirs)
-        out = self._optimise(rays, target.reshape(-1, 3)[local], B, lo, i, global_step)
+        out = self._optimise(rays, target.reshape(-1, 3), B, lo, i, global_step, pix=local)
         out["pix"] = pix
         return out
 
@@ -280,16 +358,19 @@ class TrainStep:
                                 near=self.near, far=self.far, use_viewdirs=self.use_viewdirs)
         return self._optimise(rays, target_s[lo:hi], B, lo, i, global_step)
 
-    def _optimise(self, rays, target_s, B, lo, i, global_step):
-        """rays: this rank's packed shard [n, 8|11] of a global batch of B rays starting at global ray ``lo``."""
-        self.bucket.zero_()
+    def _optimise(self, rays, target_s, B, lo, i, global_step, pix=None):
+        """rays: this rank's packed shard [n, 8|11] of a global batch of B rays starting at global ray ``lo``; target_s:
+        their targets [n, 3], or the whole image [H*W, 3] with ``pix`` = their pixel ids."""
+        self.bucket.zero_()                                      # gradients and the two squared-error sums: one fill
         scale = 2.0 / (3.0 * B)                                  # d mean((x - t)^2) / dx over the GLOBAL batch
         if self._direct:
-            sq, sq0 = self._forward_backward_direct(rays, target_s, scale, lo, i < self.constant_init)
+            coarse = self._forward_backward_direct(rays, target_s, scale, lo, i < self.constant_init, pix=pix)
         else:
-            sq, sq0 = self._forward_backward_autograd(rays, target_s, scale, lo, i < self.constant_init)
-        img_loss = sq / (3.0 * B)
-        img_loss0 = None if sq0 is None else sq0 / (3.0 * B)
+            if pix is not None:
+                target_s = target_s[pix]
+            coarse = self._forward_backward_autograd(rays, target_s, scale, lo, i < self.constant_init)
+        losses = self.bucket.extra * (1.0 / (3.0 * B))           # img2mse of the fine / coarse map (this rank's share)
+        img_loss, img_loss0 = losses[0], (losses[1] if coarse else None)
         self.bucket.allreduce_sum()
         self.optimizer.step()
         for net in self.nets:          # the update went through the flat alias: the views' version counters did not move

@@ -161,3 +161,67 @@ def test_step_rays_equals_pixel_step():
     (loss_a, g_a), (loss_b, g_b) = res
     assert abs(loss_a - loss_b) <= 2e-5 * abs(loss_a)                      # the gates of the reference-sequence test above
     assert (g_a - g_b).norm().item() <= 5e-3 * g_a.norm().item()
+
+
+def test_mse_loss_grad_vs_torch():
+    """plnerf_mse_loss_grad against img2mse x2 + autograd (run_nerf_helpers.py:17, run_plnerf.py:1289-1297), with and
+    without the pixel gather, accumulation over two calls, coarse map optional."""
+    from plnerf_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for n in (1, 37, 1024, 5000):
+        B = 2 * n
+        rgb = torch.rand(n, 3, device="cuda", generator=gen, requires_grad=True)
+        rgb0 = torch.rand(n, 3, device="cuda", generator=gen, requires_grad=True)
+        image = torch.rand(4096, 3, device="cuda", generator=gen)
+        pix = torch.randint(0, 4096, (n,), device="cuda", generator=gen)
+        tgt = image[pix]
+        loss = ((rgb - tgt) ** 2).sum() / (3 * B) + ((rgb0 - tgt) ** 2).sum() / (3 * B)
+        loss.backward()
+        sq = torch.zeros(2, device="cuda")
+        g, g0 = ops.mse_loss_grad(rgb.detach(), rgb0.detach(), image, 2.0 / (3.0 * B), sq, pix=pix)
+        assert torch.allclose(g, rgb.grad, rtol=1e-6, atol=1e-9) and torch.allclose(g0, rgb0.grad, rtol=1e-6, atol=1e-9)
+        want = torch.stack([((rgb - tgt) ** 2).sum(), ((rgb0 - tgt) ** 2).sum()]).detach()
+        assert torch.allclose(sq, want, rtol=2e-6)
+        g2, none = ops.mse_loss_grad(rgb.detach(), None, tgt, 2.0 / (3.0 * B), sq)           # explicit targets, no coarse map
+        assert none is None and torch.equal(g2, g)
+        assert torch.allclose(sq, want * torch.tensor([2.0, 1.0], device="cuda"), rtol=2e-6)
+        sq_a, sq_b = torch.zeros(2, device="cuda"), torch.zeros(2, device="cuda")            # reproducible bit for bit
+        ops.mse_loss_grad(rgb.detach(), rgb0.detach(), image, 1.0, sq_a, pix=pix)
+        ops.mse_loss_grad(rgb.detach(), rgb0.detach(), image, 1.0, sq_b, pix=pix)
+        assert torch.equal(sq_a, sq_b)
+    with pytest.raises(RuntimeError):
+        ops.mse_loss_grad(rgb.detach().cpu(), None, tgt, 1.0, sq)
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 595844 * 2 + 3])
+def test_adam_step_vs_torch_adam(n):
+    """plnerf_adam_step against torch.optim.Adam (the reference's optimiser, run_plnerf.py:431-447) over 5 updates with a
+    changing learning rate; unaligned segments (a view starting at an odd element) take the scalar path."""
+    from plnerf_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    for misalign in (0, 1):
+        store = [torch.zeros(n + 1, device="cuda") for _ in range(4)]
+        p, g, m, v = (t[misalign:misalign + n] for t in store)
+        p.copy_(torch.randn(n, device="cuda", generator=gen))
+        ref = torch.nn.Parameter(p.clone())
+        opt = torch.optim.Adam([ref], lr=5e-4, betas=(0.9, 0.999))
+        for step in range(1, 6):
+            lr = 5e-4 * (0.1 ** (step / 7.0))
+            grad = torch.randn(n, device="cuda", generator=gen) * (10.0 ** float(step - 3))
+            g.copy_(grad)
+            ref.grad = grad.clone()
+            for group in opt.param_groups:
+                group["lr"] = lr
+            opt.step()
+            ops.adam_step(p, g, m, v, lr, step)
+            assert torch.equal(g, grad)                                    # gradients are kept unless asked otherwise
+            st = opt.state[ref]
+            assert torch.allclose(m, st["exp_avg"], rtol=1e-6, atol=1e-12)
+            assert torch.allclose(v, st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
+            assert torch.allclose(p, ref.data, rtol=0, atol=2e-7 + 2e-7 * lr)
+        ops.adam_step(p, g, m, v, 0.0, 6, zero_grads=True)
+        assert not g.any()
+    with pytest.raises(RuntimeError):
+        ops.adam_step(p.cpu(), g, m, v, 1e-3, 1)
+    with pytest.raises(RuntimeError):
+        ops.adam_step(p, g, m, v, 1e-3, 0)

@@ -98,3 +98,96 @@ def test_gpu_return_u_device_draws():
     b = HP.sample_pdf_reformulation_return_u(dev(z), dev(w), dev(tau), dev(T), dev(near), dev(far), 128, load_u=u)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+# ---- f-4, differentiable form: the gradients torch autograd computes through the unmodified reference functions
+# (tests/golden/make_golden_return_u_grad.py).  Gate: every gradient array within 1e-4 of its own largest entry (the scatter
+# sums run in a different order than autograd's index_add).
+GG = None
+
+
+def grad_golden():
+    global GG
+    if GG is None:
+        GG = load_golden("return_u_grad")
+    return GG
+
+
+def scaled_err(got, want):
+    want = np.asarray(want, np.float64)
+    return float(np.abs(np.asarray(got, np.float64).reshape(want.shape) - want).max() / max(np.abs(want).max(), 1e-6))
+
+
+@pytest.mark.parametrize("name", ["lego_linear_mid", "llff_ndc_linear"])
+@pytest.mark.parametrize("which", ["grad", "grad_samples_only"])
+def test_oracle_pl_return_u_gradients(name, which):
+    g, z, w, tau, T, near, far = pl_inputs(name)
+    R = grad_golden()
+    cot = [R[f"{name}.pl.cot.{k}"] for k in ("samples", "T_below", "tau_below", "bin_below")]
+    if which == "grad_samples_only":
+        cot = [cot[0], None, None, None]
+    got = O.sample_pdf_reformulation_return_u_bwd(z, w, tau, T, near, far, g["u"], *cot)
+    for arr, key in zip(got, ("z", "near", "far", "tau", "T")):
+        assert scaled_err(arr, R[f"{name}.pl.{which}.{key}"]) < 1e-4, key
+
+
+def test_oracle_const_return_u_gradients():
+    g = load_golden("llff_ndc_constant")
+    z, w = g["z_vals0"], g["weights0"]
+    z_mid = np.float32(0.5) * (z[..., 1:] + z[..., :-1])
+    R = grad_golden()
+    g_bins, g_w = O.sample_pdf_return_u_bwd(z_mid, w[..., 1:-1], g["u"], R["llff_ndc_constant.const.cot.samples"])
+    assert scaled_err(g_bins, R["llff_ndc_constant.const.grad.bins"]) < 1e-4
+    assert scaled_err(g_w, R["llff_ndc_constant.const.grad.weights"]) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lego_linear_mid", "llff_ndc_linear"])
+@pytest.mark.parametrize("which", ["grad", "grad_samples_only"])
+def test_gpu_pl_return_u_gradients(name, which):
+    """loss.backward() through the helper mirror (autograd.Function over plnerf_sample_pdf_pl_return_u_bwd) against the
+    reference's autograd; the weights get no gradient; a second backward gives the same bits (no atomics)."""
+    from plnerf_b200 import run_nerf_helpers as HP
+    g, z, w, tau, T, near, far = pl_inputs(name)
+    R = grad_golden()
+    leaves = [dev(a).requires_grad_(True) for a in (z, w, tau, T, near, far)]
+    runs = []
+    for _ in range(2):
+        for t in leaves:
+            t.grad = None
+        outs = HP.sample_pdf_reformulation_return_u(*leaves, g["u"].shape[1], load_u=dev(g["u"]))
+        keys = ("samples", "T_below", "tau_below", "bin_below") if which == "grad" else ("samples",)
+        loss = sum((o * dev(R[f"{name}.pl.cot.{k}"])).sum() for o, k in zip(outs, keys))
+        loss.backward()
+        runs.append([None if t.grad is None else t.grad.clone() for t in leaves])
+    zg, wg, taug, Tg, ng, fg = runs[0]
+    assert wg is None or not bool(wg.any())
+    for arr, key in ((zg, "z"), (ng, "near"), (fg, "far"), (taug, "tau"), (Tg, "T")):
+        assert scaled_err(arr.cpu().numpy(), R[f"{name}.pl.{which}.{key}"]) < 1e-4, key
+    for a, b in zip(runs[0], runs[1]):
+        assert (a is None and b is None) or torch.equal(a, b)
+    # and against the oracle restatement on the same inputs
+    want = O.sample_pdf_reformulation_return_u_bwd(z, w, tau, T, near, far, g["u"], *(
+        [R[f"{name}.pl.cot.{k}"] for k in ("samples", "T_below", "tau_below", "bin_below")] if which == "grad"
+        else [R[f"{name}.pl.cot.samples"], None, None, None]))
+    for arr, ref in zip((zg, ng, fg, taug, Tg), want):
+        assert scaled_err(arr.cpu().numpy(), ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_const_return_u_gradients():
+    from plnerf_b200 import run_nerf_helpers as HP
+    g = load_golden("llff_ndc_constant")
+    z, w = g["z_vals0"], g["weights0"]
+    z_mid = np.float32(0.5) * (z[..., 1:] + z[..., :-1])
+    R = grad_golden()
+    bins = dev(z_mid).requires_grad_(True)
+    wt = dev(np.ascontiguousarray(w[..., 1:-1])).requires_grad_(True)
+    s, u = HP.sample_pdf_return_u(bins, wt, g["u"].shape[1], load_u=dev(g["u"]))
+    assert not u.requires_grad
+    (s * dev(R["llff_ndc_constant.const.cot.samples"])).sum().backward()
+    assert scaled_err(bins.grad.cpu().numpy(), R["llff_ndc_constant.const.grad.bins"]) < 1e-4
+    assert scaled_err(wt.grad.cpu().numpy(), R["llff_ndc_constant.const.grad.weights"]) < 1e-4
+    # no gradient requested: the plain forward path, same samples
+    s2, _ = HP.sample_pdf_return_u(bins.detach(), wt.detach(), g["u"].shape[1], load_u=dev(g["u"]))
+    assert torch.equal(s2, s.detach())

@@ -200,6 +200,11 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
     monkeypatch.setattr(AG, "backward_stashed", fake_backward)
     monkeypatch.setattr(ops, "invalidate_packed", lambda net: invalidated.append(net))
 
+    # torch stand-ins for the two small kernels of the step (tests/util.py)
+    from util import fake_mse_loss_grad as fake_mse, fake_adam_step as fake_adam
+    monkeypatch.setattr(ops, "mse_loss_grad", fake_mse)
+    monkeypatch.setattr(ops, "adam_step", fake_adam)
+
     class HostOnlyStep(T.TrainStep):
         def _check_device(self):       # the stand-ins above run on the host
             pass
@@ -246,3 +251,47 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
                 assert torch.equal(a.data, b.data)
         assert len(invalidated) >= 8
     assert len(invalidated) == 3 * 4 * 2
+
+
+def test_flat_adam_state_round_trips_through_the_reference_optimizer_state(monkeypatch):
+    """FlatAdam's flat moments <-> the per-tensor ``optimizer.state_dict()`` the reference checkpoints
+    (run_plnerf.py:1326-1331 saves it, :466 restores it): export after two steps loads into a stock Adam that then takes
+    the same third step; import of the stock state reproduces the flat state."""
+    from plnerf_b200 import ops
+
+    from util import fake_adam_step as fake_adam
+    monkeypatch.setattr(ops, "adam_step", fake_adam)
+    torch.manual_seed(0)
+    fine = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    coarse = [torch.nn.Parameter(torch.randn(4, 4))]
+    params = fine + coarse
+    grads = torch.zeros(sum(p.numel() for p in params))
+    flat = T.alias_parameters_flat(params)
+    opt = T.FlatAdam(flat, grads, [("fine", 22, 5e-4), ("coarse", 16, 1e-4)])
+    assert len(opt.param_groups) == 2 and opt.param_groups[1]["lr"] == 1e-4
+    for _ in range(2):
+        grads.copy_(torch.randn_like(grads))
+        opt.step()
+    sd = opt.export_reference_state("fine", fine)
+    twins = [torch.nn.Parameter(p.detach().clone()) for p in fine]
+    stock = torch.optim.Adam(twins, lr=5e-4, betas=(0.9, 0.999))
+    stock.load_state_dict(sd)
+    grads.copy_(torch.randn_like(grads))
+    off = 0
+    for t in twins:
+        t.grad = grads[off:off + t.numel()].view_as(t).clone()
+        off += t.numel()
+    opt.step()
+    stock.step()
+    for a, b in zip(fine, twins):
+        assert torch.equal(a.data, b.data)
+    # and back: a fresh flat optimiser that imports the stock state continues identically
+    opt2 = T.FlatAdam(flat.clone(), grads, [("fine", 22, 5e-4), ("coarse", 16, 1e-4)])
+    opt2.import_reference_state("fine", fine, stock.state_dict())
+    assert opt2.step_count == 3
+    assert torch.equal(opt2.exp_avg[:22], opt.exp_avg[:22]) and torch.equal(opt2.exp_avg_sq[:22], opt.exp_avg_sq[:22])
+    rt = T.FlatAdam(flat.clone(), grads, [("fine", 22, 5e-4), ("coarse", 16, 1e-4)])
+    rt.load_state_dict(opt.state_dict())
+    assert rt.step_count == 3 and torch.equal(rt.exp_avg, opt.exp_avg)
+    with pytest.raises(ValueError):
+        opt.export_reference_state("fine", coarse)

@@ -31,3 +31,27 @@ def max_rel(a, b, floor=1e-3):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+# torch stand-ins for the two small kernels of the training step (plnerf_mse_loss_grad / plnerf_adam_step), for the host-logic
+# tests that run without a GPU: written with the ops of img2mse and of torch's single-tensor Adam, so that a TrainStep driven
+# by them stays bit-identical to the reference sequence with stock optimisers
+def fake_mse_loss_grad(rgb, rgb0, target, scale, sqerr, pix=None):
+    t = target if pix is None else target[pix]
+    d = rgb - t
+    sqerr[0] += (d * d).sum()
+    if rgb0 is None:
+        return d * scale, None
+    d0 = rgb0 - t
+    sqerr[1] += (d0 * d0).sum()
+    return d * scale, d0 * scale
+
+
+def fake_adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, zero_grads=False):
+    b1, b2 = betas
+    exp_avg.lerp_(grads, 1 - b1)
+    exp_avg_sq.mul_(b2).addcmul_(grads, grads, value=1 - b2)
+    denom = (exp_avg_sq.sqrt() / ((1 - b2 ** step) ** 0.5)).add_(eps)
+    params.addcdiv_(exp_avg, denom, value=-(lr / (1 - b1 ** step)))
+    if zero_grads:
+        grads.zero_()
