@@ -1306,6 +1306,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               }
               ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
               uint8_t* t = dy_tile + A.tl.dy_off[stash_idx];
+              if (!PLNERF_DBG(32))                 // (measurement: the gradient chain without its dY stores)
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
                 stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
@@ -1513,10 +1514,11 @@ struct WgradItem {
   int32_t row_stride, col_stride, c_first, ncols;
   float* dW;   // accumulator (r, c), c in [c_first, c_first + ncols) -> dW[(128 half + r) * row_stride + (c - c_first) * col_stride]
   float* db;   // db[128 half + r] (row sums of the M side against ones) or null
+  int32_t cta0, splits;   // this item's CTAs: [cta0, cta0 + splits), each taking every splits-th tile
 };
 struct WgradArgs {
   WgradItem items[MAX_WG_ITEMS];
-  int32_t n_items, splits;
+  int32_t n_items;
   TrainLayout tl;
   const uint8_t* in_stash;
   const uint8_t* dy_stash;
@@ -1527,8 +1529,10 @@ constexpr int WG_STAGE_BYTES = 32768 + 65536;
 
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__ WgradArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const WgradItem& it = A.items[blockIdx.x / A.splits];
-  const int split = blockIdx.x % A.splits;
+  int item = 0;
+  while (item + 1 < A.n_items && (int)blockIdx.x >= A.items[item + 1].cta0) ++item;
+  const WgradItem& it = A.items[item];
+  const int split = (int)blockIdx.x - it.cta0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* m_base = it.swapped ? A.in_stash + A.tl.in_off[it.in_idx] : A.dy_stash + A.tl.dy_off[it.dy_idx];
   const uint8_t* n_base = it.swapped ? A.dy_stash + A.tl.dy_off[it.dy_idx] : A.in_stash + A.tl.in_off[it.in_idx];
@@ -1556,12 +1560,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   int64_t my_tiles = 0;
-  for (int64_t t = split; t < A.n_tiles; t += A.splits) ++my_tiles;
+  for (int64_t t = split; t < A.n_tiles; t += it.splits) ++my_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      for (int64_t t = split; t < A.n_tiles; t += A.splits) {
+      for (int64_t t = split; t < A.n_tiles; t += it.splits) {
         ptx::mbar_wait(empty(st), ph ^ 1);
         const uint32_t in_bytes = (uint32_t)Wd * 256u;
         ptx::mbar_arrive_expect_tx(full(st), 32768u + in_bytes);
@@ -1578,7 +1582,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
     const uint32_t idesc_b = ptx::idesc_bf16_f32_mn(128, 16);
     const uint64_t ones_desc = ptx::smem_desc(ptx::smem_u32(s_ones), 128, 256);
     uint32_t st = 0, ph = 0, acc = 0;
-    for (int64_t t = split; t < A.n_tiles; t += A.splits) {
+    for (int64_t t = split; t < A.n_tiles; t += it.splits) {
       ptx::mbar_wait(full(st), ph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -2031,6 +2035,7 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   if (rc) return rc;
   // (2) weight gradients
   WgradArgs w;
+  int w_ctas = 0;
   memset(&w, 0, sizeof(w));
   w.tl = a.tl; w.in_stash = sp.in; w.dy_stash = sp.dy; w.n_tiles = ceil_div(n * S, TILE_M);
   int ni = 0;
@@ -2066,11 +2071,29 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   add_head(T.idx_h0 + d->D - 1, 2, g->alpha_w, 0, 3, 1);
   add_head(T.idx_hv, 1, g->rgb_w, 128, 0, 3);
   w.n_items = ni;
-  w.splits = g_num_sms / ni > 0 ? g_num_sms / ni : 1;
-  if ((int64_t)w.splits > w.n_tiles) w.splits = (int)w.n_tiles;
+  // CTAs per item.  A CTA's time is set by the number of tiles it walks (two-stage pipeline: ~1 us per tile whatever the
+  // tile's bytes; measured -- byte-proportional counts were 40% slower), so every layer item gets the same count; the light
+  // head items take what is left of the SMs.  At most one CTA per SM in total, never more CTAs than tiles.
+  {
+    int n_light = 0;
+    for (int i = 0; i < ni; ++i) n_light += w.items[i].swapped;
+    const int n_main = ni - n_light;
+    int s_main = (g_num_sms - n_light) / (n_main > 0 ? n_main : 1);
+    if (s_main < 1) s_main = 1;
+    int s_light = n_light ? (g_num_sms - s_main * n_main) / n_light : 1;
+    if (s_light > s_main) s_light = s_main;
+    if (s_light < 1) s_light = 1;
+    int c0 = 0;
+    for (int i = 0; i < ni; ++i) {
+      int sp = w.items[i].swapped ? s_light : s_main;
+      if ((int64_t)sp > w.n_tiles) sp = (int)w.n_tiles;
+      w.items[i].splits = sp; w.items[i].cta0 = c0; c0 += sp;
+    }
+    w_ctas = c0;
+  }
   const size_t wsmem = 2 * WG_STAGE_BYTES + 1024 + 64;
   if (!g_cur->attrs_wgrad) { PLNERF_CUDA(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); g_cur->attrs_wgrad = true; }
-  k_wgrad<<<(unsigned)(ni * w.splits), WG_THREADS, wsmem, st>>>(w);
+  k_wgrad<<<(unsigned)w_ctas, WG_THREADS, wsmem, st>>>(w);
   PLNERF_LAUNCH_CHECK("k_wgrad");
   return PLNERF_OK;
 }

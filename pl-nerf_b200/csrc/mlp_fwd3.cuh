@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           uint8_t* st_t = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx] : nullptr;
           uint32_t* st_m = (STASH && P.L[l].mask_idx >= 0) ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] : nullptr;
           auto stash32 = [&](const uint32_t* pk16, uint32_t m, int h, int c2) {   // 32 columns [128 h + 64 ch + 32 c2, +32)
+            if (PLNERF3_DBG(32)) return;        // measurement: the stash forward without its activation stores
             if (st_m) st_m[(4 * h + 2 * ch + c2) * 128 + row] = m;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)

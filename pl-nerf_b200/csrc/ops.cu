@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(128) k_sample_const_bwd(const __grid_constant_
   for (int k = lane; k < nw; k += 32) tot += __fadd_rn(wrow[k], 1e-5f);
   tot = warp_sum(tot);
   if (lane == 0) {
-    float run = 0.f;
-    for (int j = nw - 1; j >= 0; --j) { run += gcdf[j + 1]; gcdf[j] = run; }     // gcdf[j] := d L / d pdf[j]
+    float run = 0.f, above = gcdf[nw];
+    for (int j = nw - 1; j >= 0; --j) { const float own = gcdf[j]; run += above; gcdf[j] = run; above = own; }   // gcdf[j] := d L / d pdf[j]
   }
   __syncwarp();
   float dot = 0.f;

@@ -44,6 +44,10 @@ SIZED = {
     # parameter gradient of the unmodified reference (loss.backward() through its own render)
     "train_c3_1024": dict(n=1024, ray_seed=13, Ns=128, Ni=64, use_viewdirs=True, white_bkgd=True, seeds=(1, 2),
                           density_boost=True, train=True),
+    # the same loss through networks WITHOUT view directions (output_linear head, run_nerf_helpers.py:100-103, :126): the
+    # unused views_linears of such a network gets no gradient from autograd (stored as zeros)
+    "train_noviews_256": dict(n=256, ray_seed=17, Ns=64, Ni=32, use_viewdirs=False, white_bkgd=True, seeds=(1, 2),
+                              density_boost=True, train=True),
 }
 GRAD_SLICE = 2048      # leading entries of every parameter gradient stored next to its norm
 
@@ -142,7 +146,7 @@ def ref_render(H, R, cfg, ro, rd, K, hwf, pc, pf):
         out["train_loss"] = np.float64(loss.item())
         for tag, net in (("c", net_c), ("f", net_f)):
             for k_, p_ in net.named_parameters():
-                g_ = p_.grad.detach().numpy().ravel()
+                g_ = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).detach().numpy().ravel()
                 out[f"gnorm_{tag}.{k_}"] = np.float64(np.linalg.norm(g_.astype(np.float64)))
                 out[f"ghead_{tag}.{k_}"] = g_[:GRAD_SLICE].copy()
     if captured:
