@@ -183,8 +183,9 @@ int plnerf_network_query(const plnerf_net_desc* desc, const void* packed, int pr
  * bf16 activations + ReLU masks (stash: plnerf_train_stash_bytes(desc, n, S) bytes, 1 KiB aligned).
  * plnerf_network_query_bwd consumes that stash and g_raw = dL/draw [n*S, g_stride>=4] and ADDS the
  * parameter gradients into `grads` (fp32, reference state_dict layout).  packed_bwd: transposed weight
- * stream from plnerf_pack_weights_bwd (plnerf_packed_bwd_bytes).  use_viewdirs networks only; the
- * sample positions carry no gradient (run_plnerf.py:728), so no input gradient is produced. */
+ * stream from plnerf_pack_weights_bwd (plnerf_packed_bwd_bytes).  Networks with view directions
+ * (raw [n,S,4]) and without (output_linear head, raw [n,S,output_ch], 4 <= output_ch <= 8; channels past the fourth get no
+ * gradient, like the unused views_linears); the sample positions carry no gradient (run_plnerf.py:728), so no input gradient is produced. */
 size_t plnerf_train_stash_bytes(const plnerf_net_desc* desc, int64_t n_rays, int S);
 int plnerf_network_query_train(const plnerf_net_desc* desc, const void* packed, int multires,
                                int multires_views, const float* rays, int64_t n, int stride,
@@ -295,7 +296,7 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
  * plnerf_render_rays_bwd: upstream gradients of the eight maps (any may be NULL) -> parameter gradients ADDED into
  * grads_coarse / grads_fine (fp32, state_dict layout; fine_* NULL = the coarse network served the fine pass).
  * `*_packed_bwd` = plnerf_pack_weights_bwd.  noise0 / noise1: the same explicit arrays as in the forward (or NULL: the
- * forward's Philox draws are regenerated from cfg->seed).  bf16 precision, use_viewdirs networks only. */
+ * forward's Philox draws are regenerated from cfg->seed).  bf16 precision; both networks with or both without view directions. */
 typedef struct plnerf_render_grads {
   const float *g_rgb_map, *g_disp_map, *g_acc_map, *g_depth_map;   /* [n,3], [n], [n], [n] */
   const float *g_rgb0, *g_disp0, *g_acc0, *g_depth0;               /* coarse maps, read when N_importance > 0 */

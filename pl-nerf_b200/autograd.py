@@ -7,7 +7,7 @@ GEMMs (k_wgrad, MN-major tcgen05 operands, TMEM-resident accumulators) and the s
 What is differentiated follows the reference: gradients flow from rgb_map / depth_map /
 acc_map / disp_map (fine and coarse) to both networks' parameters; the importance samples are
 detached (run_plnerf.py:728) and ray inputs carry no gradient.  bf16 tensor-core operands with fp32
-accumulation; use_viewdirs networks only (anything else raises).
+accumulation; networks with and without view directions (output_linear head, run_nerf_helpers.py:100-103).
 
 ``forward_stashed`` / ``backward_stashed`` are the two plain functions behind the autograd.Function; the training
 step (train.TrainStep) calls them back to back without building an autograd graph.
@@ -88,8 +88,6 @@ def render_rays_autograd(ray_batch, network_fn, network_fine, N_samples, N_impor
                          seed, ray_id_offset, retraw, precision):
     if precision not in (None, "bf16") or (precision is None and ops.get_precision() != "bf16"):
         raise NotImplementedError("plnerf_b200: gradients are implemented for precision='bf16' only")
-    if not getattr(network_fn, "use_viewdirs", False):
-        raise NotImplementedError("plnerf_b200: gradients are implemented for use_viewdirs networks only")
     rays = ray_batch.detach().float().contiguous()
     n = rays.shape[0]
     dev = rays.device

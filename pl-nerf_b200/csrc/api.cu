@@ -108,7 +108,7 @@ int plnerf_network_query_train(const plnerf_net_desc* desc, const void* packed, 
                                const float* rays, int64_t n, int stride, const float* z, int S, float* raw, void* stash,
                                size_t stash_bytes, void* ws, size_t ws_bytes, void* stream) {
   PLNERF_CHECK_ARG(desc, "network_query_train: null desc");
-  return mlp_query_train(desc, packed, multires, multires_views, rays, n, stride, z, S, raw, 4, stash, stash_bytes, ws,
+  return mlp_query_train(desc, packed, multires, multires_views, rays, n, stride, z, S, raw, desc->use_viewdirs ? 4 : desc->output_ch, stash, stash_bytes, ws,
                          ws_bytes, (cudaStream_t)stream);
 }
 
@@ -304,17 +304,18 @@ static TrainWs carve_train(const plnerf_render_cfg* c, const plnerf_net_desc* cd
   TrainWs w;
   size_t off = 0;
   const int Ns = c->N_samples, Ni = c->N_importance, S1 = Ns + Ni;
+  const int chc = cd->use_viewdirs ? 4 : cd->output_ch, chf = fd->use_viewdirs ? 4 : fd->output_ch;   // raw channels per sample
   auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   auto take = [&](size_t floats) { float* p = reinterpret_cast<float*>(base + off); off += up(floats * sizeof(float)); return p; };
   w.z0 = take((size_t)n * Ns);
-  w.raw0 = take((size_t)n * Ns * 4);
+  w.raw0 = take((size_t)n * Ns * chc);
   w.w0 = take((size_t)n * (Ns + 1));
   w.tau0 = take((size_t)n * (Ns + 2));
   w.T0 = take((size_t)n * (Ns + 2));
   w.zs = take((size_t)n * (Ni > 0 ? Ni : 1));
   w.z1 = take((size_t)n * S1);
-  w.raw1 = take((size_t)n * S1 * 4);
-  w.graw = take((size_t)n * S1 * 4);
+  w.raw1 = take((size_t)n * S1 * chf);
+  w.graw = take((size_t)n * S1 * (chc > chf ? chc : chf));     // k_composite_bwd writes d raw in raw's own layout
   w.vb_f = take((size_t)n * 128);
   w.dirpe = take((size_t)n * 32);
   w.mlp_ws = base + off;
@@ -339,11 +340,11 @@ static int check_train_args(const plnerf_render_cfg* cfg, const plnerf_net_desc*
                             const float* rays, int stride, const void* ws, size_t ws_bytes, const char* who) {
   PLNERF_CHECK_ARG(cfg && cdesc && fdesc, "%s: null argument", who);
   PLNERF_CHECK_ARG(n >= 0 && (n == 0 || rays), "%s: null rays", who);
-  PLNERF_CHECK_ARG(stride >= 11, "%s: training needs rays with a view direction (stride >= 11)", who);
+  PLNERF_CHECK_ARG(cdesc->use_viewdirs == fdesc->use_viewdirs, "%s: coarse/fine use_viewdirs differ", who);
+  PLNERF_CHECK_ARG(stride >= (cdesc->use_viewdirs ? 11 : 8), "%s: ray stride too small (networks with view directions need stride >= 11)", who);
   PLNERF_CHECK_ARG(cfg->N_samples >= 2 && cfg->N_importance >= 0, "%s: need N_samples >= 2, N_importance >= 0", who);
   PLNERF_CHECK_ARG(cfg->mode == PLNERF_MODE_LINEAR || cfg->mode == PLNERF_MODE_CONSTANT, "%s: bad mode", who);
   if (cfg->precision != PLNERF_PREC_BF16) { set_error("%s: gradients are implemented for PLNERF_PREC_BF16 only", who); return PLNERF_E_UNSUPPORTED; }
-  if (!cdesc->use_viewdirs || !fdesc->use_viewdirs) { set_error("%s: gradients are implemented for use_viewdirs networks only", who); return PLNERF_E_UNSUPPORTED; }
   const size_t need = carve_train(cfg, cdesc, fdesc, n, nullptr).total;
   if (!ws || ws_bytes < need) { set_error("%s: workspace too small: need %zu bytes, got %zu", who, need, ws_bytes); return PLNERF_E_WORKSPACE; }
   PLNERF_CHECK_ARG(((uintptr_t)ws & 1023) == 0, "%s: workspace must be 1024-byte aligned", who);
@@ -363,6 +364,7 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
   cudaStream_t st = (cudaStream_t)stream;
   TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
   const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
   const bool fine = Ni > 0;
   // depths + the view bias of both networks + the direction encoding in one launch where covered (as in the inference entry)
   const bool two_nets = fine && fpacked != cpacked;
@@ -375,17 +377,17 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
     rc = launch_stratified_z(rays, n, stride, Ns, cfg->lindisp, cfg->perturb, t_rand, cfg->seed, cfg->ray_id_offset, w.z0, st);
     if (rc) return rc;
   }
-  rc = mlp_query_train(cdesc, cpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z0, Ns, w.raw0, 4, w.stash0,
+  rc = mlp_query_train(cdesc, cpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z0, Ns, w.raw0, chc, w.stash0,
                        w.stash0_bytes, w.mlp_ws, w.mlp_ws_bytes, st, have_vb ? vb_c : nullptr, have_vb ? w.dirpe : nullptr);
   if (rc) return rc;
-  rc = launch_composite(w.raw0, 4, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+  rc = launch_composite(w.raw0, chc, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                         noise0, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE0,
                         fine ? out->rgb0 : out->rgb_map, fine ? out->disp0 : out->disp_map, fine ? out->acc0 : out->acc_map,
                         fine ? out->depth0 : out->depth_map, fine ? w.w0 : nullptr, fine ? w.tau0 : nullptr,
                         fine ? w.T0 : nullptr, st);
   if (rc) return rc;
   if (!fine) {
-    if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw0, (size_t)n * Ns * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw0, (size_t)n * Ns * chc * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (out->z_vals) PLNERF_CUDA(cudaMemcpyAsync(out->z_vals, w.z0, (size_t)n * Ns * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return PLNERF_OK;
   }
@@ -393,15 +395,15 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
   rc = launch_sample_merge(cfg->mode == PLNERF_MODE_LINEAR, w.z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed,
                            cfg->ray_id_offset, cfg->zero_tol, cfg->epsilon, w.z1, out->z_std, out->inds, st);
   if (rc) return rc;
-  rc = mlp_query_train(fdesc, fpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z1, S1, w.raw1, 4, w.stash1,
+  rc = mlp_query_train(fdesc, fpacked, cfg->multires, cfg->multires_views, rays, n, stride, w.z1, S1, w.raw1, chf, w.stash1,
                        w.stash1_bytes, w.mlp_ws, w.mlp_ws_bytes, st, have_vb ? (two_nets ? w.vb_f : vb_c) : nullptr,
                        have_vb ? w.dirpe : nullptr);
   if (rc) return rc;
-  rc = launch_composite(w.raw1, 4, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+  rc = launch_composite(w.raw1, chf, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                         noise1, noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1,
                         out->rgb_map, out->disp_map, out->acc_map, out->depth_map, nullptr, nullptr, nullptr, st);
   if (rc) return rc;
-  if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw1, (size_t)n * S1 * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw1, (size_t)n * S1 * chf * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (out->z_vals) PLNERF_CUDA(cudaMemcpyAsync(out->z_vals, w.z1, (size_t)n * S1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return PLNERF_OK;
 }
@@ -420,24 +422,25 @@ int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   cudaStream_t st = (cudaStream_t)stream;
   TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
   const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
   if (Ni > 0) {
     // fine pass: d(maps)/d(raw1) (run_plnerf.py:741 through autograd), then the fine network's parameter gradients
-    rc = launch_composite_bwd(w.raw1, 4, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+    rc = launch_composite_bwd(w.raw1, chf, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                               noise1, g->g_rgb_map, g->g_depth_map, g->g_acc_map, g->g_disp_map, w.graw, st,
                               noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1);
     if (rc) return rc;
-    rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, 4, w.stash1, w.stash1_bytes, grads_fine, st);
+    rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, chf, w.stash1, w.stash1_bytes, grads_fine, st);
     if (rc) return rc;
   }
   // coarse pass (the importance samples are detached, run_plnerf.py:728: no gradient reaches it from the fine maps)
   const float *gr = Ni > 0 ? g->g_rgb0 : g->g_rgb_map, *gd = Ni > 0 ? g->g_depth0 : g->g_depth_map;
   const float *ga = Ni > 0 ? g->g_acc0 : g->g_acc_map, *gp = Ni > 0 ? g->g_disp0 : g->g_disp_map;
   if (Ni == 0 || gr || gd || ga || gp) {
-    rc = launch_composite_bwd(w.raw0, 4, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+    rc = launch_composite_bwd(w.raw0, chc, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                               noise0, gr, gd, ga, gp, w.graw, st, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed,
                               cfg->ray_id_offset, RNG_STREAM_NOISE0);
     if (rc) return rc;
-    rc = mlp_query_bwd(cdesc, cpacked, cpacked_bwd, n, Ns, w.graw, 4, w.stash0, w.stash0_bytes, grads_coarse, st);
+    rc = mlp_query_bwd(cdesc, cpacked, cpacked_bwd, n, Ns, w.graw, chc, w.stash0, w.stash0_bytes, grads_coarse, st);
     if (rc) return rc;
   }
   return PLNERF_OK;

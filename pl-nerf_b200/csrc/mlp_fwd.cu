@@ -197,8 +197,8 @@ int build_plan(const plnerf_net_desc* d, int precision, const plnerf_net_params*
 
 // Training stash layout for a (viewdirs) network.
 int build_train_layout(const plnerf_net_desc* d, TrainLayout* out) {
-  if (!d->use_viewdirs) { set_error("training (backward) is implemented for use_viewdirs networks only"); return PLNERF_E_UNSUPPORTED; }
   if (d->D + 4 > MAX_STASH) { set_error("network too deep for the training stash"); return PLNERF_E_UNSUPPORTED; }
+  if (!d->use_viewdirs && (d->output_ch < 4 || d->output_ch > MAX_OUT_CH)) { set_error("training needs output_ch in [4,%d] (got %d)", MAX_OUT_CH, d->output_ch); return PLNERF_E_UNSUPPORTED; }
   TrainLayout& T = *out;
   memset(&T, 0, sizeof(T));
   const int pe_w = ((d->input_ch + 15) / 16) * 16;
@@ -207,21 +207,28 @@ int build_train_layout(const plnerf_net_desc* d, TrainLayout* out) {
   T.idx_pe = add_in(pe_w);
   T.idx_h0 = n;
   for (int l = 0; l < d->D; ++l) add_in(256);
-  T.idx_feat = add_in(256);
-  T.idx_hv = add_in(128);
-  T.idx_dir = add_in(32);
+  T.idx_feat = T.idx_hv = T.idx_dir = -1;          // networks without view directions end at h_{D-1} (output_linear head)
+  if (d->use_viewdirs) {
+    T.idx_feat = add_in(256);
+    T.idx_hv = add_in(128);
+    T.idx_dir = add_in(32);
+  }
   T.n_in = n; T.in_tile_bytes = off;
   n = 0; off = 0;
   auto add_dy = [&](int w) { T.dy_width[n] = w; T.dy_off[n] = off; off += w * 256; return n++; };
   T.dy_h0 = 0;
   for (int l = 0; l < d->D; ++l) add_dy(256);
-  T.dy_feat = add_dy(256);
-  T.dy_views = add_dy(128);
-  T.dy_head = add_dy(16);        // [g_rgb(3), g_alpha, 0 ...]: N operand of the alpha / rgb head weight gradients
+  T.dy_feat = T.dy_views = -1;
+  if (d->use_viewdirs) {
+    T.dy_feat = add_dy(256);
+    T.dy_views = add_dy(128);
+  }
+  T.dy_head = add_dy(16);        // [g_rgb(3), g_alpha, 0 ...]: N operand of the alpha / rgb (or output_linear) head weight gradients
   T.n_dy = n; T.dy_tile_bytes = off;
   n = 0; off = 0;
   for (int l = 0; l < d->D; ++l) { T.mask_words[n] = 8; T.mask_off[n] = off; off += 8 * 128; ++n; }
-  T.mask_views = n; T.mask_words[n] = 4; T.mask_off[n] = off; off += 4 * 128; ++n;
+  T.mask_views = -1;
+  if (d->use_viewdirs) { T.mask_views = n; T.mask_words[n] = 4; T.mask_off[n] = off; off += 4 * 128; ++n; }
   T.n_mask = n; T.mask_tile_words = off;
   return PLNERF_OK;
 }
@@ -230,23 +237,24 @@ int build_train_layout(const plnerf_net_desc* d, TrainLayout* out) {
 // weights = W^T.  Layer order: views (128->256, d_feature), feature (256->256, +alpha rank-1, mask D-1),
 // trunk D-1 .. 1 (mask l-1).  Trunk layer 0 needs no input gradient.
 int build_dgrad_plan(const plnerf_net_desc* d, const plnerf_net_params* p, NetPlan* out) {
-  if (!d->use_viewdirs) { set_error("training (backward) is implemented for use_viewdirs networks only"); return PLNERF_E_UNSUPPORTED; }
   NetPlan fwd;
   int rc = build_plan(d, PLNERF_PREC_BF16, nullptr, &fwd);
   if (rc) return rc;
   NetPlan& P = *out;
   memset(&P, 0, sizeof(P));
-  P.input_ch = d->input_ch; P.input_ch_views = d->input_ch_views; P.out_ch = 4; P.use_viewdirs = 1;
+  P.input_ch = d->input_ch; P.input_ch_views = d->use_viewdirs ? d->input_ch_views : 0; P.out_ch = fwd.out_ch;
+  P.use_viewdirs = d->use_viewdirs;
   P.pe_ks = 0; P.precision = PLNERF_PREC_BF16; P.is_dgrad = 1; P.D = d->D;
   auto is_skip = [&](int i) { for (int k = 0; k < d->n_skips; ++k) if (d->skips[k] == i) return true; return false; };
   int nl = 0;
-  {  // views: d_feature = d_hv . W_views[:, :256]
+  // (without view directions the chain starts at dh_{D-1} = (g_out . W_out) * relu'(h_{D-1}), formed by the prologue)
+  if (d->use_viewdirs) {  // views: d_feature = d_hv . W_views[:, :256]
     LayerPlan& L = P.L[nl++];
     L.n_pe_ks = 0; L.n_h_ks = 8; L.n_halves = 2; L.epi = EPI_LINEAR_A; L.flags = 0; L.bias_off = 0;
     L.stash_idx = (int16_t)(d->D); L.mask_idx = -1;                 // dY tensors: l = dY_l, D = dY_feat, D+1 = dY_views
     L.W = p ? p->views_w : nullptr; L.ldw = 256 + d->input_ch_views; L.pe_col0 = -1; L.h_col0 = 0; L.transposed = 1;
   }
-  {  // feature: dh_{D-1} = d_feature . W_feat + g_alpha * w_alpha, masked by relu(D-1)
+  if (d->use_viewdirs) {  // feature: dh_{D-1} = d_feature . W_feat + g_alpha * w_alpha, masked by relu(D-1)
     LayerPlan& L = P.L[nl++];
     L.n_pe_ks = 0; L.n_h_ks = 16; L.n_halves = 2; L.epi = EPI_RELU_A; L.flags = FLAG_ALPHA; L.bias_off = 0;
     L.stash_idx = (int16_t)(d->D - 1); L.mask_idx = (int16_t)(d->D - 1);
@@ -263,7 +271,9 @@ int build_dgrad_plan(const plnerf_net_desc* d, const plnerf_net_params* p, NetPl
   P.n_layers = nl;
   // const block: rgb_w [3][128] and alpha_w [256] (same offsets as the forward plan so the tail is shared)
   P.alpha_w_off = fwd.alpha_w_off; P.alpha_b_off = fwd.alpha_b_off; P.rgb_w_off = fwd.rgb_w_off; P.rgb_b_off = fwd.rgb_b_off;
+  P.out_w_off = fwd.out_w_off; P.out_b_off = fwd.out_b_off;
   P.const_floats = fwd.const_floats; P.tail_floats = fwd.tail_floats;
+  if (nl == 0) { set_error("training a one-layer network without view directions is not supported"); return PLNERF_E_UNSUPPORTED; }
   int64_t wb = 0;
   for (int l = 0; l < nl; ++l) wb += (int64_t)P.L[l].n_halves * P.L[l].n_h_ks * KS_BYTES;
   P.weight_bytes = wb;
@@ -860,7 +870,7 @@ __device__ __forceinline__ void pe_prologue(const MlpArgs& A, uint8_t* smem, con
       *reinterpret_cast<uint4*>(smem + SL.pe_lo + pnl * 2048 + row * 16) = l4;
     }
   }
-  if (STASH) {
+  if (STASH && A.plan.use_viewdirs) {
     // the (padded, 32-wide) viewdir encoding of this row's ray as a weight-gradient operand tile:
     // column group g writes its share of the four 8-column blocks
     const float* dp = A.dirpe + (gc / A.vb_div) * 32;
@@ -897,6 +907,34 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
     if ((threadIdx.x & 31) == 0) {
       atomicAdd(A.d_rgb_b + 0, s0); atomicAdd(A.d_rgb_b + 1, s1); atomicAdd(A.d_rgb_b + 2, s2); atomicAdd(A.d_alpha_b, s3);
     }
+  }
+  if (!P.use_viewdirs) {
+    // output_linear head (run_nerf_helpers.py:126): dh_{D-1} = (g_out . W_out) * relu'(h_{D-1}), 256 wide (g_out: the four
+    // channels raw2outputs reads; further output channels get no gradient) -> A operand + the dY_{D-1} stash tile
+    const float* ow = consts + P.out_w_off;
+    const int oc = P.out_ch < 4 ? P.out_ch : 4;
+    const float gv[4] = {gr, gg, gb, g_alpha};
+    const uint32_t* mk = A.masks + tile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.D - 1];
+    uint8_t* tile_dy = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_h0 + P.D - 1];
+    for (int c = grp * CHUNKS_PER_GRP; c < 8; c += NGRP * CHUNKS_PER_GRP) {
+      for (int cc = c; cc < c + CHUNKS_PER_GRP; ++cc) {
+        const int n0 = 32 * cc;
+        const uint32_t m = mk[cc * 128 + row];
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float v0 = 0.f, v1 = 0.f;
+          for (int ch = 0; ch < oc; ++ch) { v0 = fmaf(gv[ch], ow[ch * 256 + n0 + i], v0); v1 = fmaf(gv[ch], ow[ch * 256 + n0 + i + 1], v1); }
+          pk[i >> 1] = ptx::pack_bf16(v0, v1) & relu_mask_word(m, i >> 1);
+        }
+        ptx::tmem_st16(tmem_lane_a1 + (uint32_t)(n0 >> 1), pk);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          stash_store8(tile_dy, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+      }
+    }
+    ptx::tmem_st_wait();
+    return;
   }
   const float* rw = consts + P.rgb_w_off;
   const uint32_t* mk = A.masks + tile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[A.tl.mask_views];
@@ -1386,6 +1424,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                                              val[2 * i + 1] - ptx::bf16_round(val[2 * i + 1]));
                     ptx::tmem_st16(a_out_lo + (uint32_t)(n0 >> 1), pk);
                   }
+                } else if (STASH) {
+                  // last trunk layer of a network without view directions: no next layer reads it, but the weight
+                  // gradients of output_linear and the gradient chain's first mask do
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
+                  if (mask_idx >= 0) mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
+                  uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4)
+                    stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
                 }
               }
             }
@@ -1962,7 +2010,7 @@ int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, 
                     const float* dirpe_pre) {
   PLNERF_CHECK_ARG(d && rays && z && raw && stash, "network_query_train: null argument");
   PLNERF_CHECK_ARG((viewbias_pre == nullptr) == (dirpe_pre == nullptr), "network_query_train: view bias and direction encoding go together");
-  PLNERF_CHECK_ARG(n >= 0 && S > 0 && stride >= 11, "network_query_train: bad sizes (rays need a viewdir)");
+  PLNERF_CHECK_ARG(n >= 0 && S > 0 && stride >= (d->use_viewdirs ? 11 : 8), "network_query_train: bad sizes (rays of a view-direction network need a viewdir)");
   if (n == 0) return PLNERF_OK;
   PLNERF_CHECK_ARG(((uintptr_t)stash & 1023) == 0, "network_query_train: stash must be 1024-byte aligned");
   MlpArgs a;
@@ -1973,7 +2021,7 @@ int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, 
   if (stash_bytes < sp.total) { set_error("training stash too small: need %zu bytes, got %zu", sp.total, stash_bytes); return PLNERF_E_WORKSPACE; }
   const int want_ic = multires < 0 ? 3 : 3 + 6 * multires;
   const int want_icv = multires_views < 0 ? 3 : 3 + 6 * multires_views;
-  PLNERF_CHECK_ARG(want_ic == d->input_ch && want_icv == d->input_ch_views && multires <= 10,
+  PLNERF_CHECK_ARG(want_ic == d->input_ch && (!d->use_viewdirs || want_icv == d->input_ch_views) && multires <= 10,
                    "network_query_train: multires/multires_views do not match the network");
   a.rays = rays; a.stride = stride; a.z = z; a.S = S; a.multires = multires;
   a.vb_div = S; a.M = n * S; a.out = raw; a.out_stride = raw_stride;
@@ -2022,15 +2070,20 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
   const StashPtrs sp = carve_stash(a.tl, n * S, n, static_cast<uint8_t*>(stash));
   if (stash_bytes < sp.total) { set_error("training stash too small: need %zu bytes, got %zu", sp.total, stash_bytes); return PLNERF_E_WORKSPACE; }
   for (int i = 0; i < d->D; ++i) PLNERF_CHECK_ARG(g->pts_w[i] && g->pts_b[i], "network_query_bwd: missing gradient buffer for pts_linears.%d", i);
-  PLNERF_CHECK_ARG(g->views_w && g->views_b && g->feature_w && g->feature_b && g->alpha_w && g->alpha_b && g->rgb_w && g->rgb_b,
-                   "network_query_bwd: missing head gradient buffers");
+  if (d->use_viewdirs)
+    PLNERF_CHECK_ARG(g->views_w && g->views_b && g->feature_w && g->feature_b && g->alpha_w && g->alpha_b && g->rgb_w && g->rgb_b,
+                     "network_query_bwd: missing head gradient buffers");
+  else
+    PLNERF_CHECK_ARG(g->output_w && g->output_b, "network_query_bwd: missing output_linear gradient buffers");
   // (1) input-gradient chain -> dY stash
   a.w = static_cast<const uint8_t*>(packed_bwd);
   a.tail = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed_fwd) + fwd.weight_bytes);
   a.S = S; a.vb_div = S; a.M = n * S;
   a.in_stash = sp.in; a.dy_stash = sp.dy; a.masks = sp.masks; a.dirpe = sp.dirpe;
   a.g_raw = g_raw; a.g_stride = g_stride;
-  a.d_rgb_b = g->rgb_b; a.d_alpha_b = g->alpha_b;
+  // bias gradients of the heads = column sums of g_raw (output_linear: channels 0-2 and 3 of its bias)
+  a.d_rgb_b = d->use_viewdirs ? g->rgb_b : g->output_b;
+  a.d_alpha_b = d->use_viewdirs ? g->alpha_b : g->output_b + 3;
   rc = launch_mlp(a, st, 3);
   if (rc) return rc;
   // (2) weight gradients
@@ -2065,11 +2118,16 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
       add(T.dy_h0 + i, 2, T.idx_h0 + i - 1, g->pts_w[i], 256 + d->input_ch, d->input_ch, 256, g->pts_b[i]);
     } else add(T.dy_h0 + i, 2, T.idx_h0 + i - 1, g->pts_w[i], 256, 0, 256, g->pts_b[i]);
   }
-  add(T.dy_feat, 2, T.idx_h0 + d->D - 1, g->feature_w, 256, 0, 256, g->feature_b);
-  add(T.dy_views, 1, T.idx_feat, g->views_w, 256 + d->input_ch_views, 0, 256, g->views_b);
-  add(T.dy_views, 1, T.idx_dir, g->views_w, 256 + d->input_ch_views, 256, d->input_ch_views, nullptr);
-  add_head(T.idx_h0 + d->D - 1, 2, g->alpha_w, 0, 3, 1);
-  add_head(T.idx_hv, 1, g->rgb_w, 128, 0, 3);
+  if (d->use_viewdirs) {
+    add(T.dy_feat, 2, T.idx_h0 + d->D - 1, g->feature_w, 256, 0, 256, g->feature_b);
+    add(T.dy_views, 1, T.idx_feat, g->views_w, 256 + d->input_ch_views, 0, 256, g->views_b);
+    add(T.dy_views, 1, T.idx_dir, g->views_w, 256 + d->input_ch_views, 256, d->input_ch_views, nullptr);
+    add_head(T.idx_h0 + d->D - 1, 2, g->alpha_w, 0, 3, 1);
+    add_head(T.idx_hv, 1, g->rgb_w, 128, 0, 3);
+  } else {
+    // d output_linear.weight[c, k] = sum_m g_out[m, c] h_{D-1}[m, k], c < 4 (further channels: no gradient)
+    add_head(T.idx_h0 + d->D - 1, 2, g->output_w, 256, 0, d->output_ch < 4 ? d->output_ch : 4);
+  }
   w.n_items = ni;
   // CTAs per item.  A CTA's time is set by the number of tiles it walks (two-stage pipeline: ~1 us per tile whatever the
   // tile's bytes; measured -- byte-proportional counts were 40% slower), so every layer item gets the same count; the light

@@ -405,7 +405,7 @@ def network_query_train(net, rays, z_vals):
     pk = packed_of(net)
     buf = pk.get(net, "bf16")
     n, S = z_vals.shape
-    raw = torch.empty((n, S, 4), device=rays.device)
+    raw = torch.empty((n, S, 4 if pk.desc.use_viewdirs else pk.desc.output_ch), device=rays.device)
     sb = L.lib().plnerf_train_stash_bytes(C.byref(pk.desc), n, S)
     if sb == 0:
         L.check(-2)
@@ -417,7 +417,7 @@ def network_query_train(net, rays, z_vals):
     wsb = L.lib().plnerf_query_workspace_bytes(C.byref(pk.desc), n)
     ws = torch.empty(wsb, dtype=torch.uint8, device=rays.device)
     mr = _multires_of(pk.desc.input_ch)
-    mrv = _multires_of(pk.desc.input_ch_views)
+    mrv = _multires_of(pk.desc.input_ch_views) if pk.desc.use_viewdirs else -1
     L.check(L.lib().plnerf_network_query_train(C.byref(pk.desc), _p(buf), mr, mrv, _p(rays), n, rays.shape[1],
                                                 _p(z_vals), S, _p(raw), C.c_void_p(stash.data_ptr() + off), sb,
                                                 _p(ws), wsb, _stream()))
@@ -594,7 +594,8 @@ def render_rays_fwd_train(rays, net_coarse, net_fine, N_samples, N_importance, m
         ret[key] = t
     new("rgb_map", (n, 3)); new("disp_map", (n,)); new("acc_map", (n,)); new("depth_map", (n,))
     if retraw:
-        new("raw", (n, S_last, 4))
+        last = pkf.desc if pkf else pkc.desc
+        new("raw", (n, S_last, 4 if last.use_viewdirs else last.output_ch))
     if N_importance > 0:
         new("rgb0", (n, 3)); new("disp0", (n,)); new("depth0", (n,)); new("acc0", (n,)); new("z_std", (n,))
     opt = lambda t, nm: None if t is None else _f32(t, nm)

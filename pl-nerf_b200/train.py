@@ -24,7 +24,7 @@ Data parallel: every rank draws the SAME global pixel batch (same
 contiguous shard ``dist.shard_bounds(N_rand)`` of it with ``ray_id_offset`` = the shard's first global ray, scales
 its loss gradient by the GLOBAL batch size and sums gradients over ranks -- the W-rank job is the 1-rank job.
 
-CUDA only; gradients need ``use_viewdirs`` networks and ``precision='bf16'`` (see autograd.py).
+CUDA only; gradients need ``precision='bf16'`` (see autograd.py).
 """
 import torch
 
@@ -261,8 +261,6 @@ class TrainStep:
         # shard and chunk; explicit noise or the pytest hook go through render_rays' autograd.Function instead
         self._direct = not any(kw.get(k) is not None for k in ("noise0", "noise1")) and not kw.get("pytest")
         if self._direct:
-            if not all(getattr(n, "use_viewdirs", False) for n in self.nets):
-                raise NotImplementedError("plnerf_b200: gradients are implemented for use_viewdirs networks only")
             if kw.get("precision") not in (None, "bf16") or (kw.get("precision") is None and ops.get_precision() != "bf16"):
                 raise NotImplementedError("plnerf_b200: gradients are implemented for precision='bf16' only")
             if not all(p.requires_grad for n in self.nets for p in n.parameters()):

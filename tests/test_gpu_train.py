@@ -196,10 +196,22 @@ def test_training_loss_gradients_vs_reference(name):
                 assert rel < 0.06, (tag, k, rel)
 
 
-def test_gradients_need_viewdirs_and_bf16():
+def test_gradients_need_bf16_and_reach_networks_without_viewdirs():
+    """precision='bf16x3' has no backward (raises); a network without view directions (coarse only, output_ch = 4) does:
+    loss.backward() through render_rays fills output_linear and the trunk, leaves the unused views_linears untouched
+    (the parity of these gradients against the reference: tests/test_gpu_train_parity.py)."""
     from plnerf_b200 import run_plnerf as RP
     cfg, kw, pc, pf = case_params("coarse_only")
     net = make_net(kw, pc)
     g = load_golden("coarse_only")
     with pytest.raises(NotImplementedError):
-        RP.render_rays(dev(g["ray_batch"]), net, None, 64, "linear", "midpoint", perturb=1.0)
+        RP.render_rays(dev(g["ray_batch"]), net, None, 64, "linear", "midpoint", perturb=1.0, precision="bf16x3")
+    assert not net.use_viewdirs
+    ret = RP.render_rays(dev(g["ray_batch"]), net, None, 64, "linear", "midpoint", perturb=1.0, white_bkgd=True)
+    assert ret["rgb_map"].requires_grad
+    ((ret["rgb_map"] - 0.25) ** 2).mean().backward()
+    for k, p in net.named_parameters():
+        if k.startswith("views_linears"):
+            assert p.grad is None or not bool(p.grad.any())
+        else:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()) and float(p.grad.abs().max()) > 0, k
