@@ -302,7 +302,7 @@ def train_leg(args, dev, rank, world, ro, rd, K, H, W):
                       f"bf16 tensor-core operands, 2x fused Adam, 1 flat all-reduce ({bucket.flat.numel() * 4} B) per step"}
 
 
-def train_step_leg(dev, K, H, W, rank, world):
+def train_step_leg(dev, K, H, W, rank, world, weak=False):
     """The reference's JOB (global N_rand = 1024 rays per iteration, blender_linear.txt) through plnerf_b200.train.TrainStep:
     device-side pixel draw, ray generation of the chosen pixels, loss gradient, one flat gradient buffer, ONE fused Adam.
     With W ranks every rank draws the same global batch and renders its contiguous 1024/W-ray shard (strong scaling);
@@ -311,7 +311,7 @@ def train_step_leg(dev, K, H, W, rank, world):
     import torch.distributed as dist
     from plnerf_b200 import synth, train as T
     from plnerf_b200.run_nerf_helpers import NeRF
-    N_rand, Ns, Ni, iters, warm = 1024, 128, 64, 30, 5
+    N_rand, Ns, Ni, iters, warm = 1024 * (world if weak else 1), 128, 64, 30, 5     # weak: 1024 rays per rank
 
     def mk(seed):
         net = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
@@ -358,12 +358,18 @@ def train_step_leg(dev, K, H, W, rank, world):
         ta = torch.tensor([a0.elapsed_time(a1) / 20], device=dev, dtype=torch.float64)
         dist.all_reduce(ta, op=dist.ReduceOp.MAX)
         ar_ms = float(ta[0])
-    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()), "scaling": "strong",
+    # fraction of the tensor roofline of SURVEY.md 8d: 3 489 024 FLOP per network evaluation of a training step
+    # (forward + input-gradient chain + weight gradients), (2 Ns + Ni) evaluations per ray, against the sustained bf16 peak
+    peak_sus, _, _ = peaks()
+    tflops = (N_rand / world) * (2 * Ns + Ni) * 3489024 / ms / 1e9
+    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "final_loss": float(out["loss"].item()),
+            "scaling": "weak" if weak else "strong", "algorithmic_tflops_per_gpu": tflops,
+            "frac_of_tensor_roofline": tflops / peak_sus,
             "rays_per_iter_global": N_rand, "allreduce_ms": ar_ms, "allreduce_bytes": int(step.bucket.flat.numel() * 4),
             "config": f"plnerf_b200.train.TrainStep, global N_rand={N_rand} sharded over {world} rank(s), N_samples={Ns}, "
                       f"N_importance={Ni}: device-side pixel draws (64 iterations per batched draw) + pack_pixel_rays, direct "
                       "loss gradient, forward/backward kernels called without an autograd graph into flat gradient + "
-                      "parameter buffers, 1 flat all-reduce (sum), 1 fused Adam launch"}
+                      "parameter buffers, 1 flat all-reduce (sum), 1 flat Adam launch (plnerf_adam_step)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -504,6 +510,8 @@ def run_ours(args, wl):
         out["train"] = train_leg(args, dev, rank, world, ro, rd, K, H, W)
         try:
             out["train"]["device_side_step"] = train_step_leg(dev, K, H, W, rank, world)
+            if world > 1:      # the same step with 1024 rays per rank (weak scaling; equals the line above at one rank)
+                out["train"]["device_side_step_weak"] = train_step_leg(dev, K, H, W, rank, world, weak=True)
         except Exception as e:  # an extra: the lines above must survive its failure
             out["train"]["device_side_step"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
