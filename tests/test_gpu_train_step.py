@@ -225,3 +225,30 @@ def test_adam_step_vs_torch_adam(n):
         ops.adam_step(p.cpu(), g, m, v, 1e-3, 1)
     with pytest.raises(RuntimeError):
         ops.adam_step(p, g, m, v, 1e-3, 0)
+
+
+def test_train_step_is_chunk_invariant():
+    """N_rand rays rendered in several chunks (batchify_rays' loop, run_plnerf.py:95-107) give the step of one chunk: the
+    device draws are keyed by the global ray id, the loss sums accumulate across chunks in order, the parameter gradients
+    add up to the weight-gradient atomics' noise."""
+    from plnerf_b200 import train as T
+    H, W, focal, B = 40, 48, 55.0, 256
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = pose(40.0)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    target = torch.rand(H, W, 3, device="cuda", generator=gen)
+    pix = T.sample_pixels(H, W, B, "cuda", gen)
+    res = []
+    for chunk in (1024 * 32, 96):                     # 96: chunks of 96 + 96 + 64 rays
+        net_c, net_f = make_net(91), make_net(92)
+        step = T.TrainStep(H, W, K, _render_kwargs(net_c, net_f, seed=31), N_rand=B, chunk=chunk, lrate=5e-4, coarse_lrate=5e-4)
+        out = step(target, c2w, 0, pix=pix)
+        res.append((out["loss"].item(), out["img_loss"].item(), out["img_loss0"].item(), step.bucket.flat.clone(),
+                    step.flat_params.clone()))
+    a, b = res
+    for i in range(3):
+        assert abs(a[i] - b[i]) <= 2e-6 * abs(a[i]), (i, a[i], b[i])
+    assert abs(a[0] - (a[1] + a[2])) <= 1e-6 * abs(a[0])
+    assert (a[3] - b[3]).norm().item() <= 5e-3 * a[3].norm().item()
+    assert (a[4] - b[4]).abs().max().item() <= 2 * 5e-4 + 1e-7    # one Adam step: at most +-lr where a ~0 gradient flips sign
