@@ -30,7 +30,9 @@ def _prec(p):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # (the raw handle of torch's current stream on the current device; torch.cuda.current_stream() builds a Stream object
+    # per call, which shows in the issue time of a training step's ~10 calls)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _f32(t, name):
@@ -313,9 +315,15 @@ class PackedNet:
         self.desc = net_desc_of(net)
         self.buf = {}
         self.version = {}
+        self._params = None
+        self._prm = None
 
     def _versions(self, net):
-        return tuple((p.data_ptr(), p._version) for p in net.parameters())
+        # the module's Parameter objects, listed once (walking net.parameters() costs ~25 us a time; a NeRF's parameter set
+        # is fixed, `.to()` / `load_state_dict` keep the objects): (storage address, version counter) of each
+        if self._params is None:
+            self._params = list(net.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self._params)
 
     def get(self, net, precision):
         prec = _prec(precision)
@@ -330,39 +338,40 @@ class PackedNet:
             L.check(-2)
         if prec not in self.buf or self.buf[prec].numel() != nbytes or self.buf[prec].device != first.device:
             self.buf[prec] = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
-        prm = L.NetParams()
-        sd = {k: v.detach() for k, v in net.named_parameters()}
-        keep = []
-
-        def ptr(name):
-            t = sd[name]
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                t = t.float().contiguous()
-            keep.append(t)
-            return t.data_ptr()
-        for i in range(self.desc.D):
-            prm.pts_w[i] = ptr(f"pts_linears.{i}.weight")
-            prm.pts_b[i] = ptr(f"pts_linears.{i}.bias")
-        if self.desc.use_viewdirs:
-            for f, nme in (("views_w", "views_linears.0.weight"), ("views_b", "views_linears.0.bias"),
-                           ("feature_w", "feature_linear.weight"), ("feature_b", "feature_linear.bias"),
-                           ("alpha_w", "alpha_linear.weight"), ("alpha_b", "alpha_linear.bias"),
-                           ("rgb_w", "rgb_linear.weight"), ("rgb_b", "rgb_linear.bias")):
-                setattr(prm, f, ptr(nme))
-        else:
-            prm.output_w = ptr("output_linear.weight")
-            prm.output_b = ptr("output_linear.bias")
+        prm, keep = self.param_struct(net, ver)
         L.check(L.lib().plnerf_pack_weights(C.byref(self.desc), C.byref(prm), prec, _p(self.buf[prec]), _stream()))
+        del keep
         self.version[prec] = ver
         return self.buf[prec]
 
+    def param_struct(self, net, ver=None):
+        """plnerf_net_params of the module's parameters (+ the tensors it points into).  Rebuilt only when a parameter's
+        storage moved: a training loop repacks after every optimiser step, with the same addresses each time."""
+        ver = ver if ver is not None else self._versions(net)
+        addrs = tuple(v[0] for v in ver)
+        cached = self._prm
+        if cached is not None and cached[0] == addrs:
+            return cached[1], cached[2]
+        prm = L.NetParams()
+        keep = []
+        converted = _fill_params(prm, self.desc, {k: v.detach() for k, v in net.named_parameters()}, keep, convert=True)
+        if not converted:                      # (converted copies are snapshots: never cached)
+            self._prm = (addrs, prm, keep)
+        return prm, keep
 
-def _fill_params(struct, desc, tensors, keep):
-    """Fill a NetParams / NetGrads ctypes struct from a {state_dict name: tensor} mapping."""
+
+def _fill_params(struct, desc, tensors, keep, convert=False):
+    """Fill a NetParams / NetGrads ctypes struct from a {state_dict name: tensor} mapping.  ``convert``: tensors that are
+    not contiguous float32 are copied (parameters of a half / strided module) instead of refused; returns whether any was."""
+    converted = [False]
+
     def ptr(name):
         t = tensors[name]
         if t.dtype != torch.float32 or not t.is_contiguous():
-            raise RuntimeError(f"{name}: expected a contiguous float32 tensor")
+            if not convert:
+                raise RuntimeError(f"{name}: expected a contiguous float32 tensor")
+            t = t.float().contiguous()
+            converted[0] = True
         keep.append(t)
         return t.data_ptr()
     for i in range(desc.D):
@@ -377,6 +386,7 @@ def _fill_params(struct, desc, tensors, keep):
     else:
         struct.output_w = ptr("output_linear.weight")
         struct.output_b = ptr("output_linear.bias")
+    return converted[0]
 
 
 def packed_bwd_of(net):
@@ -390,11 +400,12 @@ def packed_bwd_of(net):
     if nbytes == 0:
         L.check(-2)
     first = next(net.parameters())
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
-    prm = L.NetParams()
-    keep = []
-    _fill_params(prm, pk.desc, {k: v.detach().float().contiguous() for k, v in net.named_parameters()}, keep)
+    buf = cache.get("buf")
+    if buf is None or buf.numel() != nbytes or buf.device != first.device:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=first.device)
+    prm, keep = pk.param_struct(net, ver)
     L.check(L.lib().plnerf_pack_weights_bwd(C.byref(pk.desc), C.byref(prm), _p(buf), _stream()))
+    del keep
     cache["ver"], cache["buf"] = ver, buf
     return buf
 
@@ -496,12 +507,17 @@ def packed_of(net):
     return pk
 
 
-def invalidate_packed(net):
+def invalidate_packed(net, params_replaced=False):
     """Forget the packed copies of a network whose parameters were modified through an alias (e.g. a flat buffer
-    that the optimizer updates in place): the parameters' own version counters do not move in that case."""
+    that the optimizer updates in place): the parameters' own version counters do not move in that case.
+    ``params_replaced``: the module's Parameter OBJECTS were exchanged (not just their values or storage): also forget
+    the cached parameter list."""
     pk = net.__dict__.get("_plnerf_packed")
     if pk is not None:
         pk.version.clear()
+        if params_replaced:
+            pk._params = None
+            pk._prm = None
     cache = net.__dict__.get("_plnerf_packed_bwd")
     if cache is not None:
         cache.pop("ver", None)
@@ -616,22 +632,30 @@ def render_rays_fwd_train(rays, net_coarse, net_fine, N_samples, N_importance, m
     return ret, ctx
 
 
+class PreparedGrads:
+    """The gradient buffers of one network ({state_dict name: fp32 tensor}) as the plnerf_net_grads struct the backward
+    entries take, built once (a training step hands over the same views of its flat gradient buffer every iteration)."""
+
+    def __init__(self, net, grads):
+        self.tensors = []
+        self.struct = L.NetGrads()
+        _fill_params(self.struct, packed_of(net).desc, grads, self.tensors)
+
+
 def render_rays_bwd(ctx, g_fine, g_coarse, grads_c, grads_f):
     """Backward of render_rays_fwd_train (plnerf_render_rays_bwd): g_fine / g_coarse = (g_rgb, g_disp, g_acc, g_depth) of the
     fine / coarse maps (entries or the whole tuple may be None; with N_importance == 0 the maps are g_fine's).  Parameter
-    gradients are ADDED into grads_c / grads_f ({state_dict name: fp32 tensor})."""
+    gradients are ADDED into grads_c / grads_f ({state_dict name: fp32 tensor}, or a PreparedGrads of it)."""
     net_c, net_f = ctx["net_c"], ctx["net_f"]
     pkc = packed_of(net_c)
     bufc, bwdc = pkc.get(net_c, "bf16"), packed_bwd_of(net_c)
     keep = []
-    gc = L.NetGrads()
-    _fill_params(gc, pkc.desc, grads_c, keep)
+    gc = (grads_c if isinstance(grads_c, PreparedGrads) else PreparedGrads(net_c, grads_c)).struct
     fdesc = buff = bwdf = gf_ref = None
     if net_f is not None:
         pkf = packed_of(net_f)
         fdesc, buff, bwdf = C.byref(pkf.desc), pkf.get(net_f, "bf16"), packed_bwd_of(net_f)
-        gf = L.NetGrads()
-        _fill_params(gf, pkf.desc, grads_f, keep)
+        gf = (grads_f if isinstance(grads_f, PreparedGrads) else PreparedGrads(net_f, grads_f)).struct
         gf_ref = C.byref(gf)
     g = L.RenderGrads()
     c = lambda t: None if t is None else _f32(t, "upstream gradient")

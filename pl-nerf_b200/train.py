@@ -257,6 +257,7 @@ class TrainStep:
         self.optimizer = FlatAdam(self.flat_params, self.bucket.flat, segs, betas=(0.9, 0.999))
         # {state_dict name: view of the flat gradient buffer} per network: what the weight-gradient kernels add into
         self._grads = {net: {k: p.grad for k, p in net.named_parameters()} for net in self.nets}
+        self._prepared = {}            # the same, as the ABI's gradient struct (built on first use: needs the CUDA library)
         # explicit depth / sampler draws (t_rand [B, N_samples], u [B, N_importance] of the GLOBAL batch) are sliced per
         # shard and chunk; explicit noise or the pytest hook go through render_rays' autograd.Function instead
         self._direct = not any(kw.get(k) is not None for k in ("noise0", "noise1")) and not kw.get("pytest")
@@ -277,6 +278,16 @@ class TrainStep:
     def pixels(self, i):
         """The global pixel batch of iteration i (precrop window for the first precrop_iters iterations)."""
         return self.sampler.next(self.precrop_frac if i < self.precrop_iters else None)
+
+    def _grad_arg(self, net):
+        """The network's gradient views as the backward entry wants them (None for a missing fine network)."""
+        if net is None:
+            return None
+        if not self.flat_params.is_cuda:       # (host-logic tests drive the step with stand-ins that take the dict)
+            return self._grads[net]
+        if net not in self._prepared:
+            self._prepared[net] = ops.PreparedGrads(net, self._grads[net])
+        return self._prepared[net]
 
     def _forward_backward_direct(self, rays, target_s, scale, ray0, constant_init, pix=None):
         """Forward (stash mode) and backward kernels called back to back, the weight-gradient kernels accumulating
@@ -309,9 +320,9 @@ class TrainStep:
                 g, g0 = ops.mse_loss_grad(outs[0], outs[5] if Ni > 0 else None, t, scale, sqerr, pix=px)
                 if Ni > 0:
                     AG.backward_stashed(cfg, saved, stashes, (g, None, None, None), (g0, None, None, None),
-                                        self._grads[self.net_c], self._grads.get(self.net_f))
+                                        self._grad_arg(self.net_c), self._grad_arg(self.net_f))
                 else:
-                    AG.backward_stashed(cfg, saved, stashes, None, (g, None, None, None), self._grads[self.net_c], None)
+                    AG.backward_stashed(cfg, saved, stashes, None, (g, None, None, None), self._grad_arg(self.net_c), None)
         return Ni > 0
 
     def _forward_backward_autograd(self, rays, target_s, scale, ray0, constant_init):

@@ -501,3 +501,37 @@ def test_fused_quadrature_paths_agree(P, Ns, Ni, mode, two_nets):
     assert bool(torch.isfinite(a["rgb_map"]).all()) and bool(torch.isfinite(a["depth_map"]).all())
     z = a["z_vals"]
     assert z.shape == (n, Ns + Ni) and bool((z[:, 1:] >= z[:, :-1]).all())
+
+
+def test_packed_weights_follow_the_parameters():
+    """The packed bf16 copy is a cache of the module's parameters: an in-place update (optimizer.step: version counters
+    move), load_state_dict, an alias update + invalidate_packed, and a storage move (.data re-homed into another buffer)
+    are all seen by the next query; an untouched module is not repacked."""
+    import plnerf_b200
+    from plnerf_b200 import ops
+    cfg, kw, pc, pf = case_params("lego_linear_mid")
+    net = make_net(kw, pc)
+    g = load_golden("lego_linear_mid")
+    rays, z = dev(g["ray_batch"]), dev(g["z_vals0"])
+    with torch.no_grad():
+        base = ops.network_query(net, rays, z).clone()
+        n0 = ops.launch_count()
+        again = ops.network_query(net, rays, z)
+        assert torch.equal(again, base) and ops.launch_count() - n0 <= 2          # no pack kernels: view bias + MLP only
+        ref_sd = {k: v.clone() for k, v in net.state_dict().items()}
+        net.alpha_linear.bias.add_(0.25)                                           # in place: the version counter moves
+        moved = ops.network_query(net, rays, z)
+        assert (moved[..., 3] - base[..., 3]).abs().max().item() > 0.2
+        net.load_state_dict(ref_sd)
+        assert torch.equal(ops.network_query(net, rays, z), base)
+        flat = torch.cat([p.data.flatten() for p in net.parameters()])             # re-home the storage (what TrainStep does)
+        off = 0
+        for p in net.parameters():
+            p.data = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        assert torch.equal(ops.network_query(net, rays, z), base)
+        flat[-net.rgb_linear.bias.numel() - net.rgb_linear.weight.numel():] *= 0.5   # alias update: no counter moves ...
+        assert torch.equal(ops.network_query(net, rays, z), base)                  # ... so the cache is (documentedly) stale
+        ops.invalidate_packed(net)
+        changed = ops.network_query(net, rays, z)
+        assert (changed[..., :3] - base[..., :3]).abs().max().item() > 1e-3 and torch.equal(changed[..., 3], base[..., 3])
