@@ -252,3 +252,48 @@ def test_train_step_is_chunk_invariant():
     assert abs(a[0] - (a[1] + a[2])) <= 1e-6 * abs(a[0])
     assert (a[3] - b[3]).norm().item() <= 5e-3 * a[3].norm().item()
     assert (a[4] - b[4]).abs().max().item() <= 2 * 5e-4 + 1e-7    # one Adam step: at most +-lr where a ~0 gradient flips sign
+
+
+@pytest.mark.parametrize("use_viewdirs", [True, False])
+def test_train_step_coarse_only(use_viewdirs):
+    """N_importance = 0 / network_fine = None (BASELINE config 1's shape, with and without view directions): one network, one
+    optimiser segment, the loss is img2mse(rgb_map) alone; against render() + autograd + a stock Adam on a twin network."""
+    from plnerf_b200 import ops, run_plnerf as RP, train as T
+    from plnerf_b200.run_nerf_helpers import NeRF
+    H, W, focal, B = 40, 48, 55.0, 192
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = pose(70.0)
+    kwn = dict(D=8, W=256, input_ch=63, input_ch_views=27 if use_viewdirs else 0, output_ch=4, skips=(4,), use_viewdirs=use_viewdirs)
+
+    def mk():
+        net = NeRF(D=8, W=256, input_ch=63, input_ch_views=kwn["input_ch_views"], output_ch=4, skips=[4], use_viewdirs=use_viewdirs)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in synth.nerf_params(5, density_boost=False, **kwn).items()})
+        return net.cuda()
+    net, twin = mk(), mk()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2)
+    target = torch.rand(H, W, 3, device="cuda", generator=gen)
+    pix = T.sample_pixels(H, W, B, "cuda", gen)
+    kw = dict(network_query_fn=None, network_fn=net, network_fine=None, N_samples=64, N_importance=0, perturb=1.0,
+              white_bkgd=True, raw_noise_std=0., mode="linear", color_mode="midpoint", use_viewdirs=use_viewdirs, ndc=False,
+              near=2., far=6., seed=11)
+    step = T.TrainStep(H, W, K, kw, N_rand=B, lrate=5e-4, coarse_lrate=5e-4)
+    assert len(step.optimizer.param_groups) == 1 and list(step.optimizer.segments) == ["coarse"]
+    out = step(target, c2w, 0, pix=pix)
+    assert out["img_loss0"] is None and out["loss"].item() == out["img_loss"].item()
+    # the reference sequence on the twin
+    full, _ = ops.pack_rays(H, W, K, c2w=c2w, ndc=False, near=2., far=6., use_viewdirs=use_viewdirs)
+    rays = torch.stack([full[pix, 0:3], full[pix, 3:6]], 0)
+    kw_t = dict(kw, network_fn=twin)
+    opt = torch.optim.Adam(twin.parameters(), lr=5e-4, betas=(0.9, 0.999))
+    rgb, disp, acc, extras = RP.render(H, W, K, chunk=1024 * 32, rays=rays, **kw_t)
+    loss = torch.mean((rgb - target.reshape(-1, 3)[pix]) ** 2)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    assert abs(out["loss"].item() - loss.item()) <= 2e-5 * abs(loss.item())
+    g_ref = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for p in twin.parameters()])
+    assert (step.bucket.flat - g_ref).norm().item() <= 5e-3 * g_ref.norm().item()
+    p_a = torch.cat([p.detach().flatten() for p in net.parameters()])
+    p_b = torch.cat([p.detach().flatten() for p in twin.parameters()])
+    assert (p_a - p_b).abs().max().item() <= 2 * 5e-4 + 1e-7
