@@ -194,6 +194,12 @@ int plnerf_network_query_train(const plnerf_net_desc* desc, const void* packed, 
 size_t plnerf_packed_bwd_bytes(const plnerf_net_desc* desc);
 int plnerf_pack_weights_bwd(const plnerf_net_desc* desc, const plnerf_net_params* params,
                             void* packed_bwd, void* stream);
+/* The repack a training loop needs after optimizer.step() (run_plnerf.py:1302-1303 changes every parameter): for each of
+ * n_nets (1 or 2) networks, plnerf_pack_weights(bf16) into packed[i] and plnerf_pack_weights_bwd into packed_bwd[i], all in
+ * ONE kernel launch. */
+int plnerf_pack_weights_train(int n_nets, const plnerf_net_desc* const* descs,
+                              const plnerf_net_params* const* params, void* const* packed,
+                              void* const* packed_bwd, void* stream);
 int plnerf_network_query_bwd(const plnerf_net_desc* desc, const void* packed, const void* packed_bwd,
                              int64_t n, int S, const float* g_raw, int g_stride, void* stash,
                              size_t stash_bytes, const plnerf_net_grads* grads, void* stream);

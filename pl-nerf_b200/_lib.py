@@ -119,6 +119,8 @@ _SIGS = {
                                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "plnerf_packed_bwd_bytes": (C.c_size_t, [C.POINTER(NetDesc)]),
     "plnerf_pack_weights_bwd": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetParams), C.c_void_p, C.c_void_p]),
+    "plnerf_pack_weights_train": (C.c_int, [C.c_int, C.POINTER(C.POINTER(NetDesc)), C.POINTER(C.POINTER(NetParams)),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "plnerf_network_query_bwd": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                            C.c_int, C.c_void_p, C.c_size_t, C.POINTER(NetGrads), C.c_void_p]),
     "plnerf_mlp_forward": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,

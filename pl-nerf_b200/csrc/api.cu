@@ -1,8 +1,10 @@
 // C ABI of libplnerf_b200 (declared in include/plnerf_b200.h): argument validation, error plumbing
 // and the render_rays orchestration (reference run_plnerf.py:627-758) on one CUDA stream.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 #include "ops.cuh"
@@ -116,6 +118,11 @@ size_t plnerf_packed_bwd_bytes(const plnerf_net_desc* desc) { return mlp_packed_
 
 int plnerf_pack_weights_bwd(const plnerf_net_desc* desc, const plnerf_net_params* params, void* packed_bwd, void* stream) {
   return mlp_pack_bwd(desc, params, packed_bwd, (cudaStream_t)stream);
+}
+
+int plnerf_pack_weights_train(int n_nets, const plnerf_net_desc* const* descs, const plnerf_net_params* const* params,
+                              void* const* packed, void* const* packed_bwd, void* stream) {
+  return mlp_pack_train(n_nets, descs, params, packed, packed_bwd, (cudaStream_t)stream);
 }
 
 int plnerf_network_query_bwd(const plnerf_net_desc* desc, const void* packed, const void* packed_bwd, int64_t n, int S,
@@ -292,10 +299,31 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   return rc;
 }
 
+// One non-blocking side stream + fork / join events per device (created on first use, kept for the life of the process).
+namespace plnerf {
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+static SideStream* side_stream() {
+  static SideStream tab[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("side_stream: bad device"); return nullptr; }
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = tab[dev];
+  if (!s.ok) {
+    cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cuda_fail(e, "side_stream"); return nullptr; }
+    s.ok = true;
+  }
+  return &s;
+}
+}  // namespace plnerf
+
 // ---- training: forward with stash + the whole backward of a ray batch, one ABI call each --------------------------
 namespace plnerf {
 struct TrainWs {
-  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw, *vb_f, *dirpe;
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw, *graw0, *vb_f, *dirpe;
   void* mlp_ws; size_t mlp_ws_bytes;
   uint8_t *stash0, *stash1; size_t stash0_bytes, stash1_bytes;
   size_t total;
@@ -316,6 +344,7 @@ static TrainWs carve_train(const plnerf_render_cfg* c, const plnerf_net_desc* cd
   w.z1 = take((size_t)n * S1);
   w.raw1 = take((size_t)n * S1 * chf);
   w.graw = take((size_t)n * S1 * (chc > chf ? chc : chf));     // k_composite_bwd writes d raw in raw's own layout
+  w.graw0 = take(Ni > 0 ? (size_t)n * Ns * chc : 1);          // the coarse pass's own d raw: its backward runs beside the fine one
   w.vb_f = take((size_t)n * 128);
   w.dirpe = take((size_t)n * 32);
   w.mlp_ws = base + off;
@@ -423,27 +452,45 @@ int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
   const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
   const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
+  // coarse pass (the importance samples are detached, run_plnerf.py:728: no gradient reaches it from the fine maps, so
+  // the two passes are independent).  With both, the coarse pass is enqueued on a side stream forked from `stream` and
+  // joined before returning: its CTAs take the SMs the fine pass's kernels leave idle (ragged last rounds, fill / drain).
+  const float *gr = Ni > 0 ? g->g_rgb0 : g->g_rgb_map, *gd = Ni > 0 ? g->g_depth0 : g->g_depth_map;
+  const float *ga = Ni > 0 ? g->g_acc0 : g->g_acc_map, *gp = Ni > 0 ? g->g_disp0 : g->g_disp_map;
+  const bool coarse = (Ni == 0 || gr || gd || ga || gp);
+  cudaStream_t sc = st;
+  SideStream* side = nullptr;
+  bool fork = Ni > 0 && coarse;
+#ifdef PLNERF_DEBUG
+  if (getenv("PLNERF_NO_SIDE")) fork = false;      // A/B switch, developer library only
+#endif
+  if (fork) {
+    side = side_stream();
+    if (!side) return PLNERF_E_CUDA;
+    PLNERF_CUDA(cudaEventRecord(side->fork, st));
+    PLNERF_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    sc = side->stream;
+  }
   if (Ni > 0) {
     // fine pass: d(maps)/d(raw1) (run_plnerf.py:741 through autograd), then the fine network's parameter gradients
     rc = launch_composite_bwd(w.raw1, chf, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
                               noise1, g->g_rgb_map, g->g_depth_map, g->g_acc_map, g->g_disp_map, w.graw, st,
                               noise1 ? 0.f : cfg->raw_noise_std, cfg->seed, cfg->ray_id_offset, RNG_STREAM_NOISE1);
-    if (rc) return rc;
-    rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, chf, w.stash1, w.stash1_bytes, grads_fine, st);
-    if (rc) return rc;
+    if (!rc) rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, chf, w.stash1, w.stash1_bytes, grads_fine, st);
   }
-  // coarse pass (the importance samples are detached, run_plnerf.py:728: no gradient reaches it from the fine maps)
-  const float *gr = Ni > 0 ? g->g_rgb0 : g->g_rgb_map, *gd = Ni > 0 ? g->g_depth0 : g->g_depth_map;
-  const float *ga = Ni > 0 ? g->g_acc0 : g->g_acc_map, *gp = Ni > 0 ? g->g_disp0 : g->g_disp_map;
-  if (Ni == 0 || gr || gd || ga || gp) {
+  if (!rc && coarse) {
+    float* graw_c = Ni > 0 ? w.graw0 : w.graw;
     rc = launch_composite_bwd(w.raw0, chc, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
-                              noise0, gr, gd, ga, gp, w.graw, st, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed,
+                              noise0, gr, gd, ga, gp, graw_c, sc, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed,
                               cfg->ray_id_offset, RNG_STREAM_NOISE0);
-    if (rc) return rc;
-    rc = mlp_query_bwd(cdesc, cpacked, cpacked_bwd, n, Ns, w.graw, chc, w.stash0, w.stash0_bytes, grads_coarse, st);
-    if (rc) return rc;
+    if (!rc) rc = mlp_query_bwd(cdesc, cpacked, cpacked_bwd, n, Ns, graw_c, chc, w.stash0, w.stash0_bytes, grads_coarse, sc);
   }
-  return PLNERF_OK;
+  if (side) {      // always join, also after an error: `stream` must not be left with a dangling fork
+    cudaError_t e = cudaEventRecord(side->join, side->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
+    if (e != cudaSuccess && !rc) rc = cuda_fail(e, "render_rays_bwd: join");
+  }
+  return rc;
 }
 
 int plnerf_mse_loss_grad(const float* rgb, const float* rgb0, const float* target, const int64_t* pix, int64_t n,

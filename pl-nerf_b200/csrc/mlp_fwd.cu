@@ -291,10 +291,10 @@ struct PackArgs {
 };
 
 // one block (256 threads) per 4 KB K-step block; thread u -> 16-byte unit (panel = u/128, row = u%128)
-__global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ PackArgs a) {
+__device__ __forceinline__ void pack_weights_block(const PackArgs& a, const int block) {
   const NetPlan& P = a.plan;
   const int nsplit = (P.precision == PLNERF_PREC_BF16X3) ? 2 : 1;
-  int blk = blockIdx.x;
+  int blk = block;
   // locate (layer, half, stage, rep, j)
   int l = 0, h = 0;
   for (; l < P.n_layers; ++l) {
@@ -336,12 +336,12 @@ __global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ Pa
   uint4 q;
   q.x = ptx::pack_bf16(v[0], v[1]); q.y = ptx::pack_bf16(v[2], v[3]);
   q.z = ptx::pack_bf16(v[4], v[5]); q.w = ptx::pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(a.dst + (int64_t)blockIdx.x * KS_BYTES + (size_t)u * 16) = q;
+  *reinterpret_cast<uint4*>(a.dst + (int64_t)block * KS_BYTES + (size_t)u * 16) = q;
 }
+__global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ PackArgs a) { pack_weights_block(a, blockIdx.x); }
 
-__global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
+__device__ __forceinline__ void pack_tail_elem(const PackArgs& a, const int i) {
   const NetPlan& P = a.plan;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.tail_floats) return;
   float v = 0.f;
   // biases
@@ -372,6 +372,27 @@ __global__ void k_pack_tail(const __grid_constant__ PackArgs a) {
     }
   }
   a.tail[i] = v;
+}
+__global__ void __launch_bounds__(256) k_pack_tail(const __grid_constant__ PackArgs a) { pack_tail_elem(a, blockIdx.x * 256 + threadIdx.x); }
+
+// Every packed copy a training step needs, in ONE launch (six separate launches cost ~45 us of a 1.8 ms iteration): per
+// network the forward stream, its fp32 tail and the transposed stream of the input-gradient chain.  Blocks are dealt to jobs
+// by ranges; the (up to four) PackArgs ride in the kernel's parameter space (sm_70+: 32 KB).
+constexpr int MAX_PACK_ARGS = 4, MAX_PACK_JOBS = 6;
+struct PackTrainArgs {
+  int32_t n_jobs;
+  int32_t blk0[MAX_PACK_JOBS + 1];   // first block of job j (blk0[n_jobs] = grid size)
+  int8_t kind[MAX_PACK_JOBS];        // 0: weight stream (one block per K-step block), 1: tail (256 floats per block)
+  int8_t arg[MAX_PACK_JOBS];
+  PackArgs args[MAX_PACK_ARGS];
+};
+__global__ void __launch_bounds__(256) k_pack_train(const __grid_constant__ PackTrainArgs t) {
+  int j = 0;
+  while (j + 1 < t.n_jobs && (int)blockIdx.x >= t.blk0[j + 1]) ++j;
+  const int b = (int)blockIdx.x - t.blk0[j];
+  const PackArgs& a = t.args[t.arg[j]];
+  if (t.kind[j] == 0) pack_weights_block(a, b);
+  else pack_tail_elem(a, b * 256 + (int)threadIdx.x);
 }
 
 // =============================================================================================
@@ -2050,6 +2071,46 @@ int mlp_pack_bwd(const plnerf_net_desc* d, const plnerf_net_params* p, void* pac
   return PLNERF_OK;
 }
 
+int mlp_pack_train(int n_nets, const plnerf_net_desc* const* descs, const plnerf_net_params* const* params, void* const* packed,
+                   void* const* packed_bwd, cudaStream_t st) {
+  PLNERF_CHECK_ARG(n_nets >= 1 && 2 * n_nets <= MAX_PACK_ARGS && descs && params && packed && packed_bwd, "pack_weights_train: need 1 or 2 networks");
+  PackTrainArgs t;
+  memset(&t, 0, sizeof(t));
+  int nj = 0, na = 0, blk = 0;
+  auto job = [&](int kind, int arg, int64_t blocks) { t.kind[nj] = (int8_t)kind; t.arg[nj] = (int8_t)arg; t.blk0[nj] = blk; blk += (int)blocks; ++nj; };
+  for (int i = 0; i < n_nets; ++i) {
+    const plnerf_net_desc* d = descs[i];
+    const plnerf_net_params* p = params[i];
+    PLNERF_CHECK_ARG(d && p && packed[i] && packed_bwd[i], "pack_weights_train: null argument (network %d)", i);
+    PLNERF_CHECK_ARG((((uintptr_t)packed[i] | (uintptr_t)packed_bwd[i]) & 15) == 0, "pack_weights_train: buffers must be 16-byte aligned");
+    for (int k = 0; k < d->D; ++k) PLNERF_CHECK_ARG(p->pts_w[k] && p->pts_b[k], "pack_weights_train: pts_linears.%d missing", k);
+    if (d->use_viewdirs) PLNERF_CHECK_ARG(p->views_w && p->views_b && p->feature_w && p->feature_b && p->alpha_w && p->alpha_b && p->rgb_w && p->rgb_b, "pack_weights_train: viewdirs head parameters missing");
+    else PLNERF_CHECK_ARG(p->output_w && p->output_b, "pack_weights_train: output_linear missing");
+    PackArgs& f = t.args[na];
+    int rc = build_plan(d, PLNERF_PREC_BF16, p, &f.plan);
+    if (rc) return rc;
+    f.dst = static_cast<uint8_t*>(packed[i]);
+    f.tail = reinterpret_cast<float*>(f.dst + f.plan.weight_bytes);
+    f.prm = *p;
+    job(0, na, f.plan.weight_bytes / KS_BYTES);
+    job(1, na, ceil_div(f.plan.tail_floats, 256));
+    ++na;
+    PackArgs& b = t.args[na];
+    rc = build_dgrad_plan(d, p, &b.plan);
+    if (rc) return rc;
+    b.dst = static_cast<uint8_t*>(packed_bwd[i]);
+    b.tail = nullptr;
+    b.prm = *p;
+    job(0, na, b.plan.weight_bytes / KS_BYTES);
+    ++na;
+  }
+  t.n_jobs = nj;
+  t.blk0[nj] = blk;
+  k_pack_train<<<(unsigned)blk, 256, 0, st>>>(t);
+  PLNERF_LAUNCH_CHECK("k_pack_train");
+  return PLNERF_OK;
+}
+
 int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* packed_bwd, int64_t n, int S,
                   const float* g_raw, int g_stride, void* stash, size_t stash_bytes, const plnerf_net_grads* g,
                   cudaStream_t st) {
@@ -2136,9 +2197,11 @@ int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* 
     int n_light = 0;
     for (int i = 0; i < ni; ++i) n_light += w.items[i].swapped;
     const int n_main = ni - n_light;
-    int s_main = (g_num_sms - n_light) / (n_main > 0 ? n_main : 1);
+    int wg_sms = g_num_sms;
+    { const int force = dbg_env("PLNERF_WGRAD_SMS"); if (force > 0 && force < wg_sms) wg_sms = force; }
+    int s_main = (wg_sms - n_light) / (n_main > 0 ? n_main : 1);
     if (s_main < 1) s_main = 1;
-    int s_light = n_light ? (g_num_sms - s_main * n_main) / n_light : 1;
+    int s_light = n_light ? (wg_sms - s_main * n_main) / n_light : 1;
     if (s_light > s_main) s_light = s_main;
     if (s_light < 1) s_light = 1;
     int c0 = 0;

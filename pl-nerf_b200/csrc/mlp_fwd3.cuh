@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           uint8_t* st_t = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx] : nullptr;
           uint32_t* st_m = (STASH && P.L[l].mask_idx >= 0) ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] : nullptr;
           auto stash32 = [&](const uint32_t* pk16, uint32_t m, int h, int c2) {   // 32 columns [128 h + 64 ch + 32 c2, +32)
+            if (st_m && !PLNERF3_DBG(64)) st_m[(4 * h + 2 * ch + c2) * 128 + row] = m;     // (64: measurement, no mask stores)
             if (PLNERF3_DBG(32)) return;        // measurement: the stash forward without its activation stores
-            if (st_m) st_m[(4 * h + 2 * ch + c2) * 128 + row] = m;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               stash_store8(st_t, 256, row, 16 * h + 8 * ch + 4 * c2 + q4, make_uint4(pk16[4 * q4], pk16[4 * q4 + 1], pk16[4 * q4 + 2], pk16[4 * q4 + 3]));
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             ptx::tmem_ld_wait();
             if (c2 == 1) arrive_ep(reads_a ? 3 : 1);   // the accumulator is drained: half b may start (layer 0: `full` follows the store)
             uint32_t m = 0;
-            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2, STASH ? &m : nullptr);
+            if (epi == EPI_RELU_A) cvt32<true>(r, bias + 32 * c2, held + 16 * c2, (STASH && !PLNERF3_DBG(64)) ? &m : nullptr);
             else cvt32<false>(r, bias + 32 * c2, held + 16 * c2);
             if (STASH) stash32(held + 16 * c2, m, 0, c2);
             if (alpha_here) alpha_acc = dot32_relu(r, aw + 32 * c2, alpha_acc);
@@ -552,10 +552,10 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             arrive_ep(1);
             PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
             uint32_t pk[16], m = 0;
-            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, STASH ? &m : nullptr); else cvt32<false>(r0, bias + 128, pk);
+            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, (STASH && !PLNERF3_DBG(64)) ? &m : nullptr); else cvt32<false>(r0, bias + 128, pk);
             ptx::tmem_st16(tm_a + 64u, pk);
             if (STASH) stash32(pk, m, 1, 0);
-            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, STASH ? &m : nullptr); else cvt32<false>(r1, bias + 160, pk);
+            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, (STASH && !PLNERF3_DBG(64)) ? &m : nullptr); else cvt32<false>(r1, bias + 160, pk);
             ptx::tmem_st16(tm_a + 80u, pk);
             if (STASH) stash32(pk, m, 1, 1);
             if (alpha_here) { alpha_acc = dot32_relu(r0, aw + 128, alpha_acc); alpha_acc = dot32_relu(r1, aw + 160, alpha_acc); }

@@ -86,6 +86,9 @@ int mlp_query_train(const plnerf_net_desc* d, const void* packed, int multires, 
                     const float* dirpe_pre = nullptr);
 size_t mlp_packed_bwd_bytes(const plnerf_net_desc* d);
 int mlp_pack_bwd(const plnerf_net_desc* d, const plnerf_net_params* p, void* packed, cudaStream_t st);
+// forward stream + tail + transposed stream of 1 or 2 networks in one launch (the training step's repack after Adam)
+int mlp_pack_train(int n_nets, const plnerf_net_desc* const* descs, const plnerf_net_params* const* params, void* const* packed,
+                   void* const* packed_bwd, cudaStream_t st);
 int mlp_query_bwd(const plnerf_net_desc* d, const void* packed_fwd, const void* packed_bwd, int64_t n, int S,
                   const float* g_raw, int g_stride, void* stash, size_t stash_bytes, const plnerf_net_grads* g,
                   cudaStream_t st);

@@ -410,6 +410,46 @@ def packed_bwd_of(net):
     return buf
 
 
+def repack_train(nets):
+    """Refresh the packed bf16 copy AND the transposed (input-gradient) copy of 1 or 2 networks in ONE launch
+    (plnerf_pack_weights_train) and mark both caches current: what a training loop does after ``optimizer.step()``
+    instead of letting the next forward / backward repack lazily (three launches per network)."""
+    if not 1 <= len(nets) <= 2:
+        raise ValueError("repack_train: 1 or 2 networks")
+    n = len(nets)
+    descs, prms = (C.POINTER(L.NetDesc) * n)(), (C.POINTER(L.NetParams) * n)()
+    bufs, bwds = (C.c_void_p * n)(), (C.c_void_p * n)()
+    keep_all, done = [], []
+    prec = _prec("bf16")
+    for i, net in enumerate(nets):
+        pk = packed_of(net)
+        ver = pk._versions(net)
+        first = pk._params[0]
+        if not first.is_cuda:
+            raise RuntimeError("plnerf_b200: the NeRF module must live on a CUDA device (no CPU fallback)")
+        nb, nbb = L.lib().plnerf_packed_bytes(C.byref(pk.desc), prec), L.lib().plnerf_packed_bwd_bytes(C.byref(pk.desc))
+        if nb == 0 or nbb == 0:
+            L.check(-2)
+        buf = pk.buf.get(prec)
+        if buf is None or buf.numel() != nb or buf.device != first.device:
+            buf = pk.buf[prec] = torch.empty(nb, dtype=torch.uint8, device=first.device)
+        cache = net.__dict__.setdefault("_plnerf_packed_bwd", {})
+        bwd = cache.get("buf")
+        if bwd is None or bwd.numel() != nbb or bwd.device != first.device:
+            bwd = cache["buf"] = torch.empty(nbb, dtype=torch.uint8, device=first.device)
+        prm, keep = pk.param_struct(net, ver)
+        keep_all.append((prm, keep))
+        descs[i], prms[i] = C.pointer(pk.desc), C.pointer(prm)
+        bufs[i], bwds[i] = _p(buf), _p(bwd)
+        done.append((pk, cache, ver))
+    with torch.cuda.device(done[0][0]._params[0].device):
+        L.check(L.lib().plnerf_pack_weights_train(n, descs, prms, bufs, bwds, _stream()))
+    for pk, cache, ver in done:
+        pk.version[prec] = ver
+        cache["ver"] = ver
+    del keep_all
+
+
 def network_query_train(net, rays, z_vals):
     """run_network forward that also stashes what the backward needs.  -> (raw [n,S,4], stash)."""
     rays, z_vals = _f32(rays, "rays"), _f32(z_vals, "z_vals")

@@ -384,6 +384,8 @@ class TrainStep:
         self.optimizer.step()
         for net in self.nets:          # the update went through the flat alias: the views' version counters did not move
             ops.invalidate_packed(net)
+        if self._direct and self.flat_params.is_cuda:      # ... and both packed copies of both networks are rebuilt in one launch
+            ops.repack_train(self.nets)
         new_lrate = decayed_lrate(self.lrate, self.lrate_decay, global_step)
         for g in self.optimizer.param_groups:                    # both groups get the fine rate (Appendix B.1)
             g["lr"] = new_lrate

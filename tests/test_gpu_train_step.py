@@ -297,3 +297,36 @@ def test_train_step_coarse_only(use_viewdirs):
     p_a = torch.cat([p.detach().flatten() for p in net.parameters()])
     p_b = torch.cat([p.detach().flatten() for p in twin.parameters()])
     assert (p_a - p_b).abs().max().item() <= 2 * 5e-4 + 1e-7
+
+
+@pytest.mark.parametrize("use_viewdirs", [True, False])
+def test_repack_train_equals_separate_packs(use_viewdirs):
+    """ops.repack_train (plnerf_pack_weights_train: forward stream + tail + transposed stream of both networks in one launch)
+    writes the same bytes as plnerf_pack_weights / plnerf_pack_weights_bwd, and leaves both caches current."""
+    from plnerf_b200 import ops
+    from plnerf_b200.run_nerf_helpers import NeRF
+    torch.manual_seed(3)
+    nets = [NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=use_viewdirs).cuda()
+            for _ in range(2)]
+    ref = [(ops.packed_of(n).get(n, "bf16").clone(), ops.packed_bwd_of(n).clone()) for n in nets]
+    launches = ops.launch_count()
+    with torch.no_grad():
+        for n in nets:
+            for p in n.parameters():
+                p.data.mul_(1.25)                    # through .data: the version counters do not move (like the flat Adam)
+    for n in nets:
+        ops.invalidate_packed(n)
+        ops.packed_of(n).buf[ops._prec("bf16")].zero_()
+        n.__dict__["_plnerf_packed_bwd"]["buf"].zero_()
+    launches = ops.launch_count()
+    ops.repack_train(nets)
+    assert ops.launch_count() - launches == 1
+    launches = ops.launch_count()
+    got = [(ops.packed_of(n).get(n, "bf16").clone(), ops.packed_bwd_of(n).clone()) for n in nets]
+    assert ops.launch_count() == launches            # caches are current: no lazy repack
+    for n in nets:
+        ops.invalidate_packed(n)
+    want = [(ops.packed_of(n).get(n, "bf16").clone(), ops.packed_bwd_of(n).clone()) for n in nets]
+    for (g0, g1), (w0, w1), (r0, r1) in zip(got, want, ref):
+        assert torch.equal(g0, w0) and torch.equal(g1, w1)
+        assert not torch.equal(g0, r0) and not torch.equal(g1, r1)     # (the parameters did change)
