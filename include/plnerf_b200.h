@@ -333,6 +333,21 @@ int plnerf_mse_loss_grad(const float* rgb, const float* rgb0, const float* targe
                          float scale, float* g_rgb, float* g_rgb0, float* sqerr, void* stream);
 int plnerf_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
                      double beta2, double eps, int64_t step, int zero_grads, void* stream);
+/* plnerf_train_rays_mse: the device work of one iteration of the reference loop on a ray batch (run_plnerf.py:1283-1299:
+ * render -> img2mse(rgb) + img2mse(rgb0) -> loss.backward()) in ONE call = plnerf_render_rays_fwd_train +
+ * plnerf_mse_loss_grad + plnerf_render_rays_bwd with the same arguments (ws: plnerf_render_train_workspace_bytes), except
+ * that the coarse pass's loss and backward are enqueued on an internal side stream as soon as the coarse maps exist and run
+ * BESIDE the fine pass (the importance samples are detached, :728: the passes are independent); the side stream is joined
+ * into `stream` before the call returns.  Gradients are ADDED into grads_*; the sums of squared errors into sqerr[0] (fine;
+ * the only map when N_importance == 0) and sqerr[1] (coarse).  `out` may be NULL, and so may any of its members: maps the
+ * caller does not ask for stay in the workspace. */
+int plnerf_train_rays_mse(const plnerf_render_cfg* cfg, const plnerf_net_desc* coarse_desc, const void* coarse_packed,
+                          const void* coarse_packed_bwd, const plnerf_net_desc* fine_desc, const void* fine_packed,
+                          const void* fine_packed_bwd, const float* rays, int64_t n, int stride, const float* t_rand,
+                          const float* u, const float* noise0, const float* noise1, const float* target,
+                          const int64_t* pix, float scale, float* sqerr, const plnerf_render_out* out,
+                          const plnerf_net_grads* grads_coarse, const plnerf_net_grads* grads_fine, void* ws,
+                          size_t ws_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py): time every fused-MLP launch with CUDA events on its own stream --
  * plnerf_profile_enable(1) starts recording (and clears old records); plnerf_profile_read

@@ -168,6 +168,11 @@ _SIGS = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "plnerf_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
                                    C.c_double, C.c_double, C.c_int64, C.c_int, C.c_void_p]),
+    "plnerf_train_rays_mse": (C.c_int, [C.POINTER(RenderCfg), C.POINTER(NetDesc), C.c_void_p, C.c_void_p,
+                                        C.POINTER(NetDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                        C.c_void_p, C.POINTER(RenderOut), C.POINTER(NetGrads), C.POINTER(NetGrads),
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "plnerf_profile_enable": (C.c_int, [C.c_int]),
     "plnerf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

@@ -10,7 +10,8 @@ detached (run_plnerf.py:728) and ray inputs carry no gradient.  bf16 tensor-core
 accumulation; networks with and without view directions (output_linear head, run_nerf_helpers.py:100-103).
 
 ``forward_stashed`` / ``backward_stashed`` are the two plain functions behind the autograd.Function; the training
-step (train.TrainStep) calls them back to back without building an autograd graph.
+step (train.TrainStep) issues forward, loss and backward of a ray batch as one C call (``train_rays_mse``) without
+building an autograd graph.
 """
 import torch
 
@@ -51,6 +52,19 @@ def backward_stashed(cfg, saved, stashes, g_fine, g_coarse, grads_c, grads_f):
         ops.render_rays_bwd(saved, g_coarse, None, grads_c, None)
     else:
         ops.render_rays_bwd(saved, g_fine, g_coarse, grads_c, grads_f if cfg["net_f"] is not None else grads_c)
+
+
+def train_rays_mse(cfg, rays, target, pix, scale, sqerr, grads_c, grads_f):
+    """``forward_stashed`` -> ``ops.mse_loss_grad`` -> ``backward_stashed`` of one ray batch as ONE C call
+    (plnerf_train_rays_mse; the coarse pass's loss + backward run beside the fine pass): what train.TrainStep issues per
+    chunk.  ``target`` [n, 3] (or the whole image [H*W, 3] with ``pix`` = the rays' pixel ids); the two sums of squared
+    errors are added to ``sqerr`` [2]; parameter gradients are ACCUMULATED into grads_c / grads_f."""
+    ops.train_rays_mse(rays, cfg["net_c"], cfg["net_f"], cfg["N_samples"], cfg["N_importance"], cfg["mode"], cfg["color_mode"],
+                       target, scale, sqerr, grads_c, grads_f if cfg["net_f"] is not None else None, pix=pix,
+                       perturb=cfg["perturb"], white_bkgd=cfg["white_bkgd"], lindisp=cfg["lindisp"], raw_noise_std=0.0,
+                       zero_tol=cfg["zero_tol"], epsilon=cfg["epsilon"], farcolorfix=cfg["farcolorfix"], t_rand=cfg["t_rand"],
+                       u=cfg["u"], noise0=cfg["noise0"], noise1=cfg["noise1"], seed=cfg["seed"],
+                       ray_id_offset=cfg["ray_id_offset"])
 
 
 class _RenderRaysFn(torch.autograd.Function):

@@ -323,7 +323,7 @@ static SideStream* side_stream() {
 // ---- training: forward with stash + the whole backward of a ray batch, one ABI call each --------------------------
 namespace plnerf {
 struct TrainWs {
-  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw, *graw0, *vb_f, *dirpe;
+  float *z0, *raw0, *w0, *tau0, *T0, *zs, *z1, *raw1, *graw, *graw0, *vb_f, *dirpe, *g_rgb, *g_rgb0, *maps;
   void* mlp_ws; size_t mlp_ws_bytes;
   uint8_t *stash0, *stash1; size_t stash0_bytes, stash1_bytes;
   size_t total;
@@ -347,6 +347,9 @@ static TrainWs carve_train(const plnerf_render_cfg* c, const plnerf_net_desc* cd
   w.graw0 = take(Ni > 0 ? (size_t)n * Ns * chc : 1);          // the coarse pass's own d raw: its backward runs beside the fine one
   w.vb_f = take((size_t)n * 128);
   w.dirpe = take((size_t)n * 32);
+  w.g_rgb = take((size_t)n * 3);                               // plnerf_train_rays_mse: the loss gradients of the two rgb maps
+  w.g_rgb0 = take((size_t)n * 3);
+  w.maps = take((size_t)n * 13);                               // ... and the maps themselves when the caller does not ask for them
   w.mlp_ws = base + off;
   w.mlp_ws_bytes = mlp_workspace_bytes(cd, n);
   off += up(w.mlp_ws_bytes);
@@ -380,18 +383,31 @@ static int check_train_args(const plnerf_render_cfg* cfg, const plnerf_net_desc*
   return PLNERF_OK;
 }
 
-int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked,
-                                 const plnerf_net_desc* fdesc, const void* fpacked, const float* rays, int64_t n, int stride,
-                                 const float* t_rand, const float* u, const float* noise0, const float* noise1,
-                                 const plnerf_render_out* out, void* ws, size_t ws_bytes, void* stream) {
-  PLNERF_CHECK_ARG(cpacked && out, "render_rays_fwd_train: null argument");
-  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; }
-  int rc = check_train_args(cfg, cdesc, fdesc, n, rays, stride, ws, ws_bytes, "render_rays_fwd_train");
-  if (rc) return rc;
-  PLNERF_CHECK_ARG(out->rgb_map && out->disp_map && out->acc_map && out->depth_map, "render_rays_fwd_train: rgb/disp/acc/depth outputs are required");
-  if (n == 0) return PLNERF_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
+// The loss and the coarse pass's backward as the fused training entry runs them: forked onto the side stream as soon as the
+// coarse maps exist (nothing of the fine pass feeds them: the importance samples are detached, run_plnerf.py:728).
+namespace plnerf {
+struct CoarseBackward {
+  const float* target; const int64_t* pix; float scale; float* sqerr;
+  const void* cpacked_bwd; const plnerf_net_grads* grads_coarse; SideStream* side;
+};
+static int coarse_backward(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked, const float* rays, int64_t n,
+                           int stride, const float* noise0, const float* rgb0, const TrainWs& w, const CoarseBackward& cb, cudaStream_t sc,
+                           float* graw_c, float* sqerr_slot) {
+  const int Ns = cfg->N_samples, chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch;
+  int rc = launch_mse_loss_grad(rgb0, nullptr, cb.target, cb.pix, n, cb.scale, w.g_rgb0, nullptr, sqerr_slot, sc);
+  if (!rc) rc = launch_composite_bwd(w.raw0, chc, w.z0, rays, n, stride, Ns, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                                     noise0, w.g_rgb0, nullptr, nullptr, nullptr, graw_c, sc, noise0 ? 0.f : cfg->raw_noise_std, cfg->seed,
+                                     cfg->ray_id_offset, RNG_STREAM_NOISE0);
+  if (!rc) rc = mlp_query_bwd(cdesc, cpacked, cb.cpacked_bwd, n, Ns, graw_c, chc, w.stash0, w.stash0_bytes, cb.grads_coarse, sc);
+  return rc;
+}
+}  // namespace plnerf
+
+static int train_forward(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked,
+                         const plnerf_net_desc* fdesc, const void* fpacked, const float* rays, int64_t n, int stride,
+                         const float* t_rand, const float* u, const float* noise0, const float* noise1,
+                         const plnerf_render_out* out, const TrainWs& w, cudaStream_t st, const CoarseBackward* cb) {
+  int rc = PLNERF_OK;
   const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
   const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
   const bool fine = Ni > 0;
@@ -421,6 +437,12 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
     return PLNERF_OK;
   }
   PLNERF_CHECK_ARG(out->rgb0 && out->disp0 && out->acc0 && out->depth0, "render_rays_fwd_train: coarse outputs are required when N_importance > 0");
+  if (cb) {      // fused training entry: the coarse loss + backward start here, beside the fine pass
+    PLNERF_CUDA(cudaEventRecord(cb->side->fork, st));
+    PLNERF_CUDA(cudaStreamWaitEvent(cb->side->stream, cb->side->fork, 0));
+    rc = coarse_backward(cfg, cdesc, cpacked, rays, n, stride, noise0, out->rgb0, w, *cb, cb->side->stream, w.graw0, cb->sqerr + 1);
+    if (rc) return rc;
+  }
   rc = launch_sample_merge(cfg->mode == PLNERF_MODE_LINEAR, w.z0, w.w0, w.tau0, w.T0, rays, n, stride, Ns, Ni, u, cfg->seed,
                            cfg->ray_id_offset, cfg->zero_tol, cfg->epsilon, w.z1, out->z_std, out->inds, st);
   if (rc) return rc;
@@ -435,6 +457,70 @@ int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_
   if (out->raw) PLNERF_CUDA(cudaMemcpyAsync(out->raw, w.raw1, (size_t)n * S1 * chf * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (out->z_vals) PLNERF_CUDA(cudaMemcpyAsync(out->z_vals, w.z1, (size_t)n * S1 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return PLNERF_OK;
+}
+
+int plnerf_render_rays_fwd_train(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked,
+                                 const plnerf_net_desc* fdesc, const void* fpacked, const float* rays, int64_t n, int stride,
+                                 const float* t_rand, const float* u, const float* noise0, const float* noise1,
+                                 const plnerf_render_out* out, void* ws, size_t ws_bytes, void* stream) {
+  PLNERF_CHECK_ARG(cpacked && out, "render_rays_fwd_train: null argument");
+  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; }
+  int rc = check_train_args(cfg, cdesc, fdesc, n, rays, stride, ws, ws_bytes, "render_rays_fwd_train");
+  if (rc) return rc;
+  PLNERF_CHECK_ARG(out->rgb_map && out->disp_map && out->acc_map && out->depth_map, "render_rays_fwd_train: rgb/disp/acc/depth outputs are required");
+  if (n == 0) return PLNERF_OK;
+  const TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
+  return train_forward(cfg, cdesc, cpacked, fdesc, fpacked, rays, n, stride, t_rand, u, noise0, noise1, out, w, (cudaStream_t)stream, nullptr);
+}
+
+int plnerf_train_rays_mse(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked, const void* cpacked_bwd,
+                          const plnerf_net_desc* fdesc, const void* fpacked, const void* fpacked_bwd, const float* rays,
+                          int64_t n, int stride, const float* t_rand, const float* u, const float* noise0, const float* noise1,
+                          const float* target, const int64_t* pix, float scale, float* sqerr, const plnerf_render_out* out,
+                          const plnerf_net_grads* grads_coarse, const plnerf_net_grads* grads_fine, void* ws, size_t ws_bytes,
+                          void* stream) {
+  PLNERF_CHECK_ARG(cpacked && cpacked_bwd && grads_coarse && sqerr && (n == 0 || target), "train_rays_mse: null argument");
+  if (!fdesc || !fpacked) { fdesc = cdesc; fpacked = cpacked; fpacked_bwd = cpacked_bwd; grads_fine = grads_coarse; }
+  PLNERF_CHECK_ARG(fpacked_bwd && grads_fine, "train_rays_mse: the fine network needs its transposed weights and gradient buffers");
+  int rc = check_train_args(cfg, cdesc, fdesc, n, rays, stride, ws, ws_bytes, "train_rays_mse");
+  if (rc) return rc;
+  if (n == 0) return PLNERF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TrainWs w = carve_train(cfg, cdesc, fdesc, n, static_cast<uint8_t*>(ws));
+  const int Ns = cfg->N_samples, Ni = cfg->N_importance, S1 = Ns + Ni;
+  const int chc = cdesc->use_viewdirs ? 4 : cdesc->output_ch, chf = fdesc->use_viewdirs ? 4 : fdesc->output_ch;
+  // maps the caller does not ask for live in the workspace
+  plnerf_render_out o;
+  memset(&o, 0, sizeof(o));
+  if (out) o = *out;
+  float* m = w.maps;
+  auto own = [&](float*& p, size_t per_ray) { if (!p) p = m; m += (size_t)n * per_ray; };
+  own(o.rgb_map, 3); own(o.disp_map, 1); own(o.acc_map, 1); own(o.depth_map, 1);
+  if (Ni > 0) { own(o.rgb0, 3); own(o.disp0, 1); own(o.acc0, 1); own(o.depth0, 1); }
+  CoarseBackward cb{target, pix, scale, sqerr, cpacked_bwd, grads_coarse, nullptr};
+  if (Ni > 0) {
+    cb.side = side_stream();
+    if (!cb.side) return PLNERF_E_CUDA;
+  }
+  rc = train_forward(cfg, cdesc, cpacked, fdesc, fpacked, rays, n, stride, t_rand, u, noise0, noise1, &o, w, st, Ni > 0 ? &cb : nullptr);
+  if (!rc) {
+    if (Ni > 0) {
+      // fine pass: img2mse(rgb_map) (run_plnerf.py:1289), d(maps)/d(raw1), the fine network's parameter gradients
+      rc = launch_mse_loss_grad(o.rgb_map, nullptr, target, pix, n, scale, w.g_rgb, nullptr, sqerr, st);
+      if (!rc) rc = launch_composite_bwd(w.raw1, chf, w.z1, rays, n, stride, S1, cfg->mode, cfg->color_mode, cfg->white_bkgd, cfg->farcolorfix,
+                                         noise1, w.g_rgb, nullptr, nullptr, nullptr, w.graw, st, noise1 ? 0.f : cfg->raw_noise_std, cfg->seed,
+                                         cfg->ray_id_offset, RNG_STREAM_NOISE1);
+      if (!rc) rc = mlp_query_bwd(fdesc, fpacked, fpacked_bwd, n, S1, w.graw, chf, w.stash1, w.stash1_bytes, grads_fine, st);
+    } else {
+      rc = coarse_backward(cfg, cdesc, cpacked, rays, n, stride, noise0, o.rgb_map, w, cb, st, w.graw, sqerr);
+    }
+  }
+  if (cb.side) {      // always join (also after an error, once the fork may have happened)
+    cudaError_t e = cudaEventRecord(cb.side->join, cb.side->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, cb.side->join, 0);
+    if (e != cudaSuccess && !rc) rc = cuda_fail(e, "train_rays_mse: join");
+  }
+  return rc;
 }
 
 int plnerf_render_rays_bwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* cdesc, const void* cpacked, const void* cpacked_bwd,

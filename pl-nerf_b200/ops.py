@@ -712,6 +712,58 @@ def render_rays_bwd(ctx, g_fine, g_coarse, grads_c, grads_f):
                                             _stream()))
 
 
+def train_rays_mse(rays, net_coarse, net_fine, N_samples, N_importance, mode, color_mode, target, scale, sqerr, grads_c,
+                   grads_f, pix=None, perturb=True, white_bkgd=False, lindisp=False, raw_noise_std=0.0, zero_tol=1e-4,
+                   epsilon=1e-3, farcolorfix=False, t_rand=None, u=None, noise0=None, noise1=None, seed=0, ray_id_offset=0,
+                   want_maps=False):
+    """The device work of one iteration of the reference loop on a ray batch -- render_rays forward (stash mode), the two
+    img2mse terms, loss.backward() -- in ONE C call (plnerf_train_rays_mse); the coarse pass's loss and backward run on a
+    side stream beside the fine pass.  ``target`` / ``pix`` / ``scale`` / ``sqerr`` as in mse_loss_grad; parameter gradients
+    are ADDED into grads_c / grads_f (dicts or PreparedGrads).  Returns the maps as a dict when ``want_maps``, else None."""
+    rays, target = _f32(rays, "rays"), _f32(target, "target")
+    n, dev = rays.shape[0], rays.device
+    fine = net_fine if (N_importance > 0 and net_fine is not None) else None
+    pkc = packed_of(net_coarse)
+    bufc, bwdc = pkc.get(net_coarse, "bf16"), packed_bwd_of(net_coarse)
+    gc = (grads_c if isinstance(grads_c, PreparedGrads) else PreparedGrads(net_coarse, grads_c)).struct
+    fdesc = buff = bwdf = gf_ref = None
+    if fine is not None:
+        pkf = packed_of(fine)
+        fdesc, buff, bwdf = C.byref(pkf.desc), pkf.get(fine, "bf16"), packed_bwd_of(fine)
+        gf = (grads_f if isinstance(grads_f, PreparedGrads) else PreparedGrads(fine, grads_f)).struct
+        gf_ref = C.byref(gf)
+    cfg = _render_cfg(pkc, N_samples, N_importance, mode, color_mode, perturb, white_bkgd, lindisp, raw_noise_std, zero_tol,
+                      epsilon, farcolorfix, seed, ray_id_offset, "bf16")
+    if pix is not None and (pix.dtype != torch.int64 or not pix.is_contiguous() or not pix.is_cuda):
+        raise RuntimeError("pix: expected a contiguous int64 CUDA tensor")
+    if sqerr.dtype != torch.float32 or sqerr.numel() < 2 or not sqerr.is_cuda:
+        raise RuntimeError("sqerr: expected a float32 CUDA tensor of 2 elements")
+    o, ret = None, None
+    if want_maps:
+        o, ret = L.RenderOut(), {}
+        keys = [("rgb_map", (n, 3)), ("disp_map", (n,)), ("acc_map", (n,)), ("depth_map", (n,))]
+        if N_importance > 0:
+            keys += [("rgb0", (n, 3)), ("disp0", (n,)), ("acc0", (n,)), ("depth0", (n,)), ("z_std", (n,))]
+        for key, shape in keys:
+            ret[key] = torch.empty(shape, device=dev)
+            setattr(o, key, ret[key].data_ptr())
+    opt = lambda t, nm: None if t is None else _f32(t, nm)
+    t_rand, u, noise0, noise1 = opt(t_rand, "t_rand"), opt(u, "u"), opt(noise0, "noise0"), opt(noise1, "noise1")
+    wsb = L.lib().plnerf_render_train_workspace_bytes(C.byref(cfg), C.byref(pkc.desc), fdesc, n)
+    if wsb == 0:
+        L.check(-2)
+    if wsb > 64 * 2 ** 30:
+        raise RuntimeError(f"plnerf_b200: the training workspace for {n} rays x {N_samples + N_importance} samples would need "
+                           f"{wsb / 2**30:.1f} GiB; use a smaller ray batch / chunk")
+    ws = torch.empty(wsb + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    L.check(L.lib().plnerf_train_rays_mse(C.byref(cfg), C.byref(pkc.desc), _p(bufc), _p(bwdc), fdesc, _p(buff), _p(bwdf), _p(rays),
+                                           n, rays.shape[1], _p(t_rand), _p(u), _p(noise0), _p(noise1), _p(target), _p(pix),
+                                           float(scale), _p(sqerr), C.byref(o) if o is not None else None, C.byref(gc), gf_ref,
+                                           C.c_void_p(ws.data_ptr() + off), wsb, _stream()))
+    return ret
+
+
 def render_rays_fwd(rays, net_coarse, net_fine, N_samples, N_importance, mode, color_mode, perturb=True,
                     white_bkgd=False, lindisp=False, raw_noise_std=0.0, zero_tol=1e-4, epsilon=1e-3, farcolorfix=False,
                     t_rand=None, u=None, noise0=None, noise1=None, seed=0, ray_id_offset=0, retraw=False,

@@ -290,9 +290,10 @@ class TrainStep:
         return self._prepared[net]
 
     def _forward_backward_direct(self, rays, target_s, scale, ray0, constant_init, pix=None):
-        """Forward (stash mode) and backward kernels called back to back, the weight-gradient kernels accumulating
-        straight into the flat gradient buffer: no autograd graph, no per-parameter AccumulateGrad add (48 launches
-        per step through ``loss.backward()``), no zero-filled placeholders for the unused map gradients.
+        """Forward (stash mode), the two MSE terms and the backward of every chunk as ONE C call
+        (``autograd.train_rays_mse``), the weight-gradient kernels accumulating straight into the flat gradient buffer: no
+        autograd graph, no per-parameter AccumulateGrad add (48 launches per step through ``loss.backward()``), no
+        zero-filled placeholders for the unused map gradients; the coarse pass's backward runs beside the fine pass.
         ``target_s`` [n, 3] holds the rays' targets, or -- with ``pix`` (their pixel ids) -- the whole image [H*W, 3]
         (the gather :1280 then happens inside the loss kernel).  The sums of squared errors of rgb_map / rgb0 are added
         to ``self.bucket.extra``; returns whether a coarse term exists."""
@@ -315,14 +316,9 @@ class TrainStep:
                            seed=kw["seed"] if kw.get("seed") is not None else RP._next_seed(), ray_id_offset=ray0 + c0)
                 if Ni > 0 and not cfg["perturb"] and cfg["u"] is None:      # det=True: the reference's linspace u (see render_rays)
                     cfg["u"] = torch.linspace(0., 1., steps=Ni, device=r.device).expand(n, Ni).contiguous()
-                outs, saved, stashes = AG.forward_stashed(cfg, r)
                 t, px = (target_s, pix[c0:c0 + n]) if pix is not None else (target_s[c0:c0 + n], None)
-                g, g0 = ops.mse_loss_grad(outs[0], outs[5] if Ni > 0 else None, t, scale, sqerr, pix=px)
-                if Ni > 0:
-                    AG.backward_stashed(cfg, saved, stashes, (g, None, None, None), (g0, None, None, None),
-                                        self._grad_arg(self.net_c), self._grad_arg(self.net_f))
-                else:
-                    AG.backward_stashed(cfg, saved, stashes, None, (g, None, None, None), self._grad_arg(self.net_c), None)
+                AG.train_rays_mse(cfg, r, t, px, scale, sqerr, self._grad_arg(self.net_c),
+                                  self._grad_arg(self.net_f) if Ni > 0 else None)
         return Ni > 0
 
     def _forward_backward_autograd(self, rays, target_s, scale, ray0, constant_init):

@@ -145,6 +145,12 @@ def _run_train_steps(n_steps):
     ops.mse_loss_grad, ops.adam_step = fake_mse_loss_grad, fake_adam_step
     AG.forward_stashed, AG.backward_stashed = _fake_forward, _fake_backward
 
+    def fake_train_rays_mse(cfg, rays, target, pix, scale, sqerr, grads_c, grads_f):   # the fused entry = the three in sequence
+        outs, saved, stashes = _fake_forward(cfg, rays)
+        g, g0 = fake_mse_loss_grad(outs[0], outs[5], target, scale, sqerr, pix=pix)
+        _fake_backward(cfg, saved, stashes, (g, None, None, None), (g0, None, None, None), grads_c, grads_f)
+    AG.train_rays_mse = fake_train_rays_mse
+
     class HostOnlyStep(T.TrainStep):
         def _check_device(self):
             pass

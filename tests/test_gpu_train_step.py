@@ -330,3 +330,55 @@ def test_repack_train_equals_separate_packs(use_viewdirs):
     for (g0, g1), (w0, w1), (r0, r1) in zip(got, want, ref):
         assert torch.equal(g0, w0) and torch.equal(g1, w1)
         assert not torch.equal(g0, r0) and not torch.equal(g1, r1)     # (the parameters did change)
+
+
+@pytest.mark.parametrize("n_importance,shared", [(64, False), (64, True), (0, False)])
+def test_train_rays_mse_equals_the_three_calls(n_importance, shared):
+    """plnerf_train_rays_mse (forward + both MSE terms + backward in one call, the coarse backward forked beside the fine
+    pass) against plnerf_render_rays_fwd_train -> plnerf_mse_loss_grad -> plnerf_render_rays_bwd on the same rays and draws:
+    maps and loss sums bit for bit, parameter gradients to the weight-gradient atomics' noise.  `shared`: network_fine=None
+    (the coarse network serves both passes, both backward passes add into the same buffers concurrently)."""
+    from plnerf_b200 import ops
+    n, Ns = 200, 64
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    H, W, focal = 40, 48, 55.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    full, _ = ops.pack_rays(H, W, K, c2w=pose(25.0), ndc=False, near=2., far=6., use_viewdirs=True)
+    pix = torch.randperm(H * W, device="cuda", generator=gen)[:n].contiguous()
+    rays = full[pix].contiguous()
+    image = torch.rand(H * W, 3, device="cuda", generator=gen)
+    net_c, net_f = make_net(61), (None if (shared or n_importance == 0) else make_net(62))
+    args = (rays, net_c, net_f, Ns, n_importance, "linear", "midpoint")
+    kw = dict(perturb=True, white_bkgd=True, seed=77, ray_id_offset=1000)
+    scale = 2.0 / (3.0 * n)
+
+    def zero_grads(net):
+        return None if net is None else {k: torch.zeros_like(p) for k, p in net.named_parameters()}
+    # the three calls
+    ga_c, ga_f, sq_a = zero_grads(net_c), zero_grads(net_f), torch.zeros(2, device="cuda")
+    ret, ctx = ops.render_rays_fwd_train(*args, **kw)
+    g, g0 = ops.mse_loss_grad(ret["rgb_map"], ret.get("rgb0"), image, scale, sq_a, pix=pix)
+    if n_importance > 0:
+        ops.render_rays_bwd(ctx, (g, None, None, None), (g0, None, None, None), ga_c, ga_f if net_f is not None else ga_c)
+    else:
+        ops.render_rays_bwd(ctx, (g, None, None, None), None, ga_c, None)
+    # one call
+    gb_c, gb_f, sq_b = zero_grads(net_c), zero_grads(net_f), torch.zeros(2, device="cuda")
+    maps = ops.train_rays_mse(*args, image, scale, sq_b, gb_c, gb_f, pix=pix, want_maps=True, **kw)
+    torch.cuda.synchronize()
+    for k in maps:       # bit for bit (as int32: a ray with zero opacity has a NaN disparity in the reference too, run_plnerf.py:608)
+        assert torch.equal(maps[k].view(torch.int32), ret[k].view(torch.int32)), k
+    assert torch.equal(sq_a, sq_b) and sq_a[0].item() > 0 and (sq_a[1].item() > 0) == (n_importance > 0)
+    for ga, gb in ((ga_c, gb_c), (ga_f, gb_f)):
+        if ga is None:
+            continue
+        fa, fb = torch.cat([v.flatten() for v in ga.values()]), torch.cat([v.flatten() for v in gb.values()])
+        assert fa.norm().item() > 0
+        assert (fa - fb).norm().item() <= 1e-4 * fa.norm().item()
+    # without map outputs: same gradients again (the maps then live in the workspace)
+    gc_c, gc_f, sq_c = zero_grads(net_c), zero_grads(net_f), torch.zeros(2, device="cuda")
+    assert ops.train_rays_mse(*args, image, scale, sq_c, gc_c, gc_f, pix=pix, **kw) is None
+    assert torch.equal(sq_c, sq_a)
+    fb, fc = torch.cat([v.flatten() for v in gb_c.values()]), torch.cat([v.flatten() for v in gc_c.values()])
+    assert (fb - fc).norm().item() <= 1e-4 * fb.norm().item()

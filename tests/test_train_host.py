@@ -198,6 +198,13 @@ def test_train_step_host_logic_equals_two_stock_adams(monkeypatch):
     monkeypatch.setattr(RP, "batchify_rays", fake_batchify)
     monkeypatch.setattr(AG, "forward_stashed", fake_forward)
     monkeypatch.setattr(AG, "backward_stashed", fake_backward)
+
+    def fake_train_rays_mse(cfg, rays, target, pix, scale, sqerr, grads_c, grads_f):
+        # the fused entry (plnerf_train_rays_mse) = forward -> the two MSE terms -> backward of the same ray batch
+        outs, saved, stashes = fake_forward(cfg, rays)
+        g, g0 = ops.mse_loss_grad(outs[0], outs[5], target, scale, sqerr, pix=pix)
+        fake_backward(cfg, saved, stashes, (g, None, None, None), (g0, None, None, None), grads_c, grads_f)
+    monkeypatch.setattr(AG, "train_rays_mse", fake_train_rays_mse)
     monkeypatch.setattr(ops, "invalidate_packed", lambda net: invalidated.append(net))
 
     # torch stand-ins for the two small kernels of the step (tests/util.py)
