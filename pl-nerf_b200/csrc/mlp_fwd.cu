@@ -460,6 +460,7 @@ struct RaySetupArgs {
   float* dirpe;                          // [n,32] or null: the (zero-padded) direction encoding itself (training stash input)
   // depths
   int Ns, lindisp, perturb; const float* t_rand; uint64_t seed, ray0; float* z;
+  int rpi;                               // rays per block iteration (<= RS_RAYS)
 };
 __device__ __forceinline__ float setup_linspace01(int i, int n, float step) {
   return (i < n / 2) ? step * (float)i : fmaf(-step, (float)(n - 1 - i), 1.0f);   // torch.linspace(0,1,n)
@@ -469,8 +470,9 @@ __device__ __forceinline__ float setup_base_z(float near, float far, float t, in
   if (!lindisp) return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
   return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near), omt), __fmul_rn(__fdiv_rn(1.0f, far), t)));
 }
+constexpr int RS_RAYS = 16;  // most rays per block iteration (two block-wide barriers per iteration; the weights stay in registers)
 __global__ void __launch_bounds__(128) k_ray_setup(const __grid_constant__ RaySetupArgs a) {
-  __shared__ float emb[VB_RAYS][32];
+  __shared__ __align__(16) float emb[RS_RAYS][32];
   const int t = threadIdx.x;
   const int icv = a.icv;                   // <= 27 on this path (multires_views <= 4)
   float wc[27], wf[27];
@@ -481,9 +483,11 @@ __global__ void __launch_bounds__(128) k_ray_setup(const __grid_constant__ RaySe
   }
   const float bc = a.tail_c[a.views_b_off + t], bf = a.vb_f ? a.tail_f[a.views_b_off + t] : 0.f;
   const float step = (a.Ns > 1) ? __fdiv_rn(1.0f, (float)(a.Ns - 1)) : 0.0f;
-  for (int64_t r0 = (int64_t)blockIdx.x * VB_RAYS; r0 < a.n; r0 += (int64_t)gridDim.x * VB_RAYS) {
-    {
-      const int rr = t >> 5, j = t & 31;
+  const int gpr = (a.Ns + 3) >> 2;         // groups of four consecutive depths per ray (one Philox block each)
+  const int rpi = a.rpi;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpi; r0 < a.n; r0 += (int64_t)gridDim.x * rpi) {
+    for (int e = t; e < rpi * 32; e += 128) {
+      const int rr = e >> 5, j = e & 31;
       const int64_t r = r0 + rr;
       float v = 0.f;
       if (r < a.n && j < icv) {
@@ -498,31 +502,55 @@ __global__ void __launch_bounds__(128) k_ray_setup(const __grid_constant__ RaySe
       emb[rr][j] = v;
       if (a.dirpe && r < a.n) a.dirpe[r * 32 + j] = v;
     }
-    // this block's depths: VB_RAYS rays x Ns samples (k_stratified_z's arithmetic, one rounding per reference op)
-    for (int e = t; e < VB_RAYS * a.Ns; e += 128) {
-      const int rr = e / a.Ns, i = e - rr * a.Ns;
+    // this block's depths: RS_RAYS rays x Ns samples (k_stratified_z's arithmetic, one rounding per reference op), four
+    // consecutive samples per thread: their draws are the four words of one Philox block, the neighbouring base depths are shared
+    for (int e = t; e < rpi * gpr; e += 128) {
+      const int rr = e / gpr, g = e - rr * gpr;
       const int64_t r = r0 + rr;
       if (r >= a.n) continue;
       const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
-      const float zi = setup_base_z(near, far, setup_linspace01(i, a.Ns, step), a.lindisp);
-      float z = zi;
-      if (a.perturb) {
-        float lower = zi, upper = zi;
-        if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(zi, setup_base_z(near, far, setup_linspace01(i - 1, a.Ns, step), a.lindisp)));
-        if (i < a.Ns - 1) upper = __fmul_rn(0.5f, __fadd_rn(setup_base_z(near, far, setup_linspace01(i + 1, a.Ns, step), a.lindisp), zi));
-        const float tr = a.t_rand ? a.t_rand[r * (int64_t)a.Ns + i] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_TRAND, (uint32_t)i);
-        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+      const int i0 = 4 * g;
+      float zb[6];                           // base depths of samples i0 - 1 .. i0 + 4
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int i = i0 - 1 + q;
+        zb[q] = (i >= 0 && i < a.Ns) ? setup_base_z(near, far, setup_linspace01(i, a.Ns, step), a.lindisp) : 0.f;
       }
-      a.z[r * (int64_t)a.Ns + i] = z;
+      uint32_t w4[4] = {0u, 0u, 0u, 0u};
+      if (a.perturb && !a.t_rand) philox4x32(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_TRAND, (uint32_t)g, w4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q;
+        if (i >= a.Ns) break;
+        const float zi = zb[q + 1];
+        float z = zi;
+        if (a.perturb) {
+          float lower = zi, upper = zi;
+          if (i > 0) lower = __fmul_rn(0.5f, __fadd_rn(zi, zb[q]));
+          if (i < a.Ns - 1) upper = __fmul_rn(0.5f, __fadd_rn(zb[q + 2], zi));
+          const float tr = a.t_rand ? a.t_rand[r * (int64_t)a.Ns + i] : (float)(w4[q] >> 8) * (1.0f / 16777216.0f);
+          z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
+        }
+        a.z[r * (int64_t)a.Ns + i] = z;
+      }
     }
     __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < VB_RAYS; ++rr) {
+#pragma unroll 4
+    for (int rr = 0; rr < rpi; ++rr) {
       const int64_t r = r0 + rr;
       if (r < a.n) {
         float acc_c = bc, acc_f = bf;
+        const float4* e4 = reinterpret_cast<const float4*>(emb[rr]);     // (broadcast reads, 16 bytes at a time; zero beyond icv)
 #pragma unroll
-        for (int j = 0; j < 27; ++j) if (j < icv) { acc_c = fmaf(wc[j], emb[rr][j], acc_c); acc_f = fmaf(wf[j], emb[rr][j], acc_f); }
+        for (int q = 0; q < 7; ++q) {
+          const float4 ev = e4[q];
+          const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 4 * q + i;
+            if (j < 27) { acc_c = fmaf(wc[j], e[i], acc_c); acc_f = fmaf(wf[j], e[i], acc_f); }
+          }
+        }
         a.vb_c[r * 128 + t] = acc_c;
         if (a.vb_f) a.vb_f[r * 128 + t] = acc_f;
       }
@@ -1894,7 +1922,11 @@ int launch_ray_setup(const plnerf_net_desc* cd, const void* cpacked, const plner
   a.views_b_off = pc.views_b_off; a.dirw_off = pc.dirw_off; a.icv = cd->input_ch_views; a.multires_views = multires_views;
   a.rays = rays; a.stride = stride; a.n = n; a.vb_c = vb_c; a.vb_f = fd ? vb_f : nullptr; a.dirpe = dirpe;
   a.Ns = Ns; a.lindisp = lindisp; a.perturb = perturb; a.t_rand = t_rand; a.seed = seed; a.ray0 = ray0; a.z = z;
-  const int64_t blocks = ceil_div(n, VB_RAYS);
+  // 16 rays per block iteration for large batches, fewer (down to 4) while that keeps every SM busy
+  int rpi = RS_RAYS;
+  while (rpi > 4 && ceil_div(n, rpi) < 4 * g_num_sms) rpi >>= 1;
+  a.rpi = rpi;
+  const int64_t blocks = ceil_div(n, rpi);
   k_ray_setup<<<(unsigned)(blocks < 8 * g_num_sms ? blocks : 8 * g_num_sms), 128, 0, st>>>(a);
   PLNERF_LAUNCH_CHECK("k_ray_setup");
   return PLNERF_OK;

@@ -342,10 +342,11 @@ __device__ __forceinline__ void pl_build(const SamplePLArgs& a, int64_t r, int l
 
 // sample k of ray r: the draw, the bracket, the closed-form inverse; writes the optional per-sample outputs
 __device__ __forceinline__ float pl_sample(const SamplePLArgs& a, int64_t r, int k, const float* cdf, const float* s,
-                                           const float* T, const float* tau) {
+                                           const float* T, const float* tau, const float* u_drawn = nullptr) {
   const int S = a.S, nk = S + 2;
   const float eps = a.eps, tol = a.zero_tol;
-  const float u = a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+  const float u = u_drawn ? u_drawn[k]
+                          : (a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k));
   const int ind = upper_bound_torch(cdf, nk, u);
   const int below = max(0, ind - 1);
   const int above = min(nk - 1, ind);
@@ -442,9 +443,11 @@ __device__ __forceinline__ void const_build(const SampleConstArgs& a, int64_t r,
   __syncwarp();
 }
 
-__device__ __forceinline__ float const_sample(const SampleConstArgs& a, int64_t r, int k, const float* cdf, const float* bins) {
+__device__ __forceinline__ float const_sample(const SampleConstArgs& a, int64_t r, int k, const float* cdf, const float* bins,
+                                              const float* u_drawn = nullptr) {
   const int nb = a.nb;
-  const float u = a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k);
+  const float u = u_drawn ? u_drawn[k]
+                          : (a.u ? a.u[r * (int64_t)a.Ni + k] : philox_uniform(a.seed, a.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)k));
   const int ind = upper_bound_torch(cdf, nb, u);
   const int below = max(0, ind - 1);
   const int above = min(nb - 1, ind);
@@ -684,6 +687,50 @@ __device__ __forceinline__ float clamp_sample(float x, float near, float far) {
   return x;
 }
 
+// Ascending bitonic sort of 32 * KPL keys held KPL per lane (element index lane * KPL + j); no NaNs.
+template <int KPL>
+__device__ __forceinline__ void warp_sort_regs(float (&v)[KPL], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * KPL; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= KPL) {
+        // partner element = same j in lane ^ (stride / KPL); bit `size` of the element index comes from the lane (size > KPL)
+        const int ls = stride / KPL;
+        const bool up = ((lane * KPL) & size) == 0, lower = (lane & ls) == 0;
+        const bool keep_min = (lower == up);
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const float o = __shfl_xor_sync(0xffffffffu, v[j], ls);
+          v[j] = keep_min ? fminf(v[j], o) : fmaxf(v[j], o);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          if ((j & stride) == 0) {
+            const bool up = ((lane * KPL + j) & size) == 0;
+            const float p = v[j], q = v[j ^ stride];
+            const float mn = fminf(p, q), mx = fmaxf(p, q);
+            v[j] = up ? mn : mx;
+            v[j ^ stride] = up ? mx : mn;
+          }
+        }
+      }
+    }
+  }
+}
+// xs[0..Ni) (shared memory, no NaNs) -> xsorted[0..32 KPL) ascending, +inf beyond the Ni keys
+template <int KPL>
+__device__ __forceinline__ void warp_sort_to(const float* xs, float* xsorted, int Ni, int lane) {
+  float v[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) { const int e = lane * KPL + j; v[j] = (e < Ni) ? xs[e] : __int_as_float(0x7f800000); }
+  warp_sort_regs<KPL>(v, lane);
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) xsorted[lane * KPL + j] = v[j];
+  __syncwarp();
+}
+
 // xs[0..Ni) clamped samples (unsorted), xsorted[0..np2) scratch, zc[0..S) ascending coarse depths (all shared memory)
 __device__ __forceinline__ void merge_ray(const float* zc, const float* xs, float* xsorted, int S, int Ni, int np2, int lane,
                                           float* out, float* z_std_out) {
@@ -696,23 +743,41 @@ __device__ __forceinline__ void merge_ray(const float* zc, const float* xs, floa
     v = warp_sum(v);
     if (lane == 0) *z_std_out = sqrtf(__fdiv_rn(v, (float)Ni));
   }
-  for (int k = lane; k < np2; k += 32) xsorted[k] = (k < Ni) ? xs[k] : __int_as_float(0x7fffffff);   // pad key: sorts after everything
-  __syncwarp();
-  auto gt = [](float p, float q) {   // total order: numbers < NaNs (like torch.sort) < pad keys
-    const bool pn = (p != p), qn = (q != q);
-    if (pn || qn) return pn && (!qn || __float_as_int(p) > __float_as_int(q));
-    return p > q;
-  };
-  for (int size = 2; size <= np2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (np2 >> 1); t += 32) {
-        const int lo = 2 * t - (t & (stride - 1));       // index with the `stride` bit clear
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const float p = xsorted[lo], q = xsorted[hi];
-        if (gt(p, q) == up) { xsorted[lo] = q; xsorted[hi] = p; }
+  // No NaN among the samples (the rule): sort in registers, KPL keys per lane (element lane * KPL + j), +inf pads -- the
+  // bitonic network's strides below KPL are register compare-exchanges, the others one shuffle + one min/max per key
+  // (equal keys have equal bits, so min / max give torch.sort's output).  ~300 instructions per lane for 128 keys against
+  // ~1000 plus shared-memory latency for the network run in shared memory, which remains for NaN inputs and Ni > 256.
+  bool has_nan = false;
+  for (int k = lane; k < Ni; k += 32) has_nan |= (xs[k] != xs[k]);
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  bool sorted_in_regs = false;
+  if (!has_nan) {
+    sorted_in_regs = true;
+    if (np2 <= 32) warp_sort_to<1>(xs, xsorted, Ni, lane);
+    else if (np2 == 64) warp_sort_to<2>(xs, xsorted, Ni, lane);
+    else if (np2 == 128) warp_sort_to<4>(xs, xsorted, Ni, lane);
+    else if (np2 == 256) warp_sort_to<8>(xs, xsorted, Ni, lane);
+    else sorted_in_regs = false;
+  }
+  if (!sorted_in_regs) {
+    for (int k = lane; k < np2; k += 32) xsorted[k] = (k < Ni) ? xs[k] : __int_as_float(0x7fffffff);   // pad key: sorts after everything
+    __syncwarp();
+    auto gt = [](float p, float q) {   // total order: numbers < NaNs (like torch.sort) < pad keys
+      const bool pn = (p != p), qn = (q != q);
+      if (pn || qn) return pn && (!qn || __float_as_int(p) > __float_as_int(q));
+      return p > q;
+    };
+    for (int size = 2; size <= np2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < (np2 >> 1); t += 32) {
+          const int lo = 2 * t - (t & (stride - 1));       // index with the `stride` bit clear
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const float p = xsorted[lo], q = xsorted[hi];
+          if (gt(p, q) == up) { xsorted[lo] = q; xsorted[hi] = p; }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   for (int i = lane; i < S; i += 32) {  // coarse i lands after every sample strictly smaller
@@ -793,17 +858,29 @@ __global__ void __launch_bounds__(128) k_sample_merge(const __grid_constant__ Sa
   float* xsorted = xs + Ni;
   const float near = a.rays[r * a.stride + 6], far = a.rays[r * a.stride + 7];
   for (int k = lane; k < S; k += 32) zc[k] = a.z[r * (int64_t)S + k];
+  // device-side draws: one Philox block yields the draws of four consecutive samples (philox_uniform(k) = word k & 3 of block
+  // k >> 2); they wait in xs[], where sample k's lane replaces its own draw by the sample
+  const float* u_drawn = nullptr;
+  if (!a.pl.u) {
+    for (int b = lane; 4 * b < Ni; b += 32) {
+      uint32_t w4[4];
+      philox4x32(a.pl.seed, a.pl.ray0 + (uint64_t)r, RNG_STREAM_U, (uint32_t)b, w4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (4 * b + i < Ni) xs[4 * b + i] = (float)(w4[i] >> 8) * (1.0f / 16777216.0f);
+    }
+    u_drawn = xs;
+  }
   if (LINEAR) {
-    pl_build(a.pl, r, lane, cdf, s, T, tau);
+    pl_build(a.pl, r, lane, cdf, s, T, tau);       // (ends with __syncwarp: the draws are visible)
     for (int k = lane; k < Ni; k += 32) {
-      const float x = pl_sample(a.pl, r, k, cdf, s, T, tau);
+      const float x = pl_sample(a.pl, r, k, cdf, s, T, tau, u_drawn);
       if (a.pl.samples) a.pl.samples[r * (int64_t)Ni + k] = x;
       xs[k] = clamp_sample(x, near, far);
     }
   } else {
     const_build(a.cs, r, lane, cdf, s);
     for (int k = lane; k < Ni; k += 32) {
-      const float x = const_sample(a.cs, r, k, cdf, s);
+      const float x = const_sample(a.cs, r, k, cdf, s, u_drawn);
       if (a.cs.samples) a.cs.samples[r * (int64_t)Ni + k] = x;
       xs[k] = clamp_sample(x, near, far);
     }
