@@ -1333,6 +1333,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       uint8_t* dy_tile = (DGRAD) ? A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes : nullptr;
       uint32_t* mask_tile = (STASH || DGRAD) ? A.masks + tile * (int64_t)A.tl.mask_tile_words : nullptr;
 
+      uint32_t m_next[CHUNKS_PER_GRP] = {};
+      auto load_masks = [&](int l2, int h2, uint32_t (&m)[CHUNKS_PER_GRP]) {
+        const int mi = P.L[l2].mask_idx;
+        if (mi < 0) return;
+#pragma unroll
+        for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc)
+          m[cc] = __ldg(mask_tile + A.tl.mask_off[mi] + ((h2 * 128 + (CHUNKS_PER_GRP * grp + cc) * 32) >> 5) * 128 + row);
+      };
+      if (DGRAD) load_masks(0, 0, m_next);
       for (int l = 0; l < P.n_layers; ++l) {
         const int epi = P.L[l].epi, flags = P.L[l].flags, n_halves = P.L[l].n_halves, bias_off = P.L[l].bias_off;
         const int stash_idx = P.L[l].stash_idx, mask_idx = P.L[l].mask_idx;
@@ -1343,6 +1352,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
           asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");     // rows were fetched by other threads
         }
         for (int h = 0; h < n_halves; ++h) {
+          // gradient chain: this thread's ReLU-mask word of the half (one per 32 columns) was requested one half-layer AHEAD
+          // (a global load on first use was the top stall of the kernel: 17% of its samples); request the next one now
+          uint32_t m_pre[CHUNKS_PER_GRP];
+          if (DGRAD) {
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc) m_pre[cc] = m_next[cc];
+            const int ln = (h + 1 < n_halves) ? l : l + 1, hn = (h + 1 < n_halves) ? h + 1 : 0;
+            if (ln < P.n_layers) load_masks(ln, hn, m_next);
+          }
           if (h == 0) {
             ptx::mbar_wait(d_full0, seen0 & 1); ++seen0;
             if (X3 && n_halves == 2) {
@@ -1387,7 +1405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
               if (mask_idx >= 0) {
-                const uint32_t m = mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row];
+                const uint32_t m = m_pre[cc];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] &= relu_mask_word(m, i);
               }
