@@ -1333,6 +1333,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       uint8_t* dy_tile = (DGRAD) ? A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes : nullptr;
       uint32_t* mask_tile = (STASH || DGRAD) ? A.masks + tile * (int64_t)A.tl.mask_tile_words : nullptr;
 
+      if (DGRAD) {
+        // the NEXT tile's ReLU masks (written by the forward two kernels ago: a DRAM read) -> L2 a whole tile ahead, so
+        // the half-layer-ahead register loads below find them there
+        auto prefetch_masks = [&](int64_t t2) {
+          if (t2 >= A.n_tiles) return;
+          const char* mb = reinterpret_cast<const char*>(A.masks + t2 * (int64_t)A.tl.mask_tile_words);
+          const int bytes = A.tl.mask_tile_words * 4;
+          for (int o = (int)threadIdx.x * 128; o < bytes; o += NUM_EPI_THREADS * 128)
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(mb + o));
+        };
+        if (tile_iter == 0) prefetch_masks(tile);
+        prefetch_masks(tile + gridDim.x);
+      }
       uint32_t m_next[CHUNKS_PER_GRP] = {};
       auto load_masks = [&](int l2, int h2, uint32_t (&m)[CHUNKS_PER_GRP]) {
         const int mi = P.L[l2].mask_idx;
