@@ -55,7 +55,11 @@ struct Smem3 {
   static constexpr uint32_t XCH_BYTES = VD ? RING_ROWS * 16u : 2u * TILE_M * MAX_OUT_CH * 4u;
   static constexpr uint32_t xch0 = vb0 + 2u * VB_RAYS_SMEM * 128u * 4u;
   static constexpr uint32_t ctrs = xch0 + XCH_BYTES;                       // flow-control counters (see the kernel)
-  static constexpr uint32_t pe0 = (ctrs + 64u + 1023u) & ~1023u;           // [2] encoding operand tiles
+  // per-layer facts the epilogue needs, one 16-byte entry per layer {epi | halves << 8 | flags << 16 | reads_a << 24,
+  // bias offset, stash byte offset, mask word offset (-1: none)}: ONE shared-memory load per layer instead of chains of
+  // register-indexed constant-bank loads (plan -> index -> offset table), which sat in the epilogue's critical path
+  static constexpr uint32_t ltab = ctrs + 64u;
+  static constexpr uint32_t pe0 = (ltab + 16u * MAX_LAYERS + 1023u) & ~1023u;   // [2] encoding operand tiles
   static constexpr uint32_t consts = pe0 + 2u * PE_TILE_BYTES;           // fp32 biases + heads (const_floats)
   uint32_t ring, total;
   int n_slots;
@@ -300,6 +304,15 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
     ptx::fence_mbar_init();
     for (int i = 0; i < 16; ++i) reinterpret_cast<uint32_t*>(smem + Smem3<VD>::ctrs)[i] = 0u;
   }
+  if ((int)threadIdx.x < P.n_layers) {
+    const LayerPlan& L = P.L[threadIdx.x];
+    int4 e;
+    e.x = (int)L.epi | ((int)L.n_halves << 8) | ((int)(uint8_t)L.flags << 16) | ((L.n_h_ks > 0 ? 1 : 0) << 24);
+    e.y = L.bias_off;
+    e.z = (STASH && L.stash_idx >= 0) ? A.tl.in_off[L.stash_idx] : 0;
+    e.w = (STASH && L.mask_idx >= 0) ? A.tl.mask_off[L.mask_idx] : -1;
+    reinterpret_cast<int4*>(smem + Smem3<VD>::ltab)[threadIdx.x] = e;
+  }
   if (warp == WARP_MMA3) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < P.const_floats; i += THREADS3) consts[i] = A.tail[i];
   ptx::fence_proxy_async_smem();
@@ -489,21 +502,25 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       const bool trace_on = (pr == 2) && lane == 0 && q == 0 && ch == 0;
       const int64_t g = row0 + (2 * (int64_t)pr + t) * TILE_M + row;
       float alpha_acc = 0.f;
+      // training stash: this tile's operand tiles and this row's mask words (layer offsets come from the layer table)
+      const int64_t gtile = STASH ? g / TILE_M : 0;
+      uint8_t* const st_base = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes : nullptr;
+      uint32_t* const m_base = STASH ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + row : nullptr;
       for (int l = 0; l < P.n_layers; ++l) {
-        const int epi = P.L[l].epi, n_halves = P.L[l].n_halves;
-        const bool reads_a = P.L[l].n_h_ks > 0;
-        const float* bias = consts + P.L[l].bias_off + 64 * ch;
+        const int4 lt = reinterpret_cast<const int4*>(smem + Smem3<VD>::ltab)[l];
+        const int epi = lt.x & 255, n_halves = (lt.x >> 8) & 255;
+        const bool reads_a = (lt.x >> 24) != 0;
+        const float* bias = consts + lt.y + 64 * ch;
         if (epi == EPI_RELU_A || epi == EPI_LINEAR_A) {
           // ---- trunk / feature layer (two 128-neuron halves): bias, (ReLU), bf16 pack -> A_t
-          const bool alpha_here = VD && (P.L[l].flags & FLAG_ALPHA);
+          const bool alpha_here = VD && (((lt.x >> 16) & 255) & FLAG_ALPHA);
           const float* aw = consts + P.alpha_w_off + 64 * ch;
           uint32_t held[32];                         // half a (packed), kept until half b's MMAs have read A_t
-          // training stash of this layer's output: tile pointers, operand tile of width 256, mask words
-          const int64_t gtile = STASH ? g / TILE_M : 0;
-          uint8_t* st_t = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx] : nullptr;
-          uint32_t* st_m = (STASH && P.L[l].mask_idx >= 0) ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] : nullptr;
+          // training stash of this layer's output: operand tile of width 256, mask words
+          uint8_t* st_t = STASH ? st_base + lt.z : nullptr;
+          uint32_t* st_m = (STASH && lt.w >= 0) ? m_base + lt.w : nullptr;
           auto stash32 = [&](const uint32_t* pk16, uint32_t m, int h, int c2) {   // 32 columns [128 h + 64 ch + 32 c2, +32)
-            if (st_m && !PLNERF3_DBG(64)) st_m[(4 * h + 2 * ch + c2) * 128 + row] = m;     // (64: measurement, no mask stores)
+            if (st_m && !PLNERF3_DBG(64)) st_m[(4 * h + 2 * ch + c2) * 128] = m;           // (64: measurement, no mask stores)
             if (PLNERF3_DBG(32)) return;        // measurement: the stash forward without its activation stores
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
@@ -598,12 +615,11 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
             }
             if (STASH) {
               // the views layer's output (128 wide) and its ReLU mask
-              const int64_t gtile = g / TILE_M;
-              uint8_t* st_t = A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes + A.tl.in_off[P.L[l].stash_idx];
+              uint8_t* st_t = st_base + lt.z;
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-              A.masks[gtile * (int64_t)A.tl.mask_tile_words + A.tl.mask_off[P.L[l].mask_idx] + (2 * ch + c2) * 128 + row] = relu_mask_from_packed(pk);
+              m_base[lt.w + (2 * ch + c2) * 128] = relu_mask_from_packed(pk);
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
                 stash_store8(st_t, 128, row, 8 * ch + 4 * c2 + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
