@@ -1054,6 +1054,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
     for (uint32_t b2 = 0; b2 < 8; ++b2) ptx::mbar_init(b_full(b2), 1);
     ptx::fence_mbar_init();
   }
+  // per-layer facts of the epilogue, 16 bytes per layer behind the barriers {epi | halves << 8 | flags << 16, bias offset,
+  // byte offset of the layer's stash tensor in a tile (forward: activations, gradient chain: dY), word offset of its ReLU
+  // mask (-1: none)}: one shared-memory load per layer instead of chained register-indexed constant-bank loads
+  static_assert(8 * (2 * MAX_STAGES + 16) + 16 * MAX_LAYERS <= 512, "layer table does not fit behind the barriers");
+  const int4* ltab = reinterpret_cast<const int4*>(smem + SL.bars + 8 * (2 * MAX_STAGES + 16));
+  if ((int)threadIdx.x < P.n_layers) {
+    const LayerPlan& L = P.L[threadIdx.x];
+    int4 e;
+    e.x = (int)L.epi | ((int)L.n_halves << 8) | ((int)(uint8_t)L.flags << 16);
+    e.y = L.bias_off;
+    e.z = ((STASH || DGRAD) && L.stash_idx >= 0) ? (DGRAD ? A.tl.dy_off[L.stash_idx] : A.tl.in_off[L.stash_idx]) : 0;
+    e.w = ((STASH || DGRAD) && L.mask_idx >= 0) ? A.tl.mask_off[L.mask_idx] : -1;
+    const_cast<int4*>(ltab)[threadIdx.x] = e;
+  }
   // ---- flattened per-tile stage program (shared by the TMA producer and the MMA issuer) ----------
   //   batch 1 of layer l: [(l,a) PE stage] (l,a) hidden K-steps 0-7      needs a_ready[a](l-1)
   //   batch 2 of layer l: (l,a) hidden 8-15, [(l,b) PE], (l,b) 0-7, 8-15  needs a_ready[b](l-1)
@@ -1348,16 +1362,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
       }
       uint32_t m_next[CHUNKS_PER_GRP] = {};
       auto load_masks = [&](int l2, int h2, uint32_t (&m)[CHUNKS_PER_GRP]) {
-        const int mi = P.L[l2].mask_idx;
-        if (mi < 0) return;
+        const int mo = ltab[l2].w;
+        if (mo < 0) return;
 #pragma unroll
         for (int cc = 0; cc < CHUNKS_PER_GRP; ++cc)
-          m[cc] = __ldg(mask_tile + A.tl.mask_off[mi] + ((h2 * 128 + (CHUNKS_PER_GRP * grp + cc) * 32) >> 5) * 128 + row);
+          m[cc] = __ldg(mask_tile + mo + ((h2 * 128 + (CHUNKS_PER_GRP * grp + cc) * 32) >> 5) * 128 + row);
       };
       if (DGRAD) load_masks(0, 0, m_next);
       for (int l = 0; l < P.n_layers; ++l) {
-        const int epi = P.L[l].epi, flags = P.L[l].flags, n_halves = P.L[l].n_halves, bias_off = P.L[l].bias_off;
-        const int stash_idx = P.L[l].stash_idx, mask_idx = P.L[l].mask_idx;
+        const int4 lt = ltab[l];
+        const int epi = lt.x & 255, flags = (lt.x >> 16) & 255, n_halves = (lt.x >> 8) & 255, bias_off = lt.y;
+        const int st_off = lt.z, m_off = lt.w;
         const uint32_t a_out = tmem + lane_addr + a_out_col(l);
         const uint32_t a_out_lo = tmem + lane_addr + COL_A1;
         if (vb_smem && epi == EPI_VIEWS) {
@@ -1417,13 +1432,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-              if (mask_idx >= 0) {
+              if (m_off >= 0) {
                 const uint32_t m = m_pre[cc];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] &= relu_mask_word(m, i);
               }
               ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
-              uint8_t* t = dy_tile + A.tl.dy_off[stash_idx];
+              uint8_t* t = dy_tile + st_off;
               if (!PLNERF_DBG(32))                 // (measurement: the gradient chain without its dY stores)
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
@@ -1439,8 +1454,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-                mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
-                uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+                mask_tile[m_off + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
+                uint8_t* t = in_tile + st_off;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                   stash_store8(t, 128, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
@@ -1491,8 +1506,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                   for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
                   ptx::tmem_st16(a_out + (uint32_t)(n0 >> 1), pk);
                   if (STASH) {
-                    if (mask_idx >= 0) mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
-                    uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+                    if (m_off >= 0) mask_tile[m_off + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
+                    uint8_t* t = in_tile + st_off;
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4)
                       stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
@@ -1509,8 +1524,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
                   // gradients of output_linear and the gradient chain's first mask do
 #pragma unroll
                   for (int i = 0; i < 16; ++i) pk[i] = ptx::pack_bf16(val[2 * i], val[2 * i + 1]);
-                  if (mask_idx >= 0) mask_tile[A.tl.mask_off[mask_idx] + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
-                  uint8_t* t = in_tile + A.tl.in_off[stash_idx];
+                  if (m_off >= 0) mask_tile[m_off + (n0 >> 5) * 128 + row] = relu_mask_from_packed(pk);
+                  uint8_t* t = in_tile + st_off;
 #pragma unroll
                   for (int q4 = 0; q4 < 4; ++q4)
                     stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
