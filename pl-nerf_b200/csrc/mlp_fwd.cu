@@ -1762,10 +1762,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
         uint32_t v[32];
         ptx::tmem_ld32(tmem + lane_addr + (uint32_t)c0, v);     // (columns past Wd: allocated, never written, filtered below)
         ptx::tmem_ld_wait();
+        if (it.col_stride == 1) {
+          // four columns per reduction (red.global.add.v4.f32) wherever the row's address is 16-byte aligned: a CTA's flush
+          // is 32 768 fp32 reductions during which it reads nothing
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i - it.c_first;
-          if (c >= 0 && c < it.ncols) atomicAdd(drow + (int64_t)c * it.col_stride, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4) {
+            const int c = c0 + i - it.c_first;
+            float* p = drow + c;
+            if (c >= 0 && c + 3 < it.ncols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                           "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3])) : "memory");
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (c + k >= 0 && c + k < it.ncols) atomicAdd(p + k, __uint_as_float(v[i + k]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i - it.c_first;
+            if (c >= 0 && c < it.ncols) atomicAdd(drow + (int64_t)c * it.col_stride, __uint_as_float(v[i]));
+          }
         }
       }
       if (it.db) {

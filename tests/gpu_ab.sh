@@ -9,7 +9,7 @@ cp pl-nerf_b200/libplnerf_b200.so /tmp/keep.so
 for i in 1 2 3; do
   for v in "$1" "$2"; do
     cp "pl-nerf_b200/ab/$v" pl-nerf_b200/libplnerf_b200.so
-    echo -n "$v: "; python tests/gpu_train_step_target.py | python -c "import json,sys; print(json.loads(sys.stdin.read())['device_ms_per_iter'])"
+    echo -n "$v: "; PLNERF_ITERS=${PLNERF_ITERS:-600} python tests/gpu_train_step_target.py | python -c "import json,sys; print(json.loads(sys.stdin.read())['device_ms_per_iter'])"
   done
 done
 cp /tmp/keep.so pl-nerf_b200/libplnerf_b200.so

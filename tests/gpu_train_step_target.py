@@ -50,7 +50,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
-    iters = 40
+    iters = int(os.environ.get("PLNERF_ITERS", "40"))
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
