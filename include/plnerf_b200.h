@@ -302,7 +302,10 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
  * plnerf_render_rays_bwd: upstream gradients of the eight maps (any may be NULL) -> parameter gradients ADDED into
  * grads_coarse / grads_fine (fp32, state_dict layout; fine_* NULL = the coarse network served the fine pass).
  * `*_packed_bwd` = plnerf_pack_weights_bwd.  noise0 / noise1: the same explicit arrays as in the forward (or NULL: the
- * forward's Philox draws are regenerated from cfg->seed).  bf16 precision; both networks with or both without view directions. */
+ * forward's Philox draws are regenerated from cfg->seed).  bf16 precision; both networks with or both without view directions.
+ * With a fine pass, plnerf_render_rays_bwd enqueues the coarse pass's backward on a side stream the library owns (one per
+ * device and host thread), forked from `stream` and joined back into it before the call returns: the two passes are
+ * independent (:728) and their kernels fill each other's idle SMs.  The caller sees ordinary stream order. */
 typedef struct plnerf_render_grads {
   const float *g_rgb_map, *g_disp_map, *g_acc_map, *g_depth_map;   /* [n,3], [n], [n], [n] */
   const float *g_rgb0, *g_disp0, *g_acc0, *g_depth0;               /* coarse maps, read when N_importance > 0 */

@@ -299,15 +299,14 @@ int plnerf_render_rays_fwd(const plnerf_render_cfg* cfg, const plnerf_net_desc* 
   return rc;
 }
 
-// One non-blocking side stream + fork / join events per device (created on first use, kept for the life of the process).
+// One non-blocking side stream + fork / join events per device and host thread (created on first use, kept for the life of
+// the thread): concurrent callers on different host threads never share fork / join events.
 namespace plnerf {
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
 static SideStream* side_stream() {
-  static SideStream tab[64] = {};
-  static std::mutex mu;
+  static thread_local SideStream tab[64] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("side_stream: bad device"); return nullptr; }
-  std::lock_guard<std::mutex> lk(mu);
   SideStream& s = tab[dev];
   if (!s.ok) {
     cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
