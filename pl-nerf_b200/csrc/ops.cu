@@ -753,7 +753,7 @@ __device__ __forceinline__ void merge_ray(const float* zc, const float* xs, floa
   bool sorted_in_regs = false;
   if (!has_nan) {
     sorted_in_regs = true;
-    if (np2 <= 32) warp_sort_to<1>(xs, xsorted, Ni, lane);
+    if (np2 == 32) warp_sort_to<1>(xs, xsorted, Ni, lane);
     else if (np2 == 64) warp_sort_to<2>(xs, xsorted, Ni, lane);
     else if (np2 == 128) warp_sort_to<4>(xs, xsorted, Ni, lane);
     else if (np2 == 256) warp_sort_to<8>(xs, xsorted, Ni, lane);
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(128) k_merge(MergeArgs a) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (r >= a.n) return;
   const int S = a.S, Ni = a.Ni;
-  int np2 = 1;
+  int np2 = 32;                      // sort scratch: a power of two >= max(N_importance, 32) (the register sort writes whole warps)
   while (np2 < Ni) np2 <<= 1;
   float* zc = smem + (size_t)wib * (S + Ni + np2);
   float* xs = zc + S;
@@ -822,7 +822,7 @@ int launch_merge(const float* z, const float* samples, const float* rays, int64_
   if (n == 0) return PLNERF_OK;
   MergeArgs a{z, samples, rays, n, stride, S, Ni, z_out, z_std};
   const int wpb = 4;
-  int np2 = 1;
+  int np2 = 32;                      // sort scratch: a power of two >= max(N_importance, 32) (the register sort writes whole warps)
   while (np2 < Ni) np2 <<= 1;
   const size_t smem = (size_t)wpb * (S + Ni + np2) * sizeof(float);
   if (smem > 48 * 1024) { set_error("merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }
@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(128) k_sample_merge(const __grid_constant__ Sa
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (r >= a.n) return;
   const int S = a.S, Ni = a.Ni, nk = S + 2;
-  int np2 = 1;
+  int np2 = 32;                      // sort scratch: a power of two >= max(N_importance, 32) (the register sort writes whole warps)
   while (np2 < Ni) np2 <<= 1;
   const int per_warp = 4 * nk + S + Ni + np2;
   float* cdf = smem + (size_t)wib * per_warp;
@@ -900,7 +900,7 @@ int launch_sample_merge(int linear, const float* z, const float* w, const float*
   a.cs = SampleConstArgs{z, S, 1, w ? w + 1 : nullptr, S, n, S - 1, Ni, u, seed, ray0, nullptr, inds, nullptr};
   a.z = z; a.rays = rays; a.n = n; a.stride = stride; a.S = S; a.Ni = Ni; a.z_out = z_out; a.z_std = z_std;
   const int wpb = 4;
-  int np2 = 1;
+  int np2 = 32;                      // sort scratch: a power of two >= max(N_importance, 32) (the register sort writes whole warps)
   while (np2 < Ni) np2 <<= 1;
   const size_t smem = (size_t)wpb * (4 * (S + 2) + S + Ni + np2) * sizeof(float);
   if (smem > 48 * 1024) { set_error("sample+merge: S=%d Ni=%d too large", S, Ni); return PLNERF_E_UNSUPPORTED; }

@@ -163,6 +163,34 @@ def test_sampler_edge_cases(P):
     np.testing.assert_array_equal(host(zm), np.sort(np.concatenate([z, np.clip(zs_o, near, far)], -1), -1))
 
 
+@pytest.mark.parametrize("Ni", [1, 5, 31, 32, 33, 64, 100, 128, 200, 256, 300])
+@pytest.mark.parametrize("with_nan", [False, True])
+def test_merge_sort_paths_vs_torch_sort(P, Ni, with_nan):
+    """clamp + sort(cat) (run_plnerf.py:728-734) over every sorting path of merge_ray: keys in registers (1, 2, 4 or 8 per
+    lane for N_importance <= 32, 64, 128, 256; pads when it is not a power of two), the shared-memory network for
+    N_importance > 256 and for rows containing NaN -- bit for bit against torch.sort, with repeated values, samples outside
+    [near, far] (clamped) and samples equal to coarse depths."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(100 + Ni)
+    n, S = 37, 64
+    z = torch.sort(torch.rand(n, S, device="cuda", generator=g) * 4 + 2, -1)[0]
+    x = torch.rand(n, Ni, device="cuda", generator=g) * 5 + 1.5          # some outside [2, 6]
+    if Ni >= 5:
+        x[:, 3] = x[:, 0]                                                  # repeats
+        x[:, 4] = z[:, 10]                                                 # ties with a coarse depth
+    if with_nan:
+        x[::3, Ni // 2] = float("nan")
+    rays = torch.zeros(n, 8, device="cuda")
+    rays[:, 3:6] = 1.0
+    rays[:, 6], rays[:, 7] = 2.0, 6.0
+    zm, zstd = P.merge_samples(z, x, rays)
+    ref = torch.sort(torch.cat([z, torch.clamp(x, 2.0, 6.0)], -1), -1)[0]
+    assert torch.equal(zm.view(torch.int32), ref.view(torch.int32))
+    clean = ~torch.isnan(x).any(-1)
+    std_ref = torch.std(torch.clamp(x, 2.0, 6.0), -1, unbiased=False)
+    assert torch.allclose(zstd[clean], std_ref[clean], rtol=1e-4, atol=1e-6)
+
+
 def test_empty_batches(P):
     rays = torch.zeros((0, 11), device="cuda")
     assert P.stratified_z(rays, 64).shape == (0, 64)
