@@ -827,7 +827,10 @@ __device__ __forceinline__ void issue_tile_x3(IssueStateX3& st, uint32_t prog_ad
 // store 8 consecutive bf16 columns (16 bytes) of row `row` into an MN-major stash tile
 __device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, int col8, uint4 v) {
   const int mh = row >> 6, m8 = (row & 63) >> 3, i = row & 7;
-  *reinterpret_cast<uint4*>(tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16) = v;
+  // streaming store (evict-first): the stash is written once and read a kernel or two later, after far more traffic than
+  // the L2 holds -- it should not displace the packed weights every CTA keeps re-reading
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ReLU masks of the training stash: one 32-bit word per (row, 32 columns).  The bit order is chosen for the gradient chain,
