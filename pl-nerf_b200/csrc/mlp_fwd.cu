@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
             for (int j = 0; j < blen; ++j) {
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               ptx::mbar_wait(w_empty(slot), phase ^ 1);
-              if (copy) ptx::bulk_g2s(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, bar);
+              if (copy) ptx::bulk_g2s_hint(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, bar, ptx::l2_policy_evict_last());
               src += bytes;
               if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }
             }
@@ -1149,7 +1149,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               const uint32_t bytes = (prog[i + j].x & 255u) * KS_BYTES;
               for (int rep = 0; rep < 2; ++rep) {
                 ptx::mbar_wait(w_empty(slot), phase ^ 1);
-                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, w_full(slot)); }
+                if (copy) { ptx::mbar_arrive_expect_tx(w_full(slot), bytes); ptx::bulk_g2s_hint(s_ring + slot * (uint32_t)STAGE_BYTES, src, bytes, w_full(slot), ptx::l2_policy_evict_last()); }
                 else ptx::mbar_arrive(w_full(slot));
                 src += bytes;
                 if (++slot == (uint32_t)A.n_stages) { slot = 0; phase ^= 1; }

@@ -105,6 +105,7 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
                                             uint32_t desc_hi, uint32_t wfull0, uint32_t wempty0, uint32_t epearly, uint32_t epfull, uint32_t peready,
                                             uint32_t n_slots, uint32_t stab_addr, uint32_t n_stab, uint32_t ring_addr,
                                             unsigned long long wbase, unsigned long long trace_ptr) {
+  const uint64_t wpolicy = ptx::l2_policy_evict_last();      // the weight stream stays in L2 (every CTA re-reads it per tile pair)
   asm volatile(
       "{\n\t.reg .pred p, pacc, pt, ptr;\n\t"
       ".reg .b32 sl, ph, n, pa, ed, ea, ef, eb, t, k, wb, c, q, psl, pph, pj, prem, so2, sb2;\n\t.reg .b64 bd, so, ad, tr, ga;\n\t"
@@ -164,7 +165,7 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
       "mbarrier.arrive.expect_tx.shared::cta.b64 _, [t], sb2;\n\t"
       "cvt.u64.u32 ga, so2;\n\tadd.u64 ga, ga, %20;\n\t"
       "shl.b32 k, psl, 15;\n\tadd.u32 k, k, %21;\n\t"
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [k], [ga], sb2, [t];\n\t"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [k], [ga], sb2, [t], %24;\n\t"
       "add.u32 psl, psl, 1;\n\tsetp.eq.u32 p, psl, %17;\n\t@p mov.b32 psl, 0;\n\t@p xor.b32 pph, pph, 1;\n\t"
       "add.u32 pj, pj, 1;\n\tsetp.eq.u32 p, pj, %22;\n\t@p mov.b32 pj, 0;\n\tsub.u32 prem, prem, 1;\n\t"
       "NOPROD3:\n\t"
@@ -173,7 +174,7 @@ __device__ __forceinline__ void issue_tile3(Issue3& st, uint32_t prog_addr, uint
       "mov.b32 %4, psl;\n\tmov.b32 %5, pph;\n\tmov.b32 %6, pj;\n\tmov.b32 %7, prem;\n\t}"
       : "+r"(st.sl), "+r"(st.ph), "+r"(st.c), "+r"(st.q), "+r"(st.psl), "+r"(st.pph), "+r"(st.pj), "+r"(st.prem)
       : "l"(ring_desc), "r"(idesc), "r"(prog_addr), "r"(n_entries), "r"(wfull0), "r"(desc_hi), "r"(epearly), "r"(peready),
-        "r"(wempty0), "r"(n_slots), "r"(stab_addr), "l"(trace_ptr), "l"(wbase), "r"(ring_addr), "r"(n_stab), "r"(epfull)
+        "r"(wempty0), "r"(n_slots), "r"(stab_addr), "l"(trace_ptr), "l"(wbase), "r"(ring_addr), "r"(n_stab), "r"(epfull), "l"(wpolicy)
       : "memory");
 }
 
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       for (uint32_t s2 = 0; s2 + REFILL_LAG < (uint32_t)n_slots && st.prem > 0; ++s2) {
         const uint2 e = stab[st.pj];
         ptx::mbar_arrive_expect_tx(w_full0 + 8u * st.psl, e.y);
-        ptx::bulk_g2s(sbase + SL.ring + st.psl * (uint32_t)STAGE_BYTES, A.w + e.x, e.y, w_full0 + 8u * st.psl);
+        ptx::bulk_g2s_hint(sbase + SL.ring + st.psl * (uint32_t)STAGE_BYTES, A.w + e.x, e.y, w_full0 + 8u * st.psl, ptx::l2_policy_evict_last());
         if (++st.psl == (uint32_t)n_slots) { st.psl = 0; st.pph ^= 1u; }
         if (++st.pj == (uint32_t)n_entries) st.pj = 0;
         --st.prem;

@@ -46,6 +46,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                : "memory");
 }
 
+// the same with an L2 eviction-priority hint (evict-last: what every CTA keeps re-reading, i.e. the packed weights, while
+// gigabytes of stash tiles stream through the L2 beside them)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
