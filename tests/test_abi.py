@@ -112,3 +112,33 @@ def test_no_cpu_fallback():
     net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.zeros(4, 90))
+
+
+def test_training_entries_reject_bad_arguments(lib):
+    """plnerf_train_rays_mse / plnerf_pack_weights_train validate before they touch the device (no GPU needed)."""
+    import ctypes
+    cfg = L.RenderCfg()
+    cfg.N_samples, cfg.N_importance, cfg.mode, cfg.precision = 64, 64, L.MODE_LINEAR, L.PREC_BF16
+    d = L.NetDesc()
+    d.D, d.W, d.input_ch, d.input_ch_views, d.output_ch, d.use_viewdirs, d.n_skips = 8, 256, 63, 27, 5, 1, 1
+    d.skips[0] = 4
+    buf = (ctypes.c_float * 64)()
+    g = L.NetGrads()
+    call = lambda cpacked, cbwd, grads, sqerr, target, n, stride: lib.plnerf_train_rays_mse(
+        C.byref(cfg), C.byref(d), cpacked, cbwd, None, None, None, buf, n, stride, None, None, None, None, target, None, 1.0,
+        sqerr, None, grads, None, None, 0, None)
+    assert call(None, buf, C.byref(g), buf, buf, 4, 11) == -1 and b"null" in lib.plnerf_last_error()       # no packed weights
+    assert call(buf, None, C.byref(g), buf, buf, 4, 11) == -1                                               # no transposed weights
+    assert call(buf, buf, None, buf, buf, 4, 11) == -1                                                      # no gradient buffers
+    assert call(buf, buf, C.byref(g), None, buf, 4, 11) == -1                                               # no loss accumulators
+    assert call(buf, buf, C.byref(g), buf, None, 4, 11) == -1                                               # rays but no target
+    assert call(buf, buf, C.byref(g), buf, buf, 4, 8) == -1 and b"stride" in lib.plnerf_last_error()        # no room for a viewdir
+    assert call(buf, buf, C.byref(g), buf, buf, 4, 11) < 0 and b"workspace" in lib.plnerf_last_error()      # no workspace
+    cfg.precision = L.PREC_BF16X3
+    assert call(buf, buf, C.byref(g), buf, buf, 4, 11) < 0 and b"BF16" in lib.plnerf_last_error()           # gradients are bf16 only
+    # the one-launch repack: 1 or 2 networks, no null entries
+    descs, prms = (C.POINTER(L.NetDesc) * 2)(), (C.POINTER(L.NetParams) * 2)()
+    bufs, bwds = (C.c_void_p * 2)(), (C.c_void_p * 2)()
+    assert lib.plnerf_pack_weights_train(0, descs, prms, bufs, bwds, None) == -1
+    assert lib.plnerf_pack_weights_train(3, descs, prms, bufs, bwds, None) == -1
+    assert lib.plnerf_pack_weights_train(1, descs, prms, bufs, bwds, None) == -1 and b"null" in lib.plnerf_last_error()

@@ -332,12 +332,13 @@ def test_repack_train_equals_separate_packs(use_viewdirs):
         assert not torch.equal(g0, r0) and not torch.equal(g1, r1)     # (the parameters did change)
 
 
-@pytest.mark.parametrize("n_importance,shared", [(64, False), (64, True), (0, False)])
-def test_train_rays_mse_equals_the_three_calls(n_importance, shared):
+@pytest.mark.parametrize("n_importance,shared,noisy", [(64, False, False), (64, True, False), (0, False, False), (64, False, True)])
+def test_train_rays_mse_equals_the_three_calls(n_importance, shared, noisy):
     """plnerf_train_rays_mse (forward + both MSE terms + backward in one call, the coarse backward forked beside the fine
     pass) against plnerf_render_rays_fwd_train -> plnerf_mse_loss_grad -> plnerf_render_rays_bwd on the same rays and draws:
     maps and loss sums bit for bit, parameter gradients to the weight-gradient atomics' noise.  `shared`: network_fine=None
-    (the coarse network serves both passes, both backward passes add into the same buffers concurrently)."""
+    (the coarse network serves both passes, both backward passes add into the same buffers concurrently); `noisy`: explicit
+    density noise and explicit draws."""
     from plnerf_b200 import ops
     n, Ns = 200, 64
     gen = torch.Generator(device="cuda")
@@ -351,6 +352,9 @@ def test_train_rays_mse_equals_the_three_calls(n_importance, shared):
     net_c, net_f = make_net(61), (None if (shared or n_importance == 0) else make_net(62))
     args = (rays, net_c, net_f, Ns, n_importance, "linear", "midpoint")
     kw = dict(perturb=True, white_bkgd=True, seed=77, ray_id_offset=1000)
+    if noisy:       # explicit density noise (raw_noise_std > 0 in the training configs): the same arrays reach forward and backward
+        kw.update(noise0=torch.randn(n, Ns, device="cuda", generator=gen), noise1=torch.randn(n, Ns + n_importance, device="cuda", generator=gen),
+                  t_rand=torch.rand(n, Ns, device="cuda", generator=gen), u=torch.rand(n, n_importance, device="cuda", generator=gen))
     scale = 2.0 / (3.0 * n)
 
     def zero_grads(net):
