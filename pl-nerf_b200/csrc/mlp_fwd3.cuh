@@ -560,23 +560,50 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
               ptx::tmem_st16(tm_a, reinterpret_cast<uint32_t(&)[16]>(held[0]));
               ptx::tmem_st16(tm_a + 16u, reinterpret_cast<uint32_t(&)[16]>(held[16]));
             }
-            // both 32-column chunks in flight (the held half's registers are free again), then the early signal: the next
-            // layer's first eight K-steps need only the accumulator drained and the first input half in place
-            uint32_t r0[32], r1[32];
-            ptx::tmem_ld32(tm_d, r0);
-            ptx::tmem_ld32(tm_d + 32u, r1);
-            ptx::tmem_ld_wait();
-            ptx::tmem_st_wait();
-            arrive_ep(1);
-            PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
-            uint32_t pk[16], m = 0;
-            if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, (STASH && !PLNERF3_DBG(64)) ? &m : nullptr); else cvt32<false>(r0, bias + 128, pk);
-            ptx::tmem_st16(tm_a + 64u, pk);
-            if (STASH) stash32(pk, m, 1, 0);
-            if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, (STASH && !PLNERF3_DBG(64)) ? &m : nullptr); else cvt32<false>(r1, bias + 160, pk);
-            ptx::tmem_st16(tm_a + 80u, pk);
-            if (STASH) stash32(pk, m, 1, 1);
-            if (alpha_here) { alpha_acc = dot32_relu(r0, aw + 128, alpha_acc); alpha_acc = dot32_relu(r1, aw + 160, alpha_acc); }
+            if (STASH) {
+              // stash forward (the epilogue is its bound, not the pipe): one 32-column chunk at a time -- with both chunks'
+              // 64 accumulator registers in flight next to the stash addresses the compiler spills more, and the reloads
+              // come from L2 (the kernel leaves the L1 a few KB); the early signal moves behind the first chunk's work
+              // (same-box A/B: -0.9% on the training step; the same order in the INFERENCE kernel costs +3.7%, see below)
+              uint32_t pk[16], m = 0;
+              {
+                uint32_t r0[32];
+                ptx::tmem_ld32(tm_d, r0);
+                ptx::tmem_ld_wait();
+                if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, !PLNERF3_DBG(64) ? &m : nullptr); else cvt32<false>(r0, bias + 128, pk);
+                if (alpha_here) alpha_acc = dot32_relu(r0, aw + 128, alpha_acc);
+              }
+              ptx::tmem_st16(tm_a + 64u, pk);
+              stash32(pk, m, 1, 0);
+              {
+                uint32_t r1[32];
+                ptx::tmem_ld32(tm_d + 32u, r1);
+                ptx::tmem_ld_wait();
+                ptx::tmem_st_wait();
+                arrive_ep(1);
+                PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
+                if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, !PLNERF3_DBG(64) ? &m : nullptr); else cvt32<false>(r1, bias + 160, pk);
+                if (alpha_here) alpha_acc = dot32_relu(r1, aw + 160, alpha_acc);
+              }
+              ptx::tmem_st16(tm_a + 80u, pk);
+              stash32(pk, m, 1, 1);
+            } else {
+              // both 32-column chunks in flight (the held half's registers are free again), then the early signal: the next
+              // layer's first eight K-steps need only the accumulator drained and the first input half in place
+              uint32_t r0[32], r1[32];
+              ptx::tmem_ld32(tm_d, r0);
+              ptx::tmem_ld32(tm_d + 32u, r1);
+              ptx::tmem_ld_wait();
+              ptx::tmem_st_wait();
+              arrive_ep(1);
+              PLNERF_TRACE(t * 2 + ch, tcnt, 5000 + l * 10 + 1);
+              uint32_t pk[16];
+              if (epi == EPI_RELU_A) cvt32<true>(r0, bias + 128, pk, nullptr); else cvt32<false>(r0, bias + 128, pk);
+              ptx::tmem_st16(tm_a + 64u, pk);
+              if (epi == EPI_RELU_A) cvt32<true>(r1, bias + 160, pk, nullptr); else cvt32<false>(r1, bias + 160, pk);
+              ptx::tmem_st16(tm_a + 80u, pk);
+              if (alpha_here) { alpha_acc = dot32_relu(r0, aw + 128, alpha_acc); alpha_acc = dot32_relu(r1, aw + 160, alpha_acc); }
+            }
           }
           ptx::tmem_st_wait();
           arrive_ep(2);
