@@ -507,6 +507,9 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
       const int64_t gtile = STASH ? g / TILE_M : 0;
       uint8_t* const st_base = STASH ? A.in_stash + gtile * (int64_t)A.tl.in_tile_bytes : nullptr;
       uint32_t* const m_base = STASH ? A.masks + gtile * (int64_t)A.tl.mask_tile_words + row : nullptr;
+      // this thread's 16-byte unit inside a 256-wide operand tile (MN-major 8x8 core matrices, see stash_store8), first of
+      // its eight 8-column groups of a half: every store of a trunk layer is then `st_row + layer offset + immediate`
+      uint8_t* const st_row = STASH ? st_base + (((row >> 6) * 32 * 8 + ((row & 63) >> 3)) * 128 + (row & 7) * 16 + 8 * ch * 1024) : nullptr;
       for (int l = 0; l < P.n_layers; ++l) {
         const int4 lt = reinterpret_cast<const int4*>(smem + Smem3<VD>::ltab)[l];
         const int epi = lt.x & 255, n_halves = (lt.x >> 8) & 255;
@@ -518,14 +521,15 @@ __global__ void __launch_bounds__(THREADS3, 1) k_mlp3(const __grid_constant__ Ml
           const float* aw = consts + P.alpha_w_off + 64 * ch;
           uint32_t held[32];                         // half a (packed), kept until half b's MMAs have read A_t
           // training stash of this layer's output: operand tile of width 256, mask words
-          uint8_t* st_t = STASH ? st_base + lt.z : nullptr;
-          uint32_t* st_m = (STASH && lt.w >= 0) ? m_base + lt.w : nullptr;
+          uint8_t* st_t = STASH ? st_row + lt.z : nullptr;
+          uint32_t* st_m = (STASH && lt.w >= 0) ? m_base + lt.w + 2 * ch * 128 : nullptr;
           auto stash32 = [&](const uint32_t* pk16, uint32_t m, int h, int c2) {   // 32 columns [128 h + 64 ch + 32 c2, +32)
-            if (st_m && !PLNERF3_DBG(64)) st_m[(4 * h + 2 * ch + c2) * 128] = m;           // (64: measurement, no mask stores)
+            if (st_m && !PLNERF3_DBG(64)) st_m[(4 * h + c2) * 128] = m;                    // (64: measurement, no mask stores)
             if (PLNERF3_DBG(32)) return;        // measurement: the stash forward without its activation stores
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
-              stash_store8(st_t, 256, row, 16 * h + 8 * ch + 4 * c2 + q4, make_uint4(pk16[4 * q4], pk16[4 * q4 + 1], pk16[4 * q4 + 2], pk16[4 * q4 + 3]));
+              asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(st_t + (16 * h + 4 * c2 + q4) * 1024), "r"(pk16[4 * q4]),
+                           "r"(pk16[4 * q4 + 1]), "r"(pk16[4 * q4 + 2]), "r"(pk16[4 * q4 + 3]) : "memory");
           };
           // half a
           PLNERF_TRACE(t * 2 + ch, tcnt, 2000 + l * 10);
