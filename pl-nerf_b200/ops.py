@@ -40,6 +40,10 @@ def _f32(t, name):
         raise TypeError(f"{name}: expected a torch.Tensor")
     if not t.is_cuda:
         raise RuntimeError(f"{name}: plnerf_b200 only runs on CUDA tensors (no CPU fallback); got device {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        # the kernels are enqueued on the CURRENT device's current stream (one process per GPU is the intended use)
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in torch.cuda.device(...)")
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()

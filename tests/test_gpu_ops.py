@@ -202,6 +202,16 @@ def test_cpu_tensor_rejected(P):
         P.encode(torch.zeros((4, 3)), 10)
 
 
+def test_tensor_on_another_device_rejected(P):
+    """The wrappers enqueue on the current device's current stream: a tensor of another GPU is refused, not mis-launched."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with pytest.raises(RuntimeError, match="current CUDA device"):
+        P.encode(torch.zeros((4, 3), device="cuda:1"), 10)
+    with torch.cuda.device(1):
+        assert P.encode(torch.zeros((4, 3), device="cuda:1"), 10).shape == (4, 63)
+
+
 # ------------------------------------------------------------------------------------------------
 def make_net(kw, params):
     from plnerf_b200.run_nerf_helpers import NeRF
