@@ -825,12 +825,16 @@ __device__ __forceinline__ void issue_tile_x3(IssueStateX3& st, uint32_t prog_ad
 
 // Positional encoding of one row -> this thread's panels of the PE tile(s).
 // store 8 consecutive bf16 columns (16 bytes) of row `row` into an MN-major stash tile
+template <bool STREAM = true>
 __device__ __forceinline__ void stash_store8(uint8_t* tile, int width, int row, int col8, uint4 v) {
   const int mh = row >> 6, m8 = (row & 63) >> 3, i = row & 7;
-  // streaming store (evict-first): the stash is written once and read a kernel or two later, after far more traffic than
-  // the L2 holds -- it should not displace the packed weights every CTA keeps re-reading
-  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16),
-               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  uint8_t* p = tile + ((size_t)((mh * (width >> 3) + col8) * 8 + m8)) * 128 + i * 16;
+  // STREAM (the forward's activation tiles): streaming, evict-first store -- written once and read two kernels later, after
+  // far more traffic than the L2 holds, they should not displace the packed weights every CTA keeps re-reading.
+  // !STREAM (the gradient chain's dY tiles): plain store -- k_wgrad reads them right after the chain, the tail is still in
+  // L2 (same-box A/B: streaming dY stores cost +0.9% on the training step, streaming activation stores save 1.3%).
+  if (STREAM) asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  else *reinterpret_cast<uint4*>(p) = v;
 }
 
 // ReLU masks of the training stash: one 32-bit word per (row, 32 columns).  The bit order is chosen for the gradient chain,
@@ -948,8 +952,8 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
     // the heads' weight gradients are k_wgrad items against this 16-column tile [g_rgb, g_alpha, 0...] (rows past the end: 0);
     // their bias gradients are its column sums
     uint8_t* tile_h = A.dy_stash + tile * (int64_t)A.tl.dy_tile_bytes + A.tl.dy_off[A.tl.dy_head];
-    stash_store8(tile_h, 16, row, 0, make_uint4(ptx::pack_bf16(gr, gg), ptx::pack_bf16(gb, g_alpha), 0u, 0u));
-    stash_store8(tile_h, 16, row, 1, make_uint4(0u, 0u, 0u, 0u));
+    stash_store8<false>(tile_h, 16, row, 0, make_uint4(ptx::pack_bf16(gr, gg), ptx::pack_bf16(gb, g_alpha), 0u, 0u));
+    stash_store8<false>(tile_h, 16, row, 1, make_uint4(0u, 0u, 0u, 0u));
     float s0 = gr, s1 = gg, s2 = gb, s3 = g_alpha;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -982,7 +986,7 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
         ptx::tmem_st16(tmem_lane_a1 + (uint32_t)(n0 >> 1), pk);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          stash_store8(tile_dy, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+          stash_store8<false>(tile_dy, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
       }
     }
     ptx::tmem_st_wait();
@@ -1004,7 +1008,7 @@ __device__ __forceinline__ void dgrad_prologue(const MlpArgs& A, const float* co
     ptx::tmem_st16(tmem_lane_a1 + (uint32_t)(n0 >> 1), pk);
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4)
-      stash_store8(tile_dy, 128, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+      stash_store8<false>(tile_dy, 128, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
   }
   ptx::tmem_st_wait();
 }
@@ -1445,7 +1449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_mlp_fwd(const __grid_constan
               if (!PLNERF_DBG(32))                 // (measurement: the gradient chain without its dY stores)
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
-                stash_store8(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
+                stash_store8<false>(t, 256, row, (n0 >> 3) + q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
             } else if (epi == EPI_VIEWS) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
